@@ -1,0 +1,95 @@
+"""CPU: the oracle restatement (oracle/vqgan_oracle.py) is pinned against fixtures produced by the
+REAL reference (oracle/make_golden.py). No GPU, no product code."""
+import os
+
+import numpy as np
+import torch
+
+from conftest import GOLDEN, rel_err
+from oracle import vqgan_oracle as O
+
+
+def _load(name):
+    return torch.load(os.path.join(GOLDEN, name), weights_only=False)
+
+
+def test_tiny_vqbase_forward_backward_matches_reference():
+    g = _load("vqbase_tiny.pt")
+    sd = {k: v.clone().requires_grad_(k in g["grads"]) for k, v in g["state_dict"].items()}
+    taps = {}
+    dec, diff, idx = O.vqbase_forward(sd, g["ddconfig"], g["x"], taps=taps)
+    assert torch.equal(idx, g["idx"])
+    assert rel_err(dec, g["dec"]) < 1e-5
+    assert abs(float(diff) - float(g["diff"])) < 1e-6
+    for k, v in g["taps"].items():
+        assert rel_err(taps[k], v) < 1e-5, k
+    loss = O.proxy_loss(g["x"], dec, diff)
+    loss.backward()
+    for k, gv in g["grads"].items():
+        assert rel_err(sd[k].grad, gv) < 2e-4, k
+
+
+def test_tiny_modes_bypass_and_eval():
+    g = _load("vqbase_tiny.pt")
+    m = _load("vqbase_tiny_modes.pt")
+    dec, diff, idx = O.vqbase_forward(g["state_dict"], g["ddconfig"], g["x"], quantize=False, training=True)
+    assert idx is None and float(diff) == 0.0
+    assert rel_err(dec, m["dec_bypass"]) < 1e-5
+    dec, diff, idx = O.vqbase_forward(g["state_dict"], g["ddconfig"], g["x"], quantize=True, training=False)
+    assert rel_err(dec, m["dec_eval"]) < 1e-5
+    assert abs(float(diff) - float(m["diff_eval"])) < 1e-6
+
+
+def test_codebook_sets():
+    sets = _load("codebook_sets.pt")
+    for name, s in sets.items():
+        z = s["z"].clone().requires_grad_(True)
+        E = s["E"].clone().requires_grad_(True)
+        z_q, loss, idx = O.codebook_forward(z, E)
+        assert torch.equal(idx, s["idx"]), name
+        assert torch.allclose(z_q, s["z_q"], atol=1e-6), name
+        assert abs(float(loss) - float(s["loss"])) < 1e-6 * max(1.0, abs(float(s["loss"]))), name
+        (z_q * torch.linspace(-1, 1, z_q.numel()).view_as(z_q)).sum().add(loss).backward()
+        assert rel_err(z.grad, s["grad_z"]) < 1e-5, name
+        assert rel_err(E.grad, s["grad_E"]) < 1e-5, name
+        assert torch.equal(O.codebook_entry(s["E"], s["idx"], (3, 4, 4, 64)), s["entry"])
+        # numpy restatement of the integer-valued argmin: identical except on exact-tie sets
+        zf = s["z"].permute(0, 2, 3, 1).reshape(-1, 64).numpy()
+        idx_np = O.codebook_argmin_numpy(zf, s["E"].numpy())
+        bad = np.nonzero(idx_np != s["idx"].numpy())[0]
+        if name in ("trained", "clustered"):
+            assert bad.size == 0, name
+        else:
+            gap, ulp = O.codebook_gap_fp64(torch.from_numpy(zf), s["E"], torch.from_numpy(idx_np), s["idx"])
+            assert bool((gap[bad] <= 4 * ulp[bad]).all()), name
+
+
+def test_blocks():
+    blocks = _load("blocks.pt")
+    fn = {"res": O.resnet_block, "attn": O.attn_block, "down": O.downsample, "up": O.upsample}
+    for name, b in blocks.items():
+        sd = {"m." + k: v.clone().requires_grad_(True) for k, v in b["state_dict"].items()}
+        x = b["x"].clone().requires_grad_(True)
+        y = fn[name.split("_")[0]](x, sd, "m")
+        assert rel_err(y, b["y"]) < 1e-5, name
+        (y * torch.linspace(-1, 1, y.numel()).view_as(y)).sum().backward()
+        assert rel_err(x.grad, b["grad_x"]) < 1e-4, name
+        for k, gv in b["grads"].items():
+            assert rel_err(sd["m." + k].grad, gv) < 1e-4, (name, k)
+
+
+def test_plans_match_img_config_layer_counts():
+    g = _load("vqbase_img_64.pt")
+    enc = O.encoder_plan(**g["ddconfig"])
+    dec = O.decoder_plan(**g["ddconfig"])
+    assert len(enc) == 23 and len(dec) == 29
+    assert sum(k == "attn" for k, *_ in enc) == 3 and sum(k == "attn" for k, *_ in dec) == 4
+
+
+def test_seg_loss():
+    g = _load("seg_loss.pt")
+    pred = g["pred"].clone().requires_grad_(True)
+    loss = O.bce_loss_with_quant(g["qloss"], g["target"], pred)
+    assert abs(float(loss) - float(g["loss"])) < 1e-6
+    loss.backward()
+    assert rel_err(pred.grad, g["grad"]) < 1e-6
