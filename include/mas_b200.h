@@ -1,0 +1,164 @@
+/* mas_b200.h — C-ABI of the B200-native VQ-IMG hot path (libmas_b200.so).
+ *
+ * The reference (CasualGANPapers/Make-A-Scene) is pure Python/PyTorch and has NO native interface;
+ * every arithmetic step of its hot path is a stock ATen/cuDNN/cuBLAS call issued from
+ * models/modules.py and models/vqvae.py.  Each entry point below replaces one such call site and
+ * cites it (file:line relative to the reference root).  SURVEY.md 8(b) is the contract:
+ *   - extern "C", plain pointers and sizes, no torch / C++ types in any signature;
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - no hidden allocation, no hidden synchronisation: scratch comes from the caller (ws/ws_bytes,
+ *     size from the matching *_ws_bytes function), work is enqueued on `stream` (a cudaStream_t
+ *     passed as void*) and the call returns immediately;
+ *   - return value: 0 = ok, <0 = error (MAS_ERR_*); mas_last_error() gives a thread-local message.
+ *
+ * Activation layout: fp32 "NHWC" (channels innermost).  Where an entry takes explicit element
+ * strides (sn, sh, sw, sc) any layout — including the reference's NCHW — is accepted, which is how
+ * the first/last convolutions read/write NCHW images without a transposing copy.
+ */
+#ifndef MAS_B200_H_
+#define MAS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAS_OK 0
+#define MAS_ERR_INVALID_ARG (-1)
+#define MAS_ERR_UNSUPPORTED (-2)
+#define MAS_ERR_LAUNCH (-3)
+#define MAS_ERR_WORKSPACE (-4)
+
+/* Input-coordinate maps of the 3x3 convolution family (modules.py:44-81). */
+#define MAS_CONV_S1 0 /* stride 1, pad 1                       — nn.Conv2d(k=3,s=1,p=1), modules.py:93-104 */
+#define MAS_CONV_S2 1 /* pad (0,1,0,1) + stride 2, pad 0       — Downsample.forward, modules.py:74-78      */
+#define MAS_CONV_UP 2 /* nearest x2 upsample then stride 1 p1  — Upsample.forward, modules.py:55-59        */
+#define MAS_CONV_ZS 3 /* zero-stuffed x2 input (data gradient of MAS_CONV_S2), stride 1 pad 1             */
+
+/* Implementation selector for the contraction kernels. */
+#define MAS_IMPL_AUTO 0  /* tcgen05 (TF32 operands, fp32 accumulate) when the shape is eligible, else SIMT */
+#define MAS_IMPL_SIMT 1  /* fp32 FFMA kernels (exact fp32; also the on-GPU checker for the tensor path)      */
+#define MAS_IMPL_TC 2    /* tcgen05 only; MAS_ERR_UNSUPPORTED if the shape is not eligible                   */
+
+typedef struct mas_tensor4 {
+  int64_t n, h, w, c;     /* logical extents */
+  int64_t sn, sh, sw, sc; /* element strides */
+} mas_tensor4;
+
+int mas_version(void);
+const char* mas_last_error(void);
+/* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
+int64_t mas_launch_count(void);
+
+/* ---- layout helpers (boundary only; the VQBASE path itself never transposes) ------------------- */
+int mas_copy_strided(const float* x, mas_tensor4 xs, float* y, mas_tensor4 ys, void* stream);
+
+/* ---- GroupNorm(32, C, eps=1e-6) + optional SiLU — Normalize / nonlinearity, modules.py:35-41 ------
+ * x, y: [N, HW, C] NHWC.  mean/rstd: [N*G].  silu=1 fuses x*sigmoid(x) (modules.py:122,126,194-196).
+ * round_tf32=1 rounds y to TF32 (round-to-nearest) so that a following tensor-core contraction sees
+ * correctly rounded operands.  Backward: dx = GN/SiLU input gradient (+ dx_add elementwise when not NULL, which
+ * folds the residual-branch gradient of ResnetBlock/AttnBlock, modules.py:136,191); dgamma/dbeta are overwritten. */
+size_t mas_gn_ws_bytes(int N, int HW, int C, int G);
+int mas_gn_stats(const float* x, int N, int HW, int C, int G, float eps, float* mean, float* rstd,
+                 void* ws, size_t ws_bytes, void* stream);
+int mas_gn_apply(const float* x, const float* mean, const float* rstd, const float* gamma,
+                 const float* beta, float* y, int N, int HW, int C, int G, int silu, int round_tf32,
+                 void* stream);
+int mas_gn_backward(const float* dy, const float* x, const float* mean, const float* rstd,
+                    const float* gamma, const float* beta, const float* dx_add, float* dx, float* dgamma,
+                    float* dbeta, int N, int HW, int C, int G, int silu, void* ws, size_t ws_bytes, void* stream);
+/* out = a + b (gradient of x+h where the two branches cannot be fused). */
+int mas_add(const float* a, const float* b, float* out, int64_t n, void* stream);
+/* Standalone Swish module (modules.py:194-196). */
+int mas_silu_forward(const float* x, float* y, int64_t n, void* stream);
+int mas_silu_backward(const float* dy, const float* x, float* dx, int64_t n, void* stream);
+
+/* ---- 3x3 convolution family — nn.Conv2d / Downsample / Upsample, modules.py:44-81,93-104 ----------
+ * w_packed: [9*Cin, Cout] row-major, row index (ty*3+tx)*Cin+ci (mas_pack_conv3x3 builds it from the
+ * reference's [Cout,Cin,3,3] parameter; flip_transpose=1 builds the data-gradient form
+ * [9*Cout, Cin] with taps flipped).  y = conv(x) + bias + residual (bias/residual may be NULL;
+ * residual has y's strides).  x and y carry explicit strides. */
+int mas_pack_conv3x3(const float* w_oihw, float* w_packed, int Cout, int Cin, int flip_transpose,
+                     int round_tf32, void* stream);
+int mas_conv3x3_fprop(const float* x, mas_tensor4 xs, const float* w_packed, const float* bias,
+                      const float* residual, float* y, mas_tensor4 ys, int mode, int impl, void* stream);
+/* Weight gradient, written in the reference's [Cout,Cin,3,3] layout; dbias [Cout] may be NULL.
+ * x is the convolution's (already normalised+activated) input, dy the output gradient. */
+size_t mas_conv3x3_wgrad_ws_bytes(mas_tensor4 xs, mas_tensor4 dys, int mode);
+int mas_conv3x3_wgrad(const float* x, mas_tensor4 xs, const float* dy, mas_tensor4 dys, float* dw_oihw,
+                      float* dbias, int mode, int impl, void* ws, size_t ws_bytes, void* stream);
+/* Weight gradient of a 1x1 convolution: dw[Cout,Cin] = dy^T x over M rows (split over rows, deterministic);
+ * dbias [Cout] may be NULL. x [M,Cin] and dy [M,Cout] are row-major with row pitches ldx / ldy (elements). */
+size_t mas_conv1x1_wgrad_ws_bytes(int64_t M, int Cin, int Cout);
+int mas_conv1x1_wgrad(const float* x, int64_t ldx, const float* dy, int64_t ldy, int64_t M, int Cin, int Cout,
+                      float* dw, float* dbias, int impl, void* ws, size_t ws_bytes, void* stream);
+/* 2x2 sum pooling: data gradient of the nearest x2 upsample (modules.py:56). x [N,2H,2W,C] -> y [N,H,W,C]. */
+int mas_sumpool2x2(const float* x, float* y, int N, int H, int W, int C, void* stream);
+
+/* ---- batched GEMM — Conv2d 1x1 (modules.py:113-117,145-164; vqvae.py:15,18) and torch.bmm
+ * (modules.py:179,186).  Row-major.  C[b] = alpha * op(A[b]) * op(B[b]) + bias[n] + residual[b].
+ * op(A) is M x K, op(B) is K x N; trans_a: A stored K x M; trans_b: B stored N x K.
+ * lda/ldb/ldc row pitches, stride_* batch pitches (elements); bias/residual may be NULL
+ * (residual shares C's ldc / stride_c). */
+int mas_gemm(const float* A, const float* B, float* C, int M, int N, int K, int batch, int64_t lda,
+             int64_t ldb, int64_t ldc, int64_t stride_a, int64_t stride_b, int64_t stride_c, int trans_a,
+             int trans_b, float alpha, const float* bias, const float* residual, int impl, void* stream);
+/* Column sums of a strided [N,H,W,C] view (bias gradients): out[c] = sum_{n,h,w} x[n,h,w,c]. Deterministic. */
+size_t mas_colsum_ws_bytes(mas_tensor4 t);
+int mas_colsum(const float* x, mas_tensor4 t, float* out, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- AttnBlock softmax over keys — modules.py:180-181,185 ------------------------------------------
+ * rows x cols row-major; forward is in place capable (p may alias s). backward: ds = p*(dp - sum(dp*p))*scale. */
+int mas_softmax_forward(const float* s, float* p, int64_t rows, int cols, void* stream);
+int mas_softmax_backward(const float* p, const float* dp, float* ds, int64_t rows, int cols, float scale,
+                         void* stream);
+
+/* ---- (Sync)BatchNorm for quant_conv[1] — vqvae.py:16 ---------------------------------------------------
+ * x [R, C] NHWC rows.  mas_bn_stats writes LOCAL [sum(C), sumsq(C)] as fp64 (2*C doubles); the caller
+ * all-reduces those 2*C numbers (+ the row count) across ranks over NCCL, then mas_bn_finalize turns the
+ * global sums into mean / invstd (biased variance) and updates running_mean / running_var (unbiased,
+ * momentum; either may be NULL) exactly like nn.SyncBatchNorm.  Backward: mas_bn_backward_reduce writes the
+ * LOCAL [sum_dy(C), sum_dy_xhat(C)] (fp64) for the second all-reduce; mas_bn_backward_apply consumes the
+ * global sums for dx and the local sums for dgamma/dbeta (DDP all-reduces parameter grads itself). */
+int mas_bn_stats(const float* x, int64_t R, int C, double* stats_out, void* stream);
+int mas_bn_finalize(const double* stats, double count, int C, float eps, float momentum, float* mean,
+                    float* invstd, float* running_mean, float* running_var, void* stream);
+int mas_bn_apply(const float* x, const float* mean, const float* invstd, const float* gamma,
+                 const float* beta, float* y, int64_t R, int C, void* stream);
+int mas_bn_backward_reduce(const float* dy, const float* x, const float* mean, const float* invstd,
+                           int64_t R, int C, double* sums_out, void* stream);
+int mas_bn_backward_apply(const float* dy, const float* x, const float* mean, const float* invstd,
+                          const float* gamma, const double* sums_global, const double* sums_local,
+                          double inv_count, float* dx, float* dgamma, float* dbeta, int64_t R, int C,
+                          void* stream);
+
+/* ---- Codebook (vector quantiser) — modules.py:470-473,501-517 ---------------------------------------
+ * z: [R, D] latent rows (NHWC order, R = B*h*w), E: [K, D] codebook.
+ * idx_out[r] = argmin_k ( (|z_r|^2 + |e_k|^2) - 2 z_r.e_k ), fp32, the reference's association and
+ * first-index tie-break (modules.py:501-505).  zq_out[r] = E[idx] (modules.py:506).
+ * loss_out (1 float) = (1+beta) * mean((zq - z)^2)  (modules.py:509; both terms are numerically equal
+ * in the forward).  The distance matrix is never materialised. */
+size_t mas_vq_ws_bytes(int64_t R, int K, int D);
+int mas_vq_forward(const float* z, const float* E, int64_t R, int K, int D, float beta, int64_t* idx_out,
+                   float* zq_out, float* loss_out, void* ws, size_t ws_bytes, void* stream);
+/* Backward (modules.py:509-512): grad_z = g_zq + g_loss*(2/(R*D))*(z - zq);
+ * grad_E[k] += g_loss*(2*beta/(R*D)) * sum_{r: idx_r = k} (e_k - z_r).  grad_E must be zeroed by the caller. */
+int mas_vq_backward(const float* g_zq, const float* g_loss, const float* z, const float* E,
+                    const int64_t* idx, int64_t R, int K, int D, float beta, float* grad_z, float* grad_E,
+                    void* stream);
+/* get_codebook_entry gather (modules.py:519-528): out[r] = E[idx[r]]. */
+int mas_vq_gather(const float* E, const int64_t* idx, int64_t R, int K, int D, float* out, void* stream);
+
+/* ---- weighted BCE-with-logits (VQ-SEG loss, losses/loss_seg.py:15-22) — "next" row ------------------
+ * logits/target: strided [N,H,W,C] views; pos_weight [C]; loss_out = mean over all elements. grad may be NULL. */
+int mas_bce_logits(const float* logits, mas_tensor4 ls, const float* target, mas_tensor4 ts,
+                   const float* pos_weight, float* loss_out, float* grad, mas_tensor4 gs, float grad_scale,
+                   void* ws, size_t ws_bytes, void* stream);
+size_t mas_bce_ws_bytes(mas_tensor4 ls);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAS_B200_H_ */

@@ -1,0 +1,626 @@
+// GroupNorm(+SiLU), Swish, softmax, BatchNorm statistics, column sums, strided copy, 2x2 sum-pool,
+// weighted BCE — the HBM-bound kernels of the VQ-IMG path.  All fp32 I/O, NHWC rows.
+// Reference call sites: modules.py:35-41 (Normalize/nonlinearity), :180-181 (softmax), vqvae.py:16 (BN).
+#include <stdarg.h>
+
+#include "mas_common.cuh"
+
+namespace mas {
+
+thread_local char g_err[512] = {0};
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int launched(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(MAS_ERR_LAUNCH, "%s: %s", what, cudaGetErrorString(e));
+  return MAS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm.  x [N, HW, C]; a block owns GN_PIX consecutive pixels of one image; thread t owns the
+// channel quad (t % U), U = C/4, and walks pixels t/U, t/U + 256/U, ...  Sums are kept in fp64
+// (cheap in an HBM-bound kernel) so that var = E[x^2]-E[x]^2 has no fp32 cancellation problem.
+// ------------------------------------------------------------------------------------------------
+constexpr int GN_THREADS = 256;
+constexpr int GN_PIX = 1024;
+
+__global__ void __launch_bounds__(GN_THREADS) gn_stats_partial(const float* __restrict__ x, int HW, int C, int G,
+                                                               double* __restrict__ part /*[N][chunks][G][2]*/) {
+  extern __shared__ double sm[];  // [C][2] then reused
+  const int U = C >> 2, n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+  const int t = threadIdx.x, u = t % U, lanes = GN_THREADS / U, pl = t / U;
+  const int p0 = chunk * GN_PIX, p1 = min(HW, p0 + GN_PIX);
+  double s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+  const float4* xp = reinterpret_cast<const float4*>(x + (size_t)n * HW * C) + u;
+  for (int p = p0 + pl; p < p1; p += lanes) {
+    float4 v = __ldg(xp + (size_t)p * U);
+    s[0] += v.x; q[0] += (double)v.x * v.x;
+    s[1] += v.y; q[1] += (double)v.y * v.y;
+    s[2] += v.z; q[2] += (double)v.z * v.z;
+    s[3] += v.w; q[3] += (double)v.w * v.w;
+  }
+  // deterministic block reduction: [lanes][C][2] in shared memory, then fixed-order sums
+  double* buf = sm;  // lanes*C*2 doubles
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    buf[((size_t)pl * C + u * 4 + i) * 2 + 0] = s[i];
+    buf[((size_t)pl * C + u * 4 + i) * 2 + 1] = q[i];
+  }
+  __syncthreads();
+  const int cpg = C / G;
+  if (t < G) {
+    double a = 0, b = 0;
+    for (int c = t * cpg; c < (t + 1) * cpg; ++c)
+      for (int l = 0; l < lanes; ++l) {
+        a += buf[((size_t)l * C + c) * 2 + 0];
+        b += buf[((size_t)l * C + c) * 2 + 1];
+      }
+    double* o = part + (((size_t)n * nchunks + chunk) * G + t) * 2;
+    o[0] = a;
+    o[1] = b;
+  }
+}
+
+__global__ void gn_stats_final(const double* __restrict__ part, int nchunks, int G, double count, float eps,
+                               float* __restrict__ mean, float* __restrict__ rstd, int NG) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NG) return;
+  int n = i / G, g = i % G;
+  double a = 0, b = 0;
+  for (int c = 0; c < nchunks; ++c) {
+    const double* o = part + (((size_t)n * nchunks + c) * G + g) * 2;
+    a += o[0];
+    b += o[1];
+  }
+  double m = a / count, var = b / count - m * m;
+  if (var < 0) var = 0;
+  mean[i] = (float)m;
+  rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                                                       const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, float* __restrict__ y, int64_t total4,
+                                                       int HW, int C, int G, int silu, int rtf32) {
+  const int U = C >> 2, cpg = C / G;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    int u = (int)(i % U);
+    int n = (int)(i / ((int64_t)HW * U));
+    float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    float in[4] = {v.x, v.y, v.z, v.w}, out[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int c = u * 4 + k, g = c / cpg;
+      float m = __ldg(mean + n * G + g), r = __ldg(rstd + n * G + g);
+      float o = (in[k] - m) * r * __ldg(gamma + c) + __ldg(beta + c);
+      if (silu) o = silu_f(o);
+      if (rtf32) o = round_tf32(o);
+      out[k] = o;
+    }
+    reinterpret_cast<float4*>(y)[i] = make_float4(out[0], out[1], out[2], out[3]);
+  }
+}
+
+// backward pass 1: per (n, chunk, channel): s1 = sum dyu*xhat, s2 = sum dyu, with dyu = dy*silu'(u)
+__global__ void __launch_bounds__(GN_THREADS) gn_bwd_partial(const float* __restrict__ dy, const float* __restrict__ x,
+                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             int HW, int C, int G, int silu,
+                                                             double* __restrict__ part /*[N][chunks][C][2]*/) {
+  extern __shared__ double sm[];
+  const int U = C >> 2, n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x, cpg = C / G;
+  const int t = threadIdx.x, u = t % U, lanes = GN_THREADS / U, pl = t / U;
+  const int p0 = chunk * GN_PIX, p1 = min(HW, p0 + GN_PIX);
+  float m[4], r[4], ga[4], be[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    int c = u * 4 + k, g = c / cpg;
+    m[k] = mean[n * G + g];
+    r[k] = rstd[n * G + g];
+    ga[k] = gamma[c];
+    be[k] = beta[c];
+  }
+  double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+  const float4* xp = reinterpret_cast<const float4*>(x + (size_t)n * HW * C) + u;
+  const float4* dp = reinterpret_cast<const float4*>(dy + (size_t)n * HW * C) + u;
+  for (int p = p0 + pl; p < p1; p += lanes) {
+    float4 xv = __ldg(xp + (size_t)p * U), dv = __ldg(dp + (size_t)p * U);
+    float xi[4] = {xv.x, xv.y, xv.z, xv.w}, di[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float xh = (xi[k] - m[k]) * r[k];
+      float d = di[k];
+      if (silu) d *= silu_grad_f(xh * ga[k] + be[k]);
+      s1[k] += (double)d * xh;
+      s2[k] += d;
+    }
+  }
+  double* buf = sm;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    buf[((size_t)pl * C + u * 4 + k) * 2 + 0] = s1[k];
+    buf[((size_t)pl * C + u * 4 + k) * 2 + 1] = s2[k];
+  }
+  __syncthreads();
+  for (int c = t; c < C; c += GN_THREADS) {
+    double a = 0, b = 0;
+    for (int l = 0; l < lanes; ++l) {
+      a += buf[((size_t)l * C + c) * 2 + 0];
+      b += buf[((size_t)l * C + c) * 2 + 1];
+    }
+    double* o = part + (((size_t)n * nchunks + chunk) * C + c) * 2;
+    o[0] = a;
+    o[1] = b;
+  }
+}
+
+// backward finalize, stage 1: per (n,c) sums over chunks
+__global__ void gn_bwd_nc(const double* __restrict__ part, int N, int nchunks, int C, double* __restrict__ nc /*[N][C][2]*/) {
+  int i = threadIdx.x + blockIdx.x * blockDim.x;
+  if (i >= N * C) return;
+  int n = i / C, c = i % C;
+  double a = 0, b = 0;
+  for (int k = 0; k < nchunks; ++k) {
+    const double* o = part + (((size_t)n * nchunks + k) * C + c) * 2;
+    a += o[0];
+    b += o[1];
+  }
+  nc[(size_t)i * 2 + 0] = a;
+  nc[(size_t)i * 2 + 1] = b;
+}
+// stage 2 (one block; N*C <= 32*512): dgamma/dbeta and per-(n,g) A,B
+__global__ void gn_bwd_final(int N, int C, int G, const float* __restrict__ gamma, const double* __restrict__ nc,
+                             float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ AB /*[N][G][2]*/,
+                             double inv_m) {
+  const int cpg = C / G;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double a = 0, b = 0;
+    for (int n = 0; n < N; ++n) {
+      a += nc[((size_t)n * C + c) * 2 + 0];
+      b += nc[((size_t)n * C + c) * 2 + 1];
+    }
+    dgamma[c] = (float)a;
+    dbeta[c] = (float)b;
+  }
+  for (int i = threadIdx.x; i < N * G; i += blockDim.x) {
+    int n = i / G, g = i % G;
+    double a = 0, b = 0;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      a += (double)gamma[c] * nc[((size_t)n * C + c) * 2 + 0];
+      b += (double)gamma[c] * nc[((size_t)n * C + c) * 2 + 1];
+    }
+    AB[i * 2 + 0] = (float)(a * inv_m);
+    AB[i * 2 + 1] = (float)(b * inv_m);
+  }
+}
+
+__global__ void __launch_bounds__(256) gn_bwd_apply(const float* __restrict__ dy, const float* __restrict__ x,
+                                                    const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                    const float* __restrict__ AB, const float* __restrict__ dx_add,
+                                                    float* __restrict__ dx, int64_t total4, int HW, int C, int G, int silu) {
+  const int U = C >> 2, cpg = C / G;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    int u = (int)(i % U);
+    int n = (int)(i / ((int64_t)HW * U));
+    float4 xv = __ldg(reinterpret_cast<const float4*>(x) + i), dv = __ldg(reinterpret_cast<const float4*>(dy) + i);
+    float xi[4] = {xv.x, xv.y, xv.z, xv.w}, di[4] = {dv.x, dv.y, dv.z, dv.w}, out[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int c = u * 4 + k, g = c / cpg;
+      float m = __ldg(mean + n * G + g), r = __ldg(rstd + n * G + g), ga = __ldg(gamma + c);
+      float xh = (xi[k] - m) * r;
+      float d = di[k];
+      if (silu) d *= silu_grad_f(xh * ga + __ldg(beta + c));
+      float A = __ldg(AB + (n * G + g) * 2), B = __ldg(AB + (n * G + g) * 2 + 1);
+      out[k] = r * (d * ga - B - xh * A);
+    }
+    if (dx_add) {
+      float4 av = __ldg(reinterpret_cast<const float4*>(dx_add) + i);
+      out[0] += av.x; out[1] += av.y; out[2] += av.z; out[3] += av.w;
+    }
+    reinterpret_cast<float4*>(dx)[i] = make_float4(out[0], out[1], out[2], out[3]);
+  }
+}
+
+__global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) o[i] = a[i] + b[i];
+}
+__global__ void silu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = silu_f(x[i]);
+}
+__global__ void silu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dx, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dx[i] = dy[i] * silu_grad_f(x[i]);
+}
+
+// ------------------------------------------------------------------------------------------------ softmax (warp per row)
+__global__ void softmax_fwd_kernel(const float* __restrict__ s, float* __restrict__ p, int64_t rows, int cols) {
+  int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  int lane = threadIdx.x & 31;
+  const float* sr = s + row * cols;
+  float* pr = p + row * cols;
+  float mx = -INFINITY;
+  for (int c = lane; c < cols; c += 32) mx = fmaxf(mx, sr[c]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int c = lane; c < cols; c += 32) sum += expf(sr[c] - mx);
+  sum = warp_sum(sum);
+  float inv = 1.0f / sum;
+  for (int c = lane; c < cols; c += 32) pr[c] = expf(sr[c] - mx) * inv;
+}
+__global__ void softmax_bwd_kernel(const float* __restrict__ p, const float* __restrict__ dp, float* __restrict__ ds,
+                                   int64_t rows, int cols, float scale) {
+  int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  int lane = threadIdx.x & 31;
+  const float* pr = p + row * cols;
+  const float* dr = dp + row * cols;
+  float dot = 0.f;
+  for (int c = lane; c < cols; c += 32) dot += pr[c] * dr[c];
+  dot = warp_sum(dot);
+  for (int c = lane; c < cols; c += 32) ds[row * cols + c] = pr[c] * (dr[c] - dot) * scale;
+}
+
+// ------------------------------------------------------------------------------------------------ BatchNorm pieces
+// one block per 32-channel tile; blockDim (32, 8); deterministic; R*C is small (8192 x 256) on this path
+__global__ void bn_stats_kernel(const float* __restrict__ x, int64_t R, int C, double* __restrict__ out /*[2C]*/) {
+  __shared__ double sh[8][32][2];
+  int c = blockIdx.x * 32 + threadIdx.x;
+  double a = 0, b = 0;
+  if (c < C)
+    for (int64_t r = threadIdx.y; r < R; r += 8) {
+      float v = x[r * C + c];
+      a += v;
+      b += (double)v * v;
+    }
+  sh[threadIdx.y][threadIdx.x][0] = a;
+  sh[threadIdx.y][threadIdx.x][1] = b;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    for (int k = 1; k < 8; ++k) {
+      a += sh[k][threadIdx.x][0];
+      b += sh[k][threadIdx.x][1];
+    }
+    out[c] = a;
+    out[C + c] = b;
+  }
+}
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, double count, int C, float eps, float momentum,
+                                   float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ run_mean,
+                                   float* __restrict__ run_var) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double m = stats[c] / count, var = stats[C + c] / count - m * m;
+  if (var < 0) var = 0;
+  mean[c] = (float)m;
+  invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (run_mean) {
+    double unb = count > 1 ? var * count / (count - 1) : var;
+    run_mean[c] = (float)((1.0 - momentum) * run_mean[c] + momentum * m);
+    run_var[c] = (float)((1.0 - momentum) * run_var[c] + momentum * unb);
+  }
+}
+__global__ void bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y,
+                                int64_t total, int C) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    y[i] = (x[i] - mean[c]) * invstd[c] * gamma[c] + beta[c];
+  }
+}
+__global__ void bn_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+                                     const float* __restrict__ invstd, int64_t R, int C, double* __restrict__ out /*[2C]*/) {
+  __shared__ double sh[8][32][2];
+  int c = blockIdx.x * 32 + threadIdx.x;
+  double a = 0, b = 0;
+  if (c < C) {
+    float m = mean[c], is = invstd[c];
+    for (int64_t r = threadIdx.y; r < R; r += 8) {
+      float d = dy[r * C + c];
+      a += d;
+      b += (double)d * ((x[r * C + c] - m) * is);
+    }
+  }
+  sh[threadIdx.y][threadIdx.x][0] = a;
+  sh[threadIdx.y][threadIdx.x][1] = b;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    for (int k = 1; k < 8; ++k) {
+      a += sh[k][threadIdx.x][0];
+      b += sh[k][threadIdx.x][1];
+    }
+    out[c] = a;
+    out[C + c] = b;
+  }
+}
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+                                    const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                    const double* __restrict__ sums /*[2C] global sums*/, double inv_count,
+                                    float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                    const double* __restrict__ local_sums, int64_t total, int C) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    float xh = (x[i] - mean[c]) * invstd[c];
+    float sd = (float)(sums[c] * inv_count), sdx = (float)(sums[C + c] * inv_count);
+    dx[i] = gamma[c] * invstd[c] * (dy[i] - sd - xh * sdx);
+    if (i < C && dgamma) {  // parameter grads are LOCAL sums (DDP all-reduces them like any other grad)
+      dbeta[c] = (float)local_sums[c];
+      dgamma[c] = (float)local_sums[C + c];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ column sums (bias grads)
+// out[c] = sum over (n,h,w) of x[n,h,w,c] for a strided view; two-stage deterministic.
+constexpr int CS_ROWS = 2048;
+__global__ void colsum_partial(const float* __restrict__ x, mas_tensor4 t, double* __restrict__ part /*[chunks][C]*/) {
+  __shared__ double sh[8][32];
+  int c = blockIdx.x * 32 + threadIdx.x;
+  int64_t rows = t.n * t.h * t.w, r0 = (int64_t)blockIdx.y * CS_ROWS, r1 = min(rows, r0 + CS_ROWS);
+  double a = 0;
+  if (c < t.c)
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
+      int64_t w = r % t.w, h = (r / t.w) % t.h, n = r / (t.w * t.h);
+      a += x[n * t.sn + h * t.sh + w * t.sw + c * t.sc];
+    }
+  sh[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < t.c) {
+    for (int k = 1; k < 8; ++k) a += sh[k][threadIdx.x];
+    part[(size_t)blockIdx.y * t.c + c] = a;
+  }
+}
+__global__ void colsum_final(const double* __restrict__ part, int chunks, int C, float* __restrict__ out) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double a = 0;
+  for (int k = 0; k < chunks; ++k) a += part[(size_t)k * C + c];
+  out[c] = (float)a;
+}
+
+__global__ void copy_strided_kernel(const float* __restrict__ x, mas_tensor4 xs, float* __restrict__ y, mas_tensor4 ys,
+                                    int64_t total) {
+  // iterate in y's fastest order when y is channel-innermost, else in x's; simple generic version
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t c, w, h, n;
+    if (ys.sc == 1) { c = i % xs.c; w = (i / xs.c) % xs.w; h = (i / (xs.c * xs.w)) % xs.h; n = i / (xs.c * xs.w * xs.h); }
+    else { w = i % xs.w; h = (i / xs.w) % xs.h; c = (i / (xs.w * xs.h)) % xs.c; n = i / (xs.w * xs.h * xs.c); }
+    y[n * ys.sn + h * ys.sh + w * ys.sw + c * ys.sc] = x[n * xs.sn + h * xs.sh + w * xs.sw + c * xs.sc];
+  }
+}
+
+__global__ void sumpool2x2_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, int C4, int64_t total4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C4);
+    int64_t p = i / C4;
+    int w = (int)(p % W), h = (int)((p / W) % H);
+    int64_t n = p / ((int64_t)W * H);
+    const float4* b = reinterpret_cast<const float4*>(x) + ((n * 2 * H + 2 * h) * 2 * W + 2 * w) * C4 + c;
+    float4 a0 = __ldg(b), a1 = __ldg(b + C4), a2 = __ldg(b + (int64_t)2 * W * C4), a3 = __ldg(b + (int64_t)2 * W * C4 + C4);
+    reinterpret_cast<float4*>(y)[i] = make_float4((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y),
+                                                  (a0.z + a1.z) + (a2.z + a3.z), (a0.w + a1.w) + (a2.w + a3.w));
+  }
+}
+
+// weighted BCE-with-logits (loss_seg.py:15-19): l = -[pw*t*log(sig(x)) + (1-t)*log(1-sig(x))]
+//   = (1-t)*x + (1+(pw-1)*t) * softplus(-x);  dl/dx = (1-t) - (1+(pw-1)*t)*sigmoid(-x)
+constexpr int BCE_CHUNK = 256 * 8;
+__global__ void __launch_bounds__(256) bce_kernel(const float* __restrict__ lg, mas_tensor4 ls, const float* __restrict__ tg,
+                                                  mas_tensor4 ts, const float* __restrict__ pw, float* __restrict__ grad,
+                                                  mas_tensor4 gs, float gscale, double* __restrict__ part, int64_t total) {
+  double acc = 0;
+  int64_t base = (int64_t)blockIdx.x * BCE_CHUNK;
+  for (int k = 0; k < 8; ++k) {
+    int64_t i = base + k * 256 + threadIdx.x;
+    if (i < total) {
+      // i enumerates (n,h,w,c) with w innermost when the logits are NCHW, else c innermost
+      int64_t c, w, h, n;
+      if (ls.sc == 1) { c = i % ls.c; w = (i / ls.c) % ls.w; h = (i / (ls.c * ls.w)) % ls.h; n = i / (ls.c * ls.w * ls.h); }
+      else { w = i % ls.w; h = (i / ls.w) % ls.h; c = (i / (ls.w * ls.h)) % ls.c; n = i / (ls.w * ls.h * ls.c); }
+      float x = lg[n * ls.sn + h * ls.sh + w * ls.sw + c * ls.sc];
+      float t = tg[n * ts.sn + h * ts.sh + w * ts.sw + c * ts.sc];
+      float coef = 1.0f + (pw[c] - 1.0f) * t;
+      float sp = fmaxf(-x, 0.f) + log1pf(expf(-fabsf(x)));  // softplus(-x)
+      acc += (double)((1.0f - t) * x + coef * sp);
+      if (grad) {
+        float sg = 1.0f / (1.0f + expf(x));  // sigmoid(-x)
+        grad[n * gs.sn + h * gs.sh + w * gs.sw + c * gs.sc] = gscale * ((1.0f - t) - coef * sg);
+      }
+    }
+  }
+  __shared__ double red[256];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[blockIdx.x] = red[0];
+}
+__global__ void sum_final_kernel(const double* __restrict__ part, int n, double scale, float* __restrict__ out) {
+  __shared__ double sh[256];
+  double a = 0;
+  for (int i = threadIdx.x; i < n; i += 256) a += part[i];
+  sh[threadIdx.x] = a;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = (float)(sh[0] * scale);
+}
+
+static inline int ew_grid(int64_t n, int threads = 256) {
+  int64_t b = cdiv(n, threads);
+  return (int)(b < 148 * 16 ? (b < 1 ? 1 : b) : 148 * 16);
+}
+
+}  // namespace mas
+
+using namespace mas;
+
+extern "C" {
+
+int mas_version(void) { return 100; }
+const char* mas_last_error(void) { return g_err; }
+int64_t mas_launch_count(void) { return g_launches.load(); }
+
+static int gn_check(int N, int HW, int C, int G) {
+  if (N <= 0 || HW <= 0 || C <= 0 || G <= 0 || C % G != 0) return fail(MAS_ERR_INVALID_ARG, "groupnorm: bad shape N=%d HW=%d C=%d G=%d", N, HW, C, G);
+  if (C % 4 != 0 || GN_THREADS % (C / 4) != 0) return fail(MAS_ERR_UNSUPPORTED, "groupnorm: C=%d must be 4*{1,2,4,...,256}", C);
+  return MAS_OK;
+}
+static int gn_chunks(int HW) { return (int)cdiv(HW, GN_PIX); }
+
+size_t mas_gn_ws_bytes(int N, int HW, int C, int G) {
+  size_t part = (size_t)N * gn_chunks(HW) * C * 2 * sizeof(double);  // backward partials are the larger use
+  size_t nc = (size_t)N * C * 2 * sizeof(double);
+  size_t ab = (size_t)N * G * 2 * sizeof(float);
+  return part + nc + ab + 256;
+}
+
+int mas_gn_stats(const float* x, int N, int HW, int C, int G, float eps, float* mean, float* rstd, void* ws, size_t ws_bytes,
+                 void* stream) {
+  if (int e = gn_check(N, HW, C, G)) return e;
+  int chunks = gn_chunks(HW);
+  size_t need = (size_t)N * chunks * G * 2 * sizeof(double);
+  if (ws_bytes < need) return fail(MAS_ERR_WORKSPACE, "gn_stats: workspace %zu < %zu", ws_bytes, need);
+  int lanes = GN_THREADS / (C / 4);
+  size_t smem = (size_t)lanes * C * 2 * sizeof(double);
+  gn_stats_partial<<<dim3(chunks, N), GN_THREADS, smem, S(stream)>>>(x, HW, C, G, (double*)ws);
+  if (int e = launched("gn_stats_partial")) return e;
+  gn_stats_final<<<(int)cdiv(N * G, 128), 128, 0, S(stream)>>>((const double*)ws, chunks, G, (double)HW * (C / G), eps, mean, rstd, N * G);
+  return launched("gn_stats_final");
+}
+
+int mas_gn_apply(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta, float* y, int N,
+                 int HW, int C, int G, int silu, int round_tf32, void* stream) {
+  if (int e = gn_check(N, HW, C, G)) return e;
+  int64_t total4 = (int64_t)N * HW * (C / 4);
+  gn_apply_kernel<<<ew_grid(total4), 256, 0, S(stream)>>>(x, mean, rstd, gamma, beta, y, total4, HW, C, G, silu, round_tf32);
+  return launched("gn_apply");
+}
+
+int mas_gn_backward(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                    const float* dx_add, float* dx, float* dgamma, float* dbeta, int N, int HW, int C, int G, int silu, void* ws,
+                    size_t ws_bytes, void* stream) {
+  if (int e = gn_check(N, HW, C, G)) return e;
+  if (ws_bytes < mas_gn_ws_bytes(N, HW, C, G)) return fail(MAS_ERR_WORKSPACE, "gn_backward: workspace too small");
+  int chunks = gn_chunks(HW);
+  double* part = (double*)ws;
+  double* nc = part + (size_t)N * chunks * C * 2;
+  float* AB = (float*)(nc + (size_t)N * C * 2);
+  int lanes = GN_THREADS / (C / 4);
+  size_t smem = (size_t)lanes * C * 2 * sizeof(double);
+  gn_bwd_partial<<<dim3(chunks, N), GN_THREADS, smem, S(stream)>>>(dy, x, mean, rstd, gamma, beta, HW, C, G, silu, part);
+  if (int e = launched("gn_bwd_partial")) return e;
+  gn_bwd_nc<<<(int)cdiv((int64_t)N * C, 128), 128, 0, S(stream)>>>(part, N, chunks, C, nc);
+  if (int e = launched("gn_bwd_nc")) return e;
+  gn_bwd_final<<<1, 1024, 0, S(stream)>>>(N, C, G, gamma, nc, dgamma, dbeta, AB, 1.0 / ((double)HW * (C / G)));
+  if (int e = launched("gn_bwd_final")) return e;
+  int64_t total4 = (int64_t)N * HW * (C / 4);
+  gn_bwd_apply<<<ew_grid(total4), 256, 0, S(stream)>>>(dy, x, mean, rstd, gamma, beta, AB, dx_add, dx, total4, HW, C, G, silu);
+  return launched("gn_bwd_apply");
+}
+
+int mas_add(const float* a, const float* b, float* out, int64_t n, void* stream) {
+  add_kernel<<<ew_grid(n), 256, 0, S(stream)>>>(a, b, out, n);
+  return launched("add");
+}
+int mas_silu_forward(const float* x, float* y, int64_t n, void* stream) {
+  silu_fwd_kernel<<<ew_grid(n), 256, 0, S(stream)>>>(x, y, n);
+  return launched("silu_fwd");
+}
+int mas_silu_backward(const float* dy, const float* x, float* dx, int64_t n, void* stream) {
+  silu_bwd_kernel<<<ew_grid(n), 256, 0, S(stream)>>>(dy, x, dx, n);
+  return launched("silu_bwd");
+}
+
+int mas_softmax_forward(const float* s, float* p, int64_t rows, int cols, void* stream) {
+  MAS_REQUIRE(rows > 0 && cols > 0, "softmax: bad shape");
+  softmax_fwd_kernel<<<(unsigned)cdiv(rows, 8), 256, 0, S(stream)>>>(s, p, rows, cols);
+  return launched("softmax_fwd");
+}
+int mas_softmax_backward(const float* p, const float* dp, float* ds, int64_t rows, int cols, float scale, void* stream) {
+  MAS_REQUIRE(rows > 0 && cols > 0, "softmax: bad shape");
+  softmax_bwd_kernel<<<(unsigned)cdiv(rows, 8), 256, 0, S(stream)>>>(p, dp, ds, rows, cols, scale);
+  return launched("softmax_bwd");
+}
+
+int mas_bn_stats(const float* x, int64_t R, int C, double* stats_out, void* stream) {
+  MAS_REQUIRE(R > 0 && C > 0, "bn_stats: bad shape");
+  bn_stats_kernel<<<(int)cdiv(C, 32), dim3(32, 8), 0, S(stream)>>>(x, R, C, stats_out);
+  return launched("bn_stats");
+}
+int mas_bn_finalize(const double* stats, double count, int C, float eps, float momentum, float* mean, float* invstd,
+                    float* running_mean, float* running_var, void* stream) {
+  bn_finalize_kernel<<<(int)cdiv(C, 128), 128, 0, S(stream)>>>(stats, count, C, eps, momentum, mean, invstd, running_mean, running_var);
+  return launched("bn_finalize");
+}
+int mas_bn_apply(const float* x, const float* mean, const float* invstd, const float* gamma, const float* beta, float* y,
+                 int64_t R, int C, void* stream) {
+  bn_apply_kernel<<<ew_grid(R * C), 256, 0, S(stream)>>>(x, mean, invstd, gamma, beta, y, R * C, C);
+  return launched("bn_apply");
+}
+int mas_bn_backward_reduce(const float* dy, const float* x, const float* mean, const float* invstd, int64_t R, int C,
+                           double* sums_out, void* stream) {
+  bn_bwd_reduce_kernel<<<(int)cdiv(C, 32), dim3(32, 8), 0, S(stream)>>>(dy, x, mean, invstd, R, C, sums_out);
+  return launched("bn_bwd_reduce");
+}
+int mas_bn_backward_apply(const float* dy, const float* x, const float* mean, const float* invstd, const float* gamma,
+                          const double* sums_global, const double* sums_local, double inv_count, float* dx, float* dgamma,
+                          float* dbeta, int64_t R, int C, void* stream) {
+  bn_bwd_apply_kernel<<<ew_grid(R * C), 256, 0, S(stream)>>>(dy, x, mean, invstd, gamma, sums_global, inv_count, dx, dgamma, dbeta,
+                                                             sums_local, R * C, C);
+  return launched("bn_bwd_apply");
+}
+
+size_t mas_colsum_ws_bytes(mas_tensor4 t) { return (size_t)cdiv(t.n * t.h * t.w, CS_ROWS) * t.c * sizeof(double) + 64; }
+int mas_colsum(const float* x, mas_tensor4 t, float* out, void* ws, size_t ws_bytes, void* stream) {
+  if (ws_bytes < mas_colsum_ws_bytes(t)) return fail(MAS_ERR_WORKSPACE, "colsum: workspace too small");
+  int chunks = (int)cdiv(t.n * t.h * t.w, CS_ROWS);
+  colsum_partial<<<dim3((unsigned)cdiv(t.c, 32), chunks), dim3(32, 8), 0, S(stream)>>>(x, t, (double*)ws);
+  if (int e = launched("colsum_partial")) return e;
+  colsum_final<<<(int)cdiv(t.c, 128), 128, 0, S(stream)>>>((const double*)ws, chunks, (int)t.c, out);
+  return launched("colsum_final");
+}
+
+int mas_copy_strided(const float* x, mas_tensor4 xs, float* y, mas_tensor4 ys, void* stream) {
+  MAS_REQUIRE(xs.n == ys.n && xs.h == ys.h && xs.w == ys.w && xs.c == ys.c, "copy_strided: shape mismatch");
+  int64_t total = xs.n * xs.h * xs.w * xs.c;
+  copy_strided_kernel<<<ew_grid(total), 256, 0, S(stream)>>>(x, xs, y, ys, total);
+  return launched("copy_strided");
+}
+
+int mas_sumpool2x2(const float* x, float* y, int N, int H, int W, int C, void* stream) {
+  MAS_REQUIRE(C % 4 == 0, "sumpool2x2: C %% 4 != 0");
+  int64_t total4 = (int64_t)N * H * W * (C / 4);
+  sumpool2x2_kernel<<<ew_grid(total4), 256, 0, S(stream)>>>(x, y, H, W, C / 4, total4);
+  return launched("sumpool2x2");
+}
+
+size_t mas_bce_ws_bytes(mas_tensor4 ls) { return (size_t)cdiv(ls.n * ls.h * ls.w * ls.c, BCE_CHUNK) * sizeof(double) + 64; }
+int mas_bce_logits(const float* logits, mas_tensor4 ls, const float* target, mas_tensor4 ts, const float* pos_weight,
+                   float* loss_out, float* grad, mas_tensor4 gs, float grad_scale, void* ws, size_t ws_bytes, void* stream) {
+  int64_t total = ls.n * ls.h * ls.w * ls.c;
+  if (ws_bytes < mas_bce_ws_bytes(ls)) return fail(MAS_ERR_WORKSPACE, "bce: workspace too small");
+  int blocks = (int)cdiv(total, BCE_CHUNK);
+  bce_kernel<<<blocks, 256, 0, S(stream)>>>(logits, ls, target, ts, pos_weight, grad, gs, grad_scale, (double*)ws, total);
+  if (int e = launched("bce")) return e;
+  sum_final_kernel<<<1, 256, 0, S(stream)>>>((const double*)ws, blocks, 1.0 / (double)total, loss_out);
+  return launched("bce_final");
+}
+
+}  // extern "C"

@@ -1,0 +1,145 @@
+"""ctypes binding of libmas_b200.so (the C-ABI declared in include/mas_b200.h).
+
+The product path has NO fallback: if the shared library is missing or a call fails, a RuntimeError is
+raised. Tensors are owned by torch (device memory, streams); only raw pointers, extents and the current
+CUDA stream cross the boundary.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libmas_b200.so")
+
+IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
+CONV_S1, CONV_S2, CONV_UP, CONV_ZS = 0, 1, 2, 3
+
+
+class Tensor4(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_int64) for k in ("n", "h", "w", "c", "sn", "sh", "sw", "sc")]
+
+
+_P, _I, _L, _F, _D, _Z, _T = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_double,
+                              ctypes.c_size_t, Tensor4)
+
+# name -> (restype, argtypes); mirrors include/mas_b200.h one to one
+_SPEC = {
+    "mas_version": (_I, []),
+    "mas_last_error": (ctypes.c_char_p, []),
+    "mas_launch_count": (_L, []),
+    "mas_copy_strided": (_I, [_P, _T, _P, _T, _P]),
+    "mas_gn_ws_bytes": (_Z, [_I, _I, _I, _I]),
+    "mas_gn_stats": (_I, [_P, _I, _I, _I, _I, _F, _P, _P, _P, _Z, _P]),
+    "mas_gn_apply": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "mas_gn_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _Z, _P]),
+    "mas_add": (_I, [_P, _P, _P, _L, _P]),
+    "mas_silu_forward": (_I, [_P, _P, _L, _P]),
+    "mas_silu_backward": (_I, [_P, _P, _P, _L, _P]),
+    "mas_pack_conv3x3": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "mas_conv3x3_fprop": (_I, [_P, _T, _P, _P, _P, _P, _T, _I, _I, _P]),
+    "mas_conv3x3_wgrad_ws_bytes": (_Z, [_T, _T, _I]),
+    "mas_conv3x3_wgrad": (_I, [_P, _T, _P, _T, _P, _P, _I, _I, _P, _Z, _P]),
+    "mas_conv1x1_wgrad_ws_bytes": (_Z, [_L, _I, _I]),
+    "mas_conv1x1_wgrad": (_I, [_P, _L, _P, _L, _L, _I, _I, _P, _P, _I, _P, _Z, _P]),
+    "mas_sumpool2x2": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "mas_gemm": (_I, [_P, _P, _P, _I, _I, _I, _I, _L, _L, _L, _L, _L, _L, _I, _I, _F, _P, _P, _I, _P]),
+    "mas_colsum_ws_bytes": (_Z, [_T]),
+    "mas_colsum": (_I, [_P, _T, _P, _P, _Z, _P]),
+    "mas_softmax_forward": (_I, [_P, _P, _L, _I, _P]),
+    "mas_softmax_backward": (_I, [_P, _P, _P, _L, _I, _F, _P]),
+    "mas_bn_stats": (_I, [_P, _L, _I, _P, _P]),
+    "mas_bn_finalize": (_I, [_P, _D, _I, _F, _F, _P, _P, _P, _P, _P]),
+    "mas_bn_apply": (_I, [_P, _P, _P, _P, _P, _P, _L, _I, _P]),
+    "mas_bn_backward_reduce": (_I, [_P, _P, _P, _P, _L, _I, _P, _P]),
+    "mas_bn_backward_apply": (_I, [_P, _P, _P, _P, _P, _P, _P, _D, _P, _P, _P, _L, _I, _P]),
+    "mas_vq_ws_bytes": (_Z, [_L, _I, _I]),
+    "mas_vq_forward": (_I, [_P, _P, _L, _I, _I, _F, _P, _P, _P, _P, _Z, _P]),
+    "mas_vq_backward": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _F, _P, _P, _P]),
+    "mas_vq_gather": (_I, [_P, _P, _L, _I, _I, _P, _P]),
+    "mas_bce_ws_bytes": (_Z, [_T]),
+    "mas_bce_logits": (_I, [_P, _T, _P, _T, _P, _P, _P, _T, _F, _P, _Z, _P]),
+}
+
+_lib = None
+
+
+def exported_symbols():
+    return sorted(_SPEC)
+
+
+def load():
+    """Load the shared library (once). Raises RuntimeError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"libmas_b200.so not found at {LIB_PATH}: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU/PyTorch fallback for this path.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SPEC.items():
+        fn = getattr(lib, name)  # AttributeError here = header/library drift, which must be loud
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if isinstance(t, torch.Tensor):
+        return ctypes.c_void_p(t.data_ptr())
+    return t
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def call(name, *args):
+    """Invoke an int-returning entry on the current CUDA stream; non-zero status -> RuntimeError."""
+    lib = load()
+    fn = getattr(lib, name)
+    conv = [_ptr(a) for a in args]
+    conv.append(stream_ptr())
+    rc = fn(*conv)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {lib.mas_last_error().decode(errors='replace')}")
+
+
+def query(name, *args):
+    """Invoke a size-returning helper (no stream argument)."""
+    return getattr(load(), name)(*[_ptr(a) for a in args])
+
+
+def launch_count() -> int:
+    return int(load().mas_launch_count())
+
+
+def t4(x: torch.Tensor) -> Tensor4:
+    """Describe a logical [N,C,H,W] tensor (any strides) as extents + element strides."""
+    n, c, h, w = x.shape
+    sn, sc, sh, sw = x.stride()
+    return Tensor4(n, h, w, c, sn, sh, sw, sc)
+
+
+def rows4(m: int, c: int) -> Tensor4:
+    return Tensor4(1, 1, m, c, m * c, m * c, c, 1)
+
+
+_ws = {}
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+    """Grow-only per-device scratch buffer (all kernels of this library run on the current stream, so a
+    single buffer is race-free)."""
+    key = (device.type, device.index)
+    buf = _ws.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _ws[key] = buf
+    return buf

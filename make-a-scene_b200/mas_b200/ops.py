@@ -1,0 +1,481 @@
+"""torch.autograd.Function wrappers over the C-ABI kernels (one Function per fused unit of the hot path).
+
+Activations are fp32 tensors of logical shape [N,C,H,W] in channels-last (NHWC) memory; any other layout
+arriving at a module boundary is converted once with mas_copy_strided. All arithmetic happens in
+libmas_b200.so; torch is used for allocation, autograd bookkeeping and (for SyncBatchNorm) the NCCL
+all-reduce of 2*C statistics.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+
+GN_GROUPS = 32
+GN_EPS = 1e-6
+
+_cfg = {"impl": L.IMPL_AUTO}
+
+
+def set_impl(impl: int):
+    """Select the contraction implementation globally (IMPL_AUTO / IMPL_SIMT / IMPL_TC)."""
+    _cfg["impl"] = int(impl)
+
+
+def get_impl() -> int:
+    return _cfg["impl"]
+
+
+def _need_cuda(x):
+    if not x.is_cuda:
+        raise RuntimeError("make-a-scene_b200 kernels run on CUDA (sm_100a) only; got a %s tensor — there is no CPU path"
+                           % x.device.type)
+    if x.dtype != torch.float32:
+        raise RuntimeError("make-a-scene_b200 kernels take float32 tensors, got %s" % x.dtype)
+
+
+def nhwc(x: torch.Tensor) -> torch.Tensor:
+    """Return x in dense channels-last memory (no copy if it already is)."""
+    _need_cuda(x)
+    if x.dim() != 4:
+        raise RuntimeError("expected a 4-D [N,C,H,W] tensor")
+    if x.is_contiguous(memory_format=torch.channels_last) and x.stride(1) == 1:
+        return x
+    y = torch.empty_like(x, memory_format=torch.channels_last)
+    L.call("mas_copy_strided", x, L.t4(x), y, L.t4(y))
+    return y
+
+
+def empty_nhwc(n, c, h, w, like):
+    return torch.empty((n, c, h, w), dtype=torch.float32, device=like.device, memory_format=torch.channels_last)
+
+
+# ------------------------------------------------------------------------------------------------ raw (no-autograd) helpers
+def gn_stats(x):
+    n, c, h, w = x.shape
+    mean = torch.empty(n * GN_GROUPS, dtype=torch.float32, device=x.device)
+    rstd = torch.empty_like(mean)
+    nb = L.query("mas_gn_ws_bytes", n, h * w, c, GN_GROUPS)
+    ws = L.workspace(nb, x.device)
+    L.call("mas_gn_stats", x, n, h * w, c, GN_GROUPS, GN_EPS, mean, rstd, ws, ws.numel())
+    return mean, rstd
+
+
+def gn_apply(x, mean, rstd, gamma, beta, silu, rtf32=False):
+    n, c, h, w = x.shape
+    y = torch.empty_like(x)
+    L.call("mas_gn_apply", x, mean, rstd, gamma, beta, y, n, h * w, c, GN_GROUPS, int(silu), int(rtf32))
+    return y
+
+
+def gn_backward(dy, x, mean, rstd, gamma, beta, silu, dx_add=None):
+    n, c, h, w = x.shape
+    dx = torch.empty_like(x)
+    dg = torch.empty_like(gamma)
+    db = torch.empty_like(beta)
+    nb = L.query("mas_gn_ws_bytes", n, h * w, c, GN_GROUPS)
+    ws = L.workspace(nb, x.device)
+    L.call("mas_gn_backward", dy, x, mean, rstd, gamma, beta, dx_add, dx, dg, db, n, h * w, c, GN_GROUPS, int(silu), ws,
+           ws.numel())
+    return dx, dg, db
+
+
+def pack3x3(weight, flip_transpose=False):
+    cout, cin = weight.shape[0], weight.shape[1]
+    out = torch.empty(9 * cout * cin, dtype=torch.float32, device=weight.device)
+    L.call("mas_pack_conv3x3", weight.contiguous(), out, cout, cin, int(flip_transpose), 0)
+    return out
+
+
+def _conv_out_hw(h, w, mode):
+    if mode == L.CONV_S1:
+        return h, w
+    if mode == L.CONV_S2:
+        return h // 2, w // 2
+    return 2 * h, 2 * w
+
+
+def conv3x3_raw(x, wpacked, cout, bias, residual, mode, out_nchw=False):
+    n, _, h, w = x.shape
+    ho, wo = _conv_out_hw(h, w, mode)
+    if out_nchw:
+        y = torch.empty((n, cout, ho, wo), dtype=torch.float32, device=x.device)
+    else:
+        y = empty_nhwc(n, cout, ho, wo, x)
+    L.call("mas_conv3x3_fprop", x, L.t4(x), wpacked, bias, residual, y, L.t4(y), mode, _cfg["impl"])
+    return y
+
+
+def conv3x3_wgrad_raw(x, dy, cout, cin, mode, want_bias=True):
+    dw = torch.empty((cout, cin, 3, 3), dtype=torch.float32, device=x.device)
+    db = torch.empty(cout, dtype=torch.float32, device=x.device) if want_bias else None
+    nb = L.query("mas_conv3x3_wgrad_ws_bytes", L.t4(x), L.t4(dy), mode)
+    ws = L.workspace(nb, x.device)
+    L.call("mas_conv3x3_wgrad", x, L.t4(x), dy, L.t4(dy), dw, db, mode, _cfg["impl"], ws, ws.numel())
+    return dw, db
+
+
+def conv3x3_dgrad_raw(dy, weight, mode):
+    """Data gradient of the 3x3 family: fprop with flipped/transposed weights (+ zero-stuffing or 2x2 sum-pool)."""
+    cout, cin = weight.shape[0], weight.shape[1]
+    wd = pack3x3(weight, flip_transpose=True)
+    if mode == L.CONV_S1:
+        return conv3x3_raw(dy, wd, cin, None, None, L.CONV_S1)
+    if mode == L.CONV_S2:
+        return conv3x3_raw(dy, wd, cin, None, None, L.CONV_ZS)
+    # CONV_UP: gradient w.r.t. the upsampled image, then sum over each 2x2 replica block
+    du = conv3x3_raw(dy, wd, cin, None, None, L.CONV_S1)
+    n, _, h2, w2 = du.shape
+    dx = empty_nhwc(n, cin, h2 // 2, w2 // 2, du)
+    L.call("mas_sumpool2x2", du, dx, n, h2 // 2, w2 // 2, cin)
+    return dx
+
+
+def gemm(A, B, C, M, N, K, batch=1, lda=None, ldb=None, ldc=None, sa=0, sb=0, sc=0, ta=False, tb=False, alpha=1.0,
+         bias=None, residual=None):
+    """Pointers may be tensors or (tensor, element_offset) pairs."""
+    def p(v):
+        if isinstance(v, tuple):
+            import ctypes
+            t, off = v
+            return ctypes.c_void_p(t.data_ptr() + 4 * off)
+        return v
+    L.call("mas_gemm", p(A), p(B), p(C), M, N, K, batch, lda, ldb, ldc, sa, sb, sc, int(ta), int(tb), float(alpha), p(bias),
+           p(residual), _cfg["impl"])
+
+
+def conv1x1_raw(x, weight, bias, residual=None):
+    """x NHWC [N,Cin,H,W] -> NHWC [N,Cout,H,W]; rows GEMM with W stored [Cout,Cin]."""
+    n, cin, h, w = x.shape
+    cout = weight.shape[0]
+    y = empty_nhwc(n, cout, h, w, x)
+    gemm(x, weight, y, n * h * w, cout, cin, lda=cin, ldb=cin, ldc=cout, tb=True, bias=bias, residual=residual)
+    return y
+
+
+def conv1x1_dgrad_raw(dy, weight, residual=None):
+    n, cout, h, w = dy.shape
+    cin = weight.shape[1]
+    dx = empty_nhwc(n, cin, h, w, dy)
+    gemm(dy, weight, dx, n * h * w, cin, cout, lda=cout, ldb=cin, ldc=cin, residual=residual)
+    return dx
+
+
+def conv1x1_wgrad_raw(x_rows, dy_rows, M, cin, cout, want_bias=True, ldx=None, ldy=None, dy_off=0):
+    import ctypes
+    dev = x_rows.device
+    dy_ptr = ctypes.c_void_p(dy_rows.data_ptr() + 4 * dy_off)
+    dw = torch.empty((cout, cin, 1, 1), dtype=torch.float32, device=dev)
+    db = torch.empty(cout, dtype=torch.float32, device=dev) if want_bias else None
+    nb = L.query("mas_conv1x1_wgrad_ws_bytes", M, cin, cout)
+    ws = L.workspace(nb, dev)
+    L.call("mas_conv1x1_wgrad", x_rows, ldx or cin, dy_ptr, ldy or cout, M, cin, cout, dw, db, _cfg["impl"], ws, ws.numel())
+    return dw, db
+
+
+# ------------------------------------------------------------------------------------------------ autograd Functions
+class GroupNormFn(torch.autograd.Function):
+    """Normalize (+ optional fused Swish) — modules.py:35-41,194-196."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, silu):
+        x = nhwc(x)
+        mean, rstd = gn_stats(x)
+        y = gn_apply(x, mean, rstd, weight, bias, silu)
+        ctx.save_for_backward(x, weight, bias, mean, rstd)
+        ctx.silu = silu
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, bias, mean, rstd = ctx.saved_tensors
+        dx, dg, db = gn_backward(nhwc(dy), x, mean, rstd, weight, bias, ctx.silu)
+        return dx, dg, db, None
+
+
+class SiLUFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        _need_cuda(x)
+        x = x.contiguous() if not (x.is_contiguous() or x.is_contiguous(memory_format=torch.channels_last)) else x
+        y = torch.empty_like(x)
+        L.call("mas_silu_forward", x, y, x.numel())
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        if dy.stride() != x.stride():
+            d2 = torch.empty_like(x)
+            if x.dim() == 4:
+                L.call("mas_copy_strided", dy, L.t4(dy), d2, L.t4(d2))
+            else:
+                d2.copy_(dy)
+            dy = d2
+        dx = torch.empty_like(x)
+        L.call("mas_silu_backward", dy, x, dx, x.numel())
+        return dx
+
+
+class Conv3x3Fn(torch.autograd.Function):
+    """nn.Conv2d 3x3 / Downsample / Upsample (modules.py:44-81,93-104) with optional fused residual add."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, mode, out_nchw):
+        _need_cuda(x)
+        cout = weight.shape[0]
+        y = conv3x3_raw(x, pack3x3(weight), cout, bias, residual, mode, out_nchw)
+        ctx.save_for_backward(x, weight)
+        ctx.mode, ctx.has_bias, ctx.has_res = mode, bias is not None, residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        cout, cin = weight.shape[0], weight.shape[1]
+        dx = dw = db = dres = None
+        if ctx.needs_input_grad[0]:
+            dx = conv3x3_dgrad_raw(dy, weight, ctx.mode)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw, db = conv3x3_wgrad_raw(x, dy, cout, cin, ctx.mode, ctx.has_bias)
+        if ctx.has_res and ctx.needs_input_grad[3]:
+            dres = dy
+        return dx, dw, db, dres, None, None
+
+
+class Conv1x1Fn(torch.autograd.Function):
+    """nn.Conv2d 1x1 (nin_shortcut, quant_conv[0], post_quant_conv — modules.py:113-117, vqvae.py:15,18)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x = nhwc(x)
+        y = conv1x1_raw(x, weight, bias)
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = nhwc(dy)
+        n, cin, h, w = x.shape
+        cout = weight.shape[0]
+        dx = conv1x1_dgrad_raw(dy, weight) if ctx.needs_input_grad[0] else None
+        dw, db = conv1x1_wgrad_raw(x, dy, n * h * w, cin, cout, ctx.has_bias)
+        return dx, dw, db
+
+
+class ResnetBlockFn(torch.autograd.Function):
+    """ResnetBlock.forward as one unit (modules.py:119-136): GN+SiLU -> conv3x3 -> GN+SiLU -> conv3x3 (+1x1 shortcut) + x.
+    The residual add is fused into conv2's epilogue; in backward the shortcut gradient is fused into the
+    GroupNorm-backward apply (identity shortcut) or into the shortcut GEMM's epilogue (nin_shortcut)."""
+
+    @staticmethod
+    def forward(ctx, x, n1w, n1b, c1w, c1b, n2w, n2b, c2w, c2b, sw, sb):
+        x = nhwc(x)
+        cout = c1w.shape[0]
+        m1, r1 = gn_stats(x)
+        a1 = gn_apply(x, m1, r1, n1w, n1b, True)
+        h1 = conv3x3_raw(a1, pack3x3(c1w), cout, c1b, None, L.CONV_S1)
+        m2, r2 = gn_stats(h1)
+        a2 = gn_apply(h1, m2, r2, n2w, n2b, True)
+        sc = x if sw is None else conv1x1_raw(x, sw, sb)
+        out = conv3x3_raw(a2, pack3x3(c2w), cout, c2b, sc, L.CONV_S1)
+        ctx.save_for_backward(x, a1, h1, a2, m1, r1, m2, r2, n1w, n1b, c1w, n2w, n2b, c2w, sw)
+        ctx.has_sc = sw is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, a1, h1, a2, m1, r1, m2, r2, n1w, n1b, c1w, n2w, n2b, c2w, sw = ctx.saved_tensors
+        dout = nhwc(dout)
+        cout, cin = c1w.shape[0], c1w.shape[1]
+        n, _, h, w = x.shape
+        d_a2 = conv3x3_dgrad_raw(dout, c2w, L.CONV_S1)
+        dc2w, dc2b = conv3x3_wgrad_raw(a2, dout, cout, cout, L.CONV_S1)
+        d_h1, dn2w, dn2b = gn_backward(d_a2, h1, m2, r2, n2w, n2b, True)
+        del d_a2
+        d_a1 = conv3x3_dgrad_raw(d_h1, c1w, L.CONV_S1)
+        dc1w, dc1b = conv3x3_wgrad_raw(a1, d_h1, cout, cin, L.CONV_S1)
+        del d_h1
+        if ctx.has_sc:
+            dxm, dn1w, dn1b = gn_backward(d_a1, x, m1, r1, n1w, n1b, True)
+            dx = conv1x1_dgrad_raw(dout, sw, residual=dxm)   # dout.Wn + dx_main
+            dsw, dsb = conv1x1_wgrad_raw(x, dout, n * h * w, cin, cout)
+        else:
+            dx, dn1w, dn1b = gn_backward(d_a1, x, m1, r1, n1w, n1b, True, dx_add=dout)
+            dsw = dsb = None
+        return dx, dn1w, dn1b, dc1w, dc1b, dn2w, dn2b, dc2w, dc2b, dsw, dsb
+
+
+class AttnBlockFn(torch.autograd.Function):
+    """AttnBlock.forward as one unit (modules.py:167-191): GN -> q,k,v 1x1 -> softmax(q^T k / sqrt(c)) over keys
+    -> v.P^T -> proj_out 1x1 -> + x."""
+
+    @staticmethod
+    def forward(ctx, x, nw, nb, qw, qb, kw, kb, vw, vb, pw, pb):
+        x = nhwc(x)
+        n, c, h, w = x.shape
+        hw, M = h * w, n * h * w
+        mean, rstd = gn_stats(x)
+        hn = gn_apply(x, mean, rstd, nw, nb, False)
+        qkv = torch.empty((M, 3 * c), dtype=torch.float32, device=x.device)
+        for i, (wt, bs) in enumerate(((qw, qb), (kw, kb), (vw, vb))):
+            gemm(hn, wt, (qkv, i * c), M, c, c, lda=c, ldb=c, ldc=3 * c, tb=True, bias=bs)
+        P = torch.empty((n, hw, hw), dtype=torch.float32, device=x.device)
+        gemm((qkv, 0), (qkv, c), P, hw, hw, c, batch=n, lda=3 * c, ldb=3 * c, ldc=hw, sa=hw * 3 * c, sb=hw * 3 * c,
+             sc=hw * hw, tb=True, alpha=float(int(c) ** (-0.5)))
+        L.call("mas_softmax_forward", P, P, n * hw, hw)
+        O = empty_nhwc(n, c, h, w, x)
+        gemm(P, (qkv, 2 * c), O, hw, c, hw, batch=n, lda=hw, ldb=3 * c, ldc=c, sa=hw * hw, sb=hw * 3 * c, sc=hw * c)
+        out = conv1x1_raw(O, pw, pb, residual=x)
+        ctx.save_for_backward(x, mean, rstd, hn, qkv, P, O, nw, nb, qw, kw, vw, pw)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, mean, rstd, hn, qkv, P, O, nw, nb, qw, kw, vw, pw = ctx.saved_tensors
+        dout = nhwc(dout)
+        n, c, h, w = x.shape
+        hw, M = h * w, n * h * w
+        scale = float(int(c) ** (-0.5))
+        dO = conv1x1_dgrad_raw(dout, pw)
+        dpw, dpb = conv1x1_wgrad_raw(O, dout, M, c, c)
+        dqkv = torch.empty_like(qkv)
+        # dV[j,c] = sum_i P[i,j] dO[i,c]
+        gemm(P, dO, (dqkv, 2 * c), hw, c, hw, batch=n, lda=hw, ldb=c, ldc=3 * c, sa=hw * hw, sb=hw * c, sc=hw * 3 * c, ta=True)
+        # dP[i,j] = sum_c dO[i,c] V[j,c]
+        dP = torch.empty_like(P)
+        gemm(dO, (qkv, 2 * c), dP, hw, hw, c, batch=n, lda=c, ldb=3 * c, ldc=hw, sa=hw * c, sb=hw * 3 * c, sc=hw * hw, tb=True)
+        L.call("mas_softmax_backward", P, dP, dP, n * hw, hw, scale)   # dP <- dS (already times 1/sqrt(c))
+        # dQ[i,c] = sum_j dS[i,j] K[j,c] ; dK[j,c] = sum_i dS[i,j] Q[i,c]
+        gemm(dP, (qkv, c), (dqkv, 0), hw, c, hw, batch=n, lda=hw, ldb=3 * c, ldc=3 * c, sa=hw * hw, sb=hw * 3 * c, sc=hw * 3 * c)
+        gemm(dP, (qkv, 0), (dqkv, c), hw, c, hw, batch=n, lda=hw, ldb=3 * c, ldc=3 * c, sa=hw * hw, sb=hw * 3 * c, sc=hw * 3 * c,
+             ta=True)
+        # dhn = dq.Wq + dk.Wk + dv.Wv (chained through the GEMM residual input)
+        dhn = empty_nhwc(n, c, h, w, x)
+        gemm((dqkv, 0), qw, dhn, M, c, c, lda=3 * c, ldb=c, ldc=c)
+        gemm((dqkv, c), kw, dhn, M, c, c, lda=3 * c, ldb=c, ldc=c, residual=dhn)
+        gemm((dqkv, 2 * c), vw, dhn, M, c, c, lda=3 * c, ldb=c, ldc=c, residual=dhn)
+        grads_w = []
+        for i in range(3):
+            grads_w.append(conv1x1_wgrad_raw(hn, dqkv, M, c, c, ldy=3 * c, dy_off=i * c))
+        dx, dnw, dnb = gn_backward(dhn, x, mean, rstd, nw, nb, False, dx_add=dout)
+        (dqw, dqb), (dkw, dkb), (dvw, dvb) = grads_w
+        return dx, dnw, dnb, dqw, dqb, dkw, dkb, dvw, dvb, dpw, dpb
+
+
+class BatchNormFn(torch.autograd.Function):
+    """nn.SyncBatchNorm(embed_dim) training forward/backward (vqvae.py:16): local sums by kernel, the 2*C
+    statistics are all-reduced over NCCL when a process group is active (the one cross-rank step of the forward)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps, sync):
+        x = nhwc(x)
+        n, c, h, w = x.shape
+        R = n * h * w
+        stats = torch.empty(2 * c, dtype=torch.float64, device=x.device)
+        L.call("mas_bn_stats", x, R, c, stats)
+        world = 1
+        if sync and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            world = dist.get_world_size()
+            dist.all_reduce(stats)
+        mean = torch.empty(c, dtype=torch.float32, device=x.device)
+        invstd = torch.empty_like(mean)
+        L.call("mas_bn_finalize", stats, float(R * world), c, float(eps), float(momentum), mean, invstd, running_mean, running_var)
+        y = torch.empty_like(x)
+        L.call("mas_bn_apply", x, mean, invstd, weight, bias, y, R, c)
+        ctx.save_for_backward(x, weight, mean, invstd)
+        ctx.world = world
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, mean, invstd = ctx.saved_tensors
+        dy = nhwc(dy)
+        n, c, h, w = x.shape
+        R = n * h * w
+        local = torch.empty(2 * c, dtype=torch.float64, device=x.device)
+        L.call("mas_bn_backward_reduce", dy, x, mean, invstd, R, c, local)
+        glob = local
+        if ctx.world > 1:
+            glob = local.clone()
+            dist.all_reduce(glob)
+        dx = torch.empty_like(x)
+        dg = torch.empty_like(weight)
+        db = torch.empty_like(weight)
+        L.call("mas_bn_backward_apply", dy, x, mean, invstd, weight, glob, local, 1.0 / float(R * ctx.world), dx, dg, db, R, c)
+        return dx, dg, db, None, None, None, None, None
+
+
+def batchnorm_eval(x, weight, bias, running_mean, running_var, eps):
+    x = nhwc(x)
+    n, c, h, w = x.shape
+    invstd = torch.rsqrt(running_var + eps)
+    y = torch.empty_like(x)
+    L.call("mas_bn_apply", x, running_mean, invstd, weight, bias, y, n * h * w, c)
+    return y
+
+
+class VQFn(torch.autograd.Function):
+    """Codebook distance+argmin+gather+loss+straight-through (modules.py:501-515) in one kernel."""
+
+    @staticmethod
+    def forward(ctx, z, E, beta):
+        z = nhwc(z)
+        n, d, h, w = z.shape
+        R, K = n * h * w, E.shape[0]
+        E = E.contiguous()
+        idx = torch.empty(R, dtype=torch.int64, device=z.device)
+        zq = torch.empty_like(z)
+        loss = torch.empty((), dtype=torch.float32, device=z.device)
+        nb = L.query("mas_vq_ws_bytes", R, K, d)
+        ws = L.workspace(nb, z.device)
+        L.call("mas_vq_forward", z, E, R, K, d, float(beta), idx, zq, loss, ws, ws.numel())
+        ctx.save_for_backward(z, E, idx)
+        ctx.beta = float(beta)
+        ctx.mark_non_differentiable(idx)
+        return zq, loss, idx
+
+    @staticmethod
+    def backward(ctx, g_zq, g_loss, _g_idx):
+        z, E, idx = ctx.saved_tensors
+        n, d, h, w = z.shape
+        R, K = n * h * w, E.shape[0]
+        g_zq = nhwc(g_zq) if g_zq is not None else None
+        if g_loss is not None:
+            g_loss = g_loss.contiguous()
+        grad_z = torch.empty_like(z) if ctx.needs_input_grad[0] else None
+        grad_E = torch.zeros_like(E) if ctx.needs_input_grad[1] else None
+        L.call("mas_vq_backward", g_zq, g_loss, z, E, idx, R, K, d, ctx.beta, grad_z, grad_E)
+        return grad_z, grad_E, None
+
+
+def vq_gather(E, idx):
+    R, (K, D) = idx.numel(), E.shape
+    out = torch.empty((R, D), dtype=torch.float32, device=E.device)
+    L.call("mas_vq_gather", E.contiguous(), idx.contiguous().view(-1), R, K, D, out)
+    return out
+
+
+class BCELogitsFn(torch.autograd.Function):
+    """binary_cross_entropy_with_logits(pos_weight) mean (losses/loss_seg.py:15-19); grad computed in the same pass."""
+
+    @staticmethod
+    def forward(ctx, logits, target, pos_weight):
+        _need_cuda(logits)
+        grad = torch.empty_like(logits)
+        loss = torch.empty((), dtype=torch.float32, device=logits.device)
+        nb = L.query("mas_bce_ws_bytes", L.t4(logits))
+        ws = L.workspace(nb, logits.device)
+        L.call("mas_bce_logits", logits, L.t4(logits), target, L.t4(target), pos_weight, loss, grad, L.t4(grad),
+               1.0 / logits.numel(), ws, ws.numel())
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None, None

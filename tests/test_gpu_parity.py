@@ -1,0 +1,354 @@
+"""GPU parity tests (run on the B200 box): every call goes through the C-ABI (ctypes -> libmas_b200.so) and is
+compared with (a) fixtures generated from the REAL reference and (b) the CPU oracle on seeded inputs.
+
+Tolerances: VQ indices bit-exact (or fp64-tie-explained on the tie-heavy sets); floating point within 1e-3
+relative (norm-wise) for the TF32 tensor path, 1e-4 for the fp32 SIMT path — north_star's stated bar is 1e-3.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL_FWD = 1e-3
+TOL_GRAD = 3e-3
+
+
+def _dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def _load(name):
+    return torch.load(os.path.join(GOLDEN, name), weights_only=False)
+
+
+def _w(y):
+    return torch.linspace(-1, 1, y.numel(), device=y.device).view(y.shape)
+
+
+@pytest.fixture(params=["auto", "simt"])
+def impl(request):
+    from mas_b200 import _lib, ops
+    ops.set_impl(_lib.IMPL_AUTO if request.param == "auto" else _lib.IMPL_SIMT)
+    yield request.param
+    ops.set_impl(_lib.IMPL_AUTO)
+
+
+# ------------------------------------------------------------------------------------------------ codebook
+def test_codebook_sets_vs_reference():
+    from models.modules import Codebook
+    from oracle import vqgan_oracle as O
+    sets = _load("codebook_sets.pt")
+    dev = _dev()
+    for name, s in sets.items():
+        cb = Codebook(256, 64, beta=0.25, init_steps=10, reservoir_size=100).to(dev).eval()
+        with torch.no_grad():
+            cb.embedding.weight.copy_(s["E"])
+        z = s["z"].to(dev).requires_grad_(True)
+        z_q, loss, idx = cb(z)
+        assert idx.dtype == torch.int64 and idx.shape == s["idx"].shape
+        bad = torch.nonzero(idx.cpu() != s["idx"]).flatten()
+        if name in ("trained", "clustered", "duplicated"):
+            # duplicated rows are bit-identical codes => exact ties => first index must win, bit-exactly
+            assert bad.numel() == 0, (name, bad)
+        else:
+            zf = s["z"].permute(0, 2, 3, 1).reshape(-1, 64)
+            gap, ulp = O.codebook_gap_fp64(zf, s["E"], idx.cpu(), s["idx"])
+            assert bool((gap[bad] <= 4 * ulp[bad]).all()), name
+        ok = (idx.cpu() == s["idx"])
+        zq_rows = z_q.detach().cpu().permute(0, 2, 3, 1).reshape(-1, 64)
+        ref_rows = s["z_q"].permute(0, 2, 3, 1).reshape(-1, 64)
+        assert torch.allclose(zq_rows[ok], ref_rows[ok], atol=1e-6), name
+        if bad.numel() == 0:
+            assert abs(float(loss) - float(s["loss"])) <= 1e-5 * abs(float(s["loss"])) + 1e-9
+            ((z_q * _w(z_q)).sum() + loss).backward()
+            assert rel_err(z.grad, s["grad_z"]) < 1e-5, name
+            assert rel_err(cb.embedding.weight.grad, s["grad_E"]) < 1e-4, name
+            ent = cb.get_codebook_entry(idx, (3, 4, 4, 64))
+            assert torch.equal(ent.cpu().contiguous(), s["entry"])
+
+
+def test_codebook_full_size_properties():
+    """K=8192, D=256, 8192 rows (BASELINE config 2/3): size-independent properties + sampled exact check."""
+    from mas_b200 import ops
+    from oracle import vqgan_oracle as O
+    dev = _dev()
+    g = torch.Generator().manual_seed(1234)
+    z = torch.randn(32, 256, 16, 16, generator=g)
+    E = torch.randn(8192, 256, generator=torch.Generator().manual_seed(4321))
+    zd, Ed = z.to(dev), E.to(dev)
+    zq, loss, idx = ops.VQFn.apply(zd, Ed, 0.25)
+    idx_c = idx.cpu()
+    assert int(idx_c.min()) >= 0 and int(idx_c.max()) < 8192
+    # oracle on a sample of rows (numpy fp32 restatement) — bit-exact on margin-safe data
+    zf = z.permute(0, 2, 3, 1).reshape(-1, 256)
+    rows = torch.arange(0, 8192, 17)
+    ref = torch.from_numpy(O.codebook_argmin_numpy(zf[rows].numpy(), E.numpy()))
+    bad = torch.nonzero(idx_c[rows] != ref).flatten()
+    if bad.numel():
+        gap, ulp = O.codebook_gap_fp64(zf[rows], E, idx_c[rows], ref)
+        assert bool((gap[bad] <= 4 * ulp[bad]).all())
+    # optimality: no code is closer (fp64) than the chosen one by more than rounding noise
+    d_best = ((zf.double() - E[idx_c].double()) ** 2).sum(1)
+    probe = torch.randint(0, 8192, (8192, 64), generator=g)
+    d_probe = ((zf.double()[:, None, :] - E[probe].double()) ** 2).sum(2)
+    assert bool((d_best[:, None] <= d_probe + 1e-3).all())
+    # idempotence: quantising the code vectors returns the same indices and zero loss
+    e_img = E[idx_c].view(32, 16, 16, 256).permute(0, 3, 1, 2).contiguous().to(dev)
+    zq2, loss2, idx2 = ops.VQFn.apply(e_img, Ed, 0.25)
+    assert torch.equal(idx2.cpu(), idx_c) and float(loss2) < 1e-10
+    # loss value
+    ref_loss = 1.25 * float(d_best.sum() / zf.numel())
+    assert abs(float(loss) - ref_loss) < 1e-5 * ref_loss
+    # first-index tie-break at full size: duplicate the codebook's first half into its second half
+    E2 = torch.cat([E[:4096], E[:4096]], 0).to(dev)
+    _, _, idx3 = ops.VQFn.apply(zd, E2, 0.25)
+    assert int(idx3.max()) < 4096
+
+
+def test_codebook_ragged_rows():
+    """R not a multiple of the 64-row tile, K not a multiple of the 128-code tile."""
+    from mas_b200 import ops
+    from oracle import vqgan_oracle as O
+    dev = _dev()
+    g = torch.Generator().manual_seed(3)
+    z = torch.randn(1, 32, 7, 11, generator=g)
+    E = torch.randn(200, 32, generator=g)
+    zq, loss, idx = ops.VQFn.apply(z.to(dev), E.to(dev), 0.25)
+    zq_o, loss_o, idx_o = O.codebook_forward(z, E)
+    assert torch.equal(idx.cpu(), idx_o)
+    assert torch.allclose(zq.cpu(), zq_o, atol=1e-6) and abs(float(loss) - float(loss_o)) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ blocks vs reference fixtures
+def _run_block(name, b, impl):
+    from models import modules as M
+    dev = _dev()
+    kind = name.split("_")[0]
+    sd = b["state_dict"]
+    if kind == "res":
+        cin, cout = sd["conv1.weight"].shape[1], sd["conv1.weight"].shape[0]
+        mod = M.ResnetBlock(in_channels=cin, out_channels=cout, dropout=0.0)
+    elif kind == "attn":
+        mod = M.AttnBlock(sd["q.weight"].shape[0])
+    elif kind == "down":
+        mod = M.Downsample(sd["conv.weight"].shape[0], True)
+    else:
+        mod = M.Upsample(sd["conv.weight"].shape[0], True)
+    mod.load_state_dict(sd)
+    mod.to(dev)
+    x = b["x"].to(dev).requires_grad_(True)
+    y = mod(x)
+    assert y.shape == b["y"].shape
+    tf, tg = (TOL_FWD, TOL_GRAD) if impl == "auto" else (1e-4, 5e-4)
+    assert rel_err(y, b["y"]) < tf, name
+    (y * _w(y)).sum().backward()
+    assert rel_err(x.grad, b["grad_x"]) < tg, name
+    for k, gv in b["grads"].items():
+        p = dict(mod.named_parameters())[k]
+        assert rel_err(p.grad, gv) < tg, (name, k)
+
+
+def test_blocks_vs_reference(impl):
+    blocks = _load("blocks.pt")
+    for name, b in blocks.items():
+        _run_block(name, b, impl)
+
+
+# ------------------------------------------------------------------------------------------------ whole model, tiny
+def test_vqbase_tiny_vs_reference(impl):
+    from models import VQBASE
+    g = _load("vqbase_tiny.pt")
+    dev = _dev()
+    m = VQBASE(g["ddconfig"], g["n_embed"], g["embed_dim"], 10, 100)
+    m.load_state_dict(g["state_dict"])
+    m.quantize.q_counter = 10 ** 6
+    m.train().to(dev)
+    x = g["x"].to(dev)
+    dec, diff = m(x)
+    assert dec.shape == g["dec"].shape and dec.is_contiguous() and diff.dim() == 0
+    tf, tg = (TOL_FWD, TOL_GRAD) if impl == "auto" else (1e-4, 1e-3)
+    assert rel_err(dec, g["dec"]) < tf
+    assert abs(float(diff) - float(g["diff"])) < tf * abs(float(g["diff"]))
+    loss = (x - dec).abs().mean() + diff
+    loss.backward()
+    for k, gv in g["grads"].items():
+        p = dict(m.named_parameters())[k]
+        assert p.grad is not None, k
+        assert rel_err(p.grad, gv) < max(tg, 2e-3), k
+    # running statistics of the (Sync)BatchNorm update like the reference's
+    assert rel_err(m.quant_conv[1].running_mean, g["running_mean"]) < 1e-4
+    assert rel_err(m.quant_conv[1].running_var, g["running_var"]) < 1e-4
+    assert int(m.quant_conv[1].num_batches_tracked) == 1
+
+
+def test_vqbase_tiny_modes():
+    from models import VQBASE
+    g = _load("vqbase_tiny.pt")
+    mo = _load("vqbase_tiny_modes.pt")
+    dev = _dev()
+    m = VQBASE(g["ddconfig"], g["n_embed"], g["embed_dim"], 10, 100)
+    m.load_state_dict(g["state_dict"])
+    m.train().to(dev)
+    dec, diff = m(g["x"].to(dev))            # q_counter=1 < q_init: warm-up bypass (modules.py:482-484)
+    assert float(diff) == 0.0 and rel_err(dec, mo["dec_bypass"]) < TOL_FWD
+    m.load_state_dict(g["state_dict"])
+    m.eval()
+    dec, diff = m(g["x"].to(dev))
+    assert rel_err(dec, mo["dec_eval"]) < TOL_FWD
+    assert abs(float(diff) - float(mo["diff_eval"])) < TOL_FWD * abs(float(mo["diff_eval"]))
+
+
+def test_reentrant_backward_last_layer():
+    """loss_img.py:57-60 runs autograd.grad(..., last_layer.weight, retain_graph=True) twice before backward()."""
+    from models import VQBASE
+    g = _load("vqbase_tiny.pt")
+    dev = _dev()
+    m = VQBASE(g["ddconfig"], g["n_embed"], g["embed_dim"], 10, 100)
+    m.load_state_dict(g["state_dict"])
+    m.quantize.q_counter = 10 ** 6
+    m.train().to(dev)
+    x = g["x"].to(dev)
+    dec, diff = m(x)
+    last = m.decoder.model[-1].weight
+    l1 = (x - dec).abs().mean()
+    g1 = torch.autograd.grad(l1, last, retain_graph=True)[0]
+    g2 = torch.autograd.grad(dec.square().mean(), last, retain_graph=True)[0]
+    (l1 + diff).backward()
+    assert rel_err(g1, g["grads"]["decoder.model.%d.weight" % (len(m.decoder.model) - 1)]) < 5e-3
+    assert torch.isfinite(g2).all() and last.grad is not None
+
+
+# ------------------------------------------------------------------------------------------------ img_config widths
+def test_vqbase_img_config_64px_vs_reference():
+    """The 95M-parameter img_config model with seeded init (bit-identical to the reference's init, see
+    tests/test_abi.py) on 2x3x64x64: outputs, indices and gradient norms against the reference fixture."""
+    from models import VQBASE
+    g = _load("vqbase_img_64.pt")
+    dev = _dev()
+    torch.manual_seed(0)
+    m = VQBASE(g["ddconfig"], 8192, 256, 3000, 12500)
+    with torch.no_grad():
+        m.quantize.embedding.weight.normal_()
+    m.quantize.q_counter = 10 ** 6
+    m.train().to(dev)
+    x = g["x"].to(dev)
+    h = {}
+    hk = m.quant_conv.register_forward_hook(lambda _m, _i, o: h.__setitem__("q", o.detach()))
+    hi = m.quantize.register_forward_hook(lambda _m, _i, o: h.__setitem__("idx", o[2].detach()))
+    dec, diff = m(x)
+    hk.remove(); hi.remove()
+    e_q = rel_err(h["q"], g["quant_in"])
+    assert e_q < 3e-3, e_q          # end-to-end TF32 drift through 23 layers (reported)
+    # indices: identical unless the encoder-side drift moves a latent across a Voronoi boundary
+    mism = int((h["idx"].cpu() != g["idx"]).sum())
+    assert mism <= 2, mism
+    if mism == 0:
+        assert rel_err(dec, g["dec"]) < 5e-3
+        loss = (x - dec).abs().mean() + diff
+        loss.backward()
+        named = dict(m.named_parameters())
+        for k, gv in g["grads_small"].items():
+            assert rel_err(named[k].grad, gv) < 2e-2, k
+        worst = max(abs(float(named[k].grad.double().norm()) / v - 1.0) for k, v in g["grad_norms"].items() if v > 1e-12)
+        assert worst < 5e-2, worst
+
+
+# ------------------------------------------------------------------------------------------------ op-level vs oracle
+@pytest.mark.parametrize("c,hw", [(32, 8), (64, 12), (128, 16), (256, 8), (512, 4)])
+def test_groupnorm_swish_vs_oracle(c, hw):
+    from models import modules as M
+    from oracle import vqgan_oracle as O
+    dev = _dev()
+    g = torch.Generator().manual_seed(c + hw)
+    x = (torch.randn(3, c, hw, hw, generator=g) * 2 + 0.5)
+    gn = M.Normalize(c)
+    with torch.no_grad():
+        gn.weight.copy_(torch.randn(c, generator=g))
+        gn.bias.copy_(torch.randn(c, generator=g))
+    sd = {"n.weight": gn.weight.detach().clone().requires_grad_(True), "n.bias": gn.bias.detach().clone().requires_grad_(True)}
+    xo = x.clone().requires_grad_(True)
+    yo = O.swish(O.normalize(xo, sd, "n"))
+    (yo * _w(yo)).sum().backward()
+    gn.to(dev)
+    xd = x.to(dev).requires_grad_(True)
+    y = gn(xd, silu=True)
+    (y * _w(y)).sum().backward()
+    assert rel_err(y, yo) < 1e-5
+    assert rel_err(xd.grad, xo.grad) < 1e-4
+    assert rel_err(gn.weight.grad, sd["n.weight"].grad) < 1e-4 and rel_err(gn.bias.grad, sd["n.bias"].grad) < 1e-4
+
+
+@pytest.mark.parametrize("cin,cout,h,w,mode", [(3, 32, 9, 7, "s1"), (32, 3, 8, 8, "s1"), (64, 64, 16, 16, "s1"),
+                                               (128, 128, 32, 32, "s1"), (128, 256, 8, 24, "s1"), (256, 128, 16, 16, "s1"),
+                                               (512, 512, 16, 16, "s1"), (64, 64, 16, 16, "s2"), (128, 128, 32, 32, "s2"),
+                                               (64, 64, 8, 8, "up"), (128, 128, 16, 16, "up"), (159, 128, 8, 8, "s1")])
+def test_conv3x3_family_vs_oracle(cin, cout, h, w, mode, impl):
+    import torch.nn.functional as F
+    from mas_b200 import _lib as L, ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(cin * 7 + cout + h)
+    x = torch.randn(2, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, 3, 3, generator=g) / (3 * cin ** 0.5)
+    b = torch.randn(cout, generator=g)
+    xo, wo, bo = x.clone().requires_grad_(True), wt.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    if mode == "s1":
+        yo = F.conv2d(xo, wo, bo, padding=1)
+        md = L.CONV_S1
+    elif mode == "s2":
+        yo = F.conv2d(F.pad(xo, (0, 1, 0, 1)), wo, bo, stride=2)
+        md = L.CONV_S2
+    else:
+        yo = F.conv2d(F.interpolate(xo, scale_factor=2.0, mode="nearest"), wo, bo, padding=1)
+        md = L.CONV_UP
+    (yo * _w(yo)).sum().backward()
+    xd, wd, bd = x.to(dev).requires_grad_(True), wt.to(dev).requires_grad_(True), b.to(dev).requires_grad_(True)
+    y = ops.Conv3x3Fn.apply(xd, wd, bd, None, md, False)      # NCHW-strided input exercises the generic-stride path
+    (y * _w(y)).sum().backward()
+    tf, tg = (TOL_FWD, TOL_GRAD) if impl == "auto" else (2e-5, 1e-4)
+    assert rel_err(y, yo) < tf
+    assert rel_err(xd.grad, xo.grad) < tg
+    assert rel_err(wd.grad, wo.grad) < tg
+    assert rel_err(bd.grad, bo.grad) < 1e-4
+
+
+@pytest.mark.parametrize("M,N,K,batch,ta,tb", [(64, 64, 64, 1, 0, 1), (256, 256, 512, 4, 0, 1), (256, 512, 256, 3, 0, 0),
+                                               (256, 512, 256, 2, 1, 0), (100, 36, 52, 2, 1, 1), (8192, 512, 512, 1, 0, 1),
+                                               (77, 130, 19, 1, 0, 0)])
+def test_gemm_vs_oracle(M, N, K, batch, ta, tb, impl):
+    from mas_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(batch, *((K, M) if ta else (M, K)), generator=g)
+    B = torch.randn(batch, *((N, K) if tb else (K, N)), generator=g)
+    bias = torch.randn(N, generator=g)
+    res = torch.randn(batch, M, N, generator=g)
+    ref = 0.5 * torch.bmm(A.transpose(1, 2) if ta else A, B.transpose(1, 2) if tb else B) + bias + res
+    Ad, Bd, Cd = A.to(dev), B.to(dev), torch.empty(batch, M, N, device=dev)
+    ops.gemm(Ad, Bd, Cd, M, N, K, batch=batch, lda=A.shape[2], ldb=B.shape[2], ldc=N, sa=A.shape[1] * A.shape[2],
+             sb=B.shape[1] * B.shape[2], sc=M * N, ta=bool(ta), tb=bool(tb), alpha=0.5, bias=bias.to(dev), residual=res.to(dev))
+    assert rel_err(Cd, ref) < (TOL_FWD if impl == "auto" else 2e-5)
+
+
+def test_seg_loss_vs_reference():
+    from mas_b200 import ops
+    g = _load("seg_loss.pt")
+    dev = _dev()
+    pred = g["pred"].to(dev).requires_grad_(True)
+    pw = torch.ones(159, device=dev)
+    pw[153:158] = 20
+    loss = ops.BCELogitsFn.apply(pred, g["target"].to(dev), pw) + g["qloss"].to(dev)
+    assert abs(float(loss) - float(g["loss"])) < 1e-5
+    loss.backward()
+    assert rel_err(pred.grad, g["grad"]) < 1e-5
+
+
+def test_native_library_is_the_path_that_ran():
+    from mas_b200 import _lib
+    assert _lib.launch_count() > 0
+    assert os.path.exists(_lib.LIB_PATH)
