@@ -84,6 +84,20 @@ int mas_pack_conv3x3(const float* w_oihw, float* w_packed, int Cout, int Cin, in
                      int round_tf32, void* stream);
 int mas_conv3x3_fprop(const float* x, mas_tensor4 xs, const float* w_packed, const float* bias,
                       const float* residual, float* y, mas_tensor4 ys, int mode, int impl, void* stream);
+/* Tensor-core (tcgen05, TF32 operands / fp32 accumulate in TMEM) form of the same convolution for dense NHWC
+ * tensors with Cin % 8 == 0, Cout % 128 == 0, Hout % 16 == 0, Wout % 8 == 0 and mode S1 / UP / ZS
+ * (mas_conv3x3_tc_eligible).  w_tc comes from mas_pack_conv3x3_tc (transpose=1: data-gradient operand with
+ * flipped taps); the packed image is what one cp.async.bulk per pipeline stage drops into shared memory. */
+int mas_conv3x3_tc_eligible(mas_tensor4 xs, mas_tensor4 ys, int mode);
+int mas_pack_conv3x3_tc(const float* w_oihw, float* w_tc, int Cout, int Cin, int transpose, void* stream);
+int mas_conv3x3_fprop_tc(const float* x, mas_tensor4 xs, const float* w_tc, const float* bias,
+                         const float* residual, float* y, mas_tensor4 ys, int mode, void* stream);
+/* Row GEMM on the tensor path for 1x1 convolutions: C[M,N] = alpha * A[M,K] . W^T + bias + residual with W
+ * [N,K] row-major packed by mas_pack_gemm_tc (transpose=1 packs W^T for the data gradient: N<->K).
+ * Needs N % 128 == 0 and K % 32 == 0 (after the optional transpose). */
+int mas_pack_gemm_tc(const float* w_nk, float* w_tc, int N, int K, int transpose, void* stream);
+int mas_gemm_rows_packed(const float* A, int64_t lda, const float* w_tc, float* C, int64_t ldc, int64_t M, int N,
+                         int K, float alpha, const float* bias, const float* residual, void* stream);
 /* Weight gradient, written in the reference's [Cout,Cin,3,3] layout; dbias [Cout] may be NULL.
  * x is the convolution's (already normalised+activated) input, dy the output gradient. */
 size_t mas_conv3x3_wgrad_ws_bytes(mas_tensor4 xs, mas_tensor4 dys, int mode);

@@ -31,10 +31,7 @@ int mas_colsum(const float* x, mas_tensor4 t, float* out, void* ws, size_t ws_by
 int mas_conv3x3_fprop(const float* x, mas_tensor4 xs, const float* w_packed, const float* bias, const float* residual, float* y,
                       mas_tensor4 ys, int mode, int impl, void* stream) {
   MAS_REQUIRE(x && w_packed && y, "conv3x3_fprop: null pointer");
-  if (impl != MAS_IMPL_SIMT) {
-    int e = conv3x3_fprop_tc_launch(x, xs, w_packed, bias, residual, y, ys, mode, S(stream));
-    if (e != MAS_ERR_UNSUPPORTED || impl == MAS_IMPL_TC) return e;
-  }
+  (void)impl;  // the tensor path takes differently packed weights: see mas_conv3x3_fprop_tc
   return conv3x3_fprop_simt_launch(x, xs, w_packed, bias, residual, y, ys, mode, 3, S(stream));
 }
 

@@ -1,16 +1,473 @@
-// tcgen05 (TF32) contraction kernels — placeholder until the tensor path lands: every entry reports
-// "unsupported" so that MAS_IMPL_AUTO falls through to the SIMT kernels.
+// tcgen05 (5th-gen tensor core) contraction kernels for sm_100a: TF32 operands, fp32 accumulation in TMEM.
+//
+//   conv3x3 family / row GEMM as a "shift-GEMM":
+//     D[m, n] = sum_{tap} sum_{k} A[slot(m) + shift(tap), k] * B_tap[n, k]
+//   * M tile  = 128 output pixels arranged as 16 rows x 8 columns of the image, so that the eight rows of a
+//     UMMA core-matrix group are eight horizontally adjacent pixels (16 B apart in the staged operand) and the
+//     group stride (SBO) is the pitch of one staged image row.  The 3x3 taps are then NINE MMAs over the SAME
+//     staged halo (18 x 10 pixels): only the descriptor start address moves by (ty*10+tx)*16 B.  The input is
+//     staged once per K chunk instead of nine times (no im2col, in memory or in shared memory).
+//   * A operand: staged by 256 producer threads (generic loads -> st.shared, K-major "interleaved" no-swizzle
+//     layout [k/4][slot][4 floats]) so that upsample (x2 nearest), zero-stuffing (stride-2 data gradient) and,
+//     later, the GroupNorm+SiLU prologue are just a different slot->pixel map / register transform.
+//   * B operand (weights): pre-packed in global memory in the exact shared-memory image and pulled in with ONE
+//     cp.async.bulk (TMA bulk copy, mbarrier complete_tx) per stage.
+//   * four M tiles (512 pixels) share every weight stage: 4 x 128 fp32 accumulator columns = all 512 TMEM
+//     columns; weight traffic from L2 drops 4x.
+//   * warp roles: warps 0-7 producers then epilogue (tcgen05.ld -> bias/residual -> global), warp 8 = single-thread
+//     MMA issuer (+TMEM alloc/dealloc), warp 9 = bulk-copy issuer.  smem full/empty mbarrier ring, 3 stages.
+//
+// Reference call sites replaced: nn.Conv2d 3x3 (modules.py:93-104), Upsample/Downsample data paths
+// (modules.py:55-59,74-78), nn.Conv2d 1x1 (modules.py:113-117,145-164).
 #include "mas_common.cuh"
+
 namespace mas {
-int conv3x3_fprop_tc_launch(const float*, mas_tensor4, const float*, const float*, const float*, float*, mas_tensor4, int, cudaStream_t) {
-  return fail(MAS_ERR_UNSUPPORTED, "tcgen05 conv path not built");
+namespace tc {
+
+constexpr int BM = 128;        // pixels per M tile (16 x 8)
+constexpr int BN = 128;        // output channels per CTA
+constexpr int TILES = 4;       // M tiles per CTA (TMEM: 4 x 128 columns)
+constexpr int NPROD = 256;     // producer threads (warps 0-7)
+constexpr int NTHREADS = 320;  // + MMA warp + bulk-copy warp
+constexpr int STAGES_CONV = 3;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], TF32 in, fp32 accumulate, issued by ONE thread
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
+      "%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor, no swizzle ("interleaved"), sm_100 version field = 1
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
+         (1ull << 46);
+}
+// instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+enum { MAP_S1 = 0, MAP_UP = 2, MAP_ZS = 3, MAP_ROWS = 4 };
+
+struct Params {
+  const float* x;    // NHWC input (dense) or row matrix
+  const float* wpk;  // packed weights [n_tile][k_chunk][tap][k/4][BN][4]
+  const float* bias; // [Cout] or null
+  const float* res;  // same layout as y, or null
+  float* y;
+  int N, Hin, Win, Cin, Hout, Wout, Cout;  // for MAP_ROWS: Hout*Wout*N = rows, Win unused
+  int map;
+  int64_t ldx, ldy;  // row pitches (elements) of x pixels and y pixels
+  int tiles_x, tiles_y;  // tiles per image row / column (image maps)
+  int64_t total_tiles;
+  float alpha;
+};
+
+// One CTA = TILES M-tiles x BN output channels, full K.
+template <int TAPS, int KC, int STAGES>
+__global__ void __launch_bounds__(NTHREADS, 1) shift_gemm_tc(const Params p) {
+  constexpr int SLOTS = (TAPS == 9) ? 180 : 132;        // staged pixels per tile (18x10 halo | 128 rows + pad)
+  constexpr int ROWP = (TAPS == 9) ? 10 : 8;            // staged pixels per image row
+  constexpr int LBO_A = SLOTS * 16;                     // bytes between k-quads of A
+  constexpr int SBO_A = ROWP * 16;                      // bytes between 8-pixel groups of A
+  constexpr int A_TILE = (KC / 4) * LBO_A;              // bytes per tile per stage
+  constexpr int A_STAGE = TILES * A_TILE;
+  constexpr int LBO_B = BN * 16;
+  constexpr int B_TAP = (KC / 4) * LBO_B;
+  constexpr int B_STAGE = TAPS * B_TAP;
+  constexpr int STAGE = A_STAGE + B_STAGE;
+  constexpr int QUADS = KC / 4;
+  constexpr int ITEMS = TILES * SLOTS * QUADS;          // float4 items staged per K chunk
+  constexpr int PER_THREAD = (ITEMS + NPROD - 1) / NPROD;
+  static_assert((SLOTS % 8) == 4, "A plane pitch must be 64 mod 128 bytes for conflict-free producer stores");
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE);
+  // bars[0..S) full, bars[S..2S) empty, bars[2S] accumulator ready; then the TMEM base address word
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t accum_bar = bar_base + 8u * (2 * STAGES);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t tile0 = (int64_t)blockIdx.x * TILES;
+  const int n0 = blockIdx.y * BN;
+  const int nchunks = p.Cin / KC;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), NPROD + 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 8) {
+    // ===================== producers: stage A (input pixels) =====================
+    const float* src[PER_THREAD];
+    uint32_t dst[PER_THREAD];
+#pragma unroll
+    for (int i = 0; i < PER_THREAD; ++i) {
+      const int item = tid + i * NPROD;
+      src[i] = nullptr;
+      dst[i] = 0xFFFFFFFFu;
+      if (item < ITEMS) {
+        const int q = item % QUADS, rest = item / QUADS, slot = rest % SLOTS, tl = rest / SLOTS;
+        dst[i] = (uint32_t)(tl * A_TILE + q * LBO_A + slot * 16);
+        const int64_t tile = tile0 + tl;
+        if (tile < p.total_tiles) {
+          if (TAPS == 9) {
+            const int tx_ = (int)(tile % p.tiles_x), ty_ = (int)((tile / p.tiles_x) % p.tiles_y);
+            const int n = (int)(tile / ((int64_t)p.tiles_x * p.tiles_y));
+            const int r = slot / 10, c = slot % 10;
+            const int vy = ty_ * 16 - 1 + r, vx = tx_ * 8 - 1 + c;  // coordinates in the (virtual) conv input image
+            int iy = vy, ix = vx;
+            bool ok;
+            if (p.map == MAP_S1) {
+              ok = (unsigned)vy < (unsigned)p.Hin && (unsigned)vx < (unsigned)p.Win;
+            } else if (p.map == MAP_UP) {
+              ok = (unsigned)vy < (unsigned)(2 * p.Hin) && (unsigned)vx < (unsigned)(2 * p.Win);
+              iy = vy >> 1; ix = vx >> 1;
+            } else {  // MAP_ZS
+              ok = vy >= 0 && vx >= 0 && (vy & 1) && (vx & 1) && (vy >> 1) < p.Hin && (vx >> 1) < p.Win;
+              iy = vy >> 1; ix = vx >> 1;
+            }
+            if (ok) src[i] = p.x + ((int64_t)(n * p.Hin + iy) * p.Win + ix) * p.ldx + q * 4;
+          } else {
+            const int64_t row = tile * BM + slot;
+            if (slot >= BM) dst[i] = 0xFFFFFFFFu;  // pad slots are never read by the MMA
+            else if (row < (int64_t)p.N * p.Hout * p.Wout) src[i] = p.x + row * p.ldx + q * 4;
+          }
+        }
+      }
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kc = 0; kc < nchunks; ++kc) {
+      mbar_wait(empty_bar(stage), phase ^ 1);
+      uint8_t* a_st = smem + (size_t)stage * STAGE;
+#pragma unroll
+      for (int i = 0; i < PER_THREAD; ++i) {
+        if (dst[i] != 0xFFFFFFFFu) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (src[i]) v = __ldg(reinterpret_cast<const float4*>(src[i] + (size_t)kc * KC));
+          *reinterpret_cast<float4*>(a_st + dst[i]) = v;
+        }
+      }
+      fence_proxy_async();  // make the generic-proxy stores visible to the tensor core (async proxy)
+      mbar_arrive(full_bar(stage));
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int lane_grp = warp & 3;           // TMEM lanes [32*lane_grp, +32)
+    const int chalf = warp >> 2;             // column half of the 128-wide tile
+    const int m = lane_grp * 32 + lane;      // row of the M tile
+#pragma unroll 1
+    for (int tl = 0; tl < TILES; ++tl) {
+      const int64_t tile = tile0 + tl;
+      int64_t pix = -1;
+      if (tile < p.total_tiles) {
+        if (TAPS == 9) {
+          const int tx_ = (int)(tile % p.tiles_x), ty_ = (int)((tile / p.tiles_x) % p.tiles_y);
+          const int n = (int)(tile / ((int64_t)p.tiles_x * p.tiles_y));
+          pix = ((int64_t)n * p.Hout + ty_ * 16 + (m >> 3)) * p.Wout + tx_ * 8 + (m & 7);
+        } else {
+          const int64_t row = tile * BM + m;
+          if (row < (int64_t)p.N * p.Hout * p.Wout) pix = row;
+        }
+      }
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        const int col = chalf * 64 + cc * 32;
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(tl * BN + col), v);
+        if (pix >= 0) {
+          float* yp = p.y + pix * p.ldy + n0 + col;
+          const float* rp = p.res ? p.res + pix * p.ldy + n0 + col : nullptr;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o = make_float4(v[j] * p.alpha, v[j + 1] * p.alpha, v[j + 2] * p.alpha, v[j + 3] * p.alpha);
+            if (p.bias) {
+              float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + col + j));
+              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            }
+            if (rp) {
+              float4 r = __ldg(reinterpret_cast<const float4*>(rp + j));
+              o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+            }
+            *reinterpret_cast<float4*>(yp + j) = o;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 8) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kc = 0; kc < nchunks; ++kc) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t a_st = smem_base + (uint32_t)stage * STAGE;
+        const uint32_t b_st = a_st + A_STAGE;
+#pragma unroll 1
+        for (int tl = 0; tl < TILES; ++tl) {
+#pragma unroll
+          for (int t = 0; t < TAPS; ++t) {
+            const uint32_t tapoff = (TAPS == 9) ? (uint32_t)(((t / 3) * 10 + (t % 3)) * 16) : 0u;
+#pragma unroll
+            for (int k8 = 0; k8 < KC / 8; ++k8) {
+              const uint64_t ad = make_desc(a_st + tl * A_TILE + tapoff + k8 * 2 * LBO_A, LBO_A, SBO_A);
+              const uint64_t bd = make_desc(b_st + t * B_TAP + k8 * 2 * LBO_B, LBO_B, 128);
+              mma_tf32_ss(tmem_base + (uint32_t)(tl * BN), ad, bd, idesc, (kc > 0 || t > 0 || k8 > 0) ? 1u : 0u);
+            }
+          }
+        }
+        mma_commit(empty_bar(stage));  // frees the smem stage when these MMAs have read it
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      mma_commit(accum_bar);  // all accumulators complete
+    }
+    __syncwarp();
+  } else {
+    // ===================== weight bulk-copy issuer (one thread) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const float* wsrc = p.wpk + (size_t)blockIdx.y * nchunks * (B_STAGE / 4);
+      for (int kc = 0; kc < nchunks; ++kc) {
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        mbar_expect_tx(full_bar(stage), B_STAGE);
+        bulk_g2s(smem_base + (uint32_t)stage * STAGE + A_STAGE, wsrc + (size_t)kc * (B_STAGE / 4), B_STAGE, full_bar(stage));
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int TAPS, int KC, int STAGES>
+constexpr size_t smem_bytes() {
+  constexpr int SLOTS = (TAPS == 9) ? 180 : 132;
+  return (size_t)STAGES * (TILES * (KC / 4) * SLOTS * 16 + TAPS * (KC / 4) * BN * 16) + (2 * STAGES + 1) * 8 + 16;
+}
+
+// weights [Cout][Cin][TAPS] (reference layout, taps innermost) -> [n_tile][k_chunk][tap][k/4][BN][4], TF32-rounded.
+// transpose=1 builds the data-gradient operand: N = Cin, K = Cout, taps flipped.
+__global__ void pack_weights_tc(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int taps, int KC, int transpose) {
+  const int N = transpose ? Cin : Cout, K = transpose ? Cout : Cin;
+  const int64_t total = (int64_t)N * K * taps;
+  const int nchunks = K / KC, quads = KC / 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i;
+    const int e = (int)(r % 4); r /= 4;
+    const int nn = (int)(r % BN); r /= BN;
+    const int q = (int)(r % quads); r /= quads;
+    const int t = (int)(r % taps); r /= taps;
+    const int kc = (int)(r % nchunks); r /= nchunks;
+    const int nt = (int)r;
+    const int n = nt * BN + nn, k = kc * KC + q * 4 + e;
+    float v;
+    if (!transpose) v = w[((size_t)n * Cin + k) * taps + t];
+    else v = w[((size_t)k * Cin + n) * taps + (taps - 1 - t)];
+    out[i] = round_tf32(v);
+  }
+}
+
+}  // namespace tc
+
+static bool dense_nhwc(const mas_tensor4& t) {
+  return t.sc == 1 && t.sw == t.c && t.sh == t.w * t.c && t.sn == t.h * t.w * t.c;
+}
+static inline bool al16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <typename K>
+static int set_smem(K kernel, size_t bytes) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return fail(MAS_ERR_LAUNCH, "cudaFuncSetAttribute(smem=%zu): %s", bytes, cudaGetErrorString(e));
+  return MAS_OK;
+}
+
+// w_tc must have been produced by mas_pack_conv3x3_tc for the matching direction.
+int conv3x3_fprop_tc_launch(const float* x, mas_tensor4 xs, const float* w_tc, const float* bias, const float* res, float* y,
+                            mas_tensor4 ys, int mode, cudaStream_t st) {
+  const int Cin = (int)xs.c, Cout = (int)ys.c;
+  if (!(mode == MAS_CONV_S1 || mode == MAS_CONV_UP || mode == MAS_CONV_ZS)) return fail(MAS_ERR_UNSUPPORTED, "tc conv: mode %d", mode);
+  if (!dense_nhwc(xs) || !dense_nhwc(ys) || Cin % 8 || Cout % tc::BN || ys.h % 16 || ys.w % 8 || !al16p(x) || !al16p(y) ||
+      (res && !al16p(res)) || (bias && !al16p(bias)) || !al16p(w_tc))
+    return fail(MAS_ERR_UNSUPPORTED, "tc conv: shape/layout not eligible (Cin=%d Cout=%d Hout=%lld Wout=%lld)", Cin, Cout,
+                (long long)ys.h, (long long)ys.w);
+  int64_t eh = (mode == MAS_CONV_S1) ? xs.h : 2 * xs.h, ew = (mode == MAS_CONV_S1) ? xs.w : 2 * xs.w;
+  if (ys.h != eh || ys.w != ew || xs.n != ys.n) return fail(MAS_ERR_INVALID_ARG, "tc conv: output extent mismatch");
+  tc::Params p;
+  p.x = x; p.wpk = w_tc; p.bias = bias; p.res = res; p.y = y;
+  p.N = (int)xs.n; p.Hin = (int)xs.h; p.Win = (int)xs.w; p.Cin = Cin; p.Hout = (int)ys.h; p.Wout = (int)ys.w; p.Cout = Cout;
+  p.map = (mode == MAS_CONV_S1) ? tc::MAP_S1 : (mode == MAS_CONV_UP ? tc::MAP_UP : tc::MAP_ZS);
+  p.ldx = Cin; p.ldy = Cout;
+  p.tiles_x = (int)(ys.w / 8); p.tiles_y = (int)(ys.h / 16);
+  p.total_tiles = (int64_t)p.N * p.tiles_x * p.tiles_y;
+  p.alpha = 1.0f;
+  constexpr size_t smem = tc::smem_bytes<9, 8, tc::STAGES_CONV>();
+  static bool configured = false;
+  if (!configured) {
+    if (int e = set_smem(tc::shift_gemm_tc<9, 8, tc::STAGES_CONV>, smem)) return e;
+    configured = true;
+  }
+  dim3 grid((unsigned)cdiv(p.total_tiles, tc::TILES), (unsigned)(Cout / tc::BN));
+  tc::shift_gemm_tc<9, 8, tc::STAGES_CONV><<<grid, tc::NTHREADS, smem, st>>>(p);
+  return launched("shift_gemm_tc<9>");
+}
+
+// Row GEMM C[M,N] = alpha * A[M,K] * Wt[N,K]^T + bias + residual with PRE-PACKED weights (mas_pack_gemm_tc).
+int gemm_rows_tc_launch(const float* A, int64_t lda, const float* w_tc, float* C, int64_t ldc, int64_t M, int N, int K, float alpha,
+                        const float* bias, const float* res, cudaStream_t st) {
+  if (K % 32 || N % tc::BN || lda % 4 || ldc % 4 || !al16p(A) || !al16p(C) || (res && !al16p(res)) || (bias && !al16p(bias)) ||
+      !al16p(w_tc))
+    return fail(MAS_ERR_UNSUPPORTED, "tc gemm: shape not eligible (M=%lld N=%d K=%d)", (long long)M, N, K);
+  tc::Params p;
+  p.x = A; p.wpk = w_tc; p.bias = bias; p.res = res; p.y = C;
+  p.N = 1; p.Hin = 1; p.Win = 1; p.Cin = K; p.Hout = 1; p.Wout = (int)M; p.Cout = N;
+  if (M > 0x7fffffff) return fail(MAS_ERR_UNSUPPORTED, "tc gemm: M too large");
+  p.map = tc::MAP_ROWS;
+  p.ldx = lda; p.ldy = ldc;
+  p.tiles_x = 1; p.tiles_y = 1;
+  p.total_tiles = cdiv(M, tc::BM);
+  p.alpha = alpha;
+  constexpr size_t smem = tc::smem_bytes<1, 32, 2>();
+  static bool configured = false;
+  if (!configured) {
+    if (int e = set_smem(tc::shift_gemm_tc<1, 32, 2>, smem)) return e;
+    configured = true;
+  }
+  dim3 grid((unsigned)cdiv(p.total_tiles, tc::TILES), (unsigned)(N / tc::BN));
+  tc::shift_gemm_tc<1, 32, 2><<<grid, tc::NTHREADS, smem, st>>>(p);
+  return launched("shift_gemm_tc<1>");
+}
+
 int gemm_tc_launch(const float*, const float*, float*, int, int, int, int, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int, int,
                    float, const float*, const float*, cudaStream_t) {
-  return fail(MAS_ERR_UNSUPPORTED, "tcgen05 gemm path not built");
+  return fail(MAS_ERR_UNSUPPORTED, "tc gemm with un-packed B operand: not available (use mas_gemm_rows_packed)");
 }
 size_t conv_wgrad_tc_ws(mas_tensor4, mas_tensor4, int) { return 0; }
 int conv_wgrad_tc_launch(const float*, mas_tensor4, const float*, mas_tensor4, float*, int, void*, size_t, cudaStream_t) {
   return fail(MAS_ERR_UNSUPPORTED, "tcgen05 wgrad path not built");
 }
+
 }  // namespace mas
+
+using namespace mas;
+
+extern "C" {
+
+int mas_pack_conv3x3_tc(const float* w_oihw, float* w_tc, int Cout, int Cin, int transpose, void* stream) {
+  const int N = transpose ? Cin : Cout, K = transpose ? Cout : Cin;
+  if (N % tc::BN || K % 8) return fail(MAS_ERR_UNSUPPORTED, "pack_conv3x3_tc: N=%d must be a multiple of 128 and K=%d of 8", N, K);
+  int64_t total = (int64_t)9 * Cout * Cin;
+  tc::pack_weights_tc<<<(int)(cdiv(total, 256) < 2368 ? cdiv(total, 256) : 2368), 256, 0, S(stream)>>>(w_oihw, w_tc, Cout, Cin, 9, 8, transpose);
+  return launched("pack_weights_tc<9>");
+}
+
+int mas_pack_gemm_tc(const float* w_nk, float* w_tc, int N, int K, int transpose, void* stream) {
+  // w_nk: [N_out][K_in] row-major (a 1x1 convolution weight); transpose=1 packs the [K_in -> N] data-gradient operand
+  const int Nn = transpose ? K : N, Kk = transpose ? N : K;
+  if (Nn % tc::BN || Kk % 32) return fail(MAS_ERR_UNSUPPORTED, "pack_gemm_tc: N=%d must be a multiple of 128 and K=%d of 32", Nn, Kk);
+  int64_t total = (int64_t)N * K;
+  tc::pack_weights_tc<<<(int)(cdiv(total, 256) < 2368 ? cdiv(total, 256) : 2368), 256, 0, S(stream)>>>(w_nk, w_tc, N, K, 1, 32, transpose);
+  return launched("pack_weights_tc<1>");
+}
+
+int mas_gemm_rows_packed(const float* A, int64_t lda, const float* w_tc, float* C, int64_t ldc, int64_t M, int N, int K, float alpha,
+                         const float* bias, const float* residual, void* stream) {
+  MAS_REQUIRE(A && w_tc && C && M > 0, "gemm_rows_packed: bad arguments");
+  return gemm_rows_tc_launch(A, lda, w_tc, C, ldc, M, N, K, alpha, bias, residual, S(stream));
+}
+
+int mas_conv3x3_tc_eligible(mas_tensor4 xs, mas_tensor4 ys, int mode) {
+  const int Cin = (int)xs.c, Cout = (int)ys.c;
+  if (!(mode == MAS_CONV_S1 || mode == MAS_CONV_UP || mode == MAS_CONV_ZS)) return 0;
+  if (!dense_nhwc(xs) || !dense_nhwc(ys) || Cin % 8 || Cout % tc::BN || ys.h % 16 || ys.w % 8) return 0;
+  return 1;
+}
+
+int mas_conv3x3_fprop_tc(const float* x, mas_tensor4 xs, const float* w_tc, const float* bias, const float* residual, float* y,
+                         mas_tensor4 ys, int mode, void* stream) {
+  MAS_REQUIRE(x && w_tc && y, "conv3x3_fprop_tc: null pointer");
+  return conv3x3_fprop_tc_launch(x, xs, w_tc, bias, residual, y, ys, mode, S(stream));
+}
+
+}  // extern "C"

@@ -40,6 +40,11 @@ _SPEC = {
     "mas_silu_backward": (_I, [_P, _P, _P, _L, _P]),
     "mas_pack_conv3x3": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "mas_conv3x3_fprop": (_I, [_P, _T, _P, _P, _P, _P, _T, _I, _I, _P]),
+    "mas_conv3x3_tc_eligible": (_I, [_T, _T, _I]),
+    "mas_pack_conv3x3_tc": (_I, [_P, _P, _I, _I, _I, _P]),
+    "mas_conv3x3_fprop_tc": (_I, [_P, _T, _P, _P, _P, _P, _T, _I, _P]),
+    "mas_pack_gemm_tc": (_I, [_P, _P, _I, _I, _I, _P]),
+    "mas_gemm_rows_packed": (_I, [_P, _L, _P, _P, _L, _L, _I, _I, _F, _P, _P, _P]),
     "mas_conv3x3_wgrad_ws_bytes": (_Z, [_T, _T, _I]),
     "mas_conv3x3_wgrad": (_I, [_P, _T, _P, _T, _P, _P, _I, _I, _P, _Z, _P]),
     "mas_conv1x1_wgrad_ws_bytes": (_Z, [_L, _I, _I]),

@@ -81,13 +81,6 @@ def gn_backward(dy, x, mean, rstd, gamma, beta, silu, dx_add=None):
     return dx, dg, db
 
 
-def pack3x3(weight, flip_transpose=False):
-    cout, cin = weight.shape[0], weight.shape[1]
-    out = torch.empty(9 * cout * cin, dtype=torch.float32, device=weight.device)
-    L.call("mas_pack_conv3x3", weight.contiguous(), out, cout, cin, int(flip_transpose), 0)
-    return out
-
-
 def _conv_out_hw(h, w, mode):
     if mode == L.CONV_S1:
         return h, w
@@ -96,14 +89,34 @@ def _conv_out_hw(h, w, mode):
     return 2 * h, 2 * w
 
 
-def conv3x3_raw(x, wpacked, cout, bias, residual, mode, out_nchw=False):
+def _tc_on():
+    return _cfg["impl"] != L.IMPL_SIMT
+
+
+def conv3x3_raw(x, weight, bias, residual, mode, out_nchw=False, transpose=False):
+    """y = conv3x3(x; weight) (+bias, +residual). transpose=True applies the data-gradient operand
+    (taps flipped, Cin<->Cout). Dense NHWC shapes with Cin%8==0, Cout%128==0, Hout%16==0, Wout%8==0 run on the
+    tcgen05 kernel; everything else (edge layers, stride-2 gather, NCHW views, small images) on the fp32 SIMT kernel."""
     n, _, h, w = x.shape
+    cout = weight.shape[1] if transpose else weight.shape[0]
+    cin = weight.shape[0] if transpose else weight.shape[1]
     ho, wo = _conv_out_hw(h, w, mode)
     if out_nchw:
         y = torch.empty((n, cout, ho, wo), dtype=torch.float32, device=x.device)
     else:
         y = empty_nhwc(n, cout, ho, wo, x)
-    L.call("mas_conv3x3_fprop", x, L.t4(x), wpacked, bias, residual, y, L.t4(y), mode, _cfg["impl"])
+    xs, ys = L.t4(x), L.t4(y)
+    wc = weight.contiguous()
+    if _tc_on() and not out_nchw and L.query("mas_conv3x3_tc_eligible", xs, ys, mode):
+        wt = torch.empty(9 * cout * cin, dtype=torch.float32, device=x.device)
+        L.call("mas_pack_conv3x3_tc", wc, wt, weight.shape[0], weight.shape[1], int(transpose))
+        L.call("mas_conv3x3_fprop_tc", x, xs, wt, bias, residual, y, ys, mode)
+    else:
+        if _cfg["impl"] == L.IMPL_TC:
+            raise RuntimeError("IMPL_TC requested but the conv shape is not eligible for the tcgen05 kernel")
+        wp = torch.empty(9 * cout * cin, dtype=torch.float32, device=x.device)
+        L.call("mas_pack_conv3x3", wc, wp, weight.shape[0], weight.shape[1], int(transpose), 0)
+        L.call("mas_conv3x3_fprop", x, xs, wp, bias, residual, y, ys, mode, L.IMPL_SIMT)
     return y
 
 
@@ -117,16 +130,14 @@ def conv3x3_wgrad_raw(x, dy, cout, cin, mode, want_bias=True):
 
 
 def conv3x3_dgrad_raw(dy, weight, mode):
-    """Data gradient of the 3x3 family: fprop with flipped/transposed weights (+ zero-stuffing or 2x2 sum-pool)."""
-    cout, cin = weight.shape[0], weight.shape[1]
-    wd = pack3x3(weight, flip_transpose=True)
+    """Data gradient of the 3x3 family: the same kernel with flipped/transposed weights (+ zero-stuffed input map for the
+    stride-2 conv, or a 2x2 sum-pool after it for the upsampling conv)."""
     if mode == L.CONV_S1:
-        return conv3x3_raw(dy, wd, cin, None, None, L.CONV_S1)
+        return conv3x3_raw(dy, weight, None, None, L.CONV_S1, transpose=True)
     if mode == L.CONV_S2:
-        return conv3x3_raw(dy, wd, cin, None, None, L.CONV_ZS)
-    # CONV_UP: gradient w.r.t. the upsampled image, then sum over each 2x2 replica block
-    du = conv3x3_raw(dy, wd, cin, None, None, L.CONV_S1)
-    n, _, h2, w2 = du.shape
+        return conv3x3_raw(dy, weight, None, None, L.CONV_ZS, transpose=True)
+    du = conv3x3_raw(dy, weight, None, None, L.CONV_S1, transpose=True)
+    n, cin, h2, w2 = du.shape
     dx = empty_nhwc(n, cin, h2 // 2, w2 // 2, du)
     L.call("mas_sumpool2x2", du, dx, n, h2 // 2, w2 // 2, cin)
     return dx
@@ -145,12 +156,32 @@ def gemm(A, B, C, M, N, K, batch=1, lda=None, ldb=None, ldc=None, sa=0, sb=0, sc
            p(residual), _cfg["impl"])
 
 
+def gemm_w(A, lda, weight, C, ldc, M, transpose=False, alpha=1.0, bias=None, residual=None):
+    """C[M,N] = alpha * A[M,K] . W^T (+bias +residual) for a 1x1-convolution weight W [Nout, Kin] (transpose=True: A . W,
+    the data gradient). A / C may be (tensor, element_offset) pairs with row pitches lda / ldc."""
+    nout, kin = weight.shape[0], weight.shape[1]
+    N, K = (kin, nout) if transpose else (nout, kin)
+    w2 = weight.contiguous()
+    if _tc_on() and N % 128 == 0 and K % 32 == 0 and lda % 4 == 0 and ldc % 4 == 0:
+        import ctypes
+
+        def p(v):
+            return ctypes.c_void_p(v[0].data_ptr() + 4 * v[1]) if isinstance(v, tuple) else v
+        dev = (A[0] if isinstance(A, tuple) else A).device
+        wt = torch.empty(N * K, dtype=torch.float32, device=dev)
+        L.call("mas_pack_gemm_tc", w2, wt, nout, kin, int(transpose))
+        L.call("mas_gemm_rows_packed", p(A), lda, wt, p(C), ldc, M, N, K, float(alpha), bias, p(residual))
+    else:
+        # W stored [Nout,Kin]: forward needs B^T (tb), the data gradient takes it as stored [K=Nout, N=Kin]
+        gemm(A, w2, C, M, N, K, lda=lda, ldb=kin, ldc=ldc, tb=not transpose, alpha=alpha, bias=bias, residual=residual)
+
+
 def conv1x1_raw(x, weight, bias, residual=None):
     """x NHWC [N,Cin,H,W] -> NHWC [N,Cout,H,W]; rows GEMM with W stored [Cout,Cin]."""
     n, cin, h, w = x.shape
     cout = weight.shape[0]
     y = empty_nhwc(n, cout, h, w, x)
-    gemm(x, weight, y, n * h * w, cout, cin, lda=cin, ldb=cin, ldc=cout, tb=True, bias=bias, residual=residual)
+    gemm_w(x, cin, weight, y, cout, n * h * w, bias=bias, residual=residual)
     return y
 
 
@@ -158,7 +189,7 @@ def conv1x1_dgrad_raw(dy, weight, residual=None):
     n, cout, h, w = dy.shape
     cin = weight.shape[1]
     dx = empty_nhwc(n, cin, h, w, dy)
-    gemm(dy, weight, dx, n * h * w, cin, cout, lda=cout, ldb=cin, ldc=cin, residual=residual)
+    gemm_w(dy, cout, weight, dx, cin, n * h * w, transpose=True, residual=residual)
     return dx
 
 
@@ -226,7 +257,7 @@ class Conv3x3Fn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, residual, mode, out_nchw):
         _need_cuda(x)
         cout = weight.shape[0]
-        y = conv3x3_raw(x, pack3x3(weight), cout, bias, residual, mode, out_nchw)
+        y = conv3x3_raw(x, weight, bias, residual, mode, out_nchw)
         ctx.save_for_backward(x, weight)
         ctx.mode, ctx.has_bias, ctx.has_res = mode, bias is not None, residual is not None
         return y
@@ -278,11 +309,11 @@ class ResnetBlockFn(torch.autograd.Function):
         cout = c1w.shape[0]
         m1, r1 = gn_stats(x)
         a1 = gn_apply(x, m1, r1, n1w, n1b, True)
-        h1 = conv3x3_raw(a1, pack3x3(c1w), cout, c1b, None, L.CONV_S1)
+        h1 = conv3x3_raw(a1, c1w, c1b, None, L.CONV_S1)
         m2, r2 = gn_stats(h1)
         a2 = gn_apply(h1, m2, r2, n2w, n2b, True)
         sc = x if sw is None else conv1x1_raw(x, sw, sb)
-        out = conv3x3_raw(a2, pack3x3(c2w), cout, c2b, sc, L.CONV_S1)
+        out = conv3x3_raw(a2, c2w, c2b, sc, L.CONV_S1)
         ctx.save_for_backward(x, a1, h1, a2, m1, r1, m2, r2, n1w, n1b, c1w, n2w, n2b, c2w, sw)
         ctx.has_sc = sw is not None
         return out
@@ -323,7 +354,7 @@ class AttnBlockFn(torch.autograd.Function):
         hn = gn_apply(x, mean, rstd, nw, nb, False)
         qkv = torch.empty((M, 3 * c), dtype=torch.float32, device=x.device)
         for i, (wt, bs) in enumerate(((qw, qb), (kw, kb), (vw, vb))):
-            gemm(hn, wt, (qkv, i * c), M, c, c, lda=c, ldb=c, ldc=3 * c, tb=True, bias=bs)
+            gemm_w(hn, c, wt, (qkv, i * c), 3 * c, M, bias=bs)
         P = torch.empty((n, hw, hw), dtype=torch.float32, device=x.device)
         gemm((qkv, 0), (qkv, c), P, hw, hw, c, batch=n, lda=3 * c, ldb=3 * c, ldc=hw, sa=hw * 3 * c, sb=hw * 3 * c,
              sc=hw * hw, tb=True, alpha=float(int(c) ** (-0.5)))
@@ -356,9 +387,9 @@ class AttnBlockFn(torch.autograd.Function):
              ta=True)
         # dhn = dq.Wq + dk.Wk + dv.Wv (chained through the GEMM residual input)
         dhn = empty_nhwc(n, c, h, w, x)
-        gemm((dqkv, 0), qw, dhn, M, c, c, lda=3 * c, ldb=c, ldc=c)
-        gemm((dqkv, c), kw, dhn, M, c, c, lda=3 * c, ldb=c, ldc=c, residual=dhn)
-        gemm((dqkv, 2 * c), vw, dhn, M, c, c, lda=3 * c, ldb=c, ldc=c, residual=dhn)
+        gemm_w((dqkv, 0), 3 * c, qw, dhn, c, M, transpose=True)
+        gemm_w((dqkv, c), 3 * c, kw, dhn, c, M, transpose=True, residual=dhn)
+        gemm_w((dqkv, 2 * c), 3 * c, vw, dhn, c, M, transpose=True, residual=dhn)
         grads_w = []
         for i in range(3):
             grads_w.append(conv1x1_wgrad_raw(hn, dqkv, M, c, c, ldy=3 * c, dy_off=i * c))

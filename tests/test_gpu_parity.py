@@ -307,8 +307,11 @@ def test_conv3x3_family_vs_oracle(cin, cout, h, w, mode, impl):
         yo = F.conv2d(F.interpolate(xo, scale_factor=2.0, mode="nearest"), wo, bo, padding=1)
         md = L.CONV_UP
     (yo * _w(yo)).sum().backward()
-    xd, wd, bd = x.to(dev).requires_grad_(True), wt.to(dev).requires_grad_(True), b.to(dev).requires_grad_(True)
-    y = ops.Conv3x3Fn.apply(xd, wd, bd, None, md, False)      # NCHW-strided input exercises the generic-stride path
+    xd = x.to(dev)
+    if (cin + cout) % 2 == 0:      # channels-last input: tensor-core eligible when the shape allows
+        xd = xd.contiguous(memory_format=torch.channels_last)
+    xd, wd, bd = xd.requires_grad_(True), wt.to(dev).requires_grad_(True), b.to(dev).requires_grad_(True)
+    y = ops.Conv3x3Fn.apply(xd, wd, bd, None, md, False)      # NCHW-strided inputs exercise the generic-stride path
     (y * _w(y)).sum().backward()
     tf, tg = (TOL_FWD, TOL_GRAD) if impl == "auto" else (2e-5, 1e-4)
     assert rel_err(y, yo) < tf
@@ -333,6 +336,53 @@ def test_gemm_vs_oracle(M, N, K, batch, ta, tb, impl):
     ops.gemm(Ad, Bd, Cd, M, N, K, batch=batch, lda=A.shape[2], ldb=B.shape[2], ldc=N, sa=A.shape[1] * A.shape[2],
              sb=B.shape[1] * B.shape[2], sc=M * N, ta=bool(ta), tb=bool(tb), alpha=0.5, bias=bias.to(dev), residual=res.to(dev))
     assert rel_err(Cd, ref) < (TOL_FWD if impl == "auto" else 2e-5)
+
+
+@pytest.mark.parametrize("cin,cout,hw,n", [(512, 512, 16, 4), (256, 128, 32, 2), (128, 256, 16, 3), (64, 32, 8, 2), (256, 256, 16, 32)])
+def test_conv1x1_vs_oracle(cin, cout, hw, n, impl):
+    import torch.nn.functional as F
+    from mas_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(cin + cout)
+    x = torch.randn(n, cin, hw, hw, generator=g)
+    wt = torch.randn(cout, cin, 1, 1, generator=g) / cin ** 0.5
+    b = torch.randn(cout, generator=g)
+    xo, wo, bo = x.clone().requires_grad_(True), wt.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yo = F.conv2d(xo, wo, bo)
+    (yo * _w(yo)).sum().backward()
+    xd, wd, bd = x.to(dev).requires_grad_(True), wt.to(dev).requires_grad_(True), b.to(dev).requires_grad_(True)
+    y = ops.Conv1x1Fn.apply(xd, wd, bd)
+    (y * _w(y)).sum().backward()
+    tf, tg = (TOL_FWD, TOL_GRAD) if impl == "auto" else (2e-5, 1e-4)
+    assert rel_err(y, yo) < tf
+    assert rel_err(xd.grad, xo.grad) < tg
+    assert rel_err(wd.grad, wo.grad) < tg and rel_err(bd.grad, bo.grad) < 1e-4
+
+
+def test_tensor_path_full_resolution_linearity():
+    """BASELINE-size conv (128->128 @256x256, batch 4 here) on the tcgen05 kernel: compared with the exact-fp32 SIMT
+    kernel on the same inputs, plus linearity conv(a*x1 + x2) = a*conv(x1) + conv(x2) (bias-free)."""
+    from mas_b200 import _lib as L, ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(99)
+    x1 = torch.randn(4, 128, 256, 256, generator=g).to(dev).contiguous(memory_format=torch.channels_last)
+    x2 = torch.randn(4, 128, 256, 256, generator=g).to(dev).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(128, 128, 3, 3, generator=g) * 0.03).to(dev)
+    b = torch.randn(128, generator=g).to(dev)
+    ops.set_impl(L.IMPL_TC)
+    try:
+        y_tc = ops.conv3x3_raw(x1, w, b, x2, L.CONV_S1)
+        l1 = ops.conv3x3_raw(2.0 * x1 + x2, w, None, None, L.CONV_S1)
+        l2 = 2.0 * ops.conv3x3_raw(x1, w, None, None, L.CONV_S1) + ops.conv3x3_raw(x2, w, None, None, L.CONV_S1)
+        d_tc = ops.conv3x3_dgrad_raw(x1, w, L.CONV_S1)
+    finally:
+        ops.set_impl(L.IMPL_SIMT)
+    y_ref = ops.conv3x3_raw(x1, w, b, x2, L.CONV_S1)
+    d_ref = ops.conv3x3_dgrad_raw(x1, w, L.CONV_S1)
+    ops.set_impl(L.IMPL_AUTO)
+    assert rel_err(y_tc, y_ref) < TOL_FWD
+    assert rel_err(d_tc, d_ref) < TOL_FWD
+    assert rel_err(l1, l2) < TOL_FWD
 
 
 def test_seg_loss_vs_reference():
