@@ -255,8 +255,11 @@ def test_vqbase_img_config_64px_vs_reference():
         named = dict(m.named_parameters())
         for k, gv in g["grads_small"].items():
             assert rel_err(named[k].grad, gv) < 2e-2, k
-        worst = max(abs(float(named[k].grad.double().norm()) / v - 1.0) for k, v in g["grad_norms"].items() if v > 1e-12)
-        assert worst < 5e-2, worst
+        # gradient norms of all 348 tensors; tensors whose true gradient is ~0 (biases feeding a GroupNorm with
+        # one channel per group, key biases of the attention) are compared on an absolute scale
+        worst = max(((abs(float(named[k].grad.double().norm()) - v) / max(v, 1e-4 * named[k].numel() ** 0.5)), k)
+                    for k, v in g["grad_norms"].items())
+        assert worst[0] < 5e-2, worst
 
 
 # ------------------------------------------------------------------------------------------------ op-level vs oracle
