@@ -193,6 +193,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="print per-entry-point CUDA-event times of one extra step")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -260,6 +261,15 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
+    if args.profile:
+        _lib.profile_start()
+        step(img_dev)
+        rep = _lib.profile_report()
+        tot = sum(t for _, t in rep.values())
+        print("per-entry profile of one step (CUDA events, ms):", file=sys.stderr)
+        for k, (c, t) in sorted(rep.items(), key=lambda kv: -kv[1][1]):
+            print("  %-28s n=%4d  %9.2f ms  %5.1f%%" % (k, c, t, 100 * t / tot), file=sys.stderr)
+        print("  total %.2f ms" % tot, file=sys.stderr)
     roof = dominant_kernel_roofline(dev, pk)
     vq = vq_metric(dev, pk)
     line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -98,6 +98,12 @@ int mas_conv3x3_fprop_tc(const float* x, mas_tensor4 xs, const float* w_tc, cons
 int mas_pack_gemm_tc(const float* w_nk, float* w_tc, int N, int K, int transpose, void* stream);
 int mas_gemm_rows_packed(const float* A, int64_t lda, const float* w_tc, float* C, int64_t ldc, int64_t M, int N,
                          int K, float alpha, const float* bias, const float* residual, void* stream);
+/* Diagnostic: one tcgen05.mma D[128x32] = A[128x8].B[32x8]^T with A from shared memory (a_src=0) or tensor memory
+ * (a_src=1) and B K-major (b_layout=0) or MN-major (1; 2 = LBO/SBO fields swapped). Used by the tests to pin the
+ * descriptor conventions the production kernels rely on. b_layout=99: B descriptor bits / instruction descriptor /
+ * start offset are taken verbatim from raw_* and the B region holds its own word indices (address reveal). */
+int mas_tc_probe(const float* A, const float* B, float* D, int a_src, int b_layout, uint64_t raw_desc,
+                 uint32_t raw_idesc, int raw_off, void* stream);
 /* Weight gradient, written in the reference's [Cout,Cin,3,3] layout; dbias [Cout] may be NULL.
  * x is the convolution's (already normalised+activated) input, dy the output gradient. */
 size_t mas_conv3x3_wgrad_ws_bytes(mas_tensor4 xs, mas_tensor4 dys, int mode);

@@ -18,7 +18,7 @@ int gemm_tc_launch(const float* A, const float* B, float* C, int M, int N, int K
                    int64_t sa, int64_t sb, int64_t sc, int ta, int tb, float alpha, const float* bias, const float* res,
                    cudaStream_t st);
 size_t conv_wgrad_tc_ws(mas_tensor4 xs, mas_tensor4 dys, int mode);
-int conv_wgrad_tc_launch(const float* x, mas_tensor4 xs, const float* dy, mas_tensor4 dys, float* dw, int mode, void* ws,
+int conv_wgrad_tc_launch(const float* x, mas_tensor4 xs, const float* dy, mas_tensor4 dys, float* dw, float* dbias, int mode, void* ws,
                          size_t ws_bytes, cudaStream_t st);
 }  // namespace mas
 
@@ -50,8 +50,9 @@ int mas_conv3x3_wgrad(const float* x, mas_tensor4 xs, const float* dy, mas_tenso
   size_t main_bytes = align256(a > b ? a : b);
   int e = MAS_ERR_UNSUPPORTED;
   if (impl != MAS_IMPL_SIMT) {
-    e = conv_wgrad_tc_launch(x, xs, dy, dys, dw_oihw, mode, ws, main_bytes, S(stream));
+    e = conv_wgrad_tc_launch(x, xs, dy, dys, dw_oihw, dbias, mode, ws, main_bytes, S(stream));
     if (e != MAS_OK && (e != MAS_ERR_UNSUPPORTED || impl == MAS_IMPL_TC)) return e;
+    if (e == MAS_OK) return MAS_OK;  // the tensor path also produced dbias
   }
   if (e == MAS_ERR_UNSUPPORTED) {
     e = conv_wgrad_simt_launch(x, xs, dy, dys, dw_oihw, mode, 3, ws, main_bytes, S(stream));

@@ -427,6 +427,11 @@ int conv_wgrad_simt_launch(const float* x, mas_tensor4 xs, const float* dy, mas_
   return launched("conv_wgrad_reduce");
 }
 
+void conv_wgrad_reduce_launch(const float* part, int splits, int ntap, int Cout, int Cin, float* dw, cudaStream_t st) {
+  int64_t total = (int64_t)ntap * Cout * Cin;
+  conv_wgrad_reduce<<<(int)(cdiv(total, 256) < 1184 ? cdiv(total, 256) : 1184), 256, 0, st>>>(part, splits, ntap, Cout, Cin, dw);
+}
+
 int gemm_simt_launch(const float* A, const float* B, float* C, int M, int N, int K, int batch, int64_t lda, int64_t ldb, int64_t ldc,
                      int64_t sa, int64_t sb, int64_t sc, int ta, int tb, float alpha, const float* bias, const float* res,
                      cudaStream_t st) {

@@ -349,7 +349,311 @@ __global__ void pack_weights_tc(const float* __restrict__ w, float* __restrict__
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Weight gradient on tcgen05:  dW[tap][co][ci] = sum_pixels dy[p][co] * xa[p + tap][ci]
+//   D (TMEM, 9 accumulators of 128 co x NT ci)  +=  A (TMEM: dy^T, lanes = co, columns = pixels)  x  B (smem: xa halo)
+//   * The reduction (K) dimension is the PIXEL index.  A lives in tensor memory (tcgen05.st from registers: lane = co makes
+//     the global reads of dy[p][co0..co0+127] coalesced and the transpose free), so the nine taps re-read it at no
+//     shared-memory cost; B is the same staged halo the forward kernel uses ([ci/4][slot][4 floats], here an
+//     MN-major operand whose K stride is one 16-byte pixel slot), and a tap is a start-address shift of the descriptor.
+//   * unit of pipelining = 8x8 output pixels (halo 10x10): 9 taps x 8 image rows = 72 MMAs of 128 x NT x 8.
+//   * CTA = (128 co) x (NT ci) x (a contiguous range of units); partial results go to the split-K workspace that the
+//     SIMT path also uses and are reduced deterministically; the per-channel sums of dy (bias gradient) fall out of
+//     the A loader for free.
+constexpr int WG_NT = 32;
+constexpr int WG_STAGES = 3;
+constexpr int WG_SLOTS = 100;          // 10 x 10 halo
+constexpr int WG_THREADS = 13 * 32;    // 8 producer warps, 4 A-loader warps, 1 MMA warp
+
+struct WParams {
+  const float* x;   // conv input (activated), NHWC dense [N,Hin,Win,Cin]
+  const float* dy;  // output gradient, NHWC dense [N,H,W,Cout]
+  float* part;      // [splits][9][Cout][Cin]
+  float* bpart;     // [splits][Cout] or null
+  int N, Hin, Win, Cin, H, W, Cout, map;
+  int units_x, units_y;
+  int64_t total_units, units_per_split;
+};
+
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
+      "%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+      "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc(const WParams p) {
+  // B (the shifted operand) must be K-major with K = pixel: tests/test_gpu_tc_probe.py shows that kind::tf32 returns
+  // zeros for MN-major shared-memory operands, so the halo is staged TRANSPOSED ([ci][pixel], 4 pixels per 16-byte
+  // chunk) once per horizontal tap offset dx (3 copies); vertical offsets are whole-chunk K advances of the descriptor.
+  constexpr int NT = WG_NT, QUADS = NT / 4;
+  constexpr int LBO_B = NT * 16;                           // bytes between 4-pixel chunks
+  constexpr int COPY_B = 20 * LBO_B;                       // one dx copy: 10 halo rows x 8 pixels = 20 chunks
+  constexpr int B_STAGE = 3 * COPY_B;
+  constexpr int ITEMS = WG_SLOTS * QUADS, PER_THREAD = (ITEMS + NPROD - 1) / NPROD;
+  constexpr uint32_t ACC_COLS = 9 * NT;                    // 288
+  // instruction descriptor: D=f32, A=tf32 (TMEM, K-major), B=tf32 K-major, M=128, N=NT
+  constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)WG_STAGES * B_STAGE);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * WG_STAGES + 1);
+  const uint32_t smem_base = smem_u32(smem), bar_base = smem_u32(bars);
+  auto fullB = [&](int s) { return bar_base + 8u * s; };
+  auto fullA = [&](int s) { return bar_base + 8u * (WG_STAGES + s); };
+  auto empty = [&](int s) { return bar_base + 8u * (2 * WG_STAGES + s); };
+  const uint32_t accum_bar = bar_base + 8u * (3 * WG_STAGES);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ci0 = blockIdx.x * NT, co0 = blockIdx.y * BM, split = blockIdx.z;
+  const int64_t u0 = (int64_t)split * p.units_per_split;
+  const int64_t u1 = min(p.total_units, u0 + p.units_per_split);
+
+  if (tid == 0) {
+    for (int s = 0; s < WG_STAGES; ++s) {
+      mbar_init(fullB(s), NPROD);
+      mbar_init(fullA(s), 128);
+      mbar_init(empty(s), 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 12) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 8) {
+    // ============ producers: xa halo (10x10 pixels x NT channels) -> shared memory, transposed, 3 dx copies ============
+    int it_r[PER_THREAD], it_c[PER_THREAD], it_q[PER_THREAD];
+#pragma unroll
+    for (int i = 0; i < PER_THREAD; ++i) {
+      const int item = tid + i * NPROD;
+      const int q = item % QUADS, slot = item / QUADS;
+      it_q[i] = q; it_r[i] = slot / 10; it_c[i] = item < ITEMS ? slot % 10 : -100;
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int64_t u = u0; u < u1; ++u) {
+      const int ux = (int)(u % p.units_x), uy = (int)((u / p.units_x) % p.units_y);
+      const int n = (int)(u / ((int64_t)p.units_x * p.units_y));
+      float4 v[PER_THREAD];
+#pragma unroll
+      for (int i = 0; i < PER_THREAD; ++i) {
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (it_c[i] >= 0) {
+          const int vy = uy * 8 - 1 + it_r[i], vx = ux * 8 - 1 + it_c[i];
+          int iy = vy, ix = vx;
+          bool ok;
+          if (p.map == MAP_S1) {
+            ok = (unsigned)vy < (unsigned)p.Hin && (unsigned)vx < (unsigned)p.Win;
+          } else {  // MAP_UP
+            ok = (unsigned)vy < (unsigned)(2 * p.Hin) && (unsigned)vx < (unsigned)(2 * p.Win);
+            iy = vy >> 1; ix = vx >> 1;
+          }
+          if (ok) v[i] = __ldg(reinterpret_cast<const float4*>(p.x + ((int64_t)(n * p.Hin + iy) * p.Win + ix) * p.Cin + ci0 + it_q[i] * 4));
+        }
+      }
+      mbar_wait(empty(stage), phase ^ 1);
+      float* b_st = reinterpret_cast<float*>(smem + (size_t)stage * B_STAGE);
+#pragma unroll
+      for (int i = 0; i < PER_THREAD; ++i) {
+        if (it_c[i] >= 0) {
+          const float e[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            const int c = it_c[i] - dx;
+            if ((unsigned)c < 8u) {
+              const int kk = it_r[i] * 8 + c;
+              float* d = b_st + dx * (COPY_B / 4) + (kk >> 2) * (LBO_B / 4) + it_q[i] * 16 + (kk & 3);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) d[j * 4] = e[j];
+            }
+          }
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(fullB(stage));
+      if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+    }
+    // ============ epilogue (warps 0-3): 9 x [128 co x NT ci] partial sums -> workspace ============
+    if (warp < 4) {
+      mbar_wait(accum_bar, 0);
+      tc_fence_after();
+      const int co = co0 + warp * 32 + lane;
+#pragma unroll 1
+      for (int t = 0; t < 9; ++t) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * NT), v);
+        float* o = p.part + (((size_t)split * 9 + t) * p.Cout + co) * p.Cin + ci0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+      tc_fence_before();
+    }
+  } else if (warp < 12) {
+    // ============ A loaders: dy[pixel][co] -> registers -> tensor memory (lane = co, column = pixel) ============
+    const int lg = warp - 8;  // TMEM lane group (warp % 4)
+    const float* dyc = p.dy + co0 + lg * 32 + lane;
+    float bsum = 0.f;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int64_t u = u0; u < u1; ++u) {
+      const int ux = (int)(u % p.units_x), uy = (int)((u / p.units_x) % p.units_y);
+      const int n = (int)(u / ((int64_t)p.units_x * p.units_y));
+      const float* base = dyc + ((int64_t)(n * p.H + uy * 8) * p.W + ux * 8) * p.Cout;
+      float v[64];
+#pragma unroll
+      for (int j = 0; j < 64; ++j) v[j] = __ldg(base + ((int64_t)(j >> 3) * p.W + (j & 7)) * p.Cout);
+#pragma unroll
+      for (int j = 0; j < 64; ++j) bsum += v[j];
+      mbar_wait(empty(stage), phase ^ 1);
+      tc_fence_after();
+      const uint32_t ta = tmem_base + ((uint32_t)(lg * 32) << 16) + ACC_COLS + (uint32_t)(stage * 64);
+      tmem_st32(ta, v);
+      tmem_st32(ta + 32, v + 32);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(fullA(stage));
+      if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+    }
+    if (p.bpart && blockIdx.x == 0) p.bpart[(size_t)split * p.Cout + co0 + lg * 32 + lane] = bsum;
+  } else {
+    // ============ MMA issuer ============
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t u = u0; u < u1; ++u) {
+        mbar_wait(fullB(stage), phase);
+        mbar_wait(fullA(stage), phase);
+        tc_fence_after();
+        const uint32_t b_st = smem_base + (uint32_t)stage * B_STAGE;
+        const uint32_t a_t = tmem_base + ACC_COLS + (uint32_t)(stage * 64);
+#pragma unroll 1
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            // copy (t % 3) holds the halo shifted by dx; image row r + dy starts at chunk 2*(r+dy) (8 pixels = 2 chunks)
+            const uint32_t off = (uint32_t)((t % 3) * COPY_B + (r + t / 3) * 2 * LBO_B);
+            const uint64_t bd = make_desc(b_st + off, LBO_B, 128);
+            mma_tf32_ts(tmem_base + (uint32_t)(t * NT), a_t + (uint32_t)(r * 8), bd, idesc, (u > u0 || r > 0) ? 1u : 0u);
+          }
+        }
+        mma_commit(empty(stage));
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+      mma_commit(accum_bar);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 12) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// Single-MMA probe (tests/test_gpu_tc_probe.py): D[128 x 32] = A[128 x 8] * B[32 x 8]^T with the operand placement /
+// descriptor conventions selected at run time — pins the hardware semantics the production kernels rely on.
+__global__ void __launch_bounds__(128, 1) mma_probe(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D,
+                                                    int a_src, int b_layout, unsigned long long raw_desc, unsigned raw_idesc,
+                                                    int raw_off) {
+  __shared__ __align__(1024) uint8_t sm[16384];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tslot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* sa = reinterpret_cast<float*>(sm);           // A: K-major, LBO = 2048 (128 rows * 16 B), SBO = 128
+  float* sb = reinterpret_cast<float*>(sm + 8192);    // B region
+  constexpr int PL = 36 * 16;                         // plane pitch of the MN-major B layout (36 slots)
+  if (tid == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(smem_u32(&tslot), 64);
+  // A[m][k] -> (k/4)*2048 + m*16 + (k%4)*4
+  for (int i = tid; i < 128 * 8; i += 128) {
+    int m = i / 8, k = i % 8;
+    sa[((k / 4) * 2048 + m * 16 + (k % 4) * 4) / 4] = A[i];
+  }
+  const int raw = b_layout == 99;      // raw mode: descriptor high bits / idesc / start offset come from the host
+  const int reveal = b_layout >= 10;   // address-reveal mode: B region holds its own word index
+  if (reveal) {
+    b_layout = raw ? 0 : b_layout - 10;
+    for (int i = tid; i < 2048; i += 128) sb[i] = (float)i;
+  } else {
+    for (int i = tid; i < 32 * 8; i += 128) {
+      int n = i / 8, k = i % 8;
+      int off = (b_layout == 0) ? ((k / 4) * 512 + n * 16 + (k % 4) * 4) : ((n / 4) * PL + k * 16 + (n % 4) * 4);
+      sb[off / 4] = B[i];
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tslot;
+  if (a_src == 1) {  // A -> TMEM columns [32, 40): lane = m, column = k (pad the x32 store with zeros)
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = j < 8 ? A[(warp * 32 + lane) * 8 + j] : 0.f;
+    tmem_st32(tb + ((uint32_t)(warp * 32) << 16) + 32, v);
+    tmem_st_wait();
+    tc_fence_before();
+  }
+  __syncthreads();
+  tc_fence_after();
+  if (tid == 0) {
+    uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    if (b_layout != 0) idesc |= (1u << 16);
+    uint64_t bd;
+    if (b_layout == 0) bd = make_desc(smem_u32(sb), 512, 128);
+    else if (b_layout == 1) bd = make_desc(smem_u32(sb), 160, PL);   // LBO field = K-group stride, SBO field = MN-quad stride
+    else bd = make_desc(smem_u32(sb), PL, 160);                      // fields swapped
+    if (raw) {
+      bd = (raw_desc & ~0x3FFFull) | (uint64_t)(((smem_u32(sb) + (uint32_t)raw_off) >> 4) & 0x3FFF);
+      idesc = raw_idesc;
+    }
+    if (a_src == 0) mma_tf32_ss(tb, make_desc(smem_u32(sa), 2048, 128), bd, idesc, 0);
+    else mma_tf32_ts(tb, tb + 32, bd, idesc, 0);
+    mma_commit(smem_u32(&bar));
+  }
+  mbar_wait(smem_u32(&bar), 0);
+  tc_fence_after();
+  float v[32];
+  tmem_ld32(tb + ((uint32_t)(warp * 32) << 16), v);
+  for (int j = 0; j < 32; ++j) D[(warp * 32 + lane) * 32 + j] = v[j];
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 64);
+}
+
+// dbias[c] = sum_split bpart[split][c]
+__global__ void bias_reduce(const float* __restrict__ bpart, int splits, int C, float* __restrict__ out) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a = 0.f;
+  for (int s = 0; s < splits; ++s) a += bpart[(size_t)s * C + c];
+  out[c] = a;
+}
+
 }  // namespace tc
+
+void conv_wgrad_reduce_launch(const float* part, int splits, int ntap, int Cout, int Cin, float* dw, cudaStream_t st);
 
 static bool dense_nhwc(const mas_tensor4& t) {
   return t.sc == 1 && t.sw == t.c && t.sh == t.w * t.c && t.sn == t.h * t.w * t.c;
@@ -423,9 +727,56 @@ int gemm_tc_launch(const float*, const float*, float*, int, int, int, int, int64
                    float, const float*, const float*, cudaStream_t) {
   return fail(MAS_ERR_UNSUPPORTED, "tc gemm with un-packed B operand: not available (use mas_gemm_rows_packed)");
 }
-size_t conv_wgrad_tc_ws(mas_tensor4, mas_tensor4, int) { return 0; }
-int conv_wgrad_tc_launch(const float*, mas_tensor4, const float*, mas_tensor4, float*, int, void*, size_t, cudaStream_t) {
-  return fail(MAS_ERR_UNSUPPORTED, "tcgen05 wgrad path not built");
+static bool wgrad_tc_ok(const mas_tensor4& xs, const mas_tensor4& dys, int mode) {
+  if (!(mode == MAS_CONV_S1 || mode == MAS_CONV_UP)) return false;
+  if (!dense_nhwc(xs) || !dense_nhwc(dys) || xs.c % tc::WG_NT || dys.c % tc::BM || dys.h % 8 || dys.w % 8) return false;
+  int64_t eh = (mode == MAS_CONV_S1) ? xs.h : 2 * xs.h, ew = (mode == MAS_CONV_S1) ? xs.w : 2 * xs.w;
+  return dys.h == eh && dys.w == ew && xs.n == dys.n;
+}
+static int wgrad_tc_splits(const mas_tensor4& xs, const mas_tensor4& dys) {
+  int64_t cps = (dys.c / tc::BM) * (xs.c / tc::WG_NT);
+  int64_t units = dys.n * (dys.h / 8) * (dys.w / 8);
+  int64_t s = 148 / cps;
+  if (s < 1) s = 1;
+  if (s > units) s = units;
+  const int64_t ups = cdiv(units, s);
+  return (int)cdiv(units, ups);  // every split owns at least one unit
+}
+size_t conv_wgrad_tc_ws(mas_tensor4 xs, mas_tensor4 dys, int mode) {
+  if (!wgrad_tc_ok(xs, dys, mode)) return 0;
+  size_t splits = wgrad_tc_splits(xs, dys);
+  return splits * 9 * (size_t)dys.c * xs.c * sizeof(float) + splits * (size_t)dys.c * sizeof(float) + 256;
+}
+// dbias (may be null) is produced here too when the tensor path runs; *did_bias tells the caller.
+int conv_wgrad_tc_launch(const float* x, mas_tensor4 xs, const float* dy, mas_tensor4 dys, float* dw, float* dbias, int mode, void* ws,
+                         size_t ws_bytes, cudaStream_t st) {
+  if (!wgrad_tc_ok(xs, dys, mode) || !al16p(x) || !al16p(dy)) return fail(MAS_ERR_UNSUPPORTED, "tc wgrad: shape/layout not eligible");
+  if (ws_bytes < conv_wgrad_tc_ws(xs, dys, mode)) return fail(MAS_ERR_WORKSPACE, "tc wgrad: workspace too small");
+  const int splits = wgrad_tc_splits(xs, dys);
+  tc::WParams p;
+  p.x = x; p.dy = dy; p.part = (float*)ws;
+  p.bpart = dbias ? (float*)ws + (size_t)splits * 9 * dys.c * xs.c : nullptr;
+  p.N = (int)xs.n; p.Hin = (int)xs.h; p.Win = (int)xs.w; p.Cin = (int)xs.c; p.H = (int)dys.h; p.W = (int)dys.w; p.Cout = (int)dys.c;
+  p.map = (mode == MAS_CONV_S1) ? tc::MAP_S1 : tc::MAP_UP;
+  p.units_x = (int)(dys.w / 8); p.units_y = (int)(dys.h / 8);
+  p.total_units = (int64_t)p.N * p.units_x * p.units_y;
+  p.units_per_split = cdiv(p.total_units, splits);
+  constexpr size_t smem = (size_t)tc::WG_STAGES * 3 * 20 * tc::WG_NT * 16 + (3 * tc::WG_STAGES + 1) * 8 + 16;
+  static bool configured = false;
+  if (!configured) {
+    if (int e = set_smem(tc::wgrad_tc, smem)) return e;
+    configured = true;
+  }
+  dim3 grid((unsigned)(xs.c / tc::WG_NT), (unsigned)(dys.c / tc::BM), (unsigned)splits);
+  tc::wgrad_tc<<<grid, tc::WG_THREADS, smem, st>>>(p);
+  if (int e = launched("wgrad_tc")) return e;
+  conv_wgrad_reduce_launch((const float*)ws, splits, 9, p.Cout, p.Cin, dw, st);
+  if (int e = launched("conv_wgrad_reduce")) return e;
+  if (dbias) {
+    tc::bias_reduce<<<(int)cdiv(p.Cout, 128), 128, 0, st>>>(p.bpart, splits, p.Cout, dbias);
+    return launched("bias_reduce");
+  }
+  return MAS_OK;
 }
 
 }  // namespace mas
@@ -455,6 +806,12 @@ int mas_gemm_rows_packed(const float* A, int64_t lda, const float* w_tc, float* 
                          const float* bias, const float* residual, void* stream) {
   MAS_REQUIRE(A && w_tc && C && M > 0, "gemm_rows_packed: bad arguments");
   return gemm_rows_tc_launch(A, lda, w_tc, C, ldc, M, N, K, alpha, bias, residual, S(stream));
+}
+
+int mas_tc_probe(const float* A, const float* B, float* D, int a_src, int b_layout, uint64_t raw_desc, uint32_t raw_idesc,
+                 int raw_off, void* stream) {
+  tc::mma_probe<<<1, 128, 0, S(stream)>>>(A, B, D, a_src, b_layout, (unsigned long long)raw_desc, raw_idesc, raw_off);
+  return launched("mma_probe");
 }
 
 int mas_conv3x3_tc_eligible(mas_tensor4 xs, mas_tensor4 ys, int mode) {

@@ -40,6 +40,7 @@ _SPEC = {
     "mas_silu_backward": (_I, [_P, _P, _P, _L, _P]),
     "mas_pack_conv3x3": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "mas_conv3x3_fprop": (_I, [_P, _T, _P, _P, _P, _P, _T, _I, _I, _P]),
+    "mas_tc_probe": (_I, [_P, _P, _P, _I, _I, ctypes.c_uint64, ctypes.c_uint32, _I, _P]),
     "mas_conv3x3_tc_eligible": (_I, [_T, _T, _I]),
     "mas_pack_conv3x3_tc": (_I, [_P, _P, _I, _I, _I, _P]),
     "mas_conv3x3_fprop_tc": (_I, [_P, _T, _P, _P, _P, _P, _T, _I, _P]),
@@ -105,15 +106,44 @@ def stream_ptr():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+_prof = None   # when a list: (name, start_event, end_event) per call — see profile_start/profile_report
+
+
 def call(name, *args):
     """Invoke an int-returning entry on the current CUDA stream; non-zero status -> RuntimeError."""
     lib = load()
     fn = getattr(lib, name)
     conv = [_ptr(a) for a in args]
     conv.append(stream_ptr())
-    rc = fn(*conv)
+    if _prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*conv)
+        e1.record()
+        _prof.append((name, e0, e1))
+    else:
+        rc = fn(*conv)
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {lib.mas_last_error().decode(errors='replace')}")
+
+
+def profile_start():
+    """Measurement aid: time every C-ABI call with CUDA events (no profiler attached, kernels run at full speed)."""
+    global _prof
+    _prof = []
+
+
+def profile_report(tag=None):
+    """Returns {entry name: (calls, total ms)} since profile_start() and stops profiling."""
+    global _prof
+    torch.cuda.synchronize()
+    agg = {}
+    for name, e0, e1 in _prof or []:
+        key = name if tag is None else tag(name)
+        c, t = agg.get(key, (0, 0.0))
+        agg[key] = (c + 1, t + e0.elapsed_time(e1))
+    _prof = None
+    return agg
 
 
 def query(name, *args):
