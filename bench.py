@@ -268,7 +268,7 @@ def main():
         tot = sum(t for _, t in rep.values())
         print("per-entry profile of one step (CUDA events, ms):", file=sys.stderr)
         for k, (c, t) in sorted(rep.items(), key=lambda kv: -kv[1][1]):
-            print("  %-28s n=%4d  %9.2f ms  %5.1f%%" % (k, c, t, 100 * t / tot), file=sys.stderr)
+            print("  %-44s n=%4d  %9.2f ms  %5.1f%%  %7.3f ms/call" % (k, c, t, 100 * t / tot, t / c), file=sys.stderr)
         print("  total %.2f ms" % tot, file=sys.stderr)
     roof = dominant_kernel_roofline(dev, pk)
     vq = vq_metric(dev, pk)

@@ -114,6 +114,19 @@ int mas_conv3x3_wgrad(const float* x, mas_tensor4 xs, const float* dy, mas_tenso
 size_t mas_conv1x1_wgrad_ws_bytes(int64_t M, int Cin, int Cout);
 int mas_conv1x1_wgrad(const float* x, int64_t ldx, const float* dy, int64_t ldy, int64_t M, int Cin, int Cout,
                       float* dw, float* dbias, int impl, void* ws, size_t ws_bytes, void* stream);
+/* Edge convolutions (3x3, stride 1, pad 1) with exactly 3 channels on one side — conv_in / conv_out of Encoder/Decoder
+ * (modules.py:219,364).  The 3-channel tensor carries explicit strides (the caller's NCHW image / reconstruction);
+ * the wide tensor is dense NHWC.  small_cin_fprop with flip_transpose=1 and w = the [3,C,3,3] weight of conv_out is
+ * conv_out's data gradient.  Weight/bias gradients are deterministic (persistent blocks + ordered reduction). */
+int mas_edge_small_cin_fprop(const float* xs, mas_tensor4 xst, const float* w, const float* bias, float* y,
+                             mas_tensor4 yst, int flip_transpose, void* stream);
+int mas_edge_small_cout_fprop(const float* a, mas_tensor4 at, const float* w, const float* bias, float* ys,
+                              mas_tensor4 yst, void* stream);
+size_t mas_edge_wgrad_ws_bytes(int Cbig);
+int mas_edge_small_cin_wgrad(const float* xs, mas_tensor4 xst, const float* dy, mas_tensor4 dyt, float* dw,
+                             float* dbias, void* ws, size_t ws_bytes, void* stream);
+int mas_edge_small_cout_wgrad(const float* a, mas_tensor4 at, const float* dys, mas_tensor4 dyt, float* dw,
+                              float* dbias, void* ws, size_t ws_bytes, void* stream);
 /* 2x2 sum pooling: data gradient of the nearest x2 upsample (modules.py:56). x [N,2H,2W,C] -> y [N,H,W,C]. */
 int mas_sumpool2x2(const float* x, float* y, int N, int H, int W, int C, void* stream);
 

@@ -20,6 +20,9 @@ int gemm_tc_launch(const float* A, const float* B, float* C, int M, int N, int K
 size_t conv_wgrad_tc_ws(mas_tensor4 xs, mas_tensor4 dys, int mode);
 int conv_wgrad_tc_launch(const float* x, mas_tensor4 xs, const float* dy, mas_tensor4 dys, float* dw, float* dbias, int mode, void* ws,
                          size_t ws_bytes, cudaStream_t st);
+size_t conv1x1_wgrad_tc_ws(int64_t M, int Cin, int Cout);
+int conv1x1_wgrad_tc_launch(const float* x, int64_t ldx, const float* dy, int64_t ldy, int64_t M, int Cin, int Cout, float* dw,
+                            float* dbias, void* ws, size_t ws_bytes, cudaStream_t st);
 }  // namespace mas
 
 using namespace mas;
@@ -69,15 +72,21 @@ static mas_tensor4 rows_t4(int64_t M, int C, int64_t ld) {
   return t;
 }
 size_t mas_conv1x1_wgrad_ws_bytes(int64_t M, int Cin, int Cout) {
-  return align256(conv_wgrad_simt_ws(rows_t4(M, Cin, Cin), rows_t4(M, Cout, Cout), 1)) + mas_colsum_ws_bytes(rows_t4(M, Cout, Cout));
+  size_t a = conv_wgrad_simt_ws(rows_t4(M, Cin, Cin), rows_t4(M, Cout, Cout), 1), b = conv1x1_wgrad_tc_ws(M, Cin, Cout);
+  return align256(a > b ? a : b) + mas_colsum_ws_bytes(rows_t4(M, Cout, Cout));
 }
 int mas_conv1x1_wgrad(const float* x, int64_t ldx, const float* dy, int64_t ldy, int64_t M, int Cin, int Cout, float* dw,
                       float* dbias, int impl, void* ws, size_t ws_bytes, void* stream) {
-  (void)impl;
   MAS_REQUIRE(x && dy && dw && M > 0 && ldx >= Cin && ldy >= Cout, "conv1x1_wgrad: bad arguments");
   if (ws_bytes < mas_conv1x1_wgrad_ws_bytes(M, Cin, Cout)) return fail(MAS_ERR_WORKSPACE, "conv1x1_wgrad: workspace too small");
   mas_tensor4 xs = rows_t4(M, Cin, ldx), ds = rows_t4(M, Cout, ldy);
-  size_t main_bytes = align256(conv_wgrad_simt_ws(xs, ds, 1));
+  size_t a = conv_wgrad_simt_ws(rows_t4(M, Cin, Cin), rows_t4(M, Cout, Cout), 1), b = conv1x1_wgrad_tc_ws(M, Cin, Cout);
+  size_t main_bytes = align256(a > b ? a : b);
+  if (impl != MAS_IMPL_SIMT) {
+    int e = conv1x1_wgrad_tc_launch(x, ldx, dy, ldy, M, Cin, Cout, dw, dbias, ws, main_bytes, S(stream));
+    if (e == MAS_OK) return MAS_OK;
+    if (e != MAS_ERR_UNSUPPORTED || impl == MAS_IMPL_TC) return e;
+  }
   if (int e = conv_wgrad_simt_launch(x, xs, dy, ds, dw, MAS_CONV_S1, 1, ws, main_bytes, S(stream))) return e;
   if (dbias) return mas_colsum(dy, ds, dbias, (char*)ws + main_bytes, ws_bytes - main_bytes, stream);
   return MAS_OK;

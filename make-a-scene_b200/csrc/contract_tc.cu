@@ -94,6 +94,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // shared-memory matrix descriptor, no swizzle ("interleaved"), sm_100 version field = 1
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
@@ -364,16 +372,16 @@ __global__ void pack_weights_tc(const float* __restrict__ w, float* __restrict__
 constexpr int WG_NT = 32;
 constexpr int WG_STAGES = 3;
 constexpr int WG_SLOTS = 100;          // 10 x 10 halo
-constexpr int WG_THREADS = 13 * 32;    // 8 producer warps, 4 A-loader warps, 1 MMA warp
+constexpr int WG_THREADS = 17 * 32;    // 8 producer warps, 2 x 4 A-loader warps (alternating units), 1 MMA warp
 
 struct WParams {
-  const float* x;   // conv input (activated), NHWC dense [N,Hin,Win,Cin]
-  const float* dy;  // output gradient, NHWC dense [N,H,W,Cout]
-  float* part;      // [splits][9][Cout][Cin]
+  const float* x;   // conv input (activated), NHWC dense [N,Hin,Win,Cin]   | rows [M, Cin] with pitch ldx (TAPS == 1)
+  const float* dy;  // output gradient, NHWC dense [N,H,W,Cout]             | rows [M, Cout] with pitch ldy
+  float* part;      // [splits][TAPS][Cout][Cin]
   float* bpart;     // [splits][Cout] or null
   int N, Hin, Win, Cin, H, W, Cout, map;
   int units_x, units_y;
-  int64_t total_units, units_per_split;
+  int64_t total_units, units_per_split, rows, ldx, ldy;
 };
 
 __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -397,18 +405,28 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// TAPS == 9: 3x3 convolution (unit = 8x8 output pixels, halo 10x10).  TAPS == 1: 1x1 convolution / row GEMM
+// (unit = 64 consecutive rows, no halo).
+template <int TAPS>
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc(const WParams p) {
   // B (the shifted operand) must be K-major with K = pixel: tests/test_gpu_tc_probe.py shows that kind::tf32 returns
   // zeros for MN-major shared-memory operands, so the halo is staged TRANSPOSED ([ci][pixel], 4 pixels per 16-byte
   // chunk) once per horizontal tap offset dx (3 copies); vertical offsets are whole-chunk K advances of the descriptor.
-  constexpr int NT = WG_NT, QUADS = NT / 4;
-  constexpr int LBO_B = NT * 16;                           // bytes between 4-pixel chunks
-  constexpr int COPY_B = 20 * LBO_B;                       // one dx copy: 10 halo rows x 8 pixels = 20 chunks
-  constexpr int B_STAGE = 3 * COPY_B;
-  constexpr int ITEMS = WG_SLOTS * QUADS, PER_THREAD = (ITEMS + NPROD - 1) / NPROD;
-  constexpr uint32_t ACC_COLS = 9 * NT;                    // 288
-  // instruction descriptor: D=f32, A=tf32 (TMEM, K-major), B=tf32 K-major, M=128, N=NT
-  constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  // Channel ci = 4q + j of the tile sits in operand row n = 8j + q: the 8 lanes of a store phase (q = 0..7) then hit 8
+  // different bank groups, and the epilogue undoes the permutation in registers.
+  // One MMA covers the three horizontal taps of a kernel row: its N = 3 x NT operand rows are [dx][channel], laid out
+  // per 4-pixel chunk as 3*NT/8 consecutive 128-byte core matrices, so a single descriptor (SBO = 128, LBO = chunk
+  // pitch) spans all three dx copies.  (N = 32 MMAs are issue-bound: ~4x slower than their 16-cycle math.)
+  constexpr int NT = (TAPS == 9) ? WG_NT : 128, QUADS = NT / 4;
+  constexpr int SLOTS = (TAPS == 9) ? WG_SLOTS : 64;
+  constexpr int COPIES = (TAPS == 9) ? 3 : 1;
+  constexpr int LBO_B = COPIES * NT * 16;                  // bytes between 4-pixel chunks
+  constexpr int B_STAGE = ((TAPS == 9) ? 20 : 16) * LBO_B; // 80 (10 halo rows x 8) or 64 pixels
+  constexpr int ITEMS = SLOTS * QUADS, PER_THREAD = (ITEMS + NPROD - 1) / NPROD;
+  constexpr uint32_t ACC_COLS = TAPS * NT;
+  constexpr int NMMA = COPIES * NT;                        // N of one MMA (96 | 128)
+  // instruction descriptor: D=f32, A=tf32 (TMEM, K-major), B=tf32 K-major, M=128, N=NMMA
+  constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NMMA >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)WG_STAGES * B_STAGE);
@@ -433,43 +451,62 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc(const WParams p) {
     mbar_init(accum_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 12) tmem_alloc(smem_u32(tmem_slot), 512);
+  if (warp == 16) tmem_alloc(smem_u32(tmem_slot), 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 8) {
-    // ============ producers: xa halo (10x10 pixels x NT channels) -> shared memory, transposed, 3 dx copies ============
+    // ============ producers: x halo / rows -> shared memory, transposed (K = pixel) ============
     int it_r[PER_THREAD], it_c[PER_THREAD], it_q[PER_THREAD];
 #pragma unroll
     for (int i = 0; i < PER_THREAD; ++i) {
       const int item = tid + i * NPROD;
-      const int q = item % QUADS, slot = item / QUADS;
-      it_q[i] = q; it_r[i] = slot / 10; it_c[i] = item < ITEMS ? slot % 10 : -100;
+      // lanes of a warp = 8 channel quads x 4 consecutive pixel slots (conflict-free transposed stores)
+      const int q = (item % 8) + 8 * (item / (8 * SLOTS)), slot = (item / 8) % SLOTS;
+      it_q[i] = q;
+      if (TAPS == 9) { it_r[i] = slot / 10; it_c[i] = item < ITEMS ? slot % 10 : -100; }
+      else { it_r[i] = slot; it_c[i] = item < ITEMS ? 0 : -100; }
     }
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int64_t u = u0; u < u1; ++u) {
-      const int ux = (int)(u % p.units_x), uy = (int)((u / p.units_x) % p.units_y);
-      const int n = (int)(u / ((int64_t)p.units_x * p.units_y));
-      float4 v[PER_THREAD];
+    auto gload = [&](int64_t u, float4* v) {
+      if (TAPS == 9) {
+        const int ux = (int)(u % p.units_x), uy = (int)((u / p.units_x) % p.units_y);
+        const int n = (int)(u / ((int64_t)p.units_x * p.units_y));
 #pragma unroll
-      for (int i = 0; i < PER_THREAD; ++i) {
-        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (it_c[i] >= 0) {
-          const int vy = uy * 8 - 1 + it_r[i], vx = ux * 8 - 1 + it_c[i];
-          int iy = vy, ix = vx;
-          bool ok;
-          if (p.map == MAP_S1) {
-            ok = (unsigned)vy < (unsigned)p.Hin && (unsigned)vx < (unsigned)p.Win;
-          } else {  // MAP_UP
-            ok = (unsigned)vy < (unsigned)(2 * p.Hin) && (unsigned)vx < (unsigned)(2 * p.Win);
-            iy = vy >> 1; ix = vx >> 1;
+        for (int i = 0; i < PER_THREAD; ++i) {
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (it_c[i] >= 0) {
+            const int vy = uy * 8 - 1 + it_r[i], vx = ux * 8 - 1 + it_c[i];
+            int iy = vy, ix = vx;
+            bool ok;
+            if (p.map == MAP_S1) {
+              ok = (unsigned)vy < (unsigned)p.Hin && (unsigned)vx < (unsigned)p.Win;
+            } else {  // MAP_UP
+              ok = (unsigned)vy < (unsigned)(2 * p.Hin) && (unsigned)vx < (unsigned)(2 * p.Win);
+              iy = vy >> 1; ix = vx >> 1;
+            }
+            if (ok) v[i] = __ldg(reinterpret_cast<const float4*>(p.x + ((int64_t)(n * p.Hin + iy) * p.Win + ix) * p.Cin + ci0 + it_q[i] * 4));
           }
-          if (ok) v[i] = __ldg(reinterpret_cast<const float4*>(p.x + ((int64_t)(n * p.Hin + iy) * p.Win + ix) * p.Cin + ci0 + it_q[i] * 4));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < PER_THREAD; ++i) {
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int64_t row = u * 64 + it_r[i];
+          if (it_c[i] >= 0 && row < p.rows) v[i] = __ldg(reinterpret_cast<const float4*>(p.x + row * p.ldx + ci0 + it_q[i] * 4));
         }
       }
+    };
+    int stage = 0;
+    uint32_t phase = 0;
+    float4 vn[PER_THREAD];
+    if (u0 < u1) gload(u0, vn);
+    for (int64_t u = u0; u < u1; ++u) {
+      float4 v[PER_THREAD];
+#pragma unroll
+      for (int i = 0; i < PER_THREAD; ++i) v[i] = vn[i];
+      if (u + 1 < u1) gload(u + 1, vn);   // next unit's global loads are in flight while this unit is stored
       mbar_wait(empty(stage), phase ^ 1);
       float* b_st = reinterpret_cast<float*>(smem + (size_t)stage * B_STAGE);
 #pragma unroll
@@ -477,13 +514,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc(const WParams p) {
         if (it_c[i] >= 0) {
           const float e[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
 #pragma unroll
-          for (int dx = 0; dx < 3; ++dx) {
+          for (int dx = 0; dx < COPIES; ++dx) {
             const int c = it_c[i] - dx;
-            if ((unsigned)c < 8u) {
-              const int kk = it_r[i] * 8 + c;
-              float* d = b_st + dx * (COPY_B / 4) + (kk >> 2) * (LBO_B / 4) + it_q[i] * 16 + (kk & 3);
+            if (TAPS == 1 || (unsigned)c < 8u) {
+              const int kk = (TAPS == 9) ? it_r[i] * 8 + c : it_r[i];
+              // channel 4q+j -> operand row (within its dx block) n = (NT/4)*j + q; byte offset = n*16
+              float* d = b_st + (kk >> 2) * (LBO_B / 4) + dx * (NT * 4) + it_q[i] * 4 + (kk & 3);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) d[j * 4] = e[j];
+              for (int j = 0; j < 4; ++j) d[j * NT] = e[j];
             }
           }
         }
@@ -492,35 +530,61 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc(const WParams p) {
       mbar_arrive(fullB(stage));
       if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
     }
-    // ============ epilogue (warps 0-3): 9 x [128 co x NT ci] partial sums -> workspace ============
+    // ============ epilogue (warps 0-3): TAPS x [128 co x NT ci] partial sums -> workspace ============
     if (warp < 4) {
       mbar_wait(accum_bar, 0);
       tc_fence_after();
       const int co = co0 + warp * 32 + lane;
 #pragma unroll 1
-      for (int t = 0; t < 9; ++t) {
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * NT), v);
-        float* o = p.part + (((size_t)split * 9 + t) * p.Cout + co) * p.Cin + ci0;
+      for (int t = 0; t < TAPS; ++t) {
+        float* o = p.part + (((size_t)split * TAPS + t) * p.Cout + co) * p.Cin + ci0;
+        if (TAPS == 9) {
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * NT), v);
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(o + q * 4) = make_float4(v[q], v[8 + q], v[16 + q], v[24 + q]);
+        } else {
+          // NT = 128: column n = 32*j + q holds channel 4q + j; gather the four j-planes, 8 quads at a time
+#pragma unroll
+          for (int qb = 0; qb < 32; qb += 8) {
+            float v0[8], v1[8], v2[8], v3[8];
+            const uint32_t tb = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)qb;
+            tmem_ld8(tb, v0);
+            tmem_ld8(tb + 32, v1);
+            tmem_ld8(tb + 64, v2);
+            tmem_ld8(tb + 96, v3);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(o + (qb + q) * 4) = make_float4(v0[q], v1[q], v2[q], v3[q]);
+          }
+        }
       }
       tc_fence_before();
     }
-  } else if (warp < 12) {
+  } else if (warp < 16) {
     // ============ A loaders: dy[pixel][co] -> registers -> tensor memory (lane = co, column = pixel) ============
-    const int lg = warp - 8;  // TMEM lane group (warp % 4)
+    // two groups of four warps take alternate units, so that one group's global-load latency hides behind the other's
+    const int lg = warp & 3;          // TMEM lane group (warp % 4)
+    const int grp = (warp - 8) >> 2;  // 0: even units, 1: odd units (relative to u0)
     const float* dyc = p.dy + co0 + lg * 32 + lane;
     float bsum = 0.f;
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int64_t u = u0; u < u1; ++u) {
-      const int ux = (int)(u % p.units_x), uy = (int)((u / p.units_x) % p.units_y);
-      const int n = (int)(u / ((int64_t)p.units_x * p.units_y));
-      const float* base = dyc + ((int64_t)(n * p.H + uy * 8) * p.W + ux * 8) * p.Cout;
+    for (int64_t u = u0 + grp; u < u1; u += 2) {
+      const int64_t k = u - u0;
+      const int stage = (int)(k % WG_STAGES);
+      const uint32_t phase = (uint32_t)((k / WG_STAGES) & 1);
       float v[64];
+      if (TAPS == 9) {
+        const int ux = (int)(u % p.units_x), uy = (int)((u / p.units_x) % p.units_y);
+        const int n = (int)(u / ((int64_t)p.units_x * p.units_y));
+        const float* base = dyc + ((int64_t)(n * p.H + uy * 8) * p.W + ux * 8) * p.Cout;
 #pragma unroll
-      for (int j = 0; j < 64; ++j) v[j] = __ldg(base + ((int64_t)(j >> 3) * p.W + (j & 7)) * p.Cout);
+        for (int j = 0; j < 64; ++j) v[j] = __ldg(base + ((int64_t)(j >> 3) * p.W + (j & 7)) * p.Cout);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+          const int64_t row = u * 64 + j;
+          v[j] = row < p.rows ? __ldg(dyc + row * p.ldy) : 0.f;
+        }
+      }
 #pragma unroll
       for (int j = 0; j < 64; ++j) bsum += v[j];
       mbar_wait(empty(stage), phase ^ 1);
@@ -531,9 +595,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc(const WParams p) {
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(fullA(stage));
-      if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
     }
-    if (p.bpart && blockIdx.x == 0) p.bpart[(size_t)split * p.Cout + co0 + lg * 32 + lane] = bsum;
+    if (p.bpart && blockIdx.x == 0) p.bpart[((size_t)split * 2 + grp) * p.Cout + co0 + lg * 32 + lane] = bsum;
   } else {
     // ============ MMA issuer ============
     if (lane == 0) {
@@ -548,11 +611,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc(const WParams p) {
 #pragma unroll 1
         for (int r = 0; r < 8; ++r) {
 #pragma unroll
-          for (int t = 0; t < 9; ++t) {
-            // copy (t % 3) holds the halo shifted by dx; image row r + dy starts at chunk 2*(r+dy) (8 pixels = 2 chunks)
-            const uint32_t off = (uint32_t)((t % 3) * COPY_B + (r + t / 3) * 2 * LBO_B);
-            const uint64_t bd = make_desc(b_st + off, LBO_B, 128);
-            mma_tf32_ts(tmem_base + (uint32_t)(t * NT), a_t + (uint32_t)(r * 8), bd, idesc, (u > u0 || r > 0) ? 1u : 0u);
+          for (int dyy = 0; dyy < ((TAPS == 9) ? 3 : 1); ++dyy) {
+            // image row r + dy starts at chunk 2*(r+dy) (8 pixels = 2 chunks); the three dx taps are the N blocks
+            const uint64_t bd = make_desc(b_st + (uint32_t)((r + dyy) * 2 * LBO_B), LBO_B, 128);
+            mma_tf32_ts(tmem_base + (uint32_t)(dyy * NMMA), a_t + (uint32_t)(r * 8), bd, idesc, (u > u0 || r > 0) ? 1u : 0u);
           }
         }
         mma_commit(empty(stage));
@@ -563,12 +625,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc(const WParams p) {
     __syncwarp();
   }
   __syncthreads();
-  if (warp == 12) {
+  if (warp == 16) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
 }
-
 
 // ------------------------------------------------------------------------------------------------------------
 // Single-MMA probe (tests/test_gpu_tc_probe.py): D[128 x 32] = A[128 x 8] * B[32 x 8]^T with the operand placement /
@@ -733,9 +794,7 @@ static bool wgrad_tc_ok(const mas_tensor4& xs, const mas_tensor4& dys, int mode)
   int64_t eh = (mode == MAS_CONV_S1) ? xs.h : 2 * xs.h, ew = (mode == MAS_CONV_S1) ? xs.w : 2 * xs.w;
   return dys.h == eh && dys.w == ew && xs.n == dys.n;
 }
-static int wgrad_tc_splits(const mas_tensor4& xs, const mas_tensor4& dys) {
-  int64_t cps = (dys.c / tc::BM) * (xs.c / tc::WG_NT);
-  int64_t units = dys.n * (dys.h / 8) * (dys.w / 8);
+static int wgrad_tc_splits(int64_t cps, int64_t units) {
   int64_t s = 148 / cps;
   if (s < 1) s = 1;
   if (s > units) s = units;
@@ -744,39 +803,67 @@ static int wgrad_tc_splits(const mas_tensor4& xs, const mas_tensor4& dys) {
 }
 size_t conv_wgrad_tc_ws(mas_tensor4 xs, mas_tensor4 dys, int mode) {
   if (!wgrad_tc_ok(xs, dys, mode)) return 0;
-  size_t splits = wgrad_tc_splits(xs, dys);
-  return splits * 9 * (size_t)dys.c * xs.c * sizeof(float) + splits * (size_t)dys.c * sizeof(float) + 256;
+  size_t splits = wgrad_tc_splits((dys.c / tc::BM) * (xs.c / tc::WG_NT), dys.n * (dys.h / 8) * (dys.w / 8));
+  return splits * 9 * (size_t)dys.c * xs.c * sizeof(float) + 2 * splits * (size_t)dys.c * sizeof(float) + 256;
 }
-// dbias (may be null) is produced here too when the tensor path runs; *did_bias tells the caller.
+template <int TAPS>
+static int wgrad_tc_run(tc::WParams& p, int splits, float* dw, float* dbias, void* ws, cudaStream_t st) {
+  p.part = (float*)ws;
+  p.bpart = dbias ? (float*)ws + (size_t)splits * TAPS * p.Cout * p.Cin : nullptr;
+  p.units_per_split = cdiv(p.total_units, splits);
+  constexpr int NT = (TAPS == 9) ? tc::WG_NT : 128;
+  constexpr size_t smem = (size_t)tc::WG_STAGES * (TAPS == 9 ? 3 * 20 : 16) * NT * 16 + (3 * tc::WG_STAGES + 1) * 8 + 16;
+  static bool configured = false;
+  if (!configured) {
+    if (int e = set_smem(tc::wgrad_tc<TAPS>, smem)) return e;
+    configured = true;
+  }
+  dim3 grid((unsigned)(p.Cin / NT), (unsigned)(p.Cout / tc::BM), (unsigned)splits);
+  tc::wgrad_tc<TAPS><<<grid, tc::WG_THREADS, smem, st>>>(p);
+  if (int e = launched("wgrad_tc")) return e;
+  conv_wgrad_reduce_launch((const float*)ws, splits, TAPS, p.Cout, p.Cin, dw, st);
+  if (int e = launched("conv_wgrad_reduce")) return e;
+  if (dbias) {
+    tc::bias_reduce<<<(int)cdiv(p.Cout, 128), 128, 0, st>>>(p.bpart, 2 * splits, p.Cout, dbias);
+    return launched("bias_reduce");
+  }
+  return MAS_OK;
+}
+// dbias (may be null) is produced here too when the tensor path runs.
 int conv_wgrad_tc_launch(const float* x, mas_tensor4 xs, const float* dy, mas_tensor4 dys, float* dw, float* dbias, int mode, void* ws,
                          size_t ws_bytes, cudaStream_t st) {
   if (!wgrad_tc_ok(xs, dys, mode) || !al16p(x) || !al16p(dy)) return fail(MAS_ERR_UNSUPPORTED, "tc wgrad: shape/layout not eligible");
   if (ws_bytes < conv_wgrad_tc_ws(xs, dys, mode)) return fail(MAS_ERR_WORKSPACE, "tc wgrad: workspace too small");
-  const int splits = wgrad_tc_splits(xs, dys);
   tc::WParams p;
-  p.x = x; p.dy = dy; p.part = (float*)ws;
-  p.bpart = dbias ? (float*)ws + (size_t)splits * 9 * dys.c * xs.c : nullptr;
+  p.x = x; p.dy = dy;
   p.N = (int)xs.n; p.Hin = (int)xs.h; p.Win = (int)xs.w; p.Cin = (int)xs.c; p.H = (int)dys.h; p.W = (int)dys.w; p.Cout = (int)dys.c;
   p.map = (mode == MAS_CONV_S1) ? tc::MAP_S1 : tc::MAP_UP;
   p.units_x = (int)(dys.w / 8); p.units_y = (int)(dys.h / 8);
   p.total_units = (int64_t)p.N * p.units_x * p.units_y;
-  p.units_per_split = cdiv(p.total_units, splits);
-  constexpr size_t smem = (size_t)tc::WG_STAGES * 3 * 20 * tc::WG_NT * 16 + (3 * tc::WG_STAGES + 1) * 8 + 16;
-  static bool configured = false;
-  if (!configured) {
-    if (int e = set_smem(tc::wgrad_tc, smem)) return e;
-    configured = true;
-  }
-  dim3 grid((unsigned)(xs.c / tc::WG_NT), (unsigned)(dys.c / tc::BM), (unsigned)splits);
-  tc::wgrad_tc<<<grid, tc::WG_THREADS, smem, st>>>(p);
-  if (int e = launched("wgrad_tc")) return e;
-  conv_wgrad_reduce_launch((const float*)ws, splits, 9, p.Cout, p.Cin, dw, st);
-  if (int e = launched("conv_wgrad_reduce")) return e;
-  if (dbias) {
-    tc::bias_reduce<<<(int)cdiv(p.Cout, 128), 128, 0, st>>>(p.bpart, splits, p.Cout, dbias);
-    return launched("bias_reduce");
-  }
-  return MAS_OK;
+  p.rows = 0; p.ldx = p.Cin; p.ldy = p.Cout;
+  const int splits = wgrad_tc_splits((dys.c / tc::BM) * (xs.c / tc::WG_NT), p.total_units);
+  return wgrad_tc_run<9>(p, splits, dw, dbias, ws, st);
+}
+static bool wgrad1_tc_ok(const float* x, int64_t ldx, const float* dy, int64_t ldy, int Cin, int Cout) {
+  return Cin % 128 == 0 && Cout % tc::BM == 0 && ldx % 4 == 0 && al16p(x) && dy != nullptr && ldy >= Cout;
+}
+size_t conv1x1_wgrad_tc_ws(int64_t M, int Cin, int Cout) {
+  if (Cin % 128 || Cout % tc::BM) return 0;
+  size_t splits = wgrad_tc_splits((int64_t)(Cout / tc::BM) * (Cin / 128), cdiv(M, 64));
+  return splits * (size_t)Cout * Cin * sizeof(float) + 2 * splits * (size_t)Cout * sizeof(float) + 256;
+}
+int conv1x1_wgrad_tc_launch(const float* x, int64_t ldx, const float* dy, int64_t ldy, int64_t M, int Cin, int Cout, float* dw,
+                            float* dbias, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!wgrad1_tc_ok(x, ldx, dy, ldy, Cin, Cout)) return fail(MAS_ERR_UNSUPPORTED, "tc wgrad 1x1: shape not eligible");
+  if (ws_bytes < conv1x1_wgrad_tc_ws(M, Cin, Cout)) return fail(MAS_ERR_WORKSPACE, "tc wgrad 1x1: workspace too small");
+  tc::WParams p;
+  p.x = x; p.dy = dy;
+  p.N = 1; p.Hin = 1; p.Win = 1; p.Cin = Cin; p.H = 1; p.W = 1; p.Cout = Cout; p.map = tc::MAP_ROWS;
+  p.units_x = 1; p.units_y = 1;
+  p.total_units = cdiv(M, 64);
+  p.rows = M; p.ldx = ldx; p.ldy = ldy;
+  const int splits = wgrad_tc_splits((int64_t)(Cout / tc::BM) * (Cin / 128), p.total_units);
+  return wgrad_tc_run<1>(p, splits, dw, dbias, ws, st);
 }
 
 }  // namespace mas

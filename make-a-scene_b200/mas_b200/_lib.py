@@ -50,6 +50,11 @@ _SPEC = {
     "mas_conv3x3_wgrad": (_I, [_P, _T, _P, _T, _P, _P, _I, _I, _P, _Z, _P]),
     "mas_conv1x1_wgrad_ws_bytes": (_Z, [_L, _I, _I]),
     "mas_conv1x1_wgrad": (_I, [_P, _L, _P, _L, _L, _I, _I, _P, _P, _I, _P, _Z, _P]),
+    "mas_edge_small_cin_fprop": (_I, [_P, _T, _P, _P, _P, _T, _I, _P]),
+    "mas_edge_small_cout_fprop": (_I, [_P, _T, _P, _P, _P, _T, _P]),
+    "mas_edge_wgrad_ws_bytes": (_Z, [_I]),
+    "mas_edge_small_cin_wgrad": (_I, [_P, _T, _P, _T, _P, _P, _P, _Z, _P]),
+    "mas_edge_small_cout_wgrad": (_I, [_P, _T, _P, _T, _P, _P, _P, _Z, _P]),
     "mas_sumpool2x2": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "mas_gemm": (_I, [_P, _P, _P, _I, _I, _I, _I, _L, _L, _L, _L, _L, _L, _I, _I, _F, _P, _P, _I, _P]),
     "mas_colsum_ws_bytes": (_Z, [_T]),
@@ -120,7 +125,8 @@ def call(name, *args):
         e0.record()
         rc = fn(*conv)
         e1.record()
-        _prof.append((name, e0, e1))
+        shp = ",".join("%dc%d" % (a.c, a.h) for a in args if isinstance(a, Tensor4))
+        _prof.append((name + ("|" + shp if shp else ""), e0, e1))
     else:
         rc = fn(*conv)
     if rc != 0:

@@ -250,16 +250,34 @@ class SiLUFn(torch.autograd.Function):
         return dx
 
 
+def _is_dense_nhwc(t):
+    return t.dim() == 4 and t.stride(1) == 1 and t.is_contiguous(memory_format=torch.channels_last)
+
+
 class Conv3x3Fn(torch.autograd.Function):
-    """nn.Conv2d 3x3 / Downsample / Upsample (modules.py:44-81,93-104) with optional fused residual add."""
+    """nn.Conv2d 3x3 / Downsample / Upsample (modules.py:44-81,93-104) with optional fused residual add.
+    3-channel edge layers (conv_in reading the NCHW image, conv_out writing the NCHW reconstruction) use the
+    direct fp32 edge kernels; everything else goes through conv3x3_raw (tcgen05 or SIMT)."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, residual, mode, out_nchw):
         _need_cuda(x)
-        cout = weight.shape[0]
-        y = conv3x3_raw(x, weight, bias, residual, mode, out_nchw)
+        cout, cin = weight.shape[0], weight.shape[1]
+        n, _, h, w = x.shape
+        edge = 0
+        if mode == L.CONV_S1 and residual is None and cin == 3 and cout > 4:
+            edge = 1
+            y = empty_nhwc(n, cout, h, w, x)
+            L.call("mas_edge_small_cin_fprop", x, L.t4(x), weight.contiguous(), bias, y, L.t4(y), 0)
+        elif mode == L.CONV_S1 and residual is None and cout == 3 and cin > 4 and cin % 4 == 0 and cin <= 1024:
+            edge = 2
+            x = nhwc(x)
+            y = (torch.empty((n, cout, h, w), dtype=torch.float32, device=x.device) if out_nchw else empty_nhwc(n, cout, h, w, x))
+            L.call("mas_edge_small_cout_fprop", x, L.t4(x), weight.contiguous(), bias, y, L.t4(y))
+        else:
+            y = conv3x3_raw(x, weight, bias, residual, mode, out_nchw)
         ctx.save_for_backward(x, weight)
-        ctx.mode, ctx.has_bias, ctx.has_res = mode, bias is not None, residual is not None
+        ctx.mode, ctx.has_bias, ctx.has_res, ctx.edge = mode, bias is not None, residual is not None, edge
         return y
 
     @staticmethod
@@ -267,10 +285,33 @@ class Conv3x3Fn(torch.autograd.Function):
         x, weight = ctx.saved_tensors
         cout, cin = weight.shape[0], weight.shape[1]
         dx = dw = db = dres = None
-        if ctx.needs_input_grad[0]:
-            dx = conv3x3_dgrad_raw(dy, weight, ctx.mode)
-        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            dw, db = conv3x3_wgrad_raw(x, dy, cout, cin, ctx.mode, ctx.has_bias)
+        want_w = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
+        if ctx.edge == 1:
+            if ctx.needs_input_grad[0]:
+                dx = conv3x3_dgrad_raw(dy, weight, ctx.mode)
+            if want_w:
+                dyd = nhwc(dy)
+                dw = torch.empty_like(weight)
+                db = torch.empty(cout, dtype=torch.float32, device=x.device)
+                ws = L.workspace(L.query("mas_edge_wgrad_ws_bytes", cout), x.device)
+                L.call("mas_edge_small_cin_wgrad", x, L.t4(x), dyd, L.t4(dyd), dw, db, ws, ws.numel())
+        elif ctx.edge == 2:
+            n, _, h, w = x.shape
+            if ctx.needs_input_grad[0]:
+                dx = empty_nhwc(n, cin, h, w, x)
+                L.call("mas_edge_small_cin_fprop", dy, L.t4(dy), weight.contiguous(), None, dx, L.t4(dx), 1)
+            if want_w:
+                dw = torch.empty_like(weight)
+                db = torch.empty(cout, dtype=torch.float32, device=x.device)
+                ws = L.workspace(L.query("mas_edge_wgrad_ws_bytes", cin), x.device)
+                L.call("mas_edge_small_cout_wgrad", x, L.t4(x), dy, L.t4(dy), dw, db, ws, ws.numel())
+        else:
+            if ctx.needs_input_grad[0]:
+                dx = conv3x3_dgrad_raw(dy, weight, ctx.mode)
+            if want_w:
+                dw, db = conv3x3_wgrad_raw(x, dy, cout, cin, ctx.mode, ctx.has_bias)
+        if not ctx.has_bias:
+            db = None
         if ctx.has_res and ctx.needs_input_grad[3]:
             dres = dy
         return dx, dw, db, dres, None, None
