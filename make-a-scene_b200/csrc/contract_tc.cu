@@ -216,17 +216,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) shift_gemm_tc(const Params p) {
     }
     int stage = 0;
     uint32_t phase = 0;
+    float4 vn[PER_THREAD];
+    auto gload = [&](int kc, float4* v) {
+#pragma unroll
+      for (int i = 0; i < PER_THREAD; ++i) {
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (src[i]) v[i] = __ldg(reinterpret_cast<const float4*>(src[i] + (size_t)kc * KC));
+      }
+    };
+    gload(0, vn);
     for (int kc = 0; kc < nchunks; ++kc) {
+      float4 v[PER_THREAD];
+#pragma unroll
+      for (int i = 0; i < PER_THREAD; ++i) v[i] = vn[i];
+      if (kc + 1 < nchunks) gload(kc + 1, vn);  // next chunk's global loads fly while this chunk is stored / consumed
       mbar_wait(empty_bar(stage), phase ^ 1);
       uint8_t* a_st = smem + (size_t)stage * STAGE;
 #pragma unroll
-      for (int i = 0; i < PER_THREAD; ++i) {
-        if (dst[i] != 0xFFFFFFFFu) {
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (src[i]) v = __ldg(reinterpret_cast<const float4*>(src[i] + (size_t)kc * KC));
-          *reinterpret_cast<float4*>(a_st + dst[i]) = v;
-        }
-      }
+      for (int i = 0; i < PER_THREAD; ++i)
+        if (dst[i] != 0xFFFFFFFFu) *reinterpret_cast<float4*>(a_st + dst[i]) = v[i];
       fence_proxy_async();  // make the generic-proxy stores visible to the tensor core (async proxy)
       mbar_arrive(full_bar(stage));
       if (++stage == STAGES) { stage = 0; phase ^= 1; }

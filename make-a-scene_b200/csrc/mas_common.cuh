@@ -19,10 +19,10 @@ int launched(const char* what);
 static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
-__device__ __forceinline__ float silu_f(float u) { return u / (1.0f + __expf(-u)); }
+__device__ __forceinline__ float silu_f(float u) { return __fdividef(u, 1.0f + __expf(-u)); }
 // d/du [u*sigmoid(u)] = s*(1+u*(1-s))
 __device__ __forceinline__ float silu_grad_f(float u) {
-  float s = 1.0f / (1.0f + __expf(-u));
+  float s = __fdividef(1.0f, 1.0f + __expf(-u));
   return s * (1.0f + u * (1.0f - s));
 }
 __device__ __forceinline__ float round_tf32(float x) {

@@ -41,7 +41,24 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_partial(const float* __re
   const int p0 = chunk * GN_PIX, p1 = min(HW, p0 + GN_PIX);
   double s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
   const float4* xp = reinterpret_cast<const float4*>(x + (size_t)n * HW * C) + u;
-  for (int p = p0 + pl; p < p1; p += lanes) {
+  // four independent 16-byte loads in flight per thread; per-quad fp32 partial sums over 4 pixels feed the fp64 totals
+  int p = p0 + pl;
+  for (; p + 3 * lanes < p1; p += 4 * lanes) {
+    float4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = __ldg(xp + (size_t)(p + k * lanes) * U);
+    float fs[4] = {0.f, 0.f, 0.f, 0.f}, fq[4] = {0.f, 0.f, 0.f, 0.f};  // fp32 over 4 pixels, fp64 across batches
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      fs[0] += v[k].x; fq[0] = fmaf(v[k].x, v[k].x, fq[0]);
+      fs[1] += v[k].y; fq[1] = fmaf(v[k].y, v[k].y, fq[1]);
+      fs[2] += v[k].z; fq[2] = fmaf(v[k].z, v[k].z, fq[2]);
+      fs[3] += v[k].w; fq[3] = fmaf(v[k].w, v[k].w, fq[3]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { s[k] += fs[k]; q[k] += fq[k]; }
+  }
+  for (; p < p1; p += lanes) {
     float4 v = __ldg(xp + (size_t)p * U);
     s[0] += v.x; q[0] += (double)v.x * v.x;
     s[1] += v.y; q[1] += (double)v.y * v.y;
@@ -87,26 +104,42 @@ __global__ void gn_stats_final(const double* __restrict__ part, int nchunks, int
   rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
-__global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean,
-                                                       const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                                       const float* __restrict__ beta, float* __restrict__ y, int64_t total4,
-                                                       int HW, int C, int G, int silu, int rtf32) {
-  const int U = C >> 2, cpg = C / G;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
-    int u = (int)(i % U);
-    int n = (int)(i / ((int64_t)HW * U));
-    float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
-    float in[4] = {v.x, v.y, v.z, v.w}, out[4];
+// apply: same block/thread mapping as the statistics kernel (block = GN_PIX pixels of one image, thread = one channel
+// quad), so the per-channel scale/shift are loop invariants and four independent 16-byte loads are in flight per thread.
+__global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                                                              const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, float* __restrict__ y, int HW, int C,
+                                                              int G, int silu, int rtf32) {
+  const int U = C >> 2, n = blockIdx.y, cpg = C / G;
+  const int t = threadIdx.x, u = t % U, lanes = GN_THREADS / U, pl = t / U;
+  const int p0 = blockIdx.x * GN_PIX, p1 = min(HW, p0 + GN_PIX);
+  float sc[4], sh[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      int c = u * 4 + k, g = c / cpg;
-      float m = __ldg(mean + n * G + g), r = __ldg(rstd + n * G + g);
-      float o = (in[k] - m) * r * __ldg(gamma + c) + __ldg(beta + c);
-      if (silu) o = silu_f(o);
-      if (rtf32) o = round_tf32(o);
-      out[k] = o;
-    }
-    reinterpret_cast<float4*>(y)[i] = make_float4(out[0], out[1], out[2], out[3]);
+  for (int k = 0; k < 4; ++k) {
+    const int c = u * 4 + k, g = c / cpg;
+    const float a = rstd[n * G + g] * gamma[c];
+    sc[k] = a;
+    sh[k] = beta[c] - mean[n * G + g] * a;
+  }
+  const float4* xp = reinterpret_cast<const float4*>(x + (size_t)n * HW * C) + u;
+  float4* yp = reinterpret_cast<float4*>(y + (size_t)n * HW * C) + u;
+  auto f = [&](float v, int k) {
+    float o = fmaf(v, sc[k], sh[k]);
+    if (silu) o = silu_f(o);
+    if (rtf32) o = round_tf32(o);
+    return o;
+  };
+  int p = p0 + pl;
+  for (; p + 3 * lanes < p1; p += 4 * lanes) {
+    float4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = __ldg(xp + (size_t)(p + k * lanes) * U);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) yp[(size_t)(p + k * lanes) * U] = make_float4(f(v[k].x, 0), f(v[k].y, 1), f(v[k].z, 2), f(v[k].w, 3));
+  }
+  for (; p < p1; p += lanes) {
+    float4 v = __ldg(xp + (size_t)p * U);
+    yp[(size_t)p * U] = make_float4(f(v.x, 0), f(v.y, 1), f(v.z, 2), f(v.w, 3));
   }
 }
 
@@ -132,18 +165,38 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_partial(const float* __rest
   double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
   const float4* xp = reinterpret_cast<const float4*>(x + (size_t)n * HW * C) + u;
   const float4* dp = reinterpret_cast<const float4*>(dy + (size_t)n * HW * C) + u;
-  for (int p = p0 + pl; p < p1; p += lanes) {
-    float4 xv = __ldg(xp + (size_t)p * U), dv = __ldg(dp + (size_t)p * U);
+  float f1[4], f2[4];
+  auto accum = [&](const float4& xv, const float4& dv) {
     float xi[4] = {xv.x, xv.y, xv.z, xv.w}, di[4] = {dv.x, dv.y, dv.z, dv.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       float xh = (xi[k] - m[k]) * r[k];
       float d = di[k];
       if (silu) d *= silu_grad_f(xh * ga[k] + be[k]);
-      s1[k] += (double)d * xh;
-      s2[k] += d;
+      f1[k] = fmaf(d, xh, f1[k]);
+      f2[k] += d;
     }
+  };
+  auto flush = [&]() {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { s1[k] += f1[k]; s2[k] += f2[k]; f1[k] = 0.f; f2[k] = 0.f; }
+  };
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { f1[k] = 0.f; f2[k] = 0.f; }
+  int p = p0 + pl;
+  for (; p + 3 * lanes < p1; p += 4 * lanes) {
+    float4 xv[4], dv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      xv[k] = __ldg(xp + (size_t)(p + k * lanes) * U);
+      dv[k] = __ldg(dp + (size_t)(p + k * lanes) * U);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) accum(xv[k], dv[k]);
+    flush();  // fp32 over 4 pixels, fp64 across batches
   }
+  for (; p < p1; p += lanes) accum(__ldg(xp + (size_t)p * U), __ldg(dp + (size_t)p * U));
+  flush();
   double* buf = sm;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -203,32 +256,49 @@ __global__ void gn_bwd_final(int N, int C, int G, const float* __restrict__ gamm
   }
 }
 
-__global__ void __launch_bounds__(256) gn_bwd_apply(const float* __restrict__ dy, const float* __restrict__ x,
-                                                    const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                    const float* __restrict__ AB, const float* __restrict__ dx_add,
-                                                    float* __restrict__ dx, int64_t total4, int HW, int C, int G, int silu) {
-  const int U = C >> 2, cpg = C / G;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
-    int u = (int)(i % U);
-    int n = (int)(i / ((int64_t)HW * U));
-    float4 xv = __ldg(reinterpret_cast<const float4*>(x) + i), dv = __ldg(reinterpret_cast<const float4*>(dy) + i);
-    float xi[4] = {xv.x, xv.y, xv.z, xv.w}, di[4] = {dv.x, dv.y, dv.z, dv.w}, out[4];
+__global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply(const float* __restrict__ dy, const float* __restrict__ x,
+                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           const float* __restrict__ AB, const float* __restrict__ dx_add,
+                                                           float* __restrict__ dx, int HW, int C, int G, int silu) {
+  const int U = C >> 2, n = blockIdx.y, cpg = C / G;
+  const int t = threadIdx.x, u = t % U, lanes = GN_THREADS / U, pl = t / U;
+  const int p0 = blockIdx.x * GN_PIX, p1 = min(HW, p0 + GN_PIX);
+  float m[4], r[4], ga[4], be[4], A[4], B[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = u * 4 + k, g = c / cpg;
+    m[k] = mean[n * G + g]; r[k] = rstd[n * G + g]; ga[k] = gamma[c]; be[k] = beta[c];
+    A[k] = AB[(n * G + g) * 2]; B[k] = AB[(n * G + g) * 2 + 1];
+  }
+  const size_t base = (size_t)n * HW * C;
+  const float4* xp = reinterpret_cast<const float4*>(x + base) + u;
+  const float4* dp = reinterpret_cast<const float4*>(dy + base) + u;
+  const float4* ap = dx_add ? reinterpret_cast<const float4*>(dx_add + base) + u : nullptr;
+  float4* op = reinterpret_cast<float4*>(dx + base) + u;
+  auto one = [&](const float4& xv, const float4& dv, const float4& av) {
+    float xi[4] = {xv.x, xv.y, xv.z, xv.w}, di[4] = {dv.x, dv.y, dv.z, dv.w}, ad[4] = {av.x, av.y, av.z, av.w}, o[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      int c = u * 4 + k, g = c / cpg;
-      float m = __ldg(mean + n * G + g), r = __ldg(rstd + n * G + g), ga = __ldg(gamma + c);
-      float xh = (xi[k] - m) * r;
+      float xh = (xi[k] - m[k]) * r[k];
       float d = di[k];
-      if (silu) d *= silu_grad_f(xh * ga + __ldg(beta + c));
-      float A = __ldg(AB + (n * G + g) * 2), B = __ldg(AB + (n * G + g) * 2 + 1);
-      out[k] = r * (d * ga - B - xh * A);
+      if (silu) d *= silu_grad_f(xh * ga[k] + be[k]);
+      o[k] = r[k] * (d * ga[k] - B[k] - xh * A[k]) + ad[k];
     }
-    if (dx_add) {
-      float4 av = __ldg(reinterpret_cast<const float4*>(dx_add) + i);
-      out[0] += av.x; out[1] += av.y; out[2] += av.z; out[3] += av.w;
-    }
-    reinterpret_cast<float4*>(dx)[i] = make_float4(out[0], out[1], out[2], out[3]);
+    return make_float4(o[0], o[1], o[2], o[3]);
+  };
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  int p = p0 + pl;
+  for (; p + lanes < p1; p += 2 * lanes) {
+    const size_t i0 = (size_t)p * U, i1 = (size_t)(p + lanes) * U;
+    float4 x0 = __ldg(xp + i0), x1 = __ldg(xp + i1), d0 = __ldg(dp + i0), d1 = __ldg(dp + i1);
+    float4 a0 = ap ? __ldg(ap + i0) : z4, a1 = ap ? __ldg(ap + i1) : z4;
+    op[i0] = one(x0, d0, a0);
+    op[i1] = one(x1, d1, a1);
+  }
+  for (; p < p1; p += lanes) {
+    const size_t i0 = (size_t)p * U;
+    op[i0] = one(__ldg(xp + i0), __ldg(dp + i0), ap ? __ldg(ap + i0) : z4);
   }
 }
 
@@ -508,8 +578,7 @@ int mas_gn_stats(const float* x, int N, int HW, int C, int G, float eps, float* 
 int mas_gn_apply(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta, float* y, int N,
                  int HW, int C, int G, int silu, int round_tf32, void* stream) {
   if (int e = gn_check(N, HW, C, G)) return e;
-  int64_t total4 = (int64_t)N * HW * (C / 4);
-  gn_apply_kernel<<<ew_grid(total4), 256, 0, S(stream)>>>(x, mean, rstd, gamma, beta, y, total4, HW, C, G, silu, round_tf32);
+  gn_apply_kernel<<<dim3(gn_chunks(HW), N), GN_THREADS, 0, S(stream)>>>(x, mean, rstd, gamma, beta, y, HW, C, G, silu, round_tf32);
   return launched("gn_apply");
 }
 
@@ -530,8 +599,7 @@ int mas_gn_backward(const float* dy, const float* x, const float* mean, const fl
   if (int e = launched("gn_bwd_nc")) return e;
   gn_bwd_final<<<1, 1024, 0, S(stream)>>>(N, C, G, gamma, nc, dgamma, dbeta, AB, 1.0 / ((double)HW * (C / G)));
   if (int e = launched("gn_bwd_final")) return e;
-  int64_t total4 = (int64_t)N * HW * (C / 4);
-  gn_bwd_apply<<<ew_grid(total4), 256, 0, S(stream)>>>(dy, x, mean, rstd, gamma, beta, AB, dx_add, dx, total4, HW, C, G, silu);
+  gn_bwd_apply<<<dim3(chunks, N), GN_THREADS, 0, S(stream)>>>(dy, x, mean, rstd, gamma, beta, AB, dx_add, dx, HW, C, G, silu);
   return launched("gn_bwd_apply");
 }
 
