@@ -240,46 +240,59 @@ __global__ void __launch_bounds__(NTHREADS, 1) shift_gemm_tc(const Params p) {
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
 
-    // ===================== epilogue: TMEM -> registers -> global =====================
+    // ===================== epilogue: TMEM -> registers -> smem transpose -> coalesced global stores =====================
+    // A thread owns one pixel row of the accumulator (32 consecutive channels per tcgen05.ld); writing that directly
+    // makes every store instruction touch 32 different 128-byte lines with 16 bytes each.  Each warp instead bounces
+    // its 32x32 block through a private shared-memory patch (the pipeline stages are idle by now) so that 8 lanes
+    // cover one full line: 4 lines per store instruction, and the residual is read the same way.
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     const int lane_grp = warp & 3;           // TMEM lanes [32*lane_grp, +32)
     const int chalf = warp >> 2;             // column half of the 128-wide tile
-    const int m = lane_grp * 32 + lane;      // row of the M tile
+    constexpr int EP_LD = 36;                // floats per staged row (144 B: conflict-free 16-byte accesses)
+    float* patch = reinterpret_cast<float*>(smem) + warp * (32 * EP_LD);
+    const int sub_r = lane >> 3, sub_c = lane & 7;
 #pragma unroll 1
     for (int tl = 0; tl < TILES; ++tl) {
       const int64_t tile = tile0 + tl;
-      int64_t pix = -1;
-      if (tile < p.total_tiles) {
-        if (TAPS == 9) {
-          const int tx_ = (int)(tile % p.tiles_x), ty_ = (int)((tile / p.tiles_x) % p.tiles_y);
-          const int n = (int)(tile / ((int64_t)p.tiles_x * p.tiles_y));
-          pix = ((int64_t)n * p.Hout + ty_ * 16 + (m >> 3)) * p.Wout + tx_ * 8 + (m & 7);
-        } else {
-          const int64_t row = tile * BM + m;
-          if (row < (int64_t)p.N * p.Hout * p.Wout) pix = row;
-        }
+      if (tile >= p.total_tiles) break;     // warp-uniform
+      int64_t pix_base = 0;                 // pixel index of accumulator row 0 of this tile (image maps: per-row formula)
+      int tx_ = 0, ty_ = 0, n_img = 0;
+      if (TAPS == 9) {
+        tx_ = (int)(tile % p.tiles_x); ty_ = (int)((tile / p.tiles_x) % p.tiles_y);
+        n_img = (int)(tile / ((int64_t)p.tiles_x * p.tiles_y));
+      } else {
+        pix_base = tile * BM;
       }
 #pragma unroll 1
       for (int cc = 0; cc < 2; ++cc) {
         const int col = chalf * 64 + cc * 32;
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(tl * BN + col), v);
-        if (pix >= 0) {
-          float* yp = p.y + pix * p.ldy + n0 + col;
-          const float* rp = p.res ? p.res + pix * p.ldy + n0 + col : nullptr;
+        __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 o = make_float4(v[j] * p.alpha, v[j + 1] * p.alpha, v[j + 2] * p.alpha, v[j + 3] * p.alpha);
-            if (p.bias) {
-              float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + col + j));
-              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(patch + lane * EP_LD + j) =
+              make_float4(v[j] * p.alpha, v[j + 1] * p.alpha, v[j + 2] * p.alpha, v[j + 3] * p.alpha);
+        __syncwarp();
+        float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) bq = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + col + sub_c * 4));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = i * 4 + sub_r;               // accumulator row within this warp's 32
+          const int m = lane_grp * 32 + row;
+          int64_t pix;
+          if (TAPS == 9) pix = ((int64_t)n_img * p.Hout + ty_ * 16 + (m >> 3)) * p.Wout + tx_ * 8 + (m & 7);
+          else pix = pix_base + m;
+          if (TAPS == 9 || pix < (int64_t)p.N * p.Hout * p.Wout) {
+            float4 o = *reinterpret_cast<const float4*>(patch + row * EP_LD + sub_c * 4);
+            o.x += bq.x; o.y += bq.y; o.z += bq.z; o.w += bq.w;
+            const int64_t off = pix * p.ldy + n0 + col + sub_c * 4;
+            if (p.res) {
+              const float4 r4 = __ldg(reinterpret_cast<const float4*>(p.res + off));
+              o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
             }
-            if (rp) {
-              float4 r = __ldg(reinterpret_cast<const float4*>(rp + j));
-              o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-            }
-            *reinterpret_cast<float4*>(yp + j) = o;
+            *reinterpret_cast<float4*>(p.y + off) = o;
           }
         }
       }
@@ -294,18 +307,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) shift_gemm_tc(const Params p) {
       for (int kc = 0; kc < nchunks; ++kc) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
+        // one base descriptor per operand per stage; every MMA of the stage is (base + compile-time constant): the
+        // start-address field is the low 14 bits (address >> 4) and never carries out for < 256 KB of shared memory, so
+        // the single issuing thread spends one add per operand per MMA instead of re-encoding descriptors.
         const uint32_t a_st = smem_base + (uint32_t)stage * STAGE;
-        const uint32_t b_st = a_st + A_STAGE;
-#pragma unroll 1
+        const uint64_t a_base = make_desc(a_st, LBO_A, SBO_A);
+        const uint64_t b_base = make_desc(a_st + A_STAGE, LBO_B, 128);
+        const uint32_t acc0 = (kc > 0) ? 1u : 0u;
+#pragma unroll
         for (int tl = 0; tl < TILES; ++tl) {
 #pragma unroll
           for (int t = 0; t < TAPS; ++t) {
             const uint32_t tapoff = (TAPS == 9) ? (uint32_t)(((t / 3) * 10 + (t % 3)) * 16) : 0u;
 #pragma unroll
             for (int k8 = 0; k8 < KC / 8; ++k8) {
-              const uint64_t ad = make_desc(a_st + tl * A_TILE + tapoff + k8 * 2 * LBO_A, LBO_A, SBO_A);
-              const uint64_t bd = make_desc(b_st + t * B_TAP + k8 * 2 * LBO_B, LBO_B, 128);
-              mma_tf32_ss(tmem_base + (uint32_t)(tl * BN), ad, bd, idesc, (kc > 0 || t > 0 || k8 > 0) ? 1u : 0u);
+              const uint64_t ad = a_base + (uint64_t)((tl * A_TILE + tapoff + k8 * 2 * LBO_A) >> 4);
+              const uint64_t bd = b_base + (uint64_t)((t * B_TAP + k8 * 2 * LBO_B) >> 4);
+              mma_tf32_ss(tmem_base + (uint32_t)(tl * BN), ad, bd, idesc, (t > 0 || k8 > 0) ? 1u : acc0);
             }
           }
         }
@@ -616,13 +634,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc(const WParams p) {
         tc_fence_after();
         const uint32_t b_st = smem_base + (uint32_t)stage * B_STAGE;
         const uint32_t a_t = tmem_base + ACC_COLS + (uint32_t)(stage * 64);
-#pragma unroll 1
+        const uint64_t b_base = make_desc(b_st, LBO_B, 128);
+        const uint32_t acc0 = (u > u0) ? 1u : 0u;
+#pragma unroll
         for (int r = 0; r < 8; ++r) {
 #pragma unroll
           for (int dyy = 0; dyy < ((TAPS == 9) ? 3 : 1); ++dyy) {
             // image row r + dy starts at chunk 2*(r+dy) (8 pixels = 2 chunks); the three dx taps are the N blocks
-            const uint64_t bd = make_desc(b_st + (uint32_t)((r + dyy) * 2 * LBO_B), LBO_B, 128);
-            mma_tf32_ts(tmem_base + (uint32_t)(dyy * NMMA), a_t + (uint32_t)(r * 8), bd, idesc, (u > u0 || r > 0) ? 1u : 0u);
+            const uint64_t bd = b_base + (uint64_t)(((r + dyy) * 2 * LBO_B) >> 4);
+            mma_tf32_ts(tmem_base + (uint32_t)(dyy * NMMA), a_t + (uint32_t)(r * 8), bd, idesc, r > 0 ? 1u : acc0);
           }
         }
         mma_commit(empty(stage));
