@@ -127,6 +127,12 @@ int mas_edge_small_cin_wgrad(const float* xs, mas_tensor4 xst, const float* dy, 
                              float* dbias, void* ws, size_t ws_bytes, void* stream);
 int mas_edge_small_cout_wgrad(const float* a, mas_tensor4 at, const float* dys, mas_tensor4 dyt, float* dw,
                               float* dbias, void* ws, size_t ws_bytes, void* stream);
+/* Stride-2 convolution (Downsample, modules.py:74-78) on the stride-1 tensor kernels: space-to-depth of the input
+ * ([N,H,W,C] -> [N,H/2,W/2,4C]) turns it into a 2x2-tap unit-stride convolution, run as a 3x3 convolution with the
+ * remapped weight W9 [Cout,4C,3,3] (mas_s2d_pack_weights); mas_s2d_unpack_wgrad maps dW9 back to dW [Cout,C,3,3]. */
+int mas_space_to_depth(const float* x, float* y, int N, int H, int W, int C, void* stream);
+int mas_s2d_pack_weights(const float* w, float* w9, int Cout, int C, void* stream);
+int mas_s2d_unpack_wgrad(const float* dw9, float* dw, int Cout, int C, void* stream);
 /* 2x2 sum pooling: data gradient of the nearest x2 upsample (modules.py:56). x [N,2H,2W,C] -> y [N,H,W,C]. */
 int mas_sumpool2x2(const float* x, float* y, int N, int H, int W, int C, void* stream);
 

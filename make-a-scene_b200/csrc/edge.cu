@@ -289,3 +289,75 @@ int mas_edge_small_cout_wgrad(const float* a, mas_tensor4 at, const float* dys, 
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------- stride-2 conv via space-to-depth
+// Downsample (modules.py:74-78) = pad(0,1,0,1) + conv3x3 stride 2.  With X4[n,i,j,(py,px,c)] = x[n,2i+py,2j+px,c] the
+// stride-2 gather becomes a unit-stride 2x2-tap convolution over 4C channels, which the tcgen05 stride-1 kernels run as a
+// 3x3 convolution whose other five taps are zero:  y[o] = sum_{a,b in {0,1}} X4[o+(a,b)] . W9[(a+1,b+1)],
+// W9[(a+1,b+1)][(py,px,c)] = W[2a+py][2b+px][c] (0 where 2a+py or 2b+px exceeds 2).  Zero padding beyond the last X4
+// row/column is exactly the reference's bottom/right pad.
+namespace mas {
+__global__ void space_to_depth_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, int C4, int64_t total4) {
+  // x [N,H,W,C] -> y [N,H/2,W/2,4C], channel block (py*2+px)
+  const int Ho = H >> 1, Wo = W >> 1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C4);
+    int64_t r = i / C4;
+    int ph = (int)(r % 4); r /= 4;
+    int j = (int)(r % Wo); r /= Wo;
+    int ii = (int)(r % Ho);
+    int64_t n = r / Ho;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + (((n * H + 2 * ii + (ph >> 1)) * W + 2 * j + (ph & 1)) * C4 + c));
+    reinterpret_cast<float4*>(y)[i] = v;
+  }
+}
+// W [Cout][C][3][3] -> W9 [Cout][4C][3][3]
+__global__ void s2d_pack_weights(const float* __restrict__ w, float* __restrict__ w9, int Cout, int C) {
+  int64_t total = (int64_t)Cout * 4 * C * 9;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int tap = (int)(i % 9);
+    int64_t r = i / 9;
+    int cc = (int)(r % (4 * C));
+    int co = (int)(r / (4 * C));
+    int ph = cc / C, c = cc % C, py = ph >> 1, px = ph & 1;
+    int a = tap / 3 - 1, b = tap % 3 - 1;  // offsets of the 3x3 tap; only a,b in {0,1} carry weight
+    float v = 0.f;
+    if (a >= 0 && b >= 0) {
+      int ty = 2 * a + py, tx = 2 * b + px;
+      if (ty <= 2 && tx <= 2) v = w[((size_t)co * C + c) * 9 + ty * 3 + tx];
+    }
+    w9[i] = v;
+  }
+}
+// dW9 [Cout][4C][3][3] -> dW [Cout][C][3][3]
+__global__ void s2d_unpack_wgrad(const float* __restrict__ dw9, float* __restrict__ dw, int Cout, int C) {
+  int64_t total = (int64_t)Cout * C * 9;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int t = (int)(i % 9);
+    int64_t r = i / 9;
+    int c = (int)(r % C), co = (int)(r / C);
+    int ty = t / 3, tx = t % 3, a = ty >> 1, py = ty & 1, b = tx >> 1, px = tx & 1;
+    dw[i] = dw9[((size_t)co * 4 * C + (py * 2 + px) * C + c) * 9 + (a + 1) * 3 + (b + 1)];
+  }
+}
+}  // namespace mas
+
+extern "C" {
+int mas_space_to_depth(const float* x, float* y, int N, int H, int W, int C, void* stream) {
+  if (C % 4 || H % 2 || W % 2) return fail(MAS_ERR_UNSUPPORTED, "space_to_depth: needs C %% 4 == 0 and even H, W");
+  int64_t total4 = (int64_t)N * H * W * (C / 4);
+  int grid = (int)(cdiv(total4, 256) < 148 * 16 ? cdiv(total4, 256) : 148 * 16);
+  space_to_depth_kernel<<<grid, 256, 0, S(stream)>>>(x, y, H, W, C / 4, total4);
+  return launched("space_to_depth");
+}
+int mas_s2d_pack_weights(const float* w, float* w9, int Cout, int C, void* stream) {
+  int64_t total = (int64_t)Cout * 4 * C * 9;
+  s2d_pack_weights<<<(int)(cdiv(total, 256) < 2368 ? cdiv(total, 256) : 2368), 256, 0, S(stream)>>>(w, w9, Cout, C);
+  return launched("s2d_pack_weights");
+}
+int mas_s2d_unpack_wgrad(const float* dw9, float* dw, int Cout, int C, void* stream) {
+  int64_t total = (int64_t)Cout * C * 9;
+  s2d_unpack_wgrad<<<(int)(cdiv(total, 256) < 2368 ? cdiv(total, 256) : 2368), 256, 0, S(stream)>>>(dw9, dw, Cout, C);
+  return launched("s2d_unpack_wgrad");
+}
+}

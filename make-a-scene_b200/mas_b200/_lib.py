@@ -55,6 +55,9 @@ _SPEC = {
     "mas_edge_wgrad_ws_bytes": (_Z, [_I]),
     "mas_edge_small_cin_wgrad": (_I, [_P, _T, _P, _T, _P, _P, _P, _Z, _P]),
     "mas_edge_small_cout_wgrad": (_I, [_P, _T, _P, _T, _P, _P, _P, _Z, _P]),
+    "mas_space_to_depth": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "mas_s2d_pack_weights": (_I, [_P, _P, _I, _I, _P]),
+    "mas_s2d_unpack_wgrad": (_I, [_P, _P, _I, _I, _P]),
     "mas_sumpool2x2": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "mas_gemm": (_I, [_P, _P, _P, _I, _I, _I, _I, _L, _L, _L, _L, _L, _L, _I, _I, _F, _P, _P, _I, _P]),
     "mas_colsum_ws_bytes": (_Z, [_T]),

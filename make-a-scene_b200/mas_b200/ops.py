@@ -274,6 +274,15 @@ class Conv3x3Fn(torch.autograd.Function):
             x = nhwc(x)
             y = (torch.empty((n, cout, h, w), dtype=torch.float32, device=x.device) if out_nchw else empty_nhwc(n, cout, h, w, x))
             L.call("mas_edge_small_cout_fprop", x, L.t4(x), weight.contiguous(), bias, y, L.t4(y))
+        elif (mode == L.CONV_S2 and _tc_on() and residual is None and not out_nchw and _is_dense_nhwc(x) and cin % 8 == 0
+              and cout % 128 == 0 and h % 32 == 0 and w % 16 == 0):
+            edge = 3  # stride-2 conv on the stride-1 tensor kernels through space-to-depth
+            x4 = empty_nhwc(n, 4 * cin, h // 2, w // 2, x)
+            L.call("mas_space_to_depth", x, x4, n, h, w, cin)
+            w9 = torch.empty((cout, 4 * cin, 3, 3), dtype=torch.float32, device=x.device)
+            L.call("mas_s2d_pack_weights", weight.contiguous(), w9, cout, cin)
+            y = conv3x3_raw(x4, w9, bias, None, L.CONV_S1)
+            x = x4   # saved for the weight gradient (the 4C-channel view carries the same data)
         else:
             y = conv3x3_raw(x, weight, bias, residual, mode, out_nchw)
         ctx.save_for_backward(x, weight)
@@ -305,6 +314,13 @@ class Conv3x3Fn(torch.autograd.Function):
                 db = torch.empty(cout, dtype=torch.float32, device=x.device)
                 ws = L.workspace(L.query("mas_edge_wgrad_ws_bytes", cin), x.device)
                 L.call("mas_edge_small_cout_wgrad", x, L.t4(x), dy, L.t4(dy), dw, db, ws, ws.numel())
+        elif ctx.edge == 3:
+            if ctx.needs_input_grad[0]:
+                dx = conv3x3_dgrad_raw(nhwc(dy), weight, ctx.mode)       # zero-stuffed map on the tensor kernel
+            if want_w:
+                dw9, db = conv3x3_wgrad_raw(x, nhwc(dy), cout, 4 * cin, L.CONV_S1, ctx.has_bias)
+                dw = torch.empty_like(weight)
+                L.call("mas_s2d_unpack_wgrad", dw9, dw, cout, cin)
         else:
             if ctx.needs_input_grad[0]:
                 dx = conv3x3_dgrad_raw(dy, weight, ctx.mode)
