@@ -90,14 +90,26 @@ int mas_conv3x3_fprop(const float* x, mas_tensor4 xs, const float* w_packed, con
  * flipped taps); the packed image is what one cp.async.bulk per pipeline stage drops into shared memory. */
 int mas_conv3x3_tc_eligible(mas_tensor4 xs, mas_tensor4 ys, int mode);
 int mas_pack_conv3x3_tc(const float* w_oihw, float* w_tc, int Cout, int Cin, int transpose, void* stream);
+/* Fusions on the tensor path (north_star: "fused GroupNorm+SiLU+Conv2d tiles"):
+ *  gn_table  [N,Cin,2] (mas_gn_table) or NULL — the A-operand producers apply a = act(x*sc + sh) while staging, so the
+ *            normalised/activated tensor of modules.py:121-126 is never written; gn_silu selects the Swish.
+ *  stats_part or NULL — the epilogue also emits per-(tile, 32-row group, channel quad) sum / sum of squares of the
+ *            stored output, [tiles][4][Cout/4][2] floats with tiles = N*(Hout/16)*(Wout/8); mas_gn_finalize_partials
+ *            turns them into the NEXT GroupNorm's mean/rstd (deterministic), replacing a full read of the tensor. */
 int mas_conv3x3_fprop_tc(const float* x, mas_tensor4 xs, const float* w_tc, const float* bias,
-                         const float* residual, float* y, mas_tensor4 ys, int mode, void* stream);
+                         const float* residual, float* y, mas_tensor4 ys, int mode, const float* gn_table,
+                         int gn_silu, float* stats_part, void* stream);
+int mas_gn_finalize_partials(const float* part, int tiles_per_image, int N, int C, int G, int64_t hw, float eps,
+                             float* mean, float* rstd, void* stream);
+int mas_gn_table(const float* mean, const float* rstd, const float* gamma, const float* beta, int N, int C, int G,
+                 float* table, void* stream);
 /* Row GEMM on the tensor path for 1x1 convolutions: C[M,N] = alpha * A[M,K] . W^T + bias + residual with W
  * [N,K] row-major packed by mas_pack_gemm_tc (transpose=1 packs W^T for the data gradient: N<->K).
  * Needs N % 128 == 0 and K % 32 == 0 (after the optional transpose). */
 int mas_pack_gemm_tc(const float* w_nk, float* w_tc, int N, int K, int transpose, void* stream);
 int mas_gemm_rows_packed(const float* A, int64_t lda, const float* w_tc, float* C, int64_t ldc, int64_t M, int N,
-                         int K, float alpha, const float* bias, const float* residual, void* stream);
+                         int K, float alpha, const float* bias, const float* residual, float* stats_part,
+                         void* stream);  /* stats_part as above with 128-row tiles: [M/128][4][N/4][2] */
 /* Diagnostic: one tcgen05.mma D[128x32] = A[128x8].B[32x8]^T with A from shared memory (a_src=0) or tensor memory
  * (a_src=1) and B K-major (b_layout=0) or MN-major (1; 2 = LBO/SBO fields swapped). Used by the tests to pin the
  * descriptor conventions the production kernels rely on. b_layout=99: B descriptor bits / instruction descriptor /
@@ -108,7 +120,8 @@ int mas_tc_probe(const float* A, const float* B, float* D, int a_src, int b_layo
  * x is the convolution's (already normalised+activated) input, dy the output gradient. */
 size_t mas_conv3x3_wgrad_ws_bytes(mas_tensor4 xs, mas_tensor4 dys, int mode);
 int mas_conv3x3_wgrad(const float* x, mas_tensor4 xs, const float* dy, mas_tensor4 dys, float* dw_oihw,
-                      float* dbias, int mode, int impl, void* ws, size_t ws_bytes, void* stream);
+                      float* dbias, int mode, int impl, const float* gn_table, int gn_silu, void* ws,
+                      size_t ws_bytes, void* stream);  /* gn_table: x is re-activated on the fly (tensor path only) */
 /* Weight gradient of a 1x1 convolution: dw[Cout,Cin] = dy^T x over M rows (split over rows, deterministic);
  * dbias [Cout] may be NULL. x [M,Cin] and dy [M,Cout] are row-major with row pitches ldx / ldy (elements). */
 size_t mas_conv1x1_wgrad_ws_bytes(int64_t M, int Cin, int Cout);

@@ -12,14 +12,13 @@ int gemm_simt_launch(const float* A, const float* B, float* C, int M, int N, int
                      int64_t sa, int64_t sb, int64_t sc, int ta, int tb, float alpha, const float* bias, const float* res,
                      cudaStream_t st);
 // tcgen05 path; return MAS_ERR_UNSUPPORTED (without touching g_err semantics) when not eligible
-int conv3x3_fprop_tc_launch(const float* x, mas_tensor4 xs, const float* w_packed, const float* bias, const float* res, float* y,
-                            mas_tensor4 ys, int mode, cudaStream_t st);
+
 int gemm_tc_launch(const float* A, const float* B, float* C, int M, int N, int K, int batch, int64_t lda, int64_t ldb, int64_t ldc,
                    int64_t sa, int64_t sb, int64_t sc, int ta, int tb, float alpha, const float* bias, const float* res,
                    cudaStream_t st);
 size_t conv_wgrad_tc_ws(mas_tensor4 xs, mas_tensor4 dys, int mode);
-int conv_wgrad_tc_launch(const float* x, mas_tensor4 xs, const float* dy, mas_tensor4 dys, float* dw, float* dbias, int mode, void* ws,
-                         size_t ws_bytes, cudaStream_t st);
+int conv_wgrad_tc_launch(const float* x, mas_tensor4 xs, const float* dy, mas_tensor4 dys, float* dw, float* dbias, int mode,
+                         const float* gn_table, int gn_silu, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t conv1x1_wgrad_tc_ws(int64_t M, int Cin, int Cout);
 int conv1x1_wgrad_tc_launch(const float* x, int64_t ldx, const float* dy, int64_t ldy, int64_t M, int Cin, int Cout, float* dw,
                             float* dbias, void* ws, size_t ws_bytes, cudaStream_t st);
@@ -46,18 +45,19 @@ size_t mas_conv3x3_wgrad_ws_bytes(mas_tensor4 xs, mas_tensor4 dys, int mode) {
 }
 
 int mas_conv3x3_wgrad(const float* x, mas_tensor4 xs, const float* dy, mas_tensor4 dys, float* dw_oihw, float* dbias, int mode,
-                      int impl, void* ws, size_t ws_bytes, void* stream) {
+                      int impl, const float* gn_table, int gn_silu, void* ws, size_t ws_bytes, void* stream) {
   MAS_REQUIRE(x && dy && dw_oihw, "conv3x3_wgrad: null pointer");
   if (ws_bytes < mas_conv3x3_wgrad_ws_bytes(xs, dys, mode)) return fail(MAS_ERR_WORKSPACE, "conv3x3_wgrad: workspace too small");
   size_t a = conv_wgrad_simt_ws(xs, dys, 3), b = conv_wgrad_tc_ws(xs, dys, mode);
   size_t main_bytes = align256(a > b ? a : b);
   int e = MAS_ERR_UNSUPPORTED;
   if (impl != MAS_IMPL_SIMT) {
-    e = conv_wgrad_tc_launch(x, xs, dy, dys, dw_oihw, dbias, mode, ws, main_bytes, S(stream));
+    e = conv_wgrad_tc_launch(x, xs, dy, dys, dw_oihw, dbias, mode, gn_table, gn_silu, ws, main_bytes, S(stream));
     if (e != MAS_OK && (e != MAS_ERR_UNSUPPORTED || impl == MAS_IMPL_TC)) return e;
     if (e == MAS_OK) return MAS_OK;  // the tensor path also produced dbias
   }
   if (e == MAS_ERR_UNSUPPORTED) {
+    if (gn_table) return fail(MAS_ERR_UNSUPPORTED, "conv3x3_wgrad: the fused GroupNorm prologue needs the tensor path (shape not eligible)");
     e = conv_wgrad_simt_launch(x, xs, dy, dys, dw_oihw, mode, 3, ws, main_bytes, S(stream));
     if (e) return e;
   }

@@ -126,6 +126,14 @@ struct Params {
   int tiles_x, tiles_y;  // tiles per image row / column (image maps)
   int64_t total_tiles;
   float alpha;
+  // fused GroupNorm(+SiLU) PROLOGUE on the A operand: a = act(x * sc + sh) with (sc, sh) per (image, input channel) in
+  // gn_table [N][Cin][2] (null = plain input).  Padding pixels stay exactly zero (the reference pads the ACTIVATED tensor).
+  const float* gn_table;
+  int gn_silu;
+  // fused GroupNorm-statistics EPILOGUE for the NEXT layer's norm: per (tile, 32-row lane group, channel quad) sum and
+  // sum of squares of the stored output, [total_tiles][4][Cout/4][2] floats (null = off); reduced deterministically
+  // per (image, group) by mas_gn_finalize_partials.
+  float* stats_part;
 };
 
 // One CTA = TILES M-tiles x BN output channels, full K.
@@ -178,11 +186,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) shift_gemm_tc(const Params p) {
   if (warp < 8) {
     // ===================== producers: stage A (input pixels) =====================
     const float* src[PER_THREAD];
+    const float* tab[(TAPS == 9) ? PER_THREAD : 1];   // prologue table pointers (3x3 convolutions only)
     uint32_t dst[PER_THREAD];
 #pragma unroll
     for (int i = 0; i < PER_THREAD; ++i) {
       const int item = tid + i * NPROD;
       src[i] = nullptr;
+      if (TAPS == 9) tab[i] = nullptr;
       dst[i] = 0xFFFFFFFFu;
       if (item < ITEMS) {
         const int q = item % QUADS, rest = item / QUADS, slot = rest % SLOTS, tl = rest / SLOTS;
@@ -205,7 +215,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) shift_gemm_tc(const Params p) {
               ok = vy >= 0 && vx >= 0 && (vy & 1) && (vx & 1) && (vy >> 1) < p.Hin && (vx >> 1) < p.Win;
               iy = vy >> 1; ix = vx >> 1;
             }
-            if (ok) src[i] = p.x + ((int64_t)(n * p.Hin + iy) * p.Win + ix) * p.ldx + q * 4;
+            if (ok) {
+              src[i] = p.x + ((int64_t)(n * p.Hin + iy) * p.Win + ix) * p.ldx + q * 4;
+              if (p.gn_table) tab[i] = p.gn_table + ((size_t)n * p.Cin + q * 4) * 2;
+            }
           } else {
             const int64_t row = tile * BM + slot;
             if (slot >= BM) dst[i] = 0xFFFFFFFFu;  // pad slots are never read by the MMA
@@ -230,6 +243,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) shift_gemm_tc(const Params p) {
 #pragma unroll
       for (int i = 0; i < PER_THREAD; ++i) v[i] = vn[i];
       if (kc + 1 < nchunks) gload(kc + 1, vn);  // next chunk's global loads fly while this chunk is stored / consumed
+      if (TAPS == 9) {
+        if (p.gn_table) {
+          // fused GroupNorm (+SiLU) prologue, applied at CONSUME time so the prefetch above stays asynchronous;
+          // the (scale, shift) pairs are L1-resident
+#pragma unroll
+          for (int i = 0; i < PER_THREAD; ++i) {
+            if (tab[i]) {
+              const float4 t0 = __ldg(reinterpret_cast<const float4*>(tab[i] + (size_t)kc * KC * 2));      // sc0 sh0 sc1 sh1
+              const float4 t1 = __ldg(reinterpret_cast<const float4*>(tab[i] + (size_t)kc * KC * 2) + 1);  // sc2 sh2 sc3 sh3
+              float a0 = fmaf(v[i].x, t0.x, t0.y), a1 = fmaf(v[i].y, t0.z, t0.w);
+              float a2 = fmaf(v[i].z, t1.x, t1.y), a3 = fmaf(v[i].w, t1.z, t1.w);
+              if (p.gn_silu) { a0 = silu_f(a0); a1 = silu_f(a1); a2 = silu_f(a2); a3 = silu_f(a3); }
+              v[i] = make_float4(a0, a1, a2, a3);
+            }
+          }
+        }
+      }
       mbar_wait(empty_bar(stage), phase ^ 1);
       uint8_t* a_st = smem + (size_t)stage * STAGE;
 #pragma unroll
@@ -277,6 +307,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) shift_gemm_tc(const Params p) {
         __syncwarp();
         float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.bias) bq = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + col + sub_c * 4));
+        float st_s = 0.f, st_q = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int row = i * 4 + sub_r;               // accumulator row within this warp's 32
@@ -293,6 +324,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) shift_gemm_tc(const Params p) {
               o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
             }
             *reinterpret_cast<float4*>(p.y + off) = o;
+            st_s += (o.x + o.y) + (o.z + o.w);
+            st_q = fmaf(o.x, o.x, fmaf(o.y, o.y, fmaf(o.z, o.z, fmaf(o.w, o.w, st_q))));
+          }
+        }
+        if (p.stats_part) {  // fixed-order combine of the four row sub-groups, one (sum, sumsq) per channel quad
+          st_s += __shfl_xor_sync(0xffffffffu, st_s, 8);
+          st_q += __shfl_xor_sync(0xffffffffu, st_q, 8);
+          st_s += __shfl_xor_sync(0xffffffffu, st_s, 16);
+          st_q += __shfl_xor_sync(0xffffffffu, st_q, 16);
+          if (lane < 8) {
+            float* sp = p.stats_part + (((size_t)tile * 4 + lane_grp) * (p.Cout >> 2) + ((n0 + col) >> 2) + sub_c) * 2;
+            sp[0] = st_s;
+            sp[1] = st_q;
           }
         }
       }
@@ -408,6 +452,8 @@ struct WParams {
   int N, Hin, Win, Cin, H, W, Cout, map;
   int units_x, units_y;
   int64_t total_units, units_per_split, rows, ldx, ldy;
+  const float* gn_table;  // fused GroupNorm(+SiLU) prologue on x, [N][Cin][2] (sc, sh), or null (3x3 only)
+  int gn_silu;
 };
 
 __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -433,7 +479,7 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 
 // TAPS == 9: 3x3 convolution (unit = 8x8 output pixels, halo 10x10).  TAPS == 1: 1x1 convolution / row GEMM
 // (unit = 64 consecutive rows, no halo).
-template <int TAPS>
+template <int TAPS, bool PRO>
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc(const WParams p) {
   // B (the shifted operand) must be K-major with K = pixel: tests/test_gpu_tc_probe.py shows that kind::tf32 returns
   // zeros for MN-major shared-memory operands, so the halo is staged TRANSPOSED ([ci][pixel], 4 pixels per 16-byte
@@ -533,6 +579,30 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc(const WParams p) {
 #pragma unroll
       for (int i = 0; i < PER_THREAD; ++i) v[i] = vn[i];
       if (u + 1 < u1) gload(u + 1, vn);   // next unit's global loads are in flight while this unit is stored
+      if (TAPS == 9 && PRO) {
+        if (p.gn_table) {
+          // the convolution's input is act(GroupNorm(x)): recomputed here (at consume time) instead of stored.
+          // Padding pixels must stay exactly zero, so validity is re-derived from the unit coordinates.
+          const int ux = (int)(u % p.units_x), uy = (int)((u / p.units_x) % p.units_y);
+          const int n = (int)(u / ((int64_t)p.units_x * p.units_y));
+#pragma unroll
+          for (int i = 0; i < PER_THREAD; ++i) {
+            if (it_c[i] >= 0) {
+              const int vy = uy * 8 - 1 + it_r[i], vx = ux * 8 - 1 + it_c[i];
+              const bool ok = (p.map == MAP_S1) ? ((unsigned)vy < (unsigned)p.Hin && (unsigned)vx < (unsigned)p.Win)
+                                                : ((unsigned)vy < (unsigned)(2 * p.Hin) && (unsigned)vx < (unsigned)(2 * p.Win));
+              if (ok) {
+                const float4* tp = reinterpret_cast<const float4*>(p.gn_table + ((size_t)n * p.Cin + ci0 + it_q[i] * 4) * 2);
+                const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1);
+                float a0 = fmaf(v[i].x, t0.x, t0.y), a1 = fmaf(v[i].y, t0.z, t0.w);
+                float a2 = fmaf(v[i].z, t1.x, t1.y), a3 = fmaf(v[i].w, t1.z, t1.w);
+                if (p.gn_silu) { a0 = silu_f(a0); a1 = silu_f(a1); a2 = silu_f(a2); a3 = silu_f(a3); }
+                v[i] = make_float4(a0, a1, a2, a3);
+              }
+            }
+          }
+        }
+      }
       mbar_wait(empty(stage), phase ^ 1);
       float* b_st = reinterpret_cast<float*>(smem + (size_t)stage * B_STAGE);
 #pragma unroll
@@ -758,7 +828,7 @@ static int set_smem(K kernel, size_t bytes) {
 
 // w_tc must have been produced by mas_pack_conv3x3_tc for the matching direction.
 int conv3x3_fprop_tc_launch(const float* x, mas_tensor4 xs, const float* w_tc, const float* bias, const float* res, float* y,
-                            mas_tensor4 ys, int mode, cudaStream_t st) {
+                            mas_tensor4 ys, int mode, const float* gn_table, int gn_silu, float* stats_part, cudaStream_t st) {
   const int Cin = (int)xs.c, Cout = (int)ys.c;
   if (!(mode == MAS_CONV_S1 || mode == MAS_CONV_UP || mode == MAS_CONV_ZS)) return fail(MAS_ERR_UNSUPPORTED, "tc conv: mode %d", mode);
   if (!dense_nhwc(xs) || !dense_nhwc(ys) || Cin % 8 || Cout % tc::BN || ys.h % 16 || ys.w % 8 || !al16p(x) || !al16p(y) ||
@@ -775,6 +845,8 @@ int conv3x3_fprop_tc_launch(const float* x, mas_tensor4 xs, const float* w_tc, c
   p.tiles_x = (int)(ys.w / 8); p.tiles_y = (int)(ys.h / 16);
   p.total_tiles = (int64_t)p.N * p.tiles_x * p.tiles_y;
   p.alpha = 1.0f;
+  p.gn_table = gn_table; p.gn_silu = gn_silu; p.stats_part = stats_part;
+  if (gn_table && !al16p(gn_table)) return fail(MAS_ERR_INVALID_ARG, "tc conv: gn_table must be 16-byte aligned");
   constexpr size_t smem = tc::smem_bytes<9, 8, tc::STAGES_CONV>();
   static bool configured = false;
   if (!configured) {
@@ -788,7 +860,7 @@ int conv3x3_fprop_tc_launch(const float* x, mas_tensor4 xs, const float* w_tc, c
 
 // Row GEMM C[M,N] = alpha * A[M,K] * Wt[N,K]^T + bias + residual with PRE-PACKED weights (mas_pack_gemm_tc).
 int gemm_rows_tc_launch(const float* A, int64_t lda, const float* w_tc, float* C, int64_t ldc, int64_t M, int N, int K, float alpha,
-                        const float* bias, const float* res, cudaStream_t st) {
+                        const float* bias, const float* res, float* stats_part, cudaStream_t st) {
   if (K % 32 || N % tc::BN || lda % 4 || ldc % 4 || !al16p(A) || !al16p(C) || (res && !al16p(res)) || (bias && !al16p(bias)) ||
       !al16p(w_tc))
     return fail(MAS_ERR_UNSUPPORTED, "tc gemm: shape not eligible (M=%lld N=%d K=%d)", (long long)M, N, K);
@@ -801,6 +873,8 @@ int gemm_rows_tc_launch(const float* A, int64_t lda, const float* w_tc, float* C
   p.tiles_x = 1; p.tiles_y = 1;
   p.total_tiles = cdiv(M, tc::BM);
   p.alpha = alpha;
+  p.gn_table = nullptr; p.gn_silu = 0; p.stats_part = stats_part;
+  if (stats_part && (M % tc::BM || ldc != N)) return fail(MAS_ERR_UNSUPPORTED, "tc gemm: fused statistics need M %% 128 == 0 and a dense output");
   constexpr size_t smem = tc::smem_bytes<1, 32, 2>();
   static bool configured = false;
   if (!configured) {
@@ -834,7 +908,7 @@ size_t conv_wgrad_tc_ws(mas_tensor4 xs, mas_tensor4 dys, int mode) {
   size_t splits = wgrad_tc_splits((dys.c / tc::BM) * (xs.c / tc::WG_NT), dys.n * (dys.h / 8) * (dys.w / 8));
   return splits * 9 * (size_t)dys.c * xs.c * sizeof(float) + 2 * splits * (size_t)dys.c * sizeof(float) + 256;
 }
-template <int TAPS>
+template <int TAPS, bool PRO>
 static int wgrad_tc_run(tc::WParams& p, int splits, float* dw, float* dbias, void* ws, cudaStream_t st) {
   p.part = (float*)ws;
   p.bpart = dbias ? (float*)ws + (size_t)splits * TAPS * p.Cout * p.Cin : nullptr;
@@ -843,11 +917,11 @@ static int wgrad_tc_run(tc::WParams& p, int splits, float* dw, float* dbias, voi
   constexpr size_t smem = (size_t)tc::WG_STAGES * (TAPS == 9 ? 3 * 20 : 16) * NT * 16 + (3 * tc::WG_STAGES + 1) * 8 + 16;
   static bool configured = false;
   if (!configured) {
-    if (int e = set_smem(tc::wgrad_tc<TAPS>, smem)) return e;
+    if (int e = set_smem(tc::wgrad_tc<TAPS, PRO>, smem)) return e;
     configured = true;
   }
   dim3 grid((unsigned)(p.Cin / NT), (unsigned)(p.Cout / tc::BM), (unsigned)splits);
-  tc::wgrad_tc<TAPS><<<grid, tc::WG_THREADS, smem, st>>>(p);
+  tc::wgrad_tc<TAPS, PRO><<<grid, tc::WG_THREADS, smem, st>>>(p);
   if (int e = launched("wgrad_tc")) return e;
   conv_wgrad_reduce_launch((const float*)ws, splits, TAPS, p.Cout, p.Cin, dw, st);
   if (int e = launched("conv_wgrad_reduce")) return e;
@@ -858,8 +932,8 @@ static int wgrad_tc_run(tc::WParams& p, int splits, float* dw, float* dbias, voi
   return MAS_OK;
 }
 // dbias (may be null) is produced here too when the tensor path runs.
-int conv_wgrad_tc_launch(const float* x, mas_tensor4 xs, const float* dy, mas_tensor4 dys, float* dw, float* dbias, int mode, void* ws,
-                         size_t ws_bytes, cudaStream_t st) {
+int conv_wgrad_tc_launch(const float* x, mas_tensor4 xs, const float* dy, mas_tensor4 dys, float* dw, float* dbias, int mode,
+                         const float* gn_table, int gn_silu, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (!wgrad_tc_ok(xs, dys, mode) || !al16p(x) || !al16p(dy)) return fail(MAS_ERR_UNSUPPORTED, "tc wgrad: shape/layout not eligible");
   if (ws_bytes < conv_wgrad_tc_ws(xs, dys, mode)) return fail(MAS_ERR_WORKSPACE, "tc wgrad: workspace too small");
   tc::WParams p;
@@ -869,8 +943,9 @@ int conv_wgrad_tc_launch(const float* x, mas_tensor4 xs, const float* dy, mas_te
   p.units_x = (int)(dys.w / 8); p.units_y = (int)(dys.h / 8);
   p.total_units = (int64_t)p.N * p.units_x * p.units_y;
   p.rows = 0; p.ldx = p.Cin; p.ldy = p.Cout;
+  p.gn_table = gn_table; p.gn_silu = gn_silu;
   const int splits = wgrad_tc_splits((dys.c / tc::BM) * (xs.c / tc::WG_NT), p.total_units);
-  return wgrad_tc_run<9>(p, splits, dw, dbias, ws, st);
+  return gn_table ? wgrad_tc_run<9, true>(p, splits, dw, dbias, ws, st) : wgrad_tc_run<9, false>(p, splits, dw, dbias, ws, st);
 }
 static bool wgrad1_tc_ok(const float* x, int64_t ldx, const float* dy, int64_t ldy, int Cin, int Cout) {
   return Cin % 128 == 0 && Cout % tc::BM == 0 && ldx % 4 == 0 && al16p(x) && dy != nullptr && ldy >= Cout;
@@ -890,8 +965,9 @@ int conv1x1_wgrad_tc_launch(const float* x, int64_t ldx, const float* dy, int64_
   p.units_x = 1; p.units_y = 1;
   p.total_units = cdiv(M, 64);
   p.rows = M; p.ldx = ldx; p.ldy = ldy;
+  p.gn_table = nullptr; p.gn_silu = 0;
   const int splits = wgrad_tc_splits((int64_t)(Cout / tc::BM) * (Cin / 128), p.total_units);
-  return wgrad_tc_run<1>(p, splits, dw, dbias, ws, st);
+  return wgrad_tc_run<1, false>(p, splits, dw, dbias, ws, st);
 }
 
 }  // namespace mas
@@ -918,9 +994,9 @@ int mas_pack_gemm_tc(const float* w_nk, float* w_tc, int N, int K, int transpose
 }
 
 int mas_gemm_rows_packed(const float* A, int64_t lda, const float* w_tc, float* C, int64_t ldc, int64_t M, int N, int K, float alpha,
-                         const float* bias, const float* residual, void* stream) {
+                         const float* bias, const float* residual, float* stats_part, void* stream) {
   MAS_REQUIRE(A && w_tc && C && M > 0, "gemm_rows_packed: bad arguments");
-  return gemm_rows_tc_launch(A, lda, w_tc, C, ldc, M, N, K, alpha, bias, residual, S(stream));
+  return gemm_rows_tc_launch(A, lda, w_tc, C, ldc, M, N, K, alpha, bias, residual, stats_part, S(stream));
 }
 
 int mas_tc_probe(const float* A, const float* B, float* D, int a_src, int b_layout, uint64_t raw_desc, uint32_t raw_idesc,
@@ -937,9 +1013,9 @@ int mas_conv3x3_tc_eligible(mas_tensor4 xs, mas_tensor4 ys, int mode) {
 }
 
 int mas_conv3x3_fprop_tc(const float* x, mas_tensor4 xs, const float* w_tc, const float* bias, const float* residual, float* y,
-                         mas_tensor4 ys, int mode, void* stream) {
+                         mas_tensor4 ys, int mode, const float* gn_table, int gn_silu, float* stats_part, void* stream) {
   MAS_REQUIRE(x && w_tc && y, "conv3x3_fprop_tc: null pointer");
-  return conv3x3_fprop_tc_launch(x, xs, w_tc, bias, residual, y, ys, mode, S(stream));
+  return conv3x3_fprop_tc_launch(x, xs, w_tc, bias, residual, y, ys, mode, gn_table, gn_silu, stats_part, S(stream));
 }
 
 }  // extern "C"

@@ -302,6 +302,41 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply(const float* __restri
   }
 }
 
+// statistics emitted by the convolution epilogues: part[tile][4][C/4][2] -> mean/rstd per (image, group); warp per (n,g)
+__global__ void gn_finalize_partials_kernel(const float* __restrict__ part, int tiles_per_image, int C, int G, double count, float eps,
+                                            float* __restrict__ mean, float* __restrict__ rstd, int NG) {
+  const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (wid >= NG) return;
+  const int n = wid / G, g = wid % G, Q = C >> 2, qpg = Q / G;  // channel quads per group (C/G >= 4)
+  double a = 0, b = 0;
+  const int rows = tiles_per_image * 4;
+  for (int r = lane; r < rows; r += 32) {
+    const float* p = part + (((size_t)n * rows + r) * Q + (size_t)g * qpg) * 2;
+    for (int q = 0; q < qpg; ++q) { a += p[q * 2]; b += p[q * 2 + 1]; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if (lane == 0) {
+    double m = a / count, var = b / count - m * m;
+    if (var < 0) var = 0;
+    mean[wid] = (float)m;
+    rstd[wid] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+}
+// (sc, sh) per (image, channel): act(GroupNorm(x)) = act(x*sc + sh)
+__global__ void gn_table_kernel(const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, int N, int C, int G, float* __restrict__ table) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C) return;
+  int n = i / C, c = i % C, g = c / (C / G);
+  float a = rstd[n * G + g] * gamma[c];
+  table[(size_t)i * 2] = a;
+  table[(size_t)i * 2 + 1] = beta[c] - mean[n * G + g] * a;
+}
+
 __global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) o[i] = a[i] + b[i];
 }
@@ -603,6 +638,18 @@ int mas_gn_backward(const float* dy, const float* x, const float* mean, const fl
   return launched("gn_bwd_apply");
 }
 
+int mas_gn_finalize_partials(const float* part, int tiles_per_image, int N, int C, int G, int64_t hw, float eps, float* mean,
+                             float* rstd, void* stream) {
+  if (C % 4 || (C / 4) % G) return fail(MAS_ERR_UNSUPPORTED, "gn_finalize_partials: need C/G >= 4");
+  gn_finalize_partials_kernel<<<(int)cdiv((int64_t)N * G, 8), 256, 0, S(stream)>>>(part, tiles_per_image, C, G, (double)hw * (C / G), eps,
+                                                                                  mean, rstd, N * G);
+  return launched("gn_finalize_partials");
+}
+int mas_gn_table(const float* mean, const float* rstd, const float* gamma, const float* beta, int N, int C, int G, float* table,
+                 void* stream) {
+  gn_table_kernel<<<(int)cdiv((int64_t)N * C, 256), 256, 0, S(stream)>>>(mean, rstd, gamma, beta, N, C, G, table);
+  return launched("gn_table");
+}
 int mas_add(const float* a, const float* b, float* out, int64_t n, void* stream) {
   add_kernel<<<ew_grid(n), 256, 0, S(stream)>>>(a, b, out, n);
   return launched("add");

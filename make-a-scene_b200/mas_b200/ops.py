@@ -93,10 +93,36 @@ def _tc_on():
     return _cfg["impl"] != L.IMPL_SIMT
 
 
-def conv3x3_raw(x, weight, bias, residual, mode, out_nchw=False, transpose=False):
+def conv_tc_eligible(x, cout, mode):
+    """True when conv3x3 of dense-NHWC x with `cout` output channels runs on the tcgen05 kernel."""
+    if not _tc_on() or not _is_dense_nhwc(x):
+        return False
+    n, _, h, w = x.shape
+    ho, wo = _conv_out_hw(h, w, mode)
+    ys = L.Tensor4(n, ho, wo, cout, ho * wo * cout, wo * cout, cout, 1)
+    return bool(L.query("mas_conv3x3_tc_eligible", L.t4(x), ys, mode))
+
+
+def gn_table(mean, rstd, gamma, beta, n, c):
+    """(scale, shift) per (image, channel): act(GroupNorm(x)) = act(x*sc + sh) — consumed by the conv producers."""
+    t = torch.empty((n, c, 2), dtype=torch.float32, device=mean.device)
+    L.call("mas_gn_table", mean, rstd, gamma, beta, n, c, GN_GROUPS, t)
+    return t
+
+
+def _finalize_stats(part, tiles_per_image, n, c, hw):
+    mean = torch.empty(n * GN_GROUPS, dtype=torch.float32, device=part.device)
+    rstd = torch.empty_like(mean)
+    L.call("mas_gn_finalize_partials", part, tiles_per_image, n, c, GN_GROUPS, hw, GN_EPS, mean, rstd)
+    return mean, rstd
+
+
+def conv3x3_raw(x, weight, bias, residual, mode, out_nchw=False, transpose=False, table=None, silu=True, want_stats=False):
     """y = conv3x3(x; weight) (+bias, +residual). transpose=True applies the data-gradient operand
     (taps flipped, Cin<->Cout). Dense NHWC shapes with Cin%8==0, Cout%128==0, Hout%16==0, Wout%8==0 run on the
-    tcgen05 kernel; everything else (edge layers, stride-2 gather, NCHW views, small images) on the fp32 SIMT kernel."""
+    tcgen05 kernel; everything else (edge layers, NCHW views, small images) on the fp32 SIMT kernel.
+    table: fused GroupNorm(+SiLU) prologue (tensor path only); want_stats: also return the output's GroupNorm
+    (mean, rstd) from the fused epilogue (None when the tensor path does not apply)."""
     n, _, h, w = x.shape
     cout = weight.shape[1] if transpose else weight.shape[0]
     cin = weight.shape[0] if transpose else weight.shape[1]
@@ -107,25 +133,37 @@ def conv3x3_raw(x, weight, bias, residual, mode, out_nchw=False, transpose=False
         y = empty_nhwc(n, cout, ho, wo, x)
     xs, ys = L.t4(x), L.t4(y)
     wc = weight.contiguous()
+    stats = None
     if _tc_on() and not out_nchw and L.query("mas_conv3x3_tc_eligible", xs, ys, mode):
         wt = torch.empty(9 * cout * cin, dtype=torch.float32, device=x.device)
         L.call("mas_pack_conv3x3_tc", wc, wt, weight.shape[0], weight.shape[1], int(transpose))
-        L.call("mas_conv3x3_fprop_tc", x, xs, wt, bias, residual, y, ys, mode)
+        part = None
+        if want_stats and cout % (4 * GN_GROUPS) == 0:
+            tiles = n * (ho // 16) * (wo // 8)
+            part = torch.empty(tiles * cout * 2, dtype=torch.float32, device=x.device)
+        L.call("mas_conv3x3_fprop_tc", x, xs, wt, bias, residual, y, ys, mode, table, int(silu), part)
+        if part is not None:
+            stats = _finalize_stats(part, (ho // 16) * (wo // 8), n, cout, ho * wo)
     else:
+        if table is not None:
+            raise RuntimeError("fused GroupNorm prologue requested for a shape that is not tensor-path eligible")
         if _cfg["impl"] == L.IMPL_TC:
             raise RuntimeError("IMPL_TC requested but the conv shape is not eligible for the tcgen05 kernel")
         wp = torch.empty(9 * cout * cin, dtype=torch.float32, device=x.device)
         L.call("mas_pack_conv3x3", wc, wp, weight.shape[0], weight.shape[1], int(transpose), 0)
         L.call("mas_conv3x3_fprop", x, xs, wp, bias, residual, y, ys, mode, L.IMPL_SIMT)
+    if want_stats:
+        return y, stats
     return y
 
 
-def conv3x3_wgrad_raw(x, dy, cout, cin, mode, want_bias=True):
+def conv3x3_wgrad_raw(x, dy, cout, cin, mode, want_bias=True, table=None, silu=True):
+    """table: x is the PRE-normalisation tensor and act(GroupNorm(x)) is recomputed while staging (tensor path only)."""
     dw = torch.empty((cout, cin, 3, 3), dtype=torch.float32, device=x.device)
     db = torch.empty(cout, dtype=torch.float32, device=x.device) if want_bias else None
     nb = L.query("mas_conv3x3_wgrad_ws_bytes", L.t4(x), L.t4(dy), mode)
     ws = L.workspace(nb, x.device)
-    L.call("mas_conv3x3_wgrad", x, L.t4(x), dy, L.t4(dy), dw, db, mode, _cfg["impl"], ws, ws.numel())
+    L.call("mas_conv3x3_wgrad", x, L.t4(x), dy, L.t4(dy), dw, db, mode, _cfg["impl"], table, int(silu), ws, ws.numel())
     return dw, db
 
 
@@ -156,7 +194,7 @@ def gemm(A, B, C, M, N, K, batch=1, lda=None, ldb=None, ldc=None, sa=0, sb=0, sc
            p(residual), _cfg["impl"])
 
 
-def gemm_w(A, lda, weight, C, ldc, M, transpose=False, alpha=1.0, bias=None, residual=None):
+def gemm_w(A, lda, weight, C, ldc, M, transpose=False, alpha=1.0, bias=None, residual=None, stats_part=None):
     """C[M,N] = alpha * A[M,K] . W^T (+bias +residual) for a 1x1-convolution weight W [Nout, Kin] (transpose=True: A . W,
     the data gradient). A / C may be (tensor, element_offset) pairs with row pitches lda / ldc."""
     nout, kin = weight.shape[0], weight.shape[1]
@@ -170,10 +208,12 @@ def gemm_w(A, lda, weight, C, ldc, M, transpose=False, alpha=1.0, bias=None, res
         dev = (A[0] if isinstance(A, tuple) else A).device
         wt = torch.empty(N * K, dtype=torch.float32, device=dev)
         L.call("mas_pack_gemm_tc", w2, wt, nout, kin, int(transpose))
-        L.call("mas_gemm_rows_packed", p(A), lda, wt, p(C), ldc, M, N, K, float(alpha), bias, p(residual))
+        L.call("mas_gemm_rows_packed", p(A), lda, wt, p(C), ldc, M, N, K, float(alpha), bias, p(residual), stats_part)
+        return True
     else:
         # W stored [Nout,Kin]: forward needs B^T (tb), the data gradient takes it as stored [K=Nout, N=Kin]
         gemm(A, w2, C, M, N, K, lda=lda, ldb=kin, ldc=ldc, tb=not transpose, alpha=alpha, bias=bias, residual=residual)
+        return False
 
 
 def conv1x1_raw(x, weight, bias, residual=None):
@@ -203,6 +243,20 @@ def conv1x1_wgrad_raw(x_rows, dy_rows, M, cin, cout, want_bias=True, ldx=None, l
     ws = L.workspace(nb, dev)
     L.call("mas_conv1x1_wgrad", x_rows, ldx or cin, dy_ptr, ldy or cout, M, cin, cout, dw, db, _cfg["impl"], ws, ws.numel())
     return dw, db
+
+
+def attach_stats(t, mean, rstd):
+    """Carry the GroupNorm statistics a kernel epilogue computed for `t` to the next module (same tensor object)."""
+    if mean is not None:
+        t._mas_gn = (mean, rstd, t._version)
+    return t
+
+
+def take_stats(t):
+    st = getattr(t, "_mas_gn", None)
+    if st is not None and st[2] == t._version and st[0].device == t.device:
+        return st[0], st[1]
+    return None, None
 
 
 # ------------------------------------------------------------------------------------------------ autograd Functions
@@ -289,6 +343,8 @@ class Conv3x3Fn(torch.autograd.Function):
         ctx.mode, ctx.has_bias, ctx.has_res, ctx.edge = mode, bias is not None, residual is not None, edge
         return y
 
+
+
     @staticmethod
     def backward(ctx, dy):
         x, weight = ctx.saved_tensors
@@ -357,36 +413,65 @@ class Conv1x1Fn(torch.autograd.Function):
 
 class ResnetBlockFn(torch.autograd.Function):
     """ResnetBlock.forward as one unit (modules.py:119-136): GN+SiLU -> conv3x3 -> GN+SiLU -> conv3x3 (+1x1 shortcut) + x.
-    The residual add is fused into conv2's epilogue; in backward the shortcut gradient is fused into the
-    GroupNorm-backward apply (identity shortcut) or into the shortcut GEMM's epilogue (nin_shortcut)."""
+    Tensor path (all img_config blocks): GroupNorm+SiLU is applied inside the convolutions' operand producers (the
+    activated tensors are never written), each convolution's epilogue emits the statistics of the NEXT GroupNorm, the
+    residual add lives in conv2's epilogue; in backward the weight-gradient kernel re-activates its input on the fly and
+    the shortcut gradient is folded into the GroupNorm-backward apply (identity) or the shortcut GEMM's epilogue (nin).
+    Returns (out, mean, rstd): the statistics of `out` for the following block's first GroupNorm (or None)."""
 
     @staticmethod
-    def forward(ctx, x, n1w, n1b, c1w, c1b, n2w, n2b, c2w, c2b, sw, sb):
+    def forward(ctx, x, mean_in, rstd_in, n1w, n1b, c1w, c1b, n2w, n2b, c2w, c2b, sw, sb):
         x = nhwc(x)
+        n, cin, h, w = x.shape
         cout = c1w.shape[0]
-        m1, r1 = gn_stats(x)
-        a1 = gn_apply(x, m1, r1, n1w, n1b, True)
-        h1 = conv3x3_raw(a1, c1w, c1b, None, L.CONV_S1)
-        m2, r2 = gn_stats(h1)
-        a2 = gn_apply(h1, m2, r2, n2w, n2b, True)
+        if mean_in is None:
+            mean_in, rstd_in = gn_stats(x)
+        m1, r1 = mean_in, rstd_in
+        fused = conv_tc_eligible(x, cout, L.CONV_S1) and cin % 8 == 0 and cout % (4 * GN_GROUPS) == 0
         sc = x if sw is None else conv1x1_raw(x, sw, sb)
-        out = conv3x3_raw(a2, c2w, c2b, sc, L.CONV_S1)
-        ctx.save_for_backward(x, a1, h1, a2, m1, r1, m2, r2, n1w, n1b, c1w, n2w, n2b, c2w, sw)
-        ctx.has_sc = sw is not None
-        return out
+        if fused:
+            t1 = gn_table(m1, r1, n1w, n1b, n, cin)
+            h1, st2 = conv3x3_raw(x, c1w, c1b, None, L.CONV_S1, table=t1, want_stats=True)
+            m2, r2 = st2
+            t2 = gn_table(m2, r2, n2w, n2b, n, cout)
+            out, st_out = conv3x3_raw(h1, c2w, c2b, sc, L.CONV_S1, table=t2, want_stats=True)
+            a1 = a2 = None
+        else:
+            a1 = gn_apply(x, m1, r1, n1w, n1b, True)
+            h1 = conv3x3_raw(a1, c1w, c1b, None, L.CONV_S1)
+            m2, r2 = gn_stats(h1)
+            a2 = gn_apply(h1, m2, r2, n2w, n2b, True)
+            out = conv3x3_raw(a2, c2w, c2b, sc, L.CONV_S1)
+            st_out = None
+        ctx.save_for_backward(x, h1, a1, a2, m1, r1, m2, r2, n1w, n1b, c1w, n2w, n2b, c2w, sw)
+        ctx.has_sc, ctx.fused = sw is not None, fused
+        if st_out is None:
+            mo = ro = None
+        else:
+            mo, ro = st_out
+            ctx.mark_non_differentiable(mo, ro)
+        return out, mo, ro
 
     @staticmethod
-    def backward(ctx, dout):
-        x, a1, h1, a2, m1, r1, m2, r2, n1w, n1b, c1w, n2w, n2b, c2w, sw = ctx.saved_tensors
+    def backward(ctx, dout, _gm, _gr):
+        x, h1, a1, a2, m1, r1, m2, r2, n1w, n1b, c1w, n2w, n2b, c2w, sw = ctx.saved_tensors
         dout = nhwc(dout)
         cout, cin = c1w.shape[0], c1w.shape[1]
         n, _, h, w = x.shape
         d_a2 = conv3x3_dgrad_raw(dout, c2w, L.CONV_S1)
+        if ctx.fused:
+            # the activated operand was never stored: re-materialise it with the streaming GN+SiLU kernel (0.1 ms at
+            # 128x256^2x32) — cheaper than re-activating inside the weight-gradient kernel's producers (measured +0.8 ms)
+            a2 = gn_apply(h1, m2, r2, n2w, n2b, True)
         dc2w, dc2b = conv3x3_wgrad_raw(a2, dout, cout, cout, L.CONV_S1)
+        del a2
         d_h1, dn2w, dn2b = gn_backward(d_a2, h1, m2, r2, n2w, n2b, True)
         del d_a2
         d_a1 = conv3x3_dgrad_raw(d_h1, c1w, L.CONV_S1)
+        if ctx.fused:
+            a1 = gn_apply(x, m1, r1, n1w, n1b, True)
         dc1w, dc1b = conv3x3_wgrad_raw(a1, d_h1, cout, cin, L.CONV_S1)
+        del a1
         del d_h1
         if ctx.has_sc:
             dxm, dn1w, dn1b = gn_backward(d_a1, x, m1, r1, n1w, n1b, True)
@@ -395,7 +480,7 @@ class ResnetBlockFn(torch.autograd.Function):
         else:
             dx, dn1w, dn1b = gn_backward(d_a1, x, m1, r1, n1w, n1b, True, dx_add=dout)
             dsw = dsb = None
-        return dx, dn1w, dn1b, dc1w, dc1b, dn2w, dn2b, dc2w, dc2b, dsw, dsb
+        return dx, None, None, dn1w, dn1b, dc1w, dc1b, dn2w, dn2b, dc2w, dc2b, dsw, dsb
 
 
 class AttnBlockFn(torch.autograd.Function):
@@ -403,11 +488,13 @@ class AttnBlockFn(torch.autograd.Function):
     -> v.P^T -> proj_out 1x1 -> + x."""
 
     @staticmethod
-    def forward(ctx, x, nw, nb, qw, qb, kw, kb, vw, vb, pw, pb):
+    def forward(ctx, x, mean_in, rstd_in, nw, nb, qw, qb, kw, kb, vw, vb, pw, pb):
         x = nhwc(x)
         n, c, h, w = x.shape
         hw, M = h * w, n * h * w
-        mean, rstd = gn_stats(x)
+        if mean_in is None:
+            mean_in, rstd_in = gn_stats(x)
+        mean, rstd = mean_in, rstd_in
         hn = gn_apply(x, mean, rstd, nw, nb, False)
         qkv = torch.empty((M, 3 * c), dtype=torch.float32, device=x.device)
         for i, (wt, bs) in enumerate(((qw, qb), (kw, kb), (vw, vb))):
@@ -418,12 +505,21 @@ class AttnBlockFn(torch.autograd.Function):
         L.call("mas_softmax_forward", P, P, n * hw, hw)
         O = empty_nhwc(n, c, h, w, x)
         gemm(P, (qkv, 2 * c), O, hw, c, hw, batch=n, lda=hw, ldb=3 * c, ldc=c, sa=hw * hw, sb=hw * 3 * c, sc=hw * c)
-        out = conv1x1_raw(O, pw, pb, residual=x)
+        # proj_out + residual; its epilogue emits the statistics of the following GroupNorm when it can
+        out = empty_nhwc(n, c, h, w, x)
+        part = None
+        if _tc_on() and hw % 128 == 0 and c % (4 * GN_GROUPS) == 0:
+            part = torch.empty((M // 128) * c * 2, dtype=torch.float32, device=x.device)
+        on_tc = gemm_w(O, c, pw, out, c, M, bias=pb, residual=x, stats_part=part)
         ctx.save_for_backward(x, mean, rstd, hn, qkv, P, O, nw, nb, qw, kw, vw, pw)
-        return out
+        if part is not None and on_tc:
+            mo, ro = _finalize_stats(part, hw // 128, n, c, hw)
+            ctx.mark_non_differentiable(mo, ro)
+            return out, mo, ro
+        return out, None, None
 
     @staticmethod
-    def backward(ctx, dout):
+    def backward(ctx, dout, _gm, _gr):
         x, mean, rstd, hn, qkv, P, O, nw, nb, qw, kw, vw, pw = ctx.saved_tensors
         dout = nhwc(dout)
         n, c, h, w = x.shape
@@ -452,7 +548,7 @@ class AttnBlockFn(torch.autograd.Function):
             grads_w.append(conv1x1_wgrad_raw(hn, dqkv, M, c, c, ldy=3 * c, dy_off=i * c))
         dx, dnw, dnb = gn_backward(dhn, x, mean, rstd, nw, nb, False, dx_add=dout)
         (dqw, dqb), (dkw, dkb), (dvw, dvb) = grads_w
-        return dx, dnw, dnb, dqw, dqb, dkw, dkb, dvw, dvb, dpw, dpb
+        return dx, None, None, dnw, dnb, dqw, dqb, dkw, dkb, dvw, dvb, dpw, dpb
 
 
 class BatchNormFn(torch.autograd.Function):

@@ -122,9 +122,11 @@ class ResnetBlock(nn.Module):
             h = self.norm2(h, silu=True)
             return self.conv2(h, residual=self.conv_shortcut(x))
         sc = self.nin_shortcut if self.in_channels != self.out_channels else None
-        return ops.ResnetBlockFn.apply(x, self.norm1.weight, self.norm1.bias, self.conv1.weight, self.conv1.bias,
-                                       self.norm2.weight, self.norm2.bias, self.conv2.weight, self.conv2.bias,
-                                       None if sc is None else sc.weight, None if sc is None else sc.bias)
+        st = ops.take_stats(x)   # GroupNorm statistics emitted by the producing kernel's epilogue, if any
+        out, mo, ro = ops.ResnetBlockFn.apply(x, st[0], st[1], self.norm1.weight, self.norm1.bias, self.conv1.weight,
+                                              self.conv1.bias, self.norm2.weight, self.norm2.bias, self.conv2.weight,
+                                              self.conv2.bias, None if sc is None else sc.weight, None if sc is None else sc.bias)
+        return ops.attach_stats(out, mo, ro)
 
 
 class AttnBlock(nn.Module):
@@ -140,8 +142,11 @@ class AttnBlock(nn.Module):
         self.proj_out = Conv2d(in_channels, in_channels, kernel_size=1, stride=1, padding=0)
 
     def forward(self, x):
-        return ops.AttnBlockFn.apply(x, self.norm.weight, self.norm.bias, self.q.weight, self.q.bias, self.k.weight,
-                                     self.k.bias, self.v.weight, self.v.bias, self.proj_out.weight, self.proj_out.bias)
+        st = ops.take_stats(x)
+        out, mo, ro = ops.AttnBlockFn.apply(x, st[0], st[1], self.norm.weight, self.norm.bias, self.q.weight, self.q.bias,
+                                            self.k.weight, self.k.bias, self.v.weight, self.v.bias, self.proj_out.weight,
+                                            self.proj_out.bias)
+        return ops.attach_stats(out, mo, ro)
 
 
 def _run(model, x):

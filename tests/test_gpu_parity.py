@@ -393,6 +393,30 @@ def test_tensor_path_full_resolution_linearity():
     assert rel_err(l1, l2) < TOL_FWD
 
 
+def test_fused_groupnorm_prologue_and_stats_epilogue():
+    """The tensor-path fusions against the unfused kernels: conv(act(GN(x))) with the prologue table == conv of the
+    materialised activation; epilogue statistics == mas_gn_stats of the stored output; same for the weight gradient."""
+    from mas_b200 import _lib as L, ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(21)
+    x = (torch.randn(3, 128, 32, 32, generator=g) * 1.5 + 0.3).to(dev).contiguous(memory_format=torch.channels_last)
+    dy = torch.randn(3, 256, 32, 32, generator=g).to(dev).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(256, 128, 3, 3, generator=g) * 0.03).to(dev)
+    b = torch.randn(256, generator=g).to(dev)
+    gamma, beta = torch.randn(128, generator=g).to(dev), torch.randn(128, generator=g).to(dev)
+    m, r = ops.gn_stats(x)
+    a = ops.gn_apply(x, m, r, gamma, beta, True)
+    tab = ops.gn_table(m, r, gamma, beta, 3, 128)
+    y_ref = ops.conv3x3_raw(a, w, b, None, L.CONV_S1)
+    y, st = ops.conv3x3_raw(x, w, b, None, L.CONV_S1, table=tab, want_stats=True)
+    assert rel_err(y, y_ref) < 1e-5          # same kernel, same operands up to the activation's rounding
+    m2, r2 = ops.gn_stats(y)
+    assert st is not None and rel_err(st[0], m2) < 1e-5 and rel_err(st[1], r2) < 1e-5
+    gw_ref, gb_ref = ops.conv3x3_wgrad_raw(a, dy, 256, 128, L.CONV_S1)
+    gw, gb = ops.conv3x3_wgrad_raw(x, dy, 256, 128, L.CONV_S1, table=tab)
+    assert rel_err(gw, gw_ref) < 1e-5 and rel_err(gb, gb_ref) < 1e-6
+
+
 def test_seg_loss_vs_reference():
     from mas_b200 import ops
     g = _load("seg_loss.pt")
