@@ -153,7 +153,7 @@ def dominant_kernel_roofline(dev, pk):
     if ops.get_impl() != L.IMPL_SIMT and L.query("mas_conv3x3_tc_eligible", xs, ys, L.CONV_S1):
         wt = torch.empty(9 * 128 * 128, device=dev)
         L.call("mas_pack_conv3x3_tc", w, wt, 128, 128, 0)
-        fn = lambda: L.call("mas_conv3x3_fprop_tc", x, xs, wt, b, None, y, ys, L.CONV_S1)
+        fn = lambda: L.call("mas_conv3x3_fprop_tc", x, xs, wt, b, None, y, ys, L.CONV_S1, None, 0, None)
         kname = "shift_gemm_tc<9> (tcgen05 TF32) conv3x3 128->128 @256^2 x32"
     else:
         wt = torch.empty(9 * 128 * 128, device=dev)
