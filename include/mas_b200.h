@@ -203,6 +203,26 @@ int mas_vq_backward(const float* g_zq, const float* g_loss, const float* z, cons
 /* get_codebook_entry gather (modules.py:519-528): out[r] = E[idx[r]]. */
 int mas_vq_gather(const float* E, const int64_t* idx, int64_t R, int K, int D, float* out, void* stream);
 
+/* ---- tier 2: token transformer (models/transformer.py) ---------------------------------------------------------
+ * LayerNorm over the last dimension of x [R,H] (+ optional fused residual add: y = LN(x) + residual, the sandwich-LN
+ * pattern of transformer.py:183-208); tanh-GELU (transformer.py:11-14); causal softmax over [mats, rows, cols] score
+ * matrices (row i sees columns 0..i+cols-rows; transformer.py:57-71,90); fused token + position embedding sum written
+ * into rows [off, off+seg) of each length-`total` sequence (transformer.py:350-364). Linear layers / attention
+ * contractions go through mas_gemm_rows_packed / mas_gemm / mas_conv1x1_wgrad. */
+int mas_layernorm_forward(const float* x, const float* gamma, const float* beta, const float* residual, float* y,
+                          float* mean, float* rstd, int64_t R, int H, float eps, void* stream);
+size_t mas_layernorm_ws_bytes(int64_t R, int H);
+int mas_layernorm_backward(const float* dy, const float* x, const float* mean, const float* rstd,
+                           const float* gamma, float* dx, float* dgamma, float* dbeta, int64_t R, int H, void* ws,
+                           size_t ws_bytes, void* stream);
+int mas_gelu_forward(const float* x, float* y, int64_t n, void* stream);
+int mas_gelu_backward(const float* dy, const float* x, float* dx, int64_t n, void* stream);
+int mas_softmax_causal_forward(const float* s, float* p, int64_t mats, int rows, int cols, void* stream);
+int mas_embed3_forward(const float* t0, const int64_t* id0, const float* t1, const int64_t* id1, const float* t2,
+                       const int64_t* id2, float* out, int64_t R, int H, int seg, int total, int off, void* stream);
+int mas_embed3_backward(const float* dout, const int64_t* id0, float* d0, const int64_t* id1, float* d1,
+                        const int64_t* id2, float* d2, int64_t R, int H, int seg, int total, int off, void* stream);
+
 /* ---- weighted BCE-with-logits (VQ-SEG loss, losses/loss_seg.py:15-22) — "next" row ------------------
  * logits/target: strided [N,H,W,C] views; pos_weight [C]; loss_out = mean over all elements. grad may be NULL. */
 int mas_bce_logits(const float* logits, mas_tensor4 ls, const float* target, mas_tensor4 ts,

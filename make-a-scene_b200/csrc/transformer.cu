@@ -1,0 +1,223 @@
+// Tier-2 token transformer (reference models/transformer.py): LayerNorm (+fused residual add, the sandwich-LN
+// pattern of transformer.py:176-210), tanh-GELU (transformer.py:11-14), causal softmax (transformer.py:57-71,90 — the
+// PB-relax shift is softmax-invariant and the -10000 fill underflows to exactly 0 in fp32, so this is plain causal
+// softmax), fused token + row/column position embedding gather (transformer.py:329-364).  Linear layers and the
+// attention contractions reuse the GEMM kernels (contract_tc.cu / contract_simt.cu).  fp32 throughout.
+#include "mas_common.cuh"
+
+namespace mas {
+
+// ---------------------------------------------------------------------------------------------------- LayerNorm (warp per row)
+__global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     const float* __restrict__ res, float* __restrict__ y, float* __restrict__ mean,
+                                     float* __restrict__ rstd, int64_t R, int H, float eps) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= R) return;
+  const int lane = threadIdx.x & 31;
+  const float* xr = x + row * H;
+  float s = 0.f;
+  for (int c = lane; c < H; c += 32) s += xr[c];
+  const float m = warp_sum(s) / (float)H;
+  float q = 0.f;
+  for (int c = lane; c < H; c += 32) {
+    float d = xr[c] - m;
+    q = fmaf(d, d, q);
+  }
+  const float rs = rsqrtf(warp_sum(q) / (float)H + eps);
+  for (int c = lane; c < H; c += 32) {
+    float o = (xr[c] - m) * rs * gamma[c] + beta[c];
+    if (res) o += res[row * H + c];
+    y[row * H + c] = o;
+  }
+  if (lane == 0) {
+    mean[row] = m;
+    rstd[row] = rs;
+  }
+}
+
+__global__ void layernorm_bwd_dx_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+                                        const float* __restrict__ rstd, const float* __restrict__ gamma, float* __restrict__ dx,
+                                        int64_t R, int H) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= R) return;
+  const int lane = threadIdx.x & 31;
+  const float m = mean[row], rs = rstd[row];
+  const float* xr = x + row * H;
+  const float* dr = dy + row * H;
+  float a = 0.f, b = 0.f;
+  for (int c = lane; c < H; c += 32) {
+    float g = dr[c] * gamma[c], xh = (xr[c] - m) * rs;
+    a = fmaf(g, xh, a);
+    b += g;
+  }
+  a = warp_sum(a) / (float)H;
+  b = warp_sum(b) / (float)H;
+  for (int c = lane; c < H; c += 32) {
+    float g = dr[c] * gamma[c], xh = (xr[c] - m) * rs;
+    dx[row * H + c] = rs * (g - b - xh * a);
+  }
+}
+
+// column sums for dgamma / dbeta: block (32,8) per 32-column tile and row chunk; deterministic two-stage
+constexpr int LN_ROWS = 1024;
+__global__ void layernorm_bwd_param_partial(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+                                            const float* __restrict__ rstd, int64_t R, int H, double* __restrict__ part) {
+  __shared__ double sh[8][32][2];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.y * LN_ROWS, r1 = min(R, r0 + LN_ROWS);
+  double a = 0, b = 0;
+  if (c < H)
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
+      float d = dy[r * H + c];
+      a += (double)d * ((x[r * H + c] - mean[r]) * rstd[r]);
+      b += d;
+    }
+  sh[threadIdx.y][threadIdx.x][0] = a;
+  sh[threadIdx.y][threadIdx.x][1] = b;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < H) {
+    for (int k = 1; k < 8; ++k) {
+      a += sh[k][threadIdx.x][0];
+      b += sh[k][threadIdx.x][1];
+    }
+    part[((size_t)blockIdx.y * H + c) * 2] = a;
+    part[((size_t)blockIdx.y * H + c) * 2 + 1] = b;
+  }
+}
+__global__ void layernorm_bwd_param_final(const double* __restrict__ part, int chunks, int H, float* __restrict__ dgamma,
+                                          float* __restrict__ dbeta) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= H) return;
+  double a = 0, b = 0;
+  for (int k = 0; k < chunks; ++k) {
+    a += part[((size_t)k * H + c) * 2];
+    b += part[((size_t)k * H + c) * 2 + 1];
+  }
+  dgamma[c] = (float)a;
+  dbeta[c] = (float)b;
+}
+
+// ---------------------------------------------------------------------------------------------------- GELU (tanh form)
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + tanhf(0.7978845608028654f * x * (1.0f + 0.044715f * x * x))); }
+__global__ void gelu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] = gelu_f(x[i]);
+}
+__global__ void gelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dx, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = x[i];
+    float u = 0.7978845608028654f * v * (1.0f + 0.044715f * v * v);
+    float t = tanhf(u);
+    float du = 0.7978845608028654f * (1.0f + 3.0f * 0.044715f * v * v);
+    dx[i] = dy[i] * (0.5f * (1.0f + t) + 0.5f * v * (1.0f - t * t) * du);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------- causal softmax (warp per row)
+__global__ void softmax_causal_kernel(const float* __restrict__ s, float* __restrict__ p, int64_t total_rows, int rows, int cols) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= total_rows) return;
+  const int lane = threadIdx.x & 31;
+  const int i = (int)(row % rows), lim = i + (cols - rows);  // columns 0..lim are visible
+  const float* sr = s + row * cols;
+  float* pr = p + row * cols;
+  float mx = -INFINITY;
+  for (int c = lane; c <= lim; c += 32) mx = fmaxf(mx, sr[c]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int c = lane; c <= lim; c += 32) sum += expf(sr[c] - mx);
+  const float inv = 1.0f / warp_sum(sum);
+  for (int c = lane; c < cols; c += 32) pr[c] = c <= lim ? expf(sr[c] - mx) * inv : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------------- embeddings
+// out[(r/seg)*total + off + r%seg][:] = T0[id0[r]] + T1[id1[r % seg or r]] + T2[...]; ids are int64; a table pointer may be null
+__global__ void embed3_fwd_kernel(const float* __restrict__ t0, const int64_t* __restrict__ id0, const float* __restrict__ t1,
+                                  const int64_t* __restrict__ id1, const float* __restrict__ t2, const int64_t* __restrict__ id2,
+                                  float* __restrict__ out, int64_t R, int H, int seg, int total, int off) {
+  const int64_t r = blockIdx.x;
+  if (r >= R) return;
+  const int64_t orow = (r / seg) * total + off + r % seg;
+  const float* a = t0 + id0[r] * H;
+  const float* b = t1 ? t1 + id1[r % seg] * H : nullptr;
+  const float* c = t2 ? t2 + id2[r % seg] * H : nullptr;
+  for (int h = threadIdx.x; h < H; h += blockDim.x) {
+    float v = a[h];
+    if (b) v += b[h];
+    if (c) v += c[h];
+    out[orow * H + h] = v;
+  }
+}
+__global__ void embed3_bwd_kernel(const float* __restrict__ dout, const int64_t* __restrict__ id0, float* __restrict__ d0,
+                                  const int64_t* __restrict__ id1, float* __restrict__ d1, const int64_t* __restrict__ id2,
+                                  float* __restrict__ d2, int64_t R, int H, int seg, int total, int off) {
+  const int64_t r = blockIdx.x;
+  if (r >= R) return;
+  const int64_t orow = (r / seg) * total + off + r % seg;
+  for (int h = threadIdx.x; h < H; h += blockDim.x) {
+    const float g = dout[orow * H + h];
+    atomicAdd(d0 + id0[r] * H + h, g);
+    if (d1) atomicAdd(d1 + id1[r % seg] * H + h, g);
+    if (d2) atomicAdd(d2 + id2[r % seg] * H + h, g);
+  }
+}
+
+static inline int ew_grid2(int64_t n) {
+  int64_t b = cdiv(n, 256);
+  return (int)(b < 148 * 16 ? (b < 1 ? 1 : b) : 148 * 16);
+}
+
+}  // namespace mas
+
+using namespace mas;
+
+extern "C" {
+
+int mas_layernorm_forward(const float* x, const float* gamma, const float* beta, const float* residual, float* y, float* mean,
+                          float* rstd, int64_t R, int H, float eps, void* stream) {
+  MAS_REQUIRE(x && gamma && beta && y && mean && rstd && R > 0 && H > 0, "layernorm_forward: bad arguments");
+  layernorm_fwd_kernel<<<(unsigned)cdiv(R, 8), 256, 0, S(stream)>>>(x, gamma, beta, residual, y, mean, rstd, R, H, eps);
+  return launched("layernorm_fwd");
+}
+size_t mas_layernorm_ws_bytes(int64_t R, int H) { return (size_t)cdiv(R, LN_ROWS) * H * 2 * sizeof(double) + 64; }
+int mas_layernorm_backward(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, float* dx,
+                           float* dgamma, float* dbeta, int64_t R, int H, void* ws, size_t ws_bytes, void* stream) {
+  MAS_REQUIRE(dy && x && mean && rstd && gamma && dx && R > 0 && H > 0, "layernorm_backward: bad arguments");
+  if (ws_bytes < mas_layernorm_ws_bytes(R, H)) return fail(MAS_ERR_WORKSPACE, "layernorm_backward: workspace too small");
+  layernorm_bwd_dx_kernel<<<(unsigned)cdiv(R, 8), 256, 0, S(stream)>>>(dy, x, mean, rstd, gamma, dx, R, H);
+  if (int e = launched("layernorm_bwd_dx")) return e;
+  if (dgamma && dbeta) {
+    const int chunks = (int)cdiv(R, LN_ROWS);
+    layernorm_bwd_param_partial<<<dim3((unsigned)cdiv(H, 32), chunks), dim3(32, 8), 0, S(stream)>>>(dy, x, mean, rstd, R, H, (double*)ws);
+    if (int e = launched("layernorm_bwd_param_partial")) return e;
+    layernorm_bwd_param_final<<<(int)cdiv(H, 128), 128, 0, S(stream)>>>((const double*)ws, chunks, H, dgamma, dbeta);
+    return launched("layernorm_bwd_param_final");
+  }
+  return MAS_OK;
+}
+int mas_gelu_forward(const float* x, float* y, int64_t n, void* stream) {
+  gelu_fwd_kernel<<<ew_grid2(n), 256, 0, S(stream)>>>(x, y, n);
+  return launched("gelu_fwd");
+}
+int mas_gelu_backward(const float* dy, const float* x, float* dx, int64_t n, void* stream) {
+  gelu_bwd_kernel<<<ew_grid2(n), 256, 0, S(stream)>>>(dy, x, dx, n);
+  return launched("gelu_bwd");
+}
+int mas_softmax_causal_forward(const float* s, float* p, int64_t mats, int rows, int cols, void* stream) {
+  MAS_REQUIRE(mats > 0 && rows > 0 && cols >= rows, "softmax_causal: bad shape");
+  softmax_causal_kernel<<<(unsigned)cdiv(mats * rows, 8), 256, 0, S(stream)>>>(s, p, mats * rows, rows, cols);
+  return launched("softmax_causal");
+}
+int mas_embed3_forward(const float* t0, const int64_t* id0, const float* t1, const int64_t* id1, const float* t2, const int64_t* id2,
+                       float* out, int64_t R, int H, int seg, int total, int off, void* stream) {
+  MAS_REQUIRE(t0 && id0 && out && R > 0 && H > 0 && seg > 0, "embed3_forward: bad arguments");
+  embed3_fwd_kernel<<<(unsigned)R, 128, 0, S(stream)>>>(t0, id0, t1, id1, t2, id2, out, R, H, seg, total, off);
+  return launched("embed3_fwd");
+}
+int mas_embed3_backward(const float* dout, const int64_t* id0, float* d0, const int64_t* id1, float* d1, const int64_t* id2, float* d2,
+                        int64_t R, int H, int seg, int total, int off, void* stream) {
+  MAS_REQUIRE(dout && id0 && d0 && R > 0 && H > 0 && seg > 0, "embed3_backward: bad arguments");
+  embed3_bwd_kernel<<<(unsigned)R, 128, 0, S(stream)>>>(dout, id0, d0, id1, d1, id2, d2, R, H, seg, total, off);
+  return launched("embed3_bwd");
+}
+
+}  // extern "C"

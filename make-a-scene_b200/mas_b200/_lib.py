@@ -75,6 +75,14 @@ _SPEC = {
     "mas_vq_forward": (_I, [_P, _P, _L, _I, _I, _F, _P, _P, _P, _P, _Z, _P]),
     "mas_vq_backward": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _F, _P, _P, _P]),
     "mas_vq_gather": (_I, [_P, _P, _L, _I, _I, _P, _P]),
+    "mas_layernorm_forward": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _F, _P]),
+    "mas_layernorm_ws_bytes": (_Z, [_L, _I]),
+    "mas_layernorm_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P, _Z, _P]),
+    "mas_gelu_forward": (_I, [_P, _P, _L, _P]),
+    "mas_gelu_backward": (_I, [_P, _P, _P, _L, _P]),
+    "mas_softmax_causal_forward": (_I, [_P, _P, _L, _I, _I, _P]),
+    "mas_embed3_forward": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P]),
+    "mas_embed3_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P]),
     "mas_bce_ws_bytes": (_Z, [_T]),
     "mas_bce_logits": (_I, [_P, _T, _P, _T, _P, _P, _P, _T, _F, _P, _Z, _P]),
 }

@@ -663,3 +663,169 @@ class BCELogitsFn(torch.autograd.Function):
     def backward(ctx, g):
         (grad,) = ctx.saved_tensors
         return grad * g, None, None
+
+
+# ------------------------------------------------------------------------------------------------ tier 2: token transformer
+class LayerNormFn(torch.autograd.Function):
+    """nn.LayerNorm(hidden, eps) over the last dim, optionally fused with a residual add: LN(x) + residual."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, eps):
+        _need_cuda(x)
+        x = x.contiguous()
+        H = x.shape[-1]
+        R = x.numel() // H
+        y = torch.empty_like(x)
+        mean = torch.empty(R, dtype=torch.float32, device=x.device)
+        rstd = torch.empty_like(mean)
+        res = residual.contiguous() if residual is not None else None
+        L.call("mas_layernorm_forward", x, weight, bias, res, y, mean, rstd, R, H, float(eps))
+        ctx.save_for_backward(x, weight, mean, rstd)
+        ctx.has_res = residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, mean, rstd = ctx.saved_tensors
+        dy = dy.contiguous()
+        H = x.shape[-1]
+        R = x.numel() // H
+        dx = torch.empty_like(x)
+        dg = torch.empty_like(weight)
+        db = torch.empty_like(weight)
+        ws = L.workspace(L.query("mas_layernorm_ws_bytes", R, H), x.device)
+        L.call("mas_layernorm_backward", dy, x, mean, rstd, weight, dx, dg, db, R, H, ws, ws.numel())
+        return dx, dg, db, (dy if ctx.has_res else None), None
+
+
+class GeluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        _need_cuda(x)
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        L.call("mas_gelu_forward", x, y, x.numel())
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dx = torch.empty_like(x)
+        L.call("mas_gelu_backward", dy.contiguous(), x, dx, x.numel())
+        return dx
+
+
+class LinearFn(torch.autograd.Function):
+    """nn.Linear on the last dim: rows GEMM on the tensor path when out%128==0 and in%32==0, else fp32 SIMT."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        _need_cuda(x)
+        x = x.contiguous()
+        K, N = x.shape[-1], weight.shape[0]
+        R = x.numel() // K
+        y = torch.empty(x.shape[:-1] + (N,), dtype=torch.float32, device=x.device)
+        gemm_w(x, K, weight, y, N, R, bias=bias)
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        K, N = x.shape[-1], weight.shape[0]
+        R = x.numel() // K
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            gemm_w(dy, N, weight, dx, K, R, transpose=True)
+        dw, db = conv1x1_wgrad_raw(x, dy, R, K, N, ctx.has_bias)
+        return dx, dw.view(N, K), db
+
+
+class CausalAttentionFn(torch.autograd.Function):
+    """softmax_causal((q / sqrt(hd)) k^T) v per (batch, head) from the fused qkv activation [B,S,3H]
+    (transformer.py:77-103; head h owns columns h*hd..(h+1)*hd of each third)."""
+
+    @staticmethod
+    def forward(ctx, qkv, heads):
+        _need_cuda(qkv)
+        qkv = qkv.contiguous()
+        B, S_, H3 = qkv.shape
+        H = H3 // 3
+        hd = H // heads
+        alpha = 1.0 / float(hd) ** 0.5
+        P = torch.empty((B, heads, S_, S_), dtype=torch.float32, device=qkv.device)
+        ctxv = torch.empty((B, S_, H), dtype=torch.float32, device=qkv.device)
+        for b in range(B):
+            base = b * S_ * H3
+            gemm((qkv, base), (qkv, base + H), (P, b * heads * S_ * S_), S_, S_, hd, batch=heads, lda=H3, ldb=H3, ldc=S_, sa=hd,
+                 sb=hd, sc=S_ * S_, tb=True, alpha=alpha)
+        L.call("mas_softmax_causal_forward", P, P, B * heads, S_, S_)
+        for b in range(B):
+            base = b * S_ * H3
+            gemm((P, b * heads * S_ * S_), (qkv, base + 2 * H), (ctxv, b * S_ * H), S_, hd, S_, batch=heads, lda=S_, ldb=H3, ldc=H,
+                 sa=S_ * S_, sb=hd, sc=hd)
+        ctx.save_for_backward(qkv, P)
+        ctx.heads = heads
+        return ctxv
+
+    @staticmethod
+    def backward(ctx, dctx):
+        qkv, P = ctx.saved_tensors
+        dctx = dctx.contiguous()
+        heads = ctx.heads
+        B, S_, H3 = qkv.shape
+        H = H3 // 3
+        hd = H // heads
+        alpha = 1.0 / float(hd) ** 0.5
+        dqkv = torch.empty_like(qkv)
+        dP = torch.empty_like(P)
+        for b in range(B):
+            base, pb, cb = b * S_ * H3, b * heads * S_ * S_, b * S_ * H
+            # dV = P^T dO ; dP = dO V^T
+            gemm((P, pb), (dctx, cb), (dqkv, base + 2 * H), S_, hd, S_, batch=heads, lda=S_, ldb=H, ldc=H3, sa=S_ * S_, sb=hd, sc=hd,
+                 ta=True)
+            gemm((dctx, cb), (qkv, base + 2 * H), (dP, pb), S_, S_, hd, batch=heads, lda=H, ldb=H3, ldc=S_, sa=hd, sb=hd,
+                 sc=S_ * S_, tb=True)
+        L.call("mas_softmax_backward", P, dP, dP, B * heads * S_, S_, alpha)     # dS (already times 1/sqrt(hd))
+        for b in range(B):
+            base, pb = b * S_ * H3, b * heads * S_ * S_
+            gemm((dP, pb), (qkv, base + H), (dqkv, base), S_, hd, S_, batch=heads, lda=S_, ldb=H3, ldc=H3, sa=S_ * S_, sb=hd, sc=hd)
+            gemm((dP, pb), (qkv, base), (dqkv, base + H), S_, hd, S_, batch=heads, lda=S_, ldb=H3, ldc=H3, sa=S_ * S_, sb=hd, sc=hd,
+                 ta=True)
+        return dqkv, None
+
+
+class EmbedFn(torch.autograd.Function):
+    """Token + (row, column | position) embedding sums for the text / segmentation / image segments, written straight
+    into the concatenated [B, total, H] sequence (transformer.py:350-364)."""
+
+    @staticmethod
+    def forward(ctx, segs, total, H, *tables):
+        # segs: list of (token_ids [B,L] int64, pos_ids_a [L] int64, pos_ids_b [L] int64 or None, offset); tables: 3 per segment
+        dev = tables[0].device
+        B = segs[0][0].shape[0]
+        out = torch.empty((B, total, H), dtype=torch.float32, device=dev)
+        for i, (ids, pa, pb, off) in enumerate(segs):
+            t0, t1, t2 = tables[3 * i:3 * i + 3]
+            Lg = ids.shape[1]
+            L.call("mas_embed3_forward", t0, ids.contiguous(), t1, pa, t2 if pb is not None else None, pb, out, B * Lg, H, Lg, total, off)
+        ctx.segs, ctx.total, ctx.H = segs, total, H
+        ctx.shapes = [t.shape for t in tables]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = dout.contiguous()
+        grads = []
+        for i, (ids, pa, pb, off) in enumerate(ctx.segs):
+            d0 = torch.zeros(ctx.shapes[3 * i], dtype=torch.float32, device=dout.device)
+            d1 = torch.zeros(ctx.shapes[3 * i + 1], dtype=torch.float32, device=dout.device)
+            d2 = torch.zeros(ctx.shapes[3 * i + 2], dtype=torch.float32, device=dout.device) if pb is not None else None
+            Lg = ids.shape[1]
+            L.call("mas_embed3_backward", dout, ids.contiguous(), d0, pa, d1, pb, d2, ids.shape[0] * Lg, ctx.H, Lg, ctx.total, off)
+            grads += [d0, d1, d2]
+        return (None, None, None) + tuple(grads)

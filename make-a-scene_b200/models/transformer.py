@@ -1,0 +1,183 @@
+"""Drop-in for reference models/transformer.py (MakeAScene token transformer, tier 2) on the sm_100a kernels.
+
+Same class names, constructor signatures, attribute names and state_dict keys (including the `transformer.mask`
+buffer). Supported configuration = the reference's defaults: cogview_pb_relax=True (a softmax-invariant shift),
+sandwich LayerNorm, no prescale, no rudalle_relax, dropout 0, no KV cache (the reference's cache path is broken:
+transformer.py:73 vs :181). Anything else raises — there is no fallback path.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from mas_b200 import ops
+
+
+def gelu(x):
+    """OpenAI tanh-GELU, transformer.py:11-14."""
+    return ops.GeluFn.apply(x)
+
+
+class LayerNorm(nn.LayerNorm):
+    def forward(self, x, residual=None):
+        return ops.LayerNormFn.apply(x, self.weight, self.bias, residual, self.eps)
+
+
+class Linear(nn.Linear):
+    def forward(self, x):
+        return ops.LinearFn.apply(x, self.weight, self.bias)
+
+
+class SelfAttention(nn.Module):
+    def __init__(self, hidden_dim, num_attn_heads, attn_dropout_prob, out_dropout_prob, cogview_pb_relax=True, rudalle_relax=False):
+        super().__init__()
+        self.hidden_dim = hidden_dim
+        self.num_attn_heads = num_attn_heads
+        self.d = math.sqrt(self.hidden_dim // self.num_attn_heads)
+        self.qkv = Linear(hidden_dim, 3 * hidden_dim)
+        self.attn_drop = nn.Dropout(attn_dropout_prob)
+        self.out_proj = Linear(hidden_dim, hidden_dim)
+        self.out_drop = nn.Dropout(out_dropout_prob)
+        self.cogview_pb_relax = cogview_pb_relax
+        self.rudalle_relax = rudalle_relax
+        if rudalle_relax or attn_dropout_prob or out_dropout_prob:
+            raise NotImplementedError("rudalle_relax / dropout>0 have no kernel (reference defaults are off)")
+
+    def forward(self, x, mask=None, use_cache=False, cache=None):
+        if use_cache or cache is not None:
+            raise NotImplementedError("KV cache: the reference path is broken (transformer.py:73 vs :181); no kernel")
+        ctx = ops.CausalAttentionFn.apply(self.qkv(x), self.num_attn_heads)
+        return self.out_proj(ctx), None
+
+
+class MLP(nn.Module):
+    def __init__(self, hidden_dim, dropout_prob, rudalle_relax=False):
+        super().__init__()
+        self.lin1 = Linear(hidden_dim, 4 * hidden_dim)
+        self.lin2 = Linear(4 * hidden_dim, hidden_dim)
+        self.dropout = nn.Dropout(dropout_prob)
+        self.rudalle_relax = rudalle_relax
+        if rudalle_relax or dropout_prob:
+            raise NotImplementedError("rudalle_relax / dropout>0 have no kernel")
+
+    def forward(self, x):
+        return self.lin2(gelu(self.lin1(x)))
+
+
+class TransformerLayer(nn.Module):
+    def __init__(self, hidden_dim, num_attn_heads, attn_dropout_prop, out_dropout_prob, cogview_pb_relax=True,
+                 cogview_sandwich_layernorm=True, cogview_layernorm_prescale=False, rudalle_relax=False):
+        super().__init__()
+        self.cogview_pb_relax = cogview_pb_relax
+        self.cogview_sandwich_layernorm = cogview_sandwich_layernorm
+        self.cogview_layernorm_prescale = cogview_layernorm_prescale
+        self.rudalle_relax = rudalle_relax
+        if cogview_layernorm_prescale or rudalle_relax:
+            raise NotImplementedError("layernorm prescale / rudalle_relax have no kernel")
+        self.ln_in = LayerNorm(hidden_dim, eps=1e-5)
+        self.ln_out = LayerNorm(hidden_dim, eps=1e-5)
+        if cogview_sandwich_layernorm:
+            self.first_ln_sandwich = LayerNorm(hidden_dim, eps=1e-5)
+            self.second_ln_sandwich = LayerNorm(hidden_dim, eps=1e-5)
+        self.attn = SelfAttention(hidden_dim=hidden_dim, num_attn_heads=num_attn_heads, attn_dropout_prob=attn_dropout_prop,
+                                  out_dropout_prob=out_dropout_prob, cogview_pb_relax=cogview_pb_relax, rudalle_relax=rudalle_relax)
+        self.mlp = MLP(hidden_dim=hidden_dim, dropout_prob=out_dropout_prob, rudalle_relax=rudalle_relax)
+
+    def forward(self, x, mask=None, cache=None, use_cache=False, mlp_cache=False):
+        if use_cache or cache is not None:
+            raise NotImplementedError("KV cache has no kernel")
+        attn_out, _ = self.attn(self.ln_in(x))
+        if self.cogview_sandwich_layernorm:
+            x = self.first_ln_sandwich(attn_out, residual=x)      # x + LN(attn_out), fused
+        else:
+            x = x + attn_out
+        mlp_out = self.mlp(self.ln_out(x))
+        if self.cogview_sandwich_layernorm:
+            x = self.second_ln_sandwich(mlp_out, residual=x)
+        else:
+            x = x + mlp_out
+        return x, None
+
+
+class Transformer(nn.Module):
+    def __init__(self, num_layers, hidden_dim, num_attn_heads, image_tokens_per_dim, seg_tokens_per_dim, text_length,
+                 attn_dropout_prop=0, out_dropout_prob=0, cogview_pb_relax=True, cogview_sandwich_layernorm=True,
+                 cogview_layernorm_prescale=False, rudalle_relax=False):
+        super().__init__()
+        self.num_layers = num_layers
+        self.cogview_pb_relax = cogview_pb_relax
+        self.rudalle_relax = rudalle_relax
+        self.layers = nn.ModuleList([
+            TransformerLayer(hidden_dim, num_attn_heads, attn_dropout_prop, out_dropout_prob, cogview_pb_relax,
+                             cogview_sandwich_layernorm, cogview_layernorm_prescale, rudalle_relax) for _ in range(num_layers)])
+        self.register_buffer("mask", self._create_mask(text_length, seg_tokens_per_dim, image_tokens_per_dim))
+        self.final_ln = LayerNorm(hidden_dim, eps=1e-5)
+
+    def _create_mask(self, text_length, seg_tokens_per_dim, image_tokens_per_dim):
+        size = text_length + seg_tokens_per_dim ** 2 + image_tokens_per_dim ** 2
+        return torch.tril(torch.ones(size, size, dtype=torch.float32))
+
+    def forward(self, x, attn_mask=None, cache=None, use_cache=None):
+        # attn_mask * self.mask is plain causal for every mask MakeAScene builds (transformer.py:262-263, 366-370):
+        # the kernels implement the causal mask directly.
+        if use_cache or cache:
+            raise NotImplementedError("KV cache has no kernel")
+        for layer in self.layers:
+            x, _ = layer(x)
+        return self.final_ln(x), {}
+
+
+class MakeAScene(nn.Module):
+    def __init__(self, num_layers, hidden_dim, num_attn_heads, image_vocab_size, seg_vocab_size, text_vocab_size,
+                 image_tokens_per_dim, seg_tokens_per_dim, text_length):
+        super().__init__()
+        self.image_tokens_per_dim = image_tokens_per_dim
+        self.seg_tokens_per_dim = seg_tokens_per_dim
+        self.image_length = image_tokens_per_dim ** 2
+        self.seg_length = seg_tokens_per_dim ** 2
+        self.text_length = text_length
+        self.total_length = self.text_length + self.seg_length + self.image_length
+        self.text_vocab_size = text_vocab_size
+        self.hidden_dim = hidden_dim
+        self.transformer = Transformer(num_layers, hidden_dim, num_attn_heads, image_tokens_per_dim, seg_tokens_per_dim, text_length)
+        self.image_token_embedding = nn.Embedding(image_vocab_size, hidden_dim)
+        self.seg_token_embedding = nn.Embedding(seg_vocab_size, hidden_dim)
+        self.text_token_embedding = nn.Embedding(text_vocab_size, hidden_dim)
+        self.text_pos_embeddings = torch.nn.Embedding(text_length, hidden_dim)
+        self.seg_row_embeddings = torch.nn.Embedding(seg_tokens_per_dim, hidden_dim)
+        self.seg_col_embeddings = torch.nn.Embedding(seg_tokens_per_dim, hidden_dim)
+        self.image_row_embeddings = torch.nn.Embedding(image_tokens_per_dim, hidden_dim)
+        self.image_col_embeddings = torch.nn.Embedding(image_tokens_per_dim, hidden_dim)
+        for m in (self.text_pos_embeddings, self.seg_row_embeddings, self.seg_col_embeddings, self.image_row_embeddings,
+                  self.image_col_embeddings):
+            self._init_weights(m)
+        self.to_logits = torch.nn.Sequential(LayerNorm(hidden_dim), Linear(hidden_dim, image_vocab_size))
+
+    def _init_weights(self, module):
+        if isinstance(module, (nn.Linear, nn.Embedding)):
+            module.weight.data.normal_(mean=0.0, std=0.02)
+            if isinstance(module, nn.Linear) and module.bias is not None:
+                module.bias.data.zero_()
+        elif isinstance(module, nn.LayerNorm):
+            module.bias.data.zero_()
+            module.weight.data.fill_(1.0)
+
+    def forward(self, text_tokens, seg_tokens, img_tokens):
+        dev = text_tokens.device
+        text_range = torch.arange(self.text_length, device=dev) + (self.text_vocab_size - self.text_length)
+        text_tokens = torch.where(text_tokens == 0, text_range, text_tokens)      # pad-id trick, transformer.py:350-353
+        ar = lambda n: torch.arange(n, dtype=torch.long, device=dev)
+        sp, ip = self.seg_tokens_per_dim, self.image_tokens_per_dim
+        segs = [(text_tokens, ar(text_tokens.shape[1]), None, 0),
+                (seg_tokens, ar(seg_tokens.shape[1]) // sp, ar(seg_tokens.shape[1]) % sp, text_tokens.shape[1])]
+        tables = [self.text_token_embedding.weight, self.text_pos_embeddings.weight, self.text_pos_embeddings.weight,
+                  self.seg_token_embedding.weight, self.seg_row_embeddings.weight, self.seg_col_embeddings.weight]
+        total = text_tokens.shape[1] + seg_tokens.shape[1]
+        if img_tokens is not None:
+            segs.append((img_tokens, ar(img_tokens.shape[1]) // ip, ar(img_tokens.shape[1]) % ip, total))
+            tables += [self.image_token_embedding.weight, self.image_row_embeddings.weight, self.image_col_embeddings.weight]
+            total += img_tokens.shape[1]
+        emb = ops.EmbedFn.apply(segs, total, self.hidden_dim, *tables)
+        out, _ = self.transformer(emb)
+        logits = self.to_logits[1](self.to_logits[0](out))
+        return logits[:, -self.image_length - 1:-1, :]

@@ -27,9 +27,10 @@ def load_reference():
         import models.modules as ref_modules  # noqa
         import models.vqvae as ref_vqvae  # noqa
         import losses.loss_seg as ref_loss_seg  # noqa
+        import models.transformer as ref_transformer  # noqa
     finally:
         sys.path.remove(REF)
-    out = (ref_models, ref_modules, ref_vqvae, ref_loss_seg)
+    out = (ref_models, ref_modules, ref_vqvae, ref_loss_seg, ref_transformer)
     for k in list(sys.modules):
         if k == "models" or k.startswith("models.") or k == "losses" or k.startswith("losses."):
             sys.modules["_ref_" + k] = sys.modules.pop(k)
@@ -46,7 +47,7 @@ IMG = dict(z_channels=256, in_channels=3, out_channels=3, channels=[128, 128, 12
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
-    ref_models, M, V, L = load_reference()
+    ref_models, M, V, L, T = load_reference()
 
     # ---- G1: tiny VQBASE fwd+bwd, VQ active, train mode --------------------------------------
     torch.manual_seed(0)
@@ -180,6 +181,29 @@ def main():
                     grads_small={k: named[k].grad.clone() for k in sel if named[k].grad.numel() <= 40000}),
                os.path.join(OUT, "vqbase_img_64.pt"))
     print("img 64 done: loss", float(loss), "n_params", sum(p.numel() for p in big.parameters()))
+
+    # ---- G6: tier-2 token transformer (tiny; CPU, non-cached forward + cross-entropy backward) -------------------
+    for tag, cfg in (("tiny", dict(num_layers=2, hidden_dim=64, num_attn_heads=4, image_vocab_size=96, seg_vocab_size=48,
+                                   text_vocab_size=80 + 12, image_tokens_per_dim=4, seg_tokens_per_dim=3, text_length=12)),
+                     ("wide", dict(num_layers=1, hidden_dim=256, num_attn_heads=4, image_vocab_size=128, seg_vocab_size=32,
+                                   text_vocab_size=64 + 8, image_tokens_per_dim=4, seg_tokens_per_dim=2, text_length=8))):
+        torch.manual_seed(3)
+        tm = T.MakeAScene(**cfg)
+        tm.device = torch.device("cpu")
+        g = torch.Generator().manual_seed(17)
+        tt = torch.randint(0, cfg["text_vocab_size"] - cfg["text_length"], (2, cfg["text_length"]), generator=g)
+        tt[0, -3:] = 0                                    # padded text positions exercise the pad-id trick (transformer.py:350-353)
+        st = torch.randint(0, cfg["seg_vocab_size"], (2, cfg["seg_tokens_per_dim"] ** 2), generator=g)
+        it = torch.randint(0, cfg["image_vocab_size"], (2, cfg["image_tokens_per_dim"] ** 2), generator=g)
+        logits = tm(tt, st, it)
+        loss = torch.nn.functional.cross_entropy(logits.reshape(-1, logits.shape[-1]), it.reshape(-1))
+        loss.backward()
+        torch.save(dict(cfg=cfg, state_dict={k: v.clone() for k, v in tm.state_dict().items()}, text=tt, seg=st, img=it,
+                        logits=logits.detach(), loss=loss.detach(),
+                        grads={k: p.grad.clone() for k, p in tm.named_parameters() if p.grad is not None and (tag == "tiny" or p.numel() <= 70000)},
+                        grad_norms={k: float(p.grad.double().norm()) for k, p in tm.named_parameters() if p.grad is not None}),
+                   os.path.join(OUT, f"transformer_{tag}.pt"))
+        print("transformer", tag, "loss", float(loss), "params", sum(p.numel() for p in tm.parameters()))
 
     # ---- G5: seg loss ---------------------------------------------------------------------------
     g = torch.Generator().manual_seed(5)

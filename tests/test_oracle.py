@@ -93,3 +93,18 @@ def test_seg_loss():
     assert abs(float(loss) - float(g["loss"])) < 1e-6
     loss.backward()
     assert rel_err(pred.grad, g["grad"]) < 1e-6
+
+
+def test_transformer_oracle_matches_reference():
+    from oracle import transformer_oracle as T
+    for tag in ("tiny", "wide"):
+        g = _load(f"transformer_{tag}.pt")
+        sd = {k: v.clone().requires_grad_(k in g["grad_norms"]) for k, v in g["state_dict"].items()}
+        logits = T.make_a_scene_forward(sd, g["cfg"], g["text"], g["seg"], g["img"])
+        assert logits.shape == g["logits"].shape
+        assert rel_err(logits, g["logits"]) < 1e-5, tag
+        loss = torch.nn.functional.cross_entropy(logits.reshape(-1, logits.shape[-1]), g["img"].reshape(-1))
+        assert abs(float(loss) - float(g["loss"])) < 1e-5
+        loss.backward()
+        for k, gv in g["grads"].items():
+            assert rel_err(sd[k].grad, gv) < 2e-4, (tag, k)
