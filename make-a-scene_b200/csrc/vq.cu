@@ -14,7 +14,8 @@ constexpr int VQ_BM = 64;    // latent rows per CTA
 constexpr int VQ_BN = 128;   // codes per tile
 constexpr int VQ_BK = 32;    // dims per smem stage
 constexpr int VQ_LDE = VQ_BK + 4;
-constexpr int VQ_THREADS = 256;
+constexpr int VQ_THREADS = 256;  // 16 (codes) x 16 (row groups); each thread owns a 4 x 8 register tile
+constexpr int VQ_TM = 4;       // (8 x 8 tiles with 128 threads measured slower: 168 registers, 12 warps/SM)
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
@@ -40,22 +41,25 @@ __global__ void vq_code_norms(const float* __restrict__ E, int K, int D, float* 
 
 __global__ void __launch_bounds__(VQ_THREADS, 2)
 vq_forward_kernel(const float* __restrict__ z, const float* __restrict__ E, const float* __restrict__ ee, int64_t R, int K, int D,
-                  int64_t* __restrict__ idx_out, float* __restrict__ zq_out, double* __restrict__ loss_part) {
+                  float* __restrict__ best_val /*[R][splits]*/, int* __restrict__ best_idx /*[R][splits]*/) {
   extern __shared__ __align__(16) float smem[];
   const int LDZ = D + 4;
   float* Zs = smem;                             // [VQ_BM][LDZ]
   float* Es = Zs + VQ_BM * LDZ;                 // [2][VQ_BN][VQ_LDE]
   float* zz_s = Es + 2 * VQ_BN * VQ_LDE;        // [VQ_BM]
   int* idx_s = reinterpret_cast<int*>(zz_s + VQ_BM);  // [VQ_BM]
-  __shared__ double red_s[VQ_THREADS / 32];
-
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int tx = t & 15, ty = t >> 4;
   const int64_t row0 = (int64_t)blockIdx.x * VQ_BM;
-  const int nkc = D / VQ_BK, ntile = (K + VQ_BN - 1) / VQ_BN, nstage = nkc * ntile;
+  // blockIdx.y selects a contiguous slice of the code tiles: two CTAs per SM (one per slice) double the resident
+  // warps of this FFMA-bound kernel; the slices are merged (smaller distance, then smaller index) by vq_merge_kernel
+  const int nkc = D / VQ_BK, ntile_all = (K + VQ_BN - 1) / VQ_BN;
+  const int tiles_per = (ntile_all + gridDim.y - 1) / gridDim.y;
+  const int tile_lo = blockIdx.y * tiles_per, tile_hi = min(ntile_all, tile_lo + tiles_per);
+  const int ntile = max(0, tile_hi - tile_lo), nstage = nkc * ntile;
 
   auto load_stage = [&](int s) {
-    const int ct = s / nkc, kc = s % nkc;
+    const int ct = tile_lo + s / nkc, kc = s % nkc;
     float* dst = Es + (s & 1) * VQ_BN * VQ_LDE;
 #pragma unroll
     for (int i = 0; i < (VQ_BN * VQ_BK / 4) / VQ_THREADS; ++i) {
@@ -65,7 +69,7 @@ vq_forward_kernel(const float* __restrict__ z, const float* __restrict__ E, cons
     }
     cp_async_commit();
   };
-  load_stage(0);
+  if (nstage > 0) load_stage(0);
 
   // z tile -> shared (zero rows beyond R), and |z|^2 per row
   for (int f = t; f < VQ_BM * (D / 4); f += VQ_THREADS) {
@@ -75,7 +79,7 @@ vq_forward_kernel(const float* __restrict__ z, const float* __restrict__ E, cons
     *reinterpret_cast<float4*>(Zs + r * LDZ + q * 4) = v;
   }
   __syncthreads();
-  for (int r = warp * (VQ_BM / 8); r < (warp + 1) * (VQ_BM / 8); ++r) {
+  for (int r = warp * (VQ_BM / (VQ_THREADS / 32)); r < (warp + 1) * (VQ_BM / (VQ_THREADS / 32)); ++r) {
     float s = 0.f;
     for (int d = lane; d < D; d += 32) {
       float v = Zs[r * LDZ + d];
@@ -85,11 +89,11 @@ vq_forward_kernel(const float* __restrict__ z, const float* __restrict__ E, cons
     if (lane == 0) zz_s[r] = s;
   }
 
-  float acc[4][8];
-  float best[4];
-  int bidx[4];
+  float acc[VQ_TM][8];
+  float best[VQ_TM];
+  int bidx[VQ_TM];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < VQ_TM; ++i) {
     best[i] = INFINITY;
     bidx[i] = 0;
 #pragma unroll
@@ -104,18 +108,18 @@ vq_forward_kernel(const float* __restrict__ z, const float* __restrict__ E, cons
       cp_async_wait<0>();
     }
     __syncthreads();
-    const int ct = s / nkc, kc = s % nkc;
+    const int ct = tile_lo + s / nkc, kc = s % nkc;
     const float* es = Es + (s & 1) * VQ_BN * VQ_LDE;
     const float* zs = Zs + kc * VQ_BK;
 #pragma unroll
     for (int k4 = 0; k4 < VQ_BK / 4; ++k4) {
-      float4 a[4], b[8];
+      float4 a[VQ_TM], b[8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(zs + (ty * 4 + i) * LDZ + k4 * 4);
+      for (int i = 0; i < VQ_TM; ++i) a[i] = *reinterpret_cast<const float4*>(zs + (ty * VQ_TM + i) * LDZ + k4 * 4);
 #pragma unroll
       for (int j = 0; j < 8; ++j) b[j] = *reinterpret_cast<const float4*>(es + (j * 16 + tx) * VQ_LDE + k4 * 4);
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < VQ_TM; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           acc[i][j] = fmaf(a[i].x, b[j].x, acc[i][j]);
@@ -131,8 +135,8 @@ vq_forward_kernel(const float* __restrict__ z, const float* __restrict__ E, cons
         if (code < K) {
           float e2 = __ldg(ee + code);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            float d = (zz_s[ty * 4 + i] + e2) - 2.0f * acc[i][j];
+          for (int i = 0; i < VQ_TM; ++i) {
+            float d = (zz_s[ty * VQ_TM + i] + e2) - 2.0f * acc[i][j];
             if (d < best[i]) {
               best[i] = d;
               bidx[i] = code;
@@ -140,7 +144,7 @@ vq_forward_kernel(const float* __restrict__ z, const float* __restrict__ E, cons
           }
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) acc[i][j] = 0.f;
+        for (int i = 0; i < VQ_TM; ++i) acc[i][j] = 0.f;
       }
     }
     __syncthreads();  // stage buffer (s&1) is refilled by the prefetch issued in iteration s+1
@@ -148,7 +152,7 @@ vq_forward_kernel(const float* __restrict__ z, const float* __restrict__ E, cons
 
   // combine the 16 tx-lanes of each row: smaller distance wins, ties -> smaller index (first occurrence)
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < VQ_TM; ++i) {
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) {
       float ov = __shfl_xor_sync(0xffffffffu, best[i], o);
@@ -158,33 +162,46 @@ vq_forward_kernel(const float* __restrict__ z, const float* __restrict__ E, cons
         bidx[i] = oi;
       }
     }
-    if (tx == 0) idx_s[ty * 4 + i] = bidx[i];
-  }
-  __syncthreads();
-
-  // gather + straight-through value + loss partial (modules.py:506-512)
-  float ls = 0.f;
-  for (int f = t; f < VQ_BM * (D / 4); f += VQ_THREADS) {
-    int r = f / (D / 4), q = f % (D / 4);
-    if (row0 + r < R) {
-      int k = idx_s[r];
-      float4 e = __ldg(reinterpret_cast<const float4*>(E + (size_t)k * D) + q);
-      float4 zv = *reinterpret_cast<const float4*>(Zs + r * LDZ + q * 4);
-      float4 df = make_float4(e.x - zv.x, e.y - zv.y, e.z - zv.z, e.w - zv.w);
-      ls += df.x * df.x + df.y * df.y + df.z * df.z + df.w * df.w;
-      // z + (z_q - z).detach(): the forward VALUE carries these two roundings in the reference too
-      reinterpret_cast<float4*>(zq_out + (size_t)(row0 + r) * D)[q] =
-          make_float4(zv.x + df.x, zv.y + df.y, zv.z + df.z, zv.w + df.w);
+    if (tx == 0 && row0 + ty * VQ_TM + i < R) {
+      best_val[(row0 + ty * VQ_TM + i) * gridDim.y + blockIdx.y] = best[i];
+      best_idx[(row0 + ty * VQ_TM + i) * gridDim.y + blockIdx.y] = bidx[i];
     }
   }
-  for (int r = t; r < VQ_BM; r += VQ_THREADS)
-    if (row0 + r < R) idx_out[row0 + r] = (int64_t)idx_s[r];
-  float w = warp_sum(ls);
-  if (lane == 0) red_s[warp] = (double)w;
+}
+
+// merge the code slices (first index wins ties), gather + straight-through value + loss partial (modules.py:505-512)
+__global__ void __launch_bounds__(256) vq_merge_kernel(const float* __restrict__ z, const float* __restrict__ E,
+                                                       const float* __restrict__ best_val, const int* __restrict__ best_idx,
+                                                       int splits, int64_t R, int D, int64_t* __restrict__ idx_out,
+                                                       float* __restrict__ zq_out, double* __restrict__ loss_part) {
+  __shared__ double red_s[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + warp;
+  float ls = 0.f;
+  if (row < R) {
+    float bv = best_val[row * splits];
+    int bi = best_idx[row * splits];
+    for (int s = 1; s < splits; ++s) {
+      float v = best_val[row * splits + s];
+      int i = best_idx[row * splits + s];
+      if (v < bv || (v == bv && i < bi)) { bv = v; bi = i; }
+    }
+    if (lane == 0) idx_out[row] = (int64_t)bi;
+    for (int q = lane; q < (D >> 2); q += 32) {
+      const float4 e = __ldg(reinterpret_cast<const float4*>(E + (size_t)bi * D) + q);
+      const float4 zv = __ldg(reinterpret_cast<const float4*>(z + (size_t)row * D) + q);
+      const float4 df = make_float4(e.x - zv.x, e.y - zv.y, e.z - zv.z, e.w - zv.w);
+      ls += df.x * df.x + df.y * df.y + df.z * df.z + df.w * df.w;
+      // z + (z_q - z).detach(): the forward VALUE carries these two roundings in the reference too
+      reinterpret_cast<float4*>(zq_out + (size_t)row * D)[q] = make_float4(zv.x + df.x, zv.y + df.y, zv.z + df.z, zv.w + df.w);
+    }
+  }
+  ls = warp_sum(ls);
+  if (lane == 0) red_s[warp] = (double)ls;
   __syncthreads();
-  if (t == 0) {
+  if (threadIdx.x == 0) {
     double a = 0;
-    for (int k = 0; k < VQ_THREADS / 32; ++k) a += red_s[k];
+    for (int k = 0; k < 8; ++k) a += red_s[k];
     loss_part[blockIdx.x] = a;
   }
 }
@@ -246,9 +263,13 @@ using namespace mas;
 
 extern "C" {
 
+static int vq_splits(int64_t R) { return cdiv(R, VQ_BM) < 148 * 2 ? 2 : 1; }
+static size_t a256(size_t v) { return (v + 255) / 256 * 256; }
+
 size_t mas_vq_ws_bytes(int64_t R, int K, int D) {
   (void)D;
-  return (size_t)K * sizeof(float) + 256 + (size_t)cdiv(R, VQ_BM) * sizeof(double);
+  return a256((size_t)K * sizeof(float)) + a256((size_t)R * 4 * sizeof(float)) + a256((size_t)R * 4 * sizeof(int)) +
+         (size_t)cdiv(R, 8) * sizeof(double) + 256;
 }
 
 int mas_vq_forward(const float* z, const float* E, int64_t R, int K, int D, float beta, int64_t* idx_out, float* zq_out,
@@ -256,9 +277,12 @@ int mas_vq_forward(const float* z, const float* E, int64_t R, int K, int D, floa
   MAS_REQUIRE(R > 0 && K > 0 && D > 0, "vq_forward: bad shape R=%lld K=%d D=%d", (long long)R, K, D);
   if (D % VQ_BK != 0) return fail(MAS_ERR_UNSUPPORTED, "vq_forward: D=%d must be a multiple of %d", D, VQ_BK);
   if (ws_bytes < mas_vq_ws_bytes(R, K, D)) return fail(MAS_ERR_WORKSPACE, "vq_forward: workspace too small");
-  float* ee = (float*)ws;
-  double* part = (double*)((char*)ws + (((size_t)K * sizeof(float) + 255) / 256) * 256);
-  int blocks = (int)cdiv(R, VQ_BM);
+  char* w = (char*)ws;
+  float* ee = (float*)w; w += a256((size_t)K * sizeof(float));
+  float* bval = (float*)w; w += a256((size_t)R * 4 * sizeof(float));
+  int* bidx = (int*)w; w += a256((size_t)R * 4 * sizeof(int));
+  double* part = (double*)w;
+  const int blocks = (int)cdiv(R, VQ_BM), splits = vq_splits(R);
   size_t smem = ((size_t)VQ_BM * (D + 4) + 2 * VQ_BN * VQ_LDE + VQ_BM) * sizeof(float) + VQ_BM * sizeof(int);
   static int configured_smem = 0;
   if ((int)smem > configured_smem) {
@@ -268,9 +292,12 @@ int mas_vq_forward(const float* z, const float* E, int64_t R, int K, int D, floa
   }
   vq_code_norms<<<(int)cdiv(K, 8), 256, 0, S(stream)>>>(E, K, D, ee);
   if (int e = launched("vq_code_norms")) return e;
-  vq_forward_kernel<<<blocks, VQ_THREADS, smem, S(stream)>>>(z, E, ee, R, K, D, idx_out, zq_out, part);
+  vq_forward_kernel<<<dim3(blocks, splits), VQ_THREADS, smem, S(stream)>>>(z, E, ee, R, K, D, bval, bidx);
   if (int e = launched("vq_forward")) return e;
-  vq_loss_final<<<1, 256, 0, S(stream)>>>(part, blocks, 1.0 / ((double)R * D), beta, loss_out);
+  const int mblocks = (int)cdiv(R, 8);
+  vq_merge_kernel<<<mblocks, 256, 0, S(stream)>>>(z, E, bval, bidx, splits, R, D, idx_out, zq_out, part);
+  if (int e = launched("vq_merge")) return e;
+  vq_loss_final<<<1, 256, 0, S(stream)>>>(part, mblocks, 1.0 / ((double)R * D), beta, loss_out);
   return launched("vq_loss_final");
 }
 
