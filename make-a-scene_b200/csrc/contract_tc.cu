@@ -26,7 +26,7 @@ namespace tc {
 
 constexpr int BM = 128;        // pixels per M tile (16 x 8)
 constexpr int BN = 128;        // output channels per CTA
-constexpr int TILES = 4;       // M tiles per CTA (TMEM: 4 x 128 columns)
+constexpr int TILES_MAX = 4;   // M tiles per CTA: 4 (all 512 TMEM columns, 1 CTA/SM) or 2 (256 columns, 2 CTAs/SM)
 constexpr int NPROD = 256;     // producer threads (warps 0-7)
 constexpr int NTHREADS = 320;  // + MMA warp + bulk-copy warp
 constexpr int STAGES_CONV = 3;
@@ -137,8 +137,8 @@ struct Params {
 };
 
 // One CTA = TILES M-tiles x BN output channels, full K.
-template <int TAPS, int KC, int STAGES>
-__global__ void __launch_bounds__(NTHREADS, 1) shift_gemm_tc(const Params p) {
+template <int TAPS, int KC, int STAGES, int TILES>
+__global__ void __launch_bounds__(NTHREADS, (TILES == 2) ? 2 : 1) shift_gemm_tc(const Params p) {
   constexpr int SLOTS = (TAPS == 9) ? 180 : 132;        // staged pixels per tile (18x10 halo | 128 rows + pad)
   constexpr int ROWP = (TAPS == 9) ? 10 : 8;            // staged pixels per image row
   constexpr int LBO_A = SLOTS * 16;                     // bytes between k-quads of A
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) shift_gemm_tc(const Params p) {
     mbar_init(accum_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(smem_u32(tmem_slot), 512);
+  if (warp == 8) tmem_alloc(smem_u32(tmem_slot), TILES * BN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -395,11 +395,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) shift_gemm_tc(const Params p) {
   __syncthreads();
   if (warp == 8) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, TILES * BN);
   }
 }
 
-template <int TAPS, int KC, int STAGES>
+template <int TAPS, int KC, int STAGES, int TILES>
 constexpr size_t smem_bytes() {
   constexpr int SLOTS = (TAPS == 9) ? 180 : 132;
   return (size_t)STAGES * (TILES * (KC / 4) * SLOTS * 16 + TAPS * (KC / 4) * BN * 16) + (2 * STAGES + 1) * 8 + 16;
@@ -847,14 +847,17 @@ int conv3x3_fprop_tc_launch(const float* x, mas_tensor4 xs, const float* w_tc, c
   p.alpha = 1.0f;
   p.gn_table = gn_table; p.gn_silu = gn_silu; p.stats_part = stats_part;
   if (gn_table && !al16p(gn_table)) return fail(MAS_ERR_INVALID_ARG, "tc conv: gn_table must be 16-byte aligned");
-  constexpr size_t smem = tc::smem_bytes<9, 8, tc::STAGES_CONV>();
+  // two co-resident CTAs per SM (2 tiles / 256 TMEM columns / 2 stages each): one CTA's epilogue and pipeline fill
+  // overlap the other's main loop
+  constexpr int T = 2, STG = 2;
+  constexpr size_t smem = tc::smem_bytes<9, 8, STG, T>();
   static bool configured = false;
   if (!configured) {
-    if (int e = set_smem(tc::shift_gemm_tc<9, 8, tc::STAGES_CONV>, smem)) return e;
+    if (int e = set_smem(tc::shift_gemm_tc<9, 8, STG, T>, smem)) return e;
     configured = true;
   }
-  dim3 grid((unsigned)cdiv(p.total_tiles, tc::TILES), (unsigned)(Cout / tc::BN));
-  tc::shift_gemm_tc<9, 8, tc::STAGES_CONV><<<grid, tc::NTHREADS, smem, st>>>(p);
+  dim3 grid((unsigned)cdiv(p.total_tiles, T), (unsigned)(Cout / tc::BN));
+  tc::shift_gemm_tc<9, 8, STG, T><<<grid, tc::NTHREADS, smem, st>>>(p);
   return launched("shift_gemm_tc<9>");
 }
 
@@ -875,14 +878,14 @@ int gemm_rows_tc_launch(const float* A, int64_t lda, const float* w_tc, float* C
   p.alpha = alpha;
   p.gn_table = nullptr; p.gn_silu = 0; p.stats_part = stats_part;
   if (stats_part && (M % tc::BM || ldc != N)) return fail(MAS_ERR_UNSUPPORTED, "tc gemm: fused statistics need M %% 128 == 0 and a dense output");
-  constexpr size_t smem = tc::smem_bytes<1, 32, 2>();
+  constexpr size_t smem = tc::smem_bytes<1, 32, 2, 4>();
   static bool configured = false;
   if (!configured) {
-    if (int e = set_smem(tc::shift_gemm_tc<1, 32, 2>, smem)) return e;
+    if (int e = set_smem(tc::shift_gemm_tc<1, 32, 2, 4>, smem)) return e;
     configured = true;
   }
-  dim3 grid((unsigned)cdiv(p.total_tiles, tc::TILES), (unsigned)(N / tc::BN));
-  tc::shift_gemm_tc<1, 32, 2><<<grid, tc::NTHREADS, smem, st>>>(p);
+  dim3 grid((unsigned)cdiv(p.total_tiles, 4), (unsigned)(N / tc::BN));
+  tc::shift_gemm_tc<1, 32, 2, 4><<<grid, tc::NTHREADS, smem, st>>>(p);
   return launched("shift_gemm_tc<1>");
 }
 
