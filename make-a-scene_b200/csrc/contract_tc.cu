@@ -878,14 +878,14 @@ int gemm_rows_tc_launch(const float* A, int64_t lda, const float* w_tc, float* C
   p.alpha = alpha;
   p.gn_table = nullptr; p.gn_silu = 0; p.stats_part = stats_part;
   if (stats_part && (M % tc::BM || ldc != N)) return fail(MAS_ERR_UNSUPPORTED, "tc gemm: fused statistics need M %% 128 == 0 and a dense output");
-  constexpr size_t smem = tc::smem_bytes<1, 32, 2, 4>();
+  constexpr size_t smem = tc::smem_bytes<1, 32, 2, 2>();
   static bool configured = false;
   if (!configured) {
-    if (int e = set_smem(tc::shift_gemm_tc<1, 32, 2, 4>, smem)) return e;
+    if (int e = set_smem(tc::shift_gemm_tc<1, 32, 2, 2>, smem)) return e;
     configured = true;
   }
-  dim3 grid((unsigned)cdiv(p.total_tiles, 4), (unsigned)(N / tc::BN));
-  tc::shift_gemm_tc<1, 32, 2, 4><<<grid, tc::NTHREADS, smem, st>>>(p);
+  dim3 grid((unsigned)cdiv(p.total_tiles, 2), (unsigned)(N / tc::BN));
+  tc::shift_gemm_tc<1, 32, 2, 2><<<grid, tc::NTHREADS, smem, st>>>(p);
   return launched("shift_gemm_tc<1>");
 }
 
