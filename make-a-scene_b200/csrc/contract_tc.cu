@@ -19,6 +19,9 @@
 //
 // Reference call sites replaced: nn.Conv2d 3x3 (modules.py:93-104), Upsample/Downsample data paths
 // (modules.py:55-59,74-78), nn.Conv2d 1x1 (modules.py:113-117,145-164).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 #include "mas_common.cuh"
 
 namespace mas {
@@ -60,6 +63,17 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
                "r"(bytes), "r"(bar)
+               : "memory");
+}
+// TMA tiled tensor copies (UTMALDG): one instruction lands a whole box of the tensor in shared memory
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
                : "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
@@ -442,7 +456,6 @@ __global__ void pack_weights_tc(const float* __restrict__ w, float* __restrict__
 constexpr int WG_NT = 32;
 constexpr int WG_STAGES = 3;
 constexpr int WG_SLOTS = 100;          // 10 x 10 halo
-constexpr int WG_THREADS_DIRECT = 17 * 32;  // direct-load variant: 8 producer warps, 2 x 4 loader warps, 1 MMA warp
 constexpr int WG_THREADS = 14 * 32;    // 8 producer warps, 4 A-loader warps, 1 MMA warp, 1 bulk-copy warp
 constexpr int WG_DY_STAGE = 64 * 128 * 4;  // staged dy tile: 64 pixels x 128 channels fp32
 
@@ -482,7 +495,7 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // TAPS == 9: 3x3 convolution (unit = 8x8 output pixels, halo 10x10).  TAPS == 1: 1x1 convolution / row GEMM
 // (unit = 64 consecutive rows, no halo).
 template <int TAPS, bool PRO>
-__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc(const WParams p) {
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc(const WParams p, const __grid_constant__ CUtensorMap dy_map) {
   // B (the shifted operand) must be K-major with K = pixel: tests/test_gpu_tc_probe.py shows that kind::tf32 returns
   // zeros for MN-major shared-memory operands, so the halo is staged TRANSPOSED ([ci][pixel], 4 pixels per 16-byte
   // chunk) once per horizontal tap offset dx (3 copies); vertical offsets are whole-chunk K advances of the descriptor.
@@ -696,36 +709,27 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc(const WParams p) {
     }
     if (p.bpart && blockIdx.x == 0) p.bpart[(size_t)split * p.Cout + co0 + cl] = bsum;
   } else if (warp == 13) {
-    // ============ dy bulk-copy issuer warp: global [pixel][co0..co0+127] -> shared [64][128] ============
-    // lane 0 waits for the stage and arms the transaction count; all 32 lanes then issue the (up to 64) 512-byte copies
-    {
+    // ============ dy TMA issuer (one thread): box [8 rows][8 pixels][128 co] (or [64 rows][128 co]) -> shared [64][128] ============
+    // a tiled tensor map (cuTensorMapEncodeTiled on the host) lets ONE cp.async.bulk.tensor fetch the whole dy tile of a
+    // unit for any Cout; rows beyond the matrix (1x1 tail) are zero-filled by the TMA unit.
+    if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int64_t u = u0; u < u1; ++u) {
         const uint32_t dst = smem_u32(dy_smem) + (uint32_t)stage * WG_DY_STAGE;
-        int nrows = 64;
-        if (TAPS == 1) nrows = (int)min((int64_t)64, p.rows - u * 64);
-        if (lane == 0) {
-          mbar_wait(empty(stage), phase ^ 1);
-          mbar_expect_tx(fullD(stage), (uint32_t)nrows * 512u);
-        }
-        __syncwarp();
+        mbar_wait(empty(stage), phase ^ 1);
+        mbar_expect_tx(fullD(stage), WG_DY_STAGE);
         if (TAPS == 9) {
           const int ux = (int)(u % p.units_x), uy = (int)((u / p.units_x) % p.units_y);
           const int n = (int)(u / ((int64_t)p.units_x * p.units_y));
-          const float* base = p.dy + ((int64_t)(n * p.H + uy * 8) * p.W + ux * 8) * p.Cout + co0;
-          if (p.Cout == 128) {
-            if (lane < 8) bulk_g2s(dst + lane * 4096, base + (int64_t)lane * p.W * p.Cout, 4096, fullD(stage));
-          } else {
-            for (int j = lane; j < 64; j += 32)
-              bulk_g2s(dst + j * 512, base + ((int64_t)(j >> 3) * p.W + (j & 7)) * p.Cout, 512, fullD(stage));
-          }
+          tma_load_4d(dst, &dy_map, co0, ux * 8, uy * 8, n, fullD(stage));
         } else {
-          for (int j = lane; j < nrows; j += 32) bulk_g2s(dst + j * 512, p.dy + (u * 64 + j) * p.ldy + co0, 512, fullD(stage));
+          tma_load_2d(dst, &dy_map, co0, (int)(u * 64), fullD(stage));
         }
         if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
       }
     }
+    __syncwarp();
   } else {
     // ============ MMA issuer ============
     if (lane == 0) {
@@ -757,259 +761,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc(const WParams p) {
   }
   __syncthreads();
   if (warp == 12) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
-// Variant with direct global loads of dy by two alternating groups of loader warps: used when the dy rows of a unit are
-// not one contiguous 4 KB run per image row (Cout != 128, 1x1 convolutions), where 64 separate 512-byte bulk copies per
-// unit measured slower than plain coalesced loads.
-template <int TAPS, bool PRO>
-__global__ void __launch_bounds__(WG_THREADS_DIRECT, 1) wgrad_tc_direct(const WParams p) {
-  // B (the shifted operand) must be K-major with K = pixel: tests/test_gpu_tc_probe.py shows that kind::tf32 returns
-  // zeros for MN-major shared-memory operands, so the halo is staged TRANSPOSED ([ci][pixel], 4 pixels per 16-byte
-  // chunk) once per horizontal tap offset dx (3 copies); vertical offsets are whole-chunk K advances of the descriptor.
-  // Channel ci = 4q + j of the tile sits in operand row n = 8j + q: the 8 lanes of a store phase (q = 0..7) then hit 8
-  // different bank groups, and the epilogue undoes the permutation in registers.
-  // One MMA covers the three horizontal taps of a kernel row: its N = 3 x NT operand rows are [dx][channel], laid out
-  // per 4-pixel chunk as 3*NT/8 consecutive 128-byte core matrices, so a single descriptor (SBO = 128, LBO = chunk
-  // pitch) spans all three dx copies.  (N = 32 MMAs are issue-bound: ~4x slower than their 16-cycle math.)
-  constexpr int NT = (TAPS == 9) ? WG_NT : 128, QUADS = NT / 4;
-  constexpr int SLOTS = (TAPS == 9) ? WG_SLOTS : 64;
-  constexpr int COPIES = (TAPS == 9) ? 3 : 1;
-  constexpr int LBO_B = COPIES * NT * 16;                  // bytes between 4-pixel chunks
-  constexpr int B_STAGE = ((TAPS == 9) ? 20 : 16) * LBO_B; // 80 (10 halo rows x 8) or 64 pixels
-  constexpr int ITEMS = SLOTS * QUADS, PER_THREAD = (ITEMS + NPROD - 1) / NPROD;
-  constexpr uint32_t ACC_COLS = TAPS * NT;
-  constexpr int NMMA = COPIES * NT;                        // N of one MMA (96 | 128)
-  // instruction descriptor: D=f32, A=tf32 (TMEM, K-major), B=tf32 K-major, M=128, N=NMMA
-  constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NMMA >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)WG_STAGES * B_STAGE);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * WG_STAGES + 1);
-  const uint32_t smem_base = smem_u32(smem), bar_base = smem_u32(bars);
-  auto fullB = [&](int s) { return bar_base + 8u * s; };
-  auto fullA = [&](int s) { return bar_base + 8u * (WG_STAGES + s); };
-  auto empty = [&](int s) { return bar_base + 8u * (2 * WG_STAGES + s); };
-  const uint32_t accum_bar = bar_base + 8u * (3 * WG_STAGES);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int ci0 = blockIdx.x * NT, co0 = blockIdx.y * BM, split = blockIdx.z;
-  const int64_t u0 = (int64_t)split * p.units_per_split;
-  const int64_t u1 = min(p.total_units, u0 + p.units_per_split);
-
-  if (tid == 0) {
-    for (int s = 0; s < WG_STAGES; ++s) {
-      mbar_init(fullB(s), NPROD);
-      mbar_init(fullA(s), 128);
-      mbar_init(empty(s), 1);
-    }
-    mbar_init(accum_bar, 1);
-    fence_barrier_init();
-  }
-  if (warp == 16) tmem_alloc(smem_u32(tmem_slot), 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp < 8) {
-    // ============ producers: x halo / rows -> shared memory, transposed (K = pixel) ============
-    int it_r[PER_THREAD], it_c[PER_THREAD], it_q[PER_THREAD];
-#pragma unroll
-    for (int i = 0; i < PER_THREAD; ++i) {
-      const int item = tid + i * NPROD;
-      // lanes of a warp = 8 channel quads x 4 consecutive pixel slots (conflict-free transposed stores)
-      const int q = (item % 8) + 8 * (item / (8 * SLOTS)), slot = (item / 8) % SLOTS;
-      it_q[i] = q;
-      if (TAPS == 9) { it_r[i] = slot / 10; it_c[i] = item < ITEMS ? slot % 10 : -100; }
-      else { it_r[i] = slot; it_c[i] = item < ITEMS ? 0 : -100; }
-    }
-    auto gload = [&](int64_t u, float4* v) {
-      if (TAPS == 9) {
-        const int ux = (int)(u % p.units_x), uy = (int)((u / p.units_x) % p.units_y);
-        const int n = (int)(u / ((int64_t)p.units_x * p.units_y));
-#pragma unroll
-        for (int i = 0; i < PER_THREAD; ++i) {
-          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (it_c[i] >= 0) {
-            const int vy = uy * 8 - 1 + it_r[i], vx = ux * 8 - 1 + it_c[i];
-            int iy = vy, ix = vx;
-            bool ok;
-            if (p.map == MAP_S1) {
-              ok = (unsigned)vy < (unsigned)p.Hin && (unsigned)vx < (unsigned)p.Win;
-            } else {  // MAP_UP
-              ok = (unsigned)vy < (unsigned)(2 * p.Hin) && (unsigned)vx < (unsigned)(2 * p.Win);
-              iy = vy >> 1; ix = vx >> 1;
-            }
-            if (ok) v[i] = __ldg(reinterpret_cast<const float4*>(p.x + ((int64_t)(n * p.Hin + iy) * p.Win + ix) * p.Cin + ci0 + it_q[i] * 4));
-          }
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < PER_THREAD; ++i) {
-          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          const int64_t row = u * 64 + it_r[i];
-          if (it_c[i] >= 0 && row < p.rows) v[i] = __ldg(reinterpret_cast<const float4*>(p.x + row * p.ldx + ci0 + it_q[i] * 4));
-        }
-      }
-    };
-    int stage = 0;
-    uint32_t phase = 0;
-    float4 vn[PER_THREAD];
-    if (u0 < u1) gload(u0, vn);
-    for (int64_t u = u0; u < u1; ++u) {
-      float4 v[PER_THREAD];
-#pragma unroll
-      for (int i = 0; i < PER_THREAD; ++i) v[i] = vn[i];
-      if (u + 1 < u1) gload(u + 1, vn);   // next unit's global loads are in flight while this unit is stored
-      if (TAPS == 9 && PRO) {
-        if (p.gn_table) {
-          // the convolution's input is act(GroupNorm(x)): recomputed here (at consume time) instead of stored.
-          // Padding pixels must stay exactly zero, so validity is re-derived from the unit coordinates.
-          const int ux = (int)(u % p.units_x), uy = (int)((u / p.units_x) % p.units_y);
-          const int n = (int)(u / ((int64_t)p.units_x * p.units_y));
-#pragma unroll
-          for (int i = 0; i < PER_THREAD; ++i) {
-            if (it_c[i] >= 0) {
-              const int vy = uy * 8 - 1 + it_r[i], vx = ux * 8 - 1 + it_c[i];
-              const bool ok = (p.map == MAP_S1) ? ((unsigned)vy < (unsigned)p.Hin && (unsigned)vx < (unsigned)p.Win)
-                                                : ((unsigned)vy < (unsigned)(2 * p.Hin) && (unsigned)vx < (unsigned)(2 * p.Win));
-              if (ok) {
-                const float4* tp = reinterpret_cast<const float4*>(p.gn_table + ((size_t)n * p.Cin + ci0 + it_q[i] * 4) * 2);
-                const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1);
-                float a0 = fmaf(v[i].x, t0.x, t0.y), a1 = fmaf(v[i].y, t0.z, t0.w);
-                float a2 = fmaf(v[i].z, t1.x, t1.y), a3 = fmaf(v[i].w, t1.z, t1.w);
-                if (p.gn_silu) { a0 = silu_f(a0); a1 = silu_f(a1); a2 = silu_f(a2); a3 = silu_f(a3); }
-                v[i] = make_float4(a0, a1, a2, a3);
-              }
-            }
-          }
-        }
-      }
-      mbar_wait(empty(stage), phase ^ 1);
-      float* b_st = reinterpret_cast<float*>(smem + (size_t)stage * B_STAGE);
-#pragma unroll
-      for (int i = 0; i < PER_THREAD; ++i) {
-        if (it_c[i] >= 0) {
-          const float e[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-#pragma unroll
-          for (int dx = 0; dx < COPIES; ++dx) {
-            const int c = it_c[i] - dx;
-            if (TAPS == 1 || (unsigned)c < 8u) {
-              const int kk = (TAPS == 9) ? it_r[i] * 8 + c : it_r[i];
-              // channel 4q+j -> operand row (within its dx block) n = (NT/4)*j + q; byte offset = n*16
-              float* d = b_st + (kk >> 2) * (LBO_B / 4) + dx * (NT * 4) + it_q[i] * 4 + (kk & 3);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) d[j * NT] = e[j];
-            }
-          }
-        }
-      }
-      fence_proxy_async();
-      mbar_arrive(fullB(stage));
-      if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
-    }
-    // ============ epilogue (warps 0-3): TAPS x [128 co x NT ci] partial sums -> workspace ============
-    if (warp < 4) {
-      mbar_wait(accum_bar, 0);
-      tc_fence_after();
-      const int co = co0 + warp * 32 + lane;
-#pragma unroll 1
-      for (int t = 0; t < TAPS; ++t) {
-        float* o = p.part + (((size_t)split * TAPS + t) * p.Cout + co) * p.Cin + ci0;
-        if (TAPS == 9) {
-          float v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * NT), v);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(o + q * 4) = make_float4(v[q], v[8 + q], v[16 + q], v[24 + q]);
-        } else {
-          // NT = 128: column n = 32*j + q holds channel 4q + j; gather the four j-planes, 8 quads at a time
-#pragma unroll
-          for (int qb = 0; qb < 32; qb += 8) {
-            float v0[8], v1[8], v2[8], v3[8];
-            const uint32_t tb = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)qb;
-            tmem_ld8(tb, v0);
-            tmem_ld8(tb + 32, v1);
-            tmem_ld8(tb + 64, v2);
-            tmem_ld8(tb + 96, v3);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(o + (qb + q) * 4) = make_float4(v0[q], v1[q], v2[q], v3[q]);
-          }
-        }
-      }
-      tc_fence_before();
-    }
-  } else if (warp < 16) {
-    // ============ A loaders: dy[pixel][co] -> registers -> tensor memory (lane = co, column = pixel) ============
-    // two groups of four warps take alternate units, so that one group's global-load latency hides behind the other's
-    const int lg = warp & 3;          // TMEM lane group (warp % 4)
-    const int grp = (warp - 8) >> 2;  // 0: even units, 1: odd units (relative to u0)
-    const float* dyc = p.dy + co0 + lg * 32 + lane;
-    float bsum = 0.f;
-    for (int64_t u = u0 + grp; u < u1; u += 2) {
-      const int64_t k = u - u0;
-      const int stage = (int)(k % WG_STAGES);
-      const uint32_t phase = (uint32_t)((k / WG_STAGES) & 1);
-      float v[64];
-      if (TAPS == 9) {
-        const int ux = (int)(u % p.units_x), uy = (int)((u / p.units_x) % p.units_y);
-        const int n = (int)(u / ((int64_t)p.units_x * p.units_y));
-        const float* base = dyc + ((int64_t)(n * p.H + uy * 8) * p.W + ux * 8) * p.Cout;
-#pragma unroll
-        for (int j = 0; j < 64; ++j) v[j] = __ldg(base + ((int64_t)(j >> 3) * p.W + (j & 7)) * p.Cout);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 64; ++j) {
-          const int64_t row = u * 64 + j;
-          v[j] = row < p.rows ? __ldg(dyc + row * p.ldy) : 0.f;
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 64; ++j) bsum += v[j];
-      mbar_wait(empty(stage), phase ^ 1);
-      tc_fence_after();
-      const uint32_t ta = tmem_base + ((uint32_t)(lg * 32) << 16) + ACC_COLS + (uint32_t)(stage * 64);
-      tmem_st32(ta, v);
-      tmem_st32(ta + 32, v + 32);
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(fullA(stage));
-    }
-    if (p.bpart && blockIdx.x == 0) p.bpart[((size_t)split * 2 + grp) * p.Cout + co0 + lg * 32 + lane] = bsum;
-  } else {
-    // ============ MMA issuer ============
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int64_t u = u0; u < u1; ++u) {
-        mbar_wait(fullB(stage), phase);
-        mbar_wait(fullA(stage), phase);
-        tc_fence_after();
-        const uint32_t b_st = smem_base + (uint32_t)stage * B_STAGE;
-        const uint32_t a_t = tmem_base + ACC_COLS + (uint32_t)(stage * 64);
-        const uint64_t b_base = make_desc(b_st, LBO_B, 128);
-        const uint32_t acc0 = (u > u0) ? 1u : 0u;
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-#pragma unroll
-          for (int dyy = 0; dyy < ((TAPS == 9) ? 3 : 1); ++dyy) {
-            // image row r + dy starts at chunk 2*(r+dy) (8 pixels = 2 chunks); the three dx taps are the N blocks
-            const uint64_t bd = b_base + (uint64_t)(((r + dyy) * 2 * LBO_B) >> 4);
-            mma_tf32_ts(tmem_base + (uint32_t)(dyy * NMMA), a_t + (uint32_t)(r * 8), bd, idesc, r > 0 ? 1u : acc0);
-          }
-        }
-        mma_commit(empty(stage));
-        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
-      }
-      mma_commit(accum_bar);
-    }
-    __syncwarp();
-  }
-  __syncthreads();
-  if (warp == 16) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -1195,29 +946,37 @@ static int wgrad_tc_splits(int64_t cps, int64_t units) {
 size_t conv_wgrad_tc_ws(mas_tensor4 xs, mas_tensor4 dys, int mode) {
   if (!wgrad_tc_ok(xs, dys, mode)) return 0;
   size_t splits = wgrad_tc_splits((dys.c / tc::BM) * (xs.c / tc::WG_NT), dys.n * (dys.h / 8) * (dys.w / 8));
-  return splits * 9 * (size_t)dys.c * xs.c * sizeof(float) + 2 * splits * (size_t)dys.c * sizeof(float) + 256;
+  return splits * 9 * (size_t)dys.c * xs.c * sizeof(float) + splits * (size_t)dys.c * sizeof(float) + 256;
 }
-template <int TAPS, bool PRO>
-static int wgrad_tc_run_direct(tc::WParams& p, int splits, float* dw, float* dbias, void* ws, cudaStream_t st) {
-  p.part = (float*)ws;
-  p.bpart = dbias ? (float*)ws + (size_t)splits * TAPS * p.Cout * p.Cin : nullptr;
-  p.units_per_split = cdiv(p.total_units, splits);
-  constexpr int NT = (TAPS == 9) ? tc::WG_NT : 128;
-  constexpr size_t smem = (size_t)tc::WG_STAGES * (TAPS == 9 ? 3 * 20 : 16) * NT * 16 + (3 * tc::WG_STAGES + 1) * 8 + 16;
-  static bool configured = false;
-  if (!configured) {
-    if (int e = set_smem(tc::wgrad_tc_direct<TAPS, PRO>, smem)) return e;
-    configured = true;
+static PFN_cuTensorMapEncodeTiled tensor_map_encoder() {
+  static PFN_cuTensorMapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(ptr);
   }
-  dim3 grid((unsigned)(p.Cin / NT), (unsigned)(p.Cout / tc::BM), (unsigned)splits);
-  tc::wgrad_tc_direct<TAPS, PRO><<<grid, tc::WG_THREADS_DIRECT, smem, st>>>(p);
-  if (int e = launched("wgrad_tc_direct")) return e;
-  conv_wgrad_reduce_launch((const float*)ws, splits, TAPS, p.Cout, p.Cin, dw, st);
-  if (int e = launched("conv_wgrad_reduce")) return e;
-  if (dbias) {
-    tc::bias_reduce<<<(int)cdiv(p.Cout, 128), 128, 0, st>>>(p.bpart, 2 * splits, p.Cout, dbias);
-    return launched("bias_reduce");
+  return fn;
+}
+// dy tile map: 3x3 -> rank 4 (co, x, y, n), box (128, 8, 8, 1); 1x1 -> rank 2 (co, row), box (128, 64)
+static int make_dy_map(CUtensorMap* map, const tc::WParams& p, int taps) {
+  PFN_cuTensorMapEncodeTiled enc = tensor_map_encoder();
+  if (!enc) return fail(MAS_ERR_LAUNCH, "cuTensorMapEncodeTiled entry point not available");
+  CUresult r;
+  if (taps == 9) {
+    cuuint64_t dims[4] = {(cuuint64_t)p.Cout, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
+    cuuint64_t strides[3] = {(cuuint64_t)p.Cout * 4, (cuuint64_t)p.W * p.Cout * 4, (cuuint64_t)p.H * p.W * p.Cout * 4};
+    cuuint32_t box[4] = {128, 8, 8, 1}, es[4] = {1, 1, 1, 1};
+    r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)p.dy, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    cuuint64_t dims[2] = {(cuuint64_t)p.Cout, (cuuint64_t)p.rows};
+    cuuint64_t strides[1] = {(cuuint64_t)p.ldy * 4};
+    cuuint32_t box[2] = {128, 64}, es[2] = {1, 1};
+    r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)p.dy, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }
+  if (r != CUDA_SUCCESS) return fail(MAS_ERR_LAUNCH, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return MAS_OK;
 }
 
@@ -1233,8 +992,10 @@ static int wgrad_tc_run(tc::WParams& p, int splits, float* dw, float* dbias, voi
     if (int e = set_smem(tc::wgrad_tc<TAPS, PRO>, smem)) return e;
     configured = true;
   }
+  CUtensorMap dy_map;
+  if (int e = make_dy_map(&dy_map, p, TAPS)) return e;
   dim3 grid((unsigned)(p.Cin / NT), (unsigned)(p.Cout / tc::BM), (unsigned)splits);
-  tc::wgrad_tc<TAPS, PRO><<<grid, tc::WG_THREADS, smem, st>>>(p);
+  tc::wgrad_tc<TAPS, PRO><<<grid, tc::WG_THREADS, smem, st>>>(p, dy_map);
   if (int e = launched("wgrad_tc")) return e;
   conv_wgrad_reduce_launch((const float*)ws, splits, TAPS, p.Cout, p.Cin, dw, st);
   if (int e = launched("conv_wgrad_reduce")) return e;
@@ -1258,8 +1019,6 @@ int conv_wgrad_tc_launch(const float* x, mas_tensor4 xs, const float* dy, mas_te
   p.rows = 0; p.ldx = p.Cin; p.ldy = p.Cout;
   p.gn_table = gn_table; p.gn_silu = gn_silu;
   const int splits = wgrad_tc_splits((dys.c / tc::BM) * (xs.c / tc::WG_NT), p.total_units);
-  if (p.Cout != 128)
-    return gn_table ? wgrad_tc_run_direct<9, true>(p, splits, dw, dbias, ws, st) : wgrad_tc_run_direct<9, false>(p, splits, dw, dbias, ws, st);
   return gn_table ? wgrad_tc_run<9, true>(p, splits, dw, dbias, ws, st) : wgrad_tc_run<9, false>(p, splits, dw, dbias, ws, st);
 }
 static bool wgrad1_tc_ok(const float* x, int64_t ldx, const float* dy, int64_t ldy, int Cin, int Cout) {
@@ -1268,7 +1027,7 @@ static bool wgrad1_tc_ok(const float* x, int64_t ldx, const float* dy, int64_t l
 size_t conv1x1_wgrad_tc_ws(int64_t M, int Cin, int Cout) {
   if (Cin % 128 || Cout % tc::BM) return 0;
   size_t splits = wgrad_tc_splits((int64_t)(Cout / tc::BM) * (Cin / 128), cdiv(M, 64));
-  return splits * (size_t)Cout * Cin * sizeof(float) + 2 * splits * (size_t)Cout * sizeof(float) + 256;
+  return splits * (size_t)Cout * Cin * sizeof(float) + splits * (size_t)Cout * sizeof(float) + 256;
 }
 int conv1x1_wgrad_tc_launch(const float* x, int64_t ldx, const float* dy, int64_t ldy, int64_t M, int Cin, int Cout, float* dw,
                             float* dbias, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -1282,7 +1041,7 @@ int conv1x1_wgrad_tc_launch(const float* x, int64_t ldx, const float* dy, int64_
   p.rows = M; p.ldx = ldx; p.ldy = ldy;
   p.gn_table = nullptr; p.gn_silu = 0;
   const int splits = wgrad_tc_splits((int64_t)(Cout / tc::BM) * (Cin / 128), p.total_units);
-  return wgrad_tc_run_direct<1, false>(p, splits, dw, dbias, ws, st);
+  return wgrad_tc_run<1, false>(p, splits, dw, dbias, ws, st);
 }
 
 }  // namespace mas
