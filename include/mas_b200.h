@@ -68,7 +68,8 @@ int mas_gn_apply(const float* x, const float* mean, const float* rstd, const flo
                  void* stream);
 int mas_gn_backward(const float* dy, const float* x, const float* mean, const float* rstd,
                     const float* gamma, const float* beta, const float* dx_add, float* dx, float* dgamma,
-                    float* dbeta, int N, int HW, int C, int G, int silu, void* ws, size_t ws_bytes, void* stream);
+                    float* dbeta, float* act_out, int N, int HW, int C, int G, int silu, void* ws, size_t ws_bytes,
+                    void* stream);  /* act_out (or NULL): also writes act(GN(x)), the operand of the following weight gradient */
 /* out = a + b (gradient of x+h where the two branches cannot be fused). */
 int mas_add(const float* a, const float* b, float* out, int64_t n, void* stream);
 /* Standalone Swish module (modules.py:194-196). */

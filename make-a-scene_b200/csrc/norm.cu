@@ -148,7 +148,8 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_partial(const float* __rest
                                                              const float* __restrict__ mean, const float* __restrict__ rstd,
                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
                                                              int HW, int C, int G, int silu,
-                                                             double* __restrict__ part /*[N][chunks][C][2]*/) {
+                                                             double* __restrict__ part /*[N][chunks][C][2]*/,
+                                                             float* __restrict__ act_out /*or null: also write act(GN(x))*/) {
   extern __shared__ double sm[];
   const int U = C >> 2, n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x, cpg = C / G;
   const int t = threadIdx.x, u = t % U, lanes = GN_THREADS / U, pl = t / U;
@@ -166,16 +167,22 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_partial(const float* __rest
   const float4* xp = reinterpret_cast<const float4*>(x + (size_t)n * HW * C) + u;
   const float4* dp = reinterpret_cast<const float4*>(dy + (size_t)n * HW * C) + u;
   float f1[4], f2[4];
-  auto accum = [&](const float4& xv, const float4& dv) {
-    float xi[4] = {xv.x, xv.y, xv.z, xv.w}, di[4] = {dv.x, dv.y, dv.z, dv.w};
+  float4* ap = act_out ? reinterpret_cast<float4*>(act_out + (size_t)n * HW * C) + u : nullptr;
+  // the activation act(GN(x)) (needed by the weight-gradient kernel, never stored in the forward) is re-materialised here
+  // as a by-product: x is being read anyway, so this replaces a separate read+write pass by one extra write
+  auto accum = [&](const float4& xv, const float4& dv, size_t idx) {
+    float xi[4] = {xv.x, xv.y, xv.z, xv.w}, di[4] = {dv.x, dv.y, dv.z, dv.w}, ao[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       float xh = (xi[k] - m[k]) * r[k];
       float d = di[k];
-      if (silu) d *= silu_grad_f(xh * ga[k] + be[k]);
+      const float uu = xh * ga[k] + be[k];
+      if (silu) d *= silu_grad_f(uu);
+      ao[k] = silu ? silu_f(uu) : uu;
       f1[k] = fmaf(d, xh, f1[k]);
       f2[k] += d;
     }
+    if (ap) ap[idx] = make_float4(ao[0], ao[1], ao[2], ao[3]);
   };
   auto flush = [&]() {
 #pragma unroll
@@ -192,10 +199,10 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_partial(const float* __rest
       dv[k] = __ldg(dp + (size_t)(p + k * lanes) * U);
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) accum(xv[k], dv[k]);
+    for (int k = 0; k < 4; ++k) accum(xv[k], dv[k], (size_t)(p + k * lanes) * U);
     flush();  // fp32 over 4 pixels, fp64 across batches
   }
-  for (; p < p1; p += lanes) accum(__ldg(xp + (size_t)p * U), __ldg(dp + (size_t)p * U));
+  for (; p < p1; p += lanes) accum(__ldg(xp + (size_t)p * U), __ldg(dp + (size_t)p * U), (size_t)p * U);
   flush();
   double* buf = sm;
 #pragma unroll
@@ -618,8 +625,8 @@ int mas_gn_apply(const float* x, const float* mean, const float* rstd, const flo
 }
 
 int mas_gn_backward(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
-                    const float* dx_add, float* dx, float* dgamma, float* dbeta, int N, int HW, int C, int G, int silu, void* ws,
-                    size_t ws_bytes, void* stream) {
+                    const float* dx_add, float* dx, float* dgamma, float* dbeta, float* act_out, int N, int HW, int C, int G, int silu,
+                    void* ws, size_t ws_bytes, void* stream) {
   if (int e = gn_check(N, HW, C, G)) return e;
   if (ws_bytes < mas_gn_ws_bytes(N, HW, C, G)) return fail(MAS_ERR_WORKSPACE, "gn_backward: workspace too small");
   int chunks = gn_chunks(HW);
@@ -628,7 +635,7 @@ int mas_gn_backward(const float* dy, const float* x, const float* mean, const fl
   float* AB = (float*)(nc + (size_t)N * C * 2);
   int lanes = GN_THREADS / (C / 4);
   size_t smem = (size_t)lanes * C * 2 * sizeof(double);
-  gn_bwd_partial<<<dim3(chunks, N), GN_THREADS, smem, S(stream)>>>(dy, x, mean, rstd, gamma, beta, HW, C, G, silu, part);
+  gn_bwd_partial<<<dim3(chunks, N), GN_THREADS, smem, S(stream)>>>(dy, x, mean, rstd, gamma, beta, HW, C, G, silu, part, act_out);
   if (int e = launched("gn_bwd_partial")) return e;
   gn_bwd_nc<<<(int)cdiv((int64_t)N * C, 128), 128, 0, S(stream)>>>(part, N, chunks, C, nc);
   if (int e = launched("gn_bwd_nc")) return e;

@@ -69,15 +69,19 @@ def gn_apply(x, mean, rstd, gamma, beta, silu, rtf32=False):
     return y
 
 
-def gn_backward(dy, x, mean, rstd, gamma, beta, silu, dx_add=None):
+def gn_backward(dy, x, mean, rstd, gamma, beta, silu, dx_add=None, want_act=False):
+    """want_act: also return act(GN(x)) (re-materialised as a by-product of the first backward pass)."""
     n, c, h, w = x.shape
     dx = torch.empty_like(x)
     dg = torch.empty_like(gamma)
     db = torch.empty_like(beta)
+    act = torch.empty_like(x) if want_act else None
     nb = L.query("mas_gn_ws_bytes", n, h * w, c, GN_GROUPS)
     ws = L.workspace(nb, x.device)
-    L.call("mas_gn_backward", dy, x, mean, rstd, gamma, beta, dx_add, dx, dg, db, n, h * w, c, GN_GROUPS, int(silu), ws,
+    L.call("mas_gn_backward", dy, x, mean, rstd, gamma, beta, dx_add, dx, dg, db, act, n, h * w, c, GN_GROUPS, int(silu), ws,
            ws.numel())
+    if want_act:
+        return dx, dg, db, act
     return dx, dg, db
 
 
@@ -459,27 +463,32 @@ class ResnetBlockFn(torch.autograd.Function):
         cout, cin = c1w.shape[0], c1w.shape[1]
         n, _, h, w = x.shape
         d_a2 = conv3x3_dgrad_raw(dout, c2w, L.CONV_S1)
+        # fused forward never stored act(GN(.)): the GroupNorm backward re-materialises it as a by-product of its first pass
+        # (cheaper than re-activating inside the weight-gradient kernel's producers: measured +0.8 ms per full-res call)
         if ctx.fused:
-            # the activated operand was never stored: re-materialise it with the streaming GN+SiLU kernel (0.1 ms at
-            # 128x256^2x32) — cheaper than re-activating inside the weight-gradient kernel's producers (measured +0.8 ms)
-            a2 = gn_apply(h1, m2, r2, n2w, n2b, True)
+            d_h1, dn2w, dn2b, a2 = gn_backward(d_a2, h1, m2, r2, n2w, n2b, True, want_act=True)
+        else:
+            d_h1, dn2w, dn2b = gn_backward(d_a2, h1, m2, r2, n2w, n2b, True)
+        del d_a2
         dc2w, dc2b = conv3x3_wgrad_raw(a2, dout, cout, cout, L.CONV_S1)
         del a2
-        d_h1, dn2w, dn2b = gn_backward(d_a2, h1, m2, r2, n2w, n2b, True)
-        del d_a2
         d_a1 = conv3x3_dgrad_raw(d_h1, c1w, L.CONV_S1)
-        if ctx.fused:
-            a1 = gn_apply(x, m1, r1, n1w, n1b, True)
-        dc1w, dc1b = conv3x3_wgrad_raw(a1, d_h1, cout, cin, L.CONV_S1)
-        del a1
-        del d_h1
         if ctx.has_sc:
-            dxm, dn1w, dn1b = gn_backward(d_a1, x, m1, r1, n1w, n1b, True)
+            r_ = gn_backward(d_a1, x, m1, r1, n1w, n1b, True, want_act=ctx.fused)
+            dxm, dn1w, dn1b = r_[0], r_[1], r_[2]
+            if ctx.fused:
+                a1 = r_[3]
             dx = conv1x1_dgrad_raw(dout, sw, residual=dxm)   # dout.Wn + dx_main
             dsw, dsb = conv1x1_wgrad_raw(x, dout, n * h * w, cin, cout)
         else:
-            dx, dn1w, dn1b = gn_backward(d_a1, x, m1, r1, n1w, n1b, True, dx_add=dout)
+            r_ = gn_backward(d_a1, x, m1, r1, n1w, n1b, True, dx_add=dout, want_act=ctx.fused)
+            dx, dn1w, dn1b = r_[0], r_[1], r_[2]
+            if ctx.fused:
+                a1 = r_[3]
             dsw = dsb = None
+        del d_a1
+        dc1w, dc1b = conv3x3_wgrad_raw(a1, d_h1, cout, cin, L.CONV_S1)
+        del a1, d_h1
         return dx, None, None, dn1w, dn1b, dc1w, dc1b, dn2w, dn2b, dc2w, dc2b, dsw, dsb
 
 
