@@ -168,6 +168,27 @@ int mas_softmax_forward(const float* s, float* p, int64_t rows, int cols, void* 
 int mas_softmax_backward(const float* p, const float* dp, float* ds, int64_t rows, int cols, float scale,
                          void* stream);
 
+/* ---- AttnBlock as one unit — replaces AttnBlock.forward (modules.py:167-191) and its autograd graph ------
+ * x, hn, O, out, dout, dx: [N*HW, C] NHWC rows; qkv: [N*HW, 3C] (q | k | v per row); P: [N, HW, HW] softmax over keys.
+ * mean/rstd: GroupNorm(G) statistics of x (mas_gn_stats or a producer's statistics epilogue).  Weights in the
+ * reference layout ([C, C(,1,1)] row-major, biases [C]).  hn, qkv, P, O are outputs of the forward that the caller
+ * keeps for the backward.  stats_part (or NULL): statistics partials of `out` for the next GroupNorm
+ * ([N*HW/128][4][C/4][2], tensor path and HW % 128 == 0 only).  dqkv_w [3C, C] / dqkv_b [3C] hold the q, k, v gradients
+ * back to back.  The 1x1 convolutions use the tcgen05 row GEMM / weight-gradient kernels when C % 128 == 0 (impl as
+ * MAS_IMPL_*); QK^T, PV and their gradients are strict fp32 like torch.bmm (modules.py:180,186). */
+size_t mas_attnblock_ws_bytes(int N, int HW, int C, int G);
+int mas_attnblock_forward(const float* x, int N, int HW, int C, int G, const float* mean, const float* rstd,
+                          const float* norm_w, const float* norm_b, const float* q_w, const float* q_b,
+                          const float* k_w, const float* k_b, const float* v_w, const float* v_b,
+                          const float* proj_w, const float* proj_b, float* hn, float* qkv, float* P, float* O,
+                          float* out, float* stats_part, int impl, void* ws, size_t ws_bytes, void* stream);
+int mas_attnblock_backward(const float* dout, const float* x, int N, int HW, int C, int G, const float* mean,
+                           const float* rstd, const float* norm_w, const float* norm_b, const float* q_w,
+                           const float* k_w, const float* v_w, const float* proj_w, const float* hn,
+                           const float* qkv, const float* P, const float* O, float* dx, float* dnorm_w,
+                           float* dnorm_b, float* dqkv_w, float* dqkv_b, float* dproj_w, float* dproj_b, int impl,
+                           void* ws, size_t ws_bytes, void* stream);
+
 /* ---- (Sync)BatchNorm for quant_conv[1] — vqvae.py:16 ---------------------------------------------------
  * x [R, C] NHWC rows.  mas_bn_stats writes LOCAL [sum(C), sumsq(C)] as fp64 (2*C doubles); the caller
  * all-reduces those 2*C numbers (+ the row count) across ranks over NCCL, then mas_bn_finalize turns the

@@ -4,16 +4,11 @@
 // written), so they get direct fp32 kernels: thread = output (or input) channel, image tile broadcast from
 // shared memory.  All four directions (fprop, data gradient, weight/bias gradient) are covered.
 #include "mas_common.cuh"
+#include "edge.cuh"
 
 namespace mas {
 
 constexpr int ET_H = 8, ET_W = 32;  // pixels per block tile
-constexpr int SC = 3;               // the "small" channel count
-
-struct EdgeGeom {
-  int N, H, W, Cbig;
-  int64_t sn, sh, sw, sc;  // strides of the SMALL-channel tensor (image / reconstruction / its gradient)
-};
 
 // ---------------------------------------------------------------------------------------------------- small Cin -> big Cout
 // y[n,oy,ox,co] = bias[co] + sum_{ci<3,tap} xs[n,ci,oy+ty-1,ox+tx-1] * W(co,ci,tap)
@@ -237,6 +232,7 @@ int mas_edge_small_cin_fprop(const float* xs, mas_tensor4 xst, const float* w, c
                              int flip_transpose, void* stream) {
   EdgeGeom g;
   if (int e = edge_geom(g, xst, yst, "edge_small_cin_fprop")) return e;
+  if (g.Cbig % 128 == 0) return small_cin_fprop_q_launch(xs, w, bias, y, g, flip_transpose, S(stream));
   dim3 grid((unsigned)cdiv(g.W, ET_W), (unsigned)cdiv(g.H, ET_H), (unsigned)(g.N * cdiv(g.Cbig, 128)));
   small_cin_fprop<<<grid, 256, 0, S(stream)>>>(xs, w, bias, y, g, flip_transpose);
   return launched("small_cin_fprop");
@@ -249,6 +245,11 @@ int mas_edge_small_cin_wgrad(const float* xs, mas_tensor4 xst, const float* dy, 
   EdgeGeom g;
   if (int e = edge_geom(g, xst, dyt, "edge_small_cin_wgrad")) return e;
   if (ws_bytes < mas_edge_wgrad_ws_bytes(g.Cbig)) return fail(MAS_ERR_WORKSPACE, "edge wgrad: workspace too small");
+  if (g.Cbig % 128 == 0) {
+    if (int e = small_cin_wgrad_q_launch(xs, dy, (float*)ws, g, S(stream))) return e;
+    small_cin_wgrad_reduce<<<(int)cdiv((SC * 9 + 1) * g.Cbig, 128), 128, 0, S(stream)>>>((const float*)ws, EDGE_Q_BLOCKS, g.Cbig, dw, dbias);
+    return launched("small_cin_wgrad_reduce");
+  }
   const int tx = (int)cdiv(g.W, ET_W), ty = (int)cdiv(g.H, ET_H);
   const int64_t ntiles = (int64_t)g.N * tx * ty;
   const int blocks = (int)(ntiles < EDGE_PBLOCKS ? ntiles : EDGE_PBLOCKS);
@@ -264,6 +265,7 @@ int mas_edge_small_cout_fprop(const float* a, mas_tensor4 at, const float* w, co
                               void* stream) {
   EdgeGeom g;
   if (int e = edge_geom(g, yst, at, "edge_small_cout_fprop")) return e;
+  if (g.Cbig == 128) return small_cout_fprop_q_launch(a, w, bias, ys, g, S(stream));
   if (g.Cbig % 4) return fail(MAS_ERR_UNSUPPORTED, "edge_small_cout_fprop: Cin %% 4 != 0");
   size_t smem = (size_t)SC * 9 * g.Cbig * sizeof(float);
   if (smem > 48 * 1024) return fail(MAS_ERR_UNSUPPORTED, "edge_small_cout_fprop: Cin=%d too wide", g.Cbig);
@@ -277,6 +279,11 @@ int mas_edge_small_cout_wgrad(const float* a, mas_tensor4 at, const float* dys, 
   EdgeGeom g;
   if (int e = edge_geom(g, dyt, at, "edge_small_cout_wgrad")) return e;
   if (ws_bytes < mas_edge_wgrad_ws_bytes(g.Cbig)) return fail(MAS_ERR_WORKSPACE, "edge wgrad: workspace too small");
+  if (g.Cbig % 128 == 0) {
+    if (int e = small_cout_wgrad_q_launch(a, dys, (float*)ws, g, S(stream))) return e;
+    small_cout_wgrad_reduce<<<(int)cdiv((SC * 9 + SC) * g.Cbig, 128), 128, 0, S(stream)>>>((const float*)ws, EDGE_Q_BLOCKS, g.Cbig, dw, dbias);
+    return launched("small_cout_wgrad_reduce");
+  }
   const int tx = (int)cdiv(g.W, ET_W), ty = (int)cdiv(g.H, ET_H);
   const int64_t ntiles = (int64_t)g.N * tx * ty;
   const int blocks = (int)(ntiles < EDGE_PBLOCKS ? ntiles : EDGE_PBLOCKS);

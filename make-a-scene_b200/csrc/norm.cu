@@ -31,14 +31,15 @@ int launched(const char* what) {
 // (cheap in an HBM-bound kernel) so that var = E[x^2]-E[x]^2 has no fp32 cancellation problem.
 // ------------------------------------------------------------------------------------------------
 constexpr int GN_THREADS = 256;
-constexpr int GN_PIX = 1024;
+constexpr int GN_PIX = 1024;  // pixels per block for large images; small ones get smaller chunks (gn_chunks) so the grid fills the GPU
 
 __global__ void __launch_bounds__(GN_THREADS) gn_stats_partial(const float* __restrict__ x, int HW, int C, int G,
                                                                double* __restrict__ part /*[N][chunks][G][2]*/) {
   extern __shared__ double sm[];  // [C][2] then reused
   const int U = C >> 2, n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
   const int t = threadIdx.x, u = t % U, lanes = GN_THREADS / U, pl = t / U;
-  const int p0 = chunk * GN_PIX, p1 = min(HW, p0 + GN_PIX);
+  const int PIX = (HW + gridDim.x - 1) / gridDim.x;
+  const int p0 = chunk * PIX, p1 = min(HW, p0 + PIX);
   double s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
   const float4* xp = reinterpret_cast<const float4*>(x + (size_t)n * HW * C) + u;
   // four independent 16-byte loads in flight per thread; per-quad fp32 partial sums over 4 pixels feed the fp64 totals
@@ -112,7 +113,8 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const float* __res
                                                               int G, int silu, int rtf32) {
   const int U = C >> 2, n = blockIdx.y, cpg = C / G;
   const int t = threadIdx.x, u = t % U, lanes = GN_THREADS / U, pl = t / U;
-  const int p0 = blockIdx.x * GN_PIX, p1 = min(HW, p0 + GN_PIX);
+  const int PIX = (HW + gridDim.x - 1) / gridDim.x;
+  const int p0 = blockIdx.x * PIX, p1 = min(HW, p0 + PIX);
   float sc[4], sh[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -153,7 +155,8 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_partial(const float* __rest
   extern __shared__ double sm[];
   const int U = C >> 2, n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x, cpg = C / G;
   const int t = threadIdx.x, u = t % U, lanes = GN_THREADS / U, pl = t / U;
-  const int p0 = chunk * GN_PIX, p1 = min(HW, p0 + GN_PIX);
+  const int PIX = (HW + gridDim.x - 1) / gridDim.x;
+  const int p0 = chunk * PIX, p1 = min(HW, p0 + PIX);
   float m[4], r[4], ga[4], be[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -270,7 +273,8 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply(const float* __restri
                                                            float* __restrict__ dx, int HW, int C, int G, int silu) {
   const int U = C >> 2, n = blockIdx.y, cpg = C / G;
   const int t = threadIdx.x, u = t % U, lanes = GN_THREADS / U, pl = t / U;
-  const int p0 = blockIdx.x * GN_PIX, p1 = min(HW, p0 + GN_PIX);
+  const int PIX = (HW + gridDim.x - 1) / gridDim.x;
+  const int p0 = blockIdx.x * PIX, p1 = min(HW, p0 + PIX);
   float m[4], r[4], ga[4], be[4], A[4], B[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -317,10 +321,22 @@ __global__ void gn_finalize_partials_kernel(const float* __restrict__ part, int 
   const int n = wid / G, g = wid % G, Q = C >> 2, qpg = Q / G;  // channel quads per group (C/G >= 4)
   double a = 0, b = 0;
   const int rows = tiles_per_image * 4;
-  for (int r = lane; r < rows; r += 32) {
-    const float* p = part + (((size_t)n * rows + r) * Q + (size_t)g * qpg) * 2;
-    for (int q = 0; q < qpg; ++q) { a += p[q * 2]; b += p[q * 2 + 1]; }
+  const float2* pb = reinterpret_cast<const float2*>(part) + (size_t)n * rows * Q + (size_t)g * qpg;
+  int r = lane;
+  for (; r + 7 * 32 < rows; r += 8 * 32) {  // eight rows in flight per lane: the loop is latency-bound (L2 hits, 8 of 256 bytes per row)
+    for (int q = 0; q < qpg; ++q) {
+      float2 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = __ldg(pb + (size_t)(r + k * 32) * Q + q);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { a += v[k].x; b += v[k].y; }
+    }
   }
+  for (; r < rows; r += 32)
+    for (int q = 0; q < qpg; ++q) {
+      const float2 v = __ldg(pb + (size_t)r * Q + q);
+      a += v.x; b += v.y;
+    }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     a += __shfl_xor_sync(0xffffffffu, a, o);
@@ -594,10 +610,17 @@ static int gn_check(int N, int HW, int C, int G) {
   if (C % 4 != 0 || GN_THREADS % (C / 4) != 0) return fail(MAS_ERR_UNSUPPORTED, "groupnorm: C=%d must be 4*{1,2,4,...,256}", C);
   return MAS_OK;
 }
-static int gn_chunks(int HW) { return (int)cdiv(HW, GN_PIX); }
+// chunks per image: GN_PIX pixels per block, halved until the grid has ~4 blocks per SM (the 16x16 and 32x32 levels would
+// otherwise run on 32 blocks) but never below four pixels per thread-lane
+static int gn_chunks(int N, int HW, int C) {
+  const int lanes = GN_THREADS / (C / 4);
+  int pix = GN_PIX;
+  while (pix > 4 * lanes && pix > 8 && (int64_t)N * cdiv(HW, pix) < 4 * 148) pix >>= 1;
+  return (int)cdiv(HW, pix);
+}
 
 size_t mas_gn_ws_bytes(int N, int HW, int C, int G) {
-  size_t part = (size_t)N * gn_chunks(HW) * C * 2 * sizeof(double);  // backward partials are the larger use
+  size_t part = (size_t)N * gn_chunks(N, HW, C) * C * 2 * sizeof(double);  // backward partials are the larger use
   size_t nc = (size_t)N * C * 2 * sizeof(double);
   size_t ab = (size_t)N * G * 2 * sizeof(float);
   return part + nc + ab + 256;
@@ -606,7 +629,7 @@ size_t mas_gn_ws_bytes(int N, int HW, int C, int G) {
 int mas_gn_stats(const float* x, int N, int HW, int C, int G, float eps, float* mean, float* rstd, void* ws, size_t ws_bytes,
                  void* stream) {
   if (int e = gn_check(N, HW, C, G)) return e;
-  int chunks = gn_chunks(HW);
+  int chunks = gn_chunks(N, HW, C);
   size_t need = (size_t)N * chunks * G * 2 * sizeof(double);
   if (ws_bytes < need) return fail(MAS_ERR_WORKSPACE, "gn_stats: workspace %zu < %zu", ws_bytes, need);
   int lanes = GN_THREADS / (C / 4);
@@ -620,7 +643,7 @@ int mas_gn_stats(const float* x, int N, int HW, int C, int G, float eps, float* 
 int mas_gn_apply(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta, float* y, int N,
                  int HW, int C, int G, int silu, int round_tf32, void* stream) {
   if (int e = gn_check(N, HW, C, G)) return e;
-  gn_apply_kernel<<<dim3(gn_chunks(HW), N), GN_THREADS, 0, S(stream)>>>(x, mean, rstd, gamma, beta, y, HW, C, G, silu, round_tf32);
+  gn_apply_kernel<<<dim3(gn_chunks(N, HW, C), N), GN_THREADS, 0, S(stream)>>>(x, mean, rstd, gamma, beta, y, HW, C, G, silu, round_tf32);
   return launched("gn_apply");
 }
 
@@ -629,7 +652,7 @@ int mas_gn_backward(const float* dy, const float* x, const float* mean, const fl
                     void* ws, size_t ws_bytes, void* stream) {
   if (int e = gn_check(N, HW, C, G)) return e;
   if (ws_bytes < mas_gn_ws_bytes(N, HW, C, G)) return fail(MAS_ERR_WORKSPACE, "gn_backward: workspace too small");
-  int chunks = gn_chunks(HW);
+  int chunks = gn_chunks(N, HW, C);
   double* part = (double*)ws;
   double* nc = part + (size_t)N * chunks * C * 2;
   float* AB = (float*)(nc + (size_t)N * C * 2);

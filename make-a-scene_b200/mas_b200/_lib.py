@@ -64,6 +64,9 @@ _SPEC = {
     "mas_gemm": (_I, [_P, _P, _P, _I, _I, _I, _I, _L, _L, _L, _L, _L, _L, _I, _I, _F, _P, _P, _I, _P]),
     "mas_colsum_ws_bytes": (_Z, [_T]),
     "mas_colsum": (_I, [_P, _T, _P, _P, _Z, _P]),
+    "mas_attnblock_ws_bytes": (_Z, [_I, _I, _I, _I]),
+    "mas_attnblock_forward": (_I, [_P, _I, _I, _I, _I] + [_P] * 18 + [_I, _P, _Z, _P]),
+    "mas_attnblock_backward": (_I, [_P, _P, _I, _I, _I, _I] + [_P] * 19 + [_I, _P, _Z, _P]),
     "mas_softmax_forward": (_I, [_P, _P, _L, _I, _P]),
     "mas_softmax_backward": (_I, [_P, _P, _P, _L, _I, _F, _P]),
     "mas_bn_stats": (_I, [_P, _L, _I, _P, _P]),
@@ -139,6 +142,9 @@ def call(name, *args):
         rc = fn(*conv)
         e1.record()
         shp = ",".join("%dc%d" % (a.c, a.h) for a in args if isinstance(a, Tensor4))
+        if not shp and name.startswith("mas_gn_"):   # (N, HW, C) travel as plain ints there
+            ints = [a for a in args if isinstance(a, int) and not isinstance(a, bool)]
+            shp = "x".join(str(v) for v in ints[:3])
         _prof.append((name + ("|" + shp if shp else ""), e0, e1))
     else:
         rc = fn(*conv)

@@ -504,24 +504,21 @@ class AttnBlockFn(torch.autograd.Function):
         if mean_in is None:
             mean_in, rstd_in = gn_stats(x)
         mean, rstd = mean_in, rstd_in
-        hn = gn_apply(x, mean, rstd, nw, nb, False)
-        qkv = torch.empty((M, 3 * c), dtype=torch.float32, device=x.device)
-        for i, (wt, bs) in enumerate(((qw, qb), (kw, kb), (vw, vb))):
-            gemm_w(hn, c, wt, (qkv, i * c), 3 * c, M, bias=bs)
-        P = torch.empty((n, hw, hw), dtype=torch.float32, device=x.device)
-        gemm((qkv, 0), (qkv, c), P, hw, hw, c, batch=n, lda=3 * c, ldb=3 * c, ldc=hw, sa=hw * 3 * c, sb=hw * 3 * c,
-             sc=hw * hw, tb=True, alpha=float(int(c) ** (-0.5)))
-        L.call("mas_softmax_forward", P, P, n * hw, hw)
+        dev = x.device
+        hn = empty_nhwc(n, c, h, w, x)
+        qkv = torch.empty((M, 3 * c), dtype=torch.float32, device=dev)
+        P = torch.empty((n, hw, hw), dtype=torch.float32, device=dev)
         O = empty_nhwc(n, c, h, w, x)
-        gemm(P, (qkv, 2 * c), O, hw, c, hw, batch=n, lda=hw, ldb=3 * c, ldc=c, sa=hw * hw, sb=hw * 3 * c, sc=hw * c)
-        # proj_out + residual; its epilogue emits the statistics of the following GroupNorm when it can
         out = empty_nhwc(n, c, h, w, x)
+        # proj_out's epilogue emits the statistics of the following GroupNorm when it runs on the tensor path
         part = None
-        if _tc_on() and hw % 128 == 0 and c % (4 * GN_GROUPS) == 0:
-            part = torch.empty((M // 128) * c * 2, dtype=torch.float32, device=x.device)
-        on_tc = gemm_w(O, c, pw, out, c, M, bias=pb, residual=x, stats_part=part)
+        if _tc_on() and hw % 128 == 0 and c % 128 == 0:
+            part = torch.empty((M // 128) * c * 2, dtype=torch.float32, device=dev)
+        ws = L.workspace(L.query("mas_attnblock_ws_bytes", n, hw, c, GN_GROUPS), dev)
+        L.call("mas_attnblock_forward", x, n, hw, c, GN_GROUPS, mean, rstd, nw, nb, qw.contiguous(), qb, kw.contiguous(), kb,
+               vw.contiguous(), vb, pw.contiguous(), pb, hn, qkv, P, O, out, part, _cfg["impl"], ws, ws.numel())
         ctx.save_for_backward(x, mean, rstd, hn, qkv, P, O, nw, nb, qw, kw, vw, pw)
-        if part is not None and on_tc:
+        if part is not None:
             mo, ro = _finalize_stats(part, hw // 128, n, c, hw)
             ctx.mark_non_differentiable(mo, ro)
             return out, mo, ro
@@ -532,32 +529,20 @@ class AttnBlockFn(torch.autograd.Function):
         x, mean, rstd, hn, qkv, P, O, nw, nb, qw, kw, vw, pw = ctx.saved_tensors
         dout = nhwc(dout)
         n, c, h, w = x.shape
-        hw, M = h * w, n * h * w
-        scale = float(int(c) ** (-0.5))
-        dO = conv1x1_dgrad_raw(dout, pw)
-        dpw, dpb = conv1x1_wgrad_raw(O, dout, M, c, c)
-        dqkv = torch.empty_like(qkv)
-        # dV[j,c] = sum_i P[i,j] dO[i,c]
-        gemm(P, dO, (dqkv, 2 * c), hw, c, hw, batch=n, lda=hw, ldb=c, ldc=3 * c, sa=hw * hw, sb=hw * c, sc=hw * 3 * c, ta=True)
-        # dP[i,j] = sum_c dO[i,c] V[j,c]
-        dP = torch.empty_like(P)
-        gemm(dO, (qkv, 2 * c), dP, hw, hw, c, batch=n, lda=c, ldb=3 * c, ldc=hw, sa=hw * c, sb=hw * 3 * c, sc=hw * hw, tb=True)
-        L.call("mas_softmax_backward", P, dP, dP, n * hw, hw, scale)   # dP <- dS (already times 1/sqrt(c))
-        # dQ[i,c] = sum_j dS[i,j] K[j,c] ; dK[j,c] = sum_i dS[i,j] Q[i,c]
-        gemm(dP, (qkv, c), (dqkv, 0), hw, c, hw, batch=n, lda=hw, ldb=3 * c, ldc=3 * c, sa=hw * hw, sb=hw * 3 * c, sc=hw * 3 * c)
-        gemm(dP, (qkv, 0), (dqkv, c), hw, c, hw, batch=n, lda=hw, ldb=3 * c, ldc=3 * c, sa=hw * hw, sb=hw * 3 * c, sc=hw * 3 * c,
-             ta=True)
-        # dhn = dq.Wq + dk.Wk + dv.Wv (chained through the GEMM residual input)
-        dhn = empty_nhwc(n, c, h, w, x)
-        gemm_w((dqkv, 0), 3 * c, qw, dhn, c, M, transpose=True)
-        gemm_w((dqkv, c), 3 * c, kw, dhn, c, M, transpose=True, residual=dhn)
-        gemm_w((dqkv, 2 * c), 3 * c, vw, dhn, c, M, transpose=True, residual=dhn)
-        grads_w = []
-        for i in range(3):
-            grads_w.append(conv1x1_wgrad_raw(hn, dqkv, M, c, c, ldy=3 * c, dy_off=i * c))
-        dx, dnw, dnb = gn_backward(dhn, x, mean, rstd, nw, nb, False, dx_add=dout)
-        (dqw, dqb), (dkw, dkb), (dvw, dvb) = grads_w
-        return dx, None, None, dnw, dnb, dqw, dqb, dkw, dkb, dvw, dvb, dpw, dpb
+        hw = h * w
+        dev = x.device
+        dx = torch.empty_like(x)
+        dnw, dnb = torch.empty_like(nw), torch.empty_like(nb)
+        dqkv_w = torch.empty((3 * c,) + tuple(qw.shape[1:]), dtype=torch.float32, device=dev)
+        dqkv_b = torch.empty(3 * c, dtype=torch.float32, device=dev)
+        dpw = torch.empty_like(pw, memory_format=torch.contiguous_format)
+        dpb = torch.empty(c, dtype=torch.float32, device=dev)
+        ws = L.workspace(L.query("mas_attnblock_ws_bytes", n, hw, c, GN_GROUPS), dev)
+        L.call("mas_attnblock_backward", dout, x, n, hw, c, GN_GROUPS, mean, rstd, nw, nb, qw.contiguous(), kw.contiguous(),
+               vw.contiguous(), pw.contiguous(), hn, qkv, P, O, dx, dnw, dnb, dqkv_w, dqkv_b, dpw, dpb, _cfg["impl"], ws,
+               ws.numel())
+        return (dx, None, None, dnw, dnb, dqkv_w[:c], dqkv_b[:c], dqkv_w[c:2 * c], dqkv_b[c:2 * c], dqkv_w[2 * c:], dqkv_b[2 * c:],
+                dpw, dpb)
 
 
 class BatchNormFn(torch.autograd.Function):

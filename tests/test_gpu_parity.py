@@ -292,7 +292,10 @@ def test_groupnorm_swish_vs_oracle(c, hw):
 @pytest.mark.parametrize("cin,cout,h,w,mode", [(3, 32, 9, 7, "s1"), (32, 3, 8, 8, "s1"), (64, 64, 16, 16, "s1"),
                                                (128, 128, 32, 32, "s1"), (128, 256, 8, 24, "s1"), (256, 128, 16, 16, "s1"),
                                                (512, 512, 16, 16, "s1"), (64, 64, 16, 16, "s2"), (128, 128, 32, 32, "s2"),
-                                               (64, 64, 8, 8, "up"), (128, 128, 16, 16, "up"), (159, 128, 8, 8, "s1")])
+                                               (64, 64, 8, 8, "up"), (128, 128, 16, 16, "up"), (159, 128, 8, 8, "s1"),
+                                               # register-tiled edge kernels (wide side % 128 == 0), ragged strips / tiles
+                                               (3, 128, 19, 37, "s1"), (3, 256, 9, 7, "s1"), (128, 3, 21, 35, "s1"),
+                                               (256, 3, 8, 8, "s1"), (3, 128, 32, 64, "s1"), (128, 3, 32, 64, "s1")])
 def test_conv3x3_family_vs_oracle(cin, cout, h, w, mode, impl):
     import torch.nn.functional as F
     from mas_b200 import _lib as L, ops
