@@ -100,6 +100,8 @@ int mas_pack_conv3x3_tc(const float* w_oihw, float* w_tc, int Cout, int Cin, int
 int mas_conv3x3_fprop_tc(const float* x, mas_tensor4 xs, const float* w_tc, const float* bias,
                          const float* residual, float* y, mas_tensor4 ys, int mode, const float* gn_table,
                          int gn_silu, float* stats_part, void* stream);
+/* Both packings of one weight (transpose = 0 and 1 of mas_pack_conv3x3_tc) in a single pass; Cout % 128 == Cin % 128 == 0. */
+int mas_pack_conv3x3_tc_pair(const float* w_oihw, float* w_tc_fwd, float* w_tc_dgrad, int Cout, int Cin, void* stream);
 int mas_gn_finalize_partials(const float* part, int tiles_per_image, int N, int C, int G, int64_t hw, float eps,
                              float* mean, float* rstd, void* stream);
 int mas_gn_table(const float* mean, const float* rstd, const float* gamma, const float* beta, int N, int C, int G,

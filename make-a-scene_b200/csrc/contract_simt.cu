@@ -354,6 +354,99 @@ __global__ void __launch_bounds__(256) gemm_simt(const float* __restrict__ A, co
   }
 }
 
+// Large aligned case (the AttnBlock token contractions: M, N multiples of 128, K of 16, 16-byte aligned operands):
+// 128x128 tile, 8x8 accumulators per thread as 2x2 blocks of 4x4 (so every shared-memory read is a conflict-free LDS.128
+// and four of them feed 64 FMAs), K step 16, register-prefetched global loads into a double-buffered tile: one barrier
+// per K step.  Strict fp32 like torch.bmm (modules.py:180,186).
+constexpr int G2_BK = 16, G2_LD = 132;
+__global__ void __launch_bounds__(256, 2) gemm_simt128(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int K,
+                                                    int64_t lda, int64_t ldb, int64_t ldc, int64_t sa, int64_t sb, int64_t sc, int ta, int tb,
+                                                    float alpha, const float* __restrict__ bias, const float* __restrict__ res) {
+  __shared__ __align__(16) float As[2][G2_BK][G2_LD];
+  __shared__ __align__(16) float Bs[2][G2_BK][G2_LD];
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+  const int m0 = blockIdx.y * 128, n0 = blockIdx.x * 128;
+  A += (int64_t)blockIdx.z * sa;
+  B += (int64_t)blockIdx.z * sb;
+  C += (int64_t)blockIdx.z * sc;
+  if (res) res += (int64_t)blockIdx.z * sc;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  float4 ra[2], rb[2];
+  // operand stored [rows = M or N][K] (K contiguous): thread reads 4 consecutive k of row (t>>2)+64*i -> transposed scalar stores
+  // operand stored [K][rows]          (rows contiguous): thread reads 4 consecutive rows of k = (t>>5)+8*i -> one 16-byte store
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      ra[i] = ta ? __ldg(reinterpret_cast<const float4*>(A + (int64_t)(k0 + (t >> 5) + 8 * i) * lda + m0 + (t & 31) * 4))
+                 : __ldg(reinterpret_cast<const float4*>(A + (int64_t)(m0 + (t >> 2) + 64 * i) * lda + k0 + (t & 3) * 4));
+      rb[i] = tb ? __ldg(reinterpret_cast<const float4*>(B + (int64_t)(n0 + (t >> 2) + 64 * i) * ldb + k0 + (t & 3) * 4))
+                 : __ldg(reinterpret_cast<const float4*>(B + (int64_t)(k0 + (t >> 5) + 8 * i) * ldb + n0 + (t & 31) * 4));
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      if (ta) *reinterpret_cast<float4*>(&As[buf][(t >> 5) + 8 * i][(t & 31) * 4]) = ra[i];
+      else {
+        const int r = (t >> 2) + 64 * i, k = (t & 3) * 4;
+        As[buf][k + 0][r] = ra[i].x; As[buf][k + 1][r] = ra[i].y; As[buf][k + 2][r] = ra[i].z; As[buf][k + 3][r] = ra[i].w;
+      }
+      if (!tb) *reinterpret_cast<float4*>(&Bs[buf][(t >> 5) + 8 * i][(t & 31) * 4]) = rb[i];
+      else {
+        const int r = (t >> 2) + 64 * i, k = (t & 3) * 4;
+        Bs[buf][k + 0][r] = rb[i].x; Bs[buf][k + 1][r] = rb[i].y; Bs[buf][k + 2][r] = rb[i].z; Bs[buf][k + 3][r] = rb[i].w;
+      }
+    }
+  };
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = 0; k0 < K; k0 += G2_BK) {
+    const bool more = k0 + G2_BK < K;
+    if (more) gload(k0 + G2_BK);
+#pragma unroll
+    for (int k = 0; k < G2_BK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (more) {
+      sstore(buf ^ 1);   // the other buffer was last read before the previous barrier
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int n = n0 + h * 64 + tx * 4;
+      float4 v = make_float4(alpha * acc[i][h * 4 + 0], alpha * acc[i][h * 4 + 1], alpha * acc[i][h * 4 + 2], alpha * acc[i][h * 4 + 3]);
+      if (bias) {
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + n));
+        v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+      }
+      if (res) {
+        const float4 r = __ldg(reinterpret_cast<const float4*>(res + (int64_t)m * ldc + n));
+        v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+      }
+      *reinterpret_cast<float4*>(C + (int64_t)m * ldc + n) = v;
+    }
+  }
+}
+
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 int conv_geom(ConvGeom& g, mas_tensor4 xs, mas_tensor4 ys, int Cin, int Cout, int mode, int ks) {
@@ -437,6 +530,10 @@ int gemm_simt_launch(const float* A, const float* B, float* C, int M, int N, int
                      cudaStream_t st) {
   int vecA = al16(A) && lda % 4 == 0 && sa % 4 == 0, vecB = al16(B) && ldb % 4 == 0 && sb % 4 == 0;
   int vecC = al16(C) && ldc % 4 == 0 && sc % 4 == 0 && (!res || al16(res));
+  if (M % 128 == 0 && N % 128 == 0 && K % G2_BK == 0 && vecA && vecB && vecC && (!bias || al16(bias))) {
+    gemm_simt128<<<dim3(N / 128, M / 128, batch), 256, 0, st>>>(A, B, C, K, lda, ldb, ldc, sa, sb, sc, ta, tb, alpha, bias, res);
+    return launched("gemm_simt128");
+  }
   dim3 grid((unsigned)cdiv(N, 64), (unsigned)cdiv(M, 64), batch);
   gemm_simt<<<grid, 256, 0, st>>>(A, B, C, M, N, K, lda, ldb, ldc, sa, sb, sc, ta, tb, alpha, bias, res, vecA, vecB, vecC);
   return launched("gemm_simt");

@@ -441,6 +441,29 @@ __global__ void pack_weights_tc(const float* __restrict__ w, float* __restrict__
   }
 }
 
+// forward and data-gradient packings of one 3x3 weight in a single pass over it (both are needed every training step)
+__global__ void pack_weights_tc_pair(const float* __restrict__ w, float* __restrict__ out_f, float* __restrict__ out_d, int Cout, int Cin) {
+  constexpr int taps = 9, KC = 8, quads = KC / 4;
+  const int64_t total = (int64_t)Cout * Cin * taps;
+  const int nchunks = Cin / KC, nchunks_d = Cout / KC;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i;
+    const int e = (int)(r % 4); r /= 4;
+    const int nn = (int)(r % BN); r /= BN;
+    const int q = (int)(r % quads); r /= quads;
+    const int t = (int)(r % taps); r /= taps;
+    const int kc = (int)(r % nchunks); r /= nchunks;
+    const int nt = (int)r;
+    const int n = nt * BN + nn, k = kc * KC + q * 4 + e;  // n = cout, k = cin
+    const float v = round_tf32(w[((size_t)n * Cin + k) * taps + t]);
+    out_f[i] = v;
+    // data-gradient operand: N = cin, K = cout, taps flipped
+    const int td = taps - 1 - t;
+    const int64_t j = ((((int64_t)(k / BN) * nchunks_d + n / KC) * taps + td) * quads + (n % KC) / 4) * BN * 4 + (int64_t)(k % BN) * 4 + (n % 4);
+    out_d[j] = v;
+  }
+}
+
 
 // ------------------------------------------------------------------------------------------------------------
 // Weight gradient on tcgen05:  dW[tap][co][ci] = sum_pixels dy[p][co] * xa[p + tap][ci]
@@ -1056,6 +1079,13 @@ int mas_pack_conv3x3_tc(const float* w_oihw, float* w_tc, int Cout, int Cin, int
   int64_t total = (int64_t)9 * Cout * Cin;
   tc::pack_weights_tc<<<(int)(cdiv(total, 256) < 2368 ? cdiv(total, 256) : 2368), 256, 0, S(stream)>>>(w_oihw, w_tc, Cout, Cin, 9, 8, transpose);
   return launched("pack_weights_tc<9>");
+}
+
+int mas_pack_conv3x3_tc_pair(const float* w_oihw, float* w_tc_fwd, float* w_tc_dgrad, int Cout, int Cin, void* stream) {
+  if (Cout % tc::BN || Cin % tc::BN) return fail(MAS_ERR_UNSUPPORTED, "pack_conv3x3_tc_pair: Cout=%d and Cin=%d must be multiples of 128", Cout, Cin);
+  int64_t total = (int64_t)9 * Cout * Cin;
+  tc::pack_weights_tc_pair<<<(int)(cdiv(total, 256) < 2368 ? cdiv(total, 256) : 2368), 256, 0, S(stream)>>>(w_oihw, w_tc_fwd, w_tc_dgrad, Cout, Cin);
+  return launched("pack_weights_tc_pair");
 }
 
 int mas_pack_gemm_tc(const float* w_nk, float* w_tc, int N, int K, int transpose, void* stream) {

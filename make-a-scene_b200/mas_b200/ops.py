@@ -121,7 +121,8 @@ def _finalize_stats(part, tiles_per_image, n, c, hw):
     return mean, rstd
 
 
-def conv3x3_raw(x, weight, bias, residual, mode, out_nchw=False, transpose=False, table=None, silu=True, want_stats=False):
+def conv3x3_raw(x, weight, bias, residual, mode, out_nchw=False, transpose=False, table=None, silu=True, want_stats=False,
+                prepack=False):
     """y = conv3x3(x; weight) (+bias, +residual). transpose=True applies the data-gradient operand
     (taps flipped, Cin<->Cout). Dense NHWC shapes with Cin%8==0, Cout%128==0, Hout%16==0, Wout%8==0 run on the
     tcgen05 kernel; everything else (edge layers, NCHW views, small images) on the fp32 SIMT kernel.
@@ -139,8 +140,7 @@ def conv3x3_raw(x, weight, bias, residual, mode, out_nchw=False, transpose=False
     wc = weight.contiguous()
     stats = None
     if _tc_on() and not out_nchw and L.query("mas_conv3x3_tc_eligible", xs, ys, mode):
-        wt = torch.empty(9 * cout * cin, dtype=torch.float32, device=x.device)
-        L.call("mas_pack_conv3x3_tc", wc, wt, weight.shape[0], weight.shape[1], int(transpose))
+        wt = _packed_conv_weight(wc, weight, cout, cin, transpose, x.device, prepack)
         part = None
         if want_stats and cout % (4 * GN_GROUPS) == 0:
             tiles = n * (ho // 16) * (wo // 8)
@@ -159,6 +159,29 @@ def conv3x3_raw(x, weight, bias, residual, mode, out_nchw=False, transpose=False
     if want_stats:
         return y, stats
     return y
+
+
+# data-gradient packings produced together with the forward packing (one pass over the weight), consumed by the backward
+# of the same step; keyed by storage address and checked against the tensor version, so a weight that changed in between
+# (or a second backward through a retained graph) simply repacks
+_dgrad_packs = {}
+
+
+def _packed_conv_weight(wc, weight, cout, cin, transpose, dev, prepack=False):
+    key = wc.data_ptr()
+    if transpose:
+        hit = _dgrad_packs.pop(key, None)
+        if hit is not None and hit[0] == weight._version and hit[1].device == dev:
+            return hit[1]
+    wt = torch.empty(9 * cout * cin, dtype=torch.float32, device=dev)
+    if prepack and not transpose and cout % 128 == 0 and cin % 128 == 0:
+        # forward of a training step whose backward will run the data gradient: it wants the transposed packing
+        wd = torch.empty(9 * cout * cin, dtype=torch.float32, device=dev)
+        L.call("mas_pack_conv3x3_tc_pair", wc, wt, wd, weight.shape[0], weight.shape[1])
+        _dgrad_packs[key] = (weight._version, wd)
+        return wt
+    L.call("mas_pack_conv3x3_tc", wc, wt, weight.shape[0], weight.shape[1], int(transpose))
+    return wt
 
 
 def conv3x3_wgrad_raw(x, dy, cout, cin, mode, want_bias=True, table=None, silu=True):
@@ -342,7 +365,7 @@ class Conv3x3Fn(torch.autograd.Function):
             y = conv3x3_raw(x4, w9, bias, None, L.CONV_S1)
             x = x4   # saved for the weight gradient (the 4C-channel view carries the same data)
         else:
-            y = conv3x3_raw(x, weight, bias, residual, mode, out_nchw)
+            y = conv3x3_raw(x, weight, bias, residual, mode, out_nchw, prepack=ctx.needs_input_grad[0])
         ctx.save_for_backward(x, weight)
         ctx.mode, ctx.has_bias, ctx.has_res, ctx.edge = mode, bias is not None, residual is not None, edge
         return y
@@ -435,17 +458,17 @@ class ResnetBlockFn(torch.autograd.Function):
         sc = x if sw is None else conv1x1_raw(x, sw, sb)
         if fused:
             t1 = gn_table(m1, r1, n1w, n1b, n, cin)
-            h1, st2 = conv3x3_raw(x, c1w, c1b, None, L.CONV_S1, table=t1, want_stats=True)
+            h1, st2 = conv3x3_raw(x, c1w, c1b, None, L.CONV_S1, table=t1, want_stats=True, prepack=ctx.needs_input_grad[0])
             m2, r2 = st2
             t2 = gn_table(m2, r2, n2w, n2b, n, cout)
-            out, st_out = conv3x3_raw(h1, c2w, c2b, sc, L.CONV_S1, table=t2, want_stats=True)
+            out, st_out = conv3x3_raw(h1, c2w, c2b, sc, L.CONV_S1, table=t2, want_stats=True, prepack=any(ctx.needs_input_grad))
             a1 = a2 = None
         else:
             a1 = gn_apply(x, m1, r1, n1w, n1b, True)
-            h1 = conv3x3_raw(a1, c1w, c1b, None, L.CONV_S1)
+            h1 = conv3x3_raw(a1, c1w, c1b, None, L.CONV_S1, prepack=ctx.needs_input_grad[0])
             m2, r2 = gn_stats(h1)
             a2 = gn_apply(h1, m2, r2, n2w, n2b, True)
-            out = conv3x3_raw(a2, c2w, c2b, sc, L.CONV_S1)
+            out = conv3x3_raw(a2, c2w, c2b, sc, L.CONV_S1, prepack=any(ctx.needs_input_grad))
             st_out = None
         ctx.save_for_backward(x, h1, a1, a2, m1, r1, m2, r2, n1w, n1b, c1w, n2w, n2b, c2w, sw)
         ctx.has_sc, ctx.fused = sw is not None, fused
