@@ -286,7 +286,10 @@ class Codebook(nn.Module):
         if self.training:
             self.q_counter += 1
             if self.q_counter > self.q_start_collect:
-                self._collect(z)
+                if getattr(self, "defer_collect", False):   # under a captured step (mas_b200.graph): sampled after the replay
+                    self._deferred_z = z.detach()
+                else:
+                    self._collect(z)
             if self.q_counter < self.q_init:
                 return ops.nhwc(z), z.new_tensor(0), None  # warm-up bypass, modules.py:482-484
             if self.q_init <= self.q_counter < self.q_re_end:

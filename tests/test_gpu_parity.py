@@ -206,6 +206,47 @@ def test_vqbase_tiny_modes():
     assert abs(float(diff) - float(mo["diff_eval"])) < TOL_FWD * abs(float(mo["diff_eval"]))
 
 
+def test_graphed_step_matches_eager():
+    """mas_b200.graph.GraphedStep: the captured step replays to the same loss / gradients as eager launches, for changing
+    inputs, and keeps the host-side codebook state (q_counter, reservoir) advancing like eager steps do."""
+    from models import VQBASE
+    from mas_b200.graph import GraphedStep
+    g = _load("vqbase_tiny.pt")
+    dev = _dev()
+
+    def make():
+        m = VQBASE(g["ddconfig"], g["n_embed"], g["embed_dim"], 10, 100)
+        m.load_state_dict(g["state_dict"])
+        m.quantize.q_counter = 10 ** 6
+        return m.train().to(dev)
+
+    def loss_fn(m, x):
+        dec, diff = m(x)
+        return (x - dec).abs().mean() + diff
+    xs = [g["x"].to(dev), (g["x"] * 0.5 + 0.25).to(dev), g["x"].flip(0).contiguous().to(dev)]
+    me, mg = make(), make()
+    gs = GraphedStep(mg, loss_fn, xs[0], warmup=2)
+    for _ in range(2):                       # the two eager warm-up steps inside GraphedStep advance BN statistics too
+        me.zero_grad(set_to_none=True)
+        loss_fn(me, xs[0]).backward()
+    assert mg.quantize.q_counter == me.quantize.q_counter
+    for x in xs:
+        me.zero_grad(set_to_none=True)
+        le = loss_fn(me, x)
+        le.backward()
+        lg = gs(x)
+        assert abs(float(lg) - float(le)) <= 1e-6 * abs(float(le)) + 1e-9
+        for (k, pe), (_, pg) in zip(me.named_parameters(), mg.named_parameters()):
+            assert pg.grad is not None and rel_err(pg.grad, pe.grad) < 1e-6, k
+        assert mg.quantize.q_counter == me.quantize.q_counter
+        assert mg.quantize.reservoir.shape == me.quantize.reservoir.shape
+    assert rel_err(mg.quant_conv[1].running_mean, me.quant_conv[1].running_mean) < 1e-6
+    gs.close()
+    mg.zero_grad(set_to_none=True)
+    loss_fn(mg, xs[0]).backward()            # eager stepping works again after close()
+    assert mg.decoder.model[-1].weight.grad is not None
+
+
 def test_reentrant_backward_last_layer():
     """loss_img.py:57-60 runs autograd.grad(..., last_layer.weight, retain_graph=True) twice before backward()."""
     from models import VQBASE
