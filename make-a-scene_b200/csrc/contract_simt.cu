@@ -232,7 +232,15 @@ __global__ void __launch_bounds__(256) conv_wgrad_simt(const float* __restrict__
     }
 }
 // dw[co][ci][tap] = sum_split part[split][tap][co][ci]
-__global__ void conv_wgrad_reduce(const float* __restrict__ part, int splits, int ntap, int Cout, int Cin, float* __restrict__ dw) {
+// optionally also dbias[c] = sum_split bpart[split][c] (the tensor-path kernel emits bias partials next to the weight partials)
+__global__ void conv_wgrad_reduce(const float* __restrict__ part, int splits, int ntap, int Cout, int Cin, float* __restrict__ dw,
+                                  const float* __restrict__ bpart = nullptr, float* __restrict__ dbias = nullptr) {
+  if (bpart)
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < Cout; c += gridDim.x * blockDim.x) {
+      float a = 0.f;
+      for (int s = 0; s < splits; ++s) a += bpart[(size_t)s * Cout + c];
+      dbias[c] = a;
+    }
   int64_t total = (int64_t)Cout * Cin * ntap;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int tap = (int)(i / ((int64_t)Cout * Cin));
@@ -520,9 +528,11 @@ int conv_wgrad_simt_launch(const float* x, mas_tensor4 xs, const float* dy, mas_
   return launched("conv_wgrad_reduce");
 }
 
-void conv_wgrad_reduce_launch(const float* part, int splits, int ntap, int Cout, int Cin, float* dw, cudaStream_t st) {
+void conv_wgrad_reduce_launch(const float* part, int splits, int ntap, int Cout, int Cin, float* dw, const float* bpart, float* dbias,
+                              cudaStream_t st) {
   int64_t total = (int64_t)ntap * Cout * Cin;
-  conv_wgrad_reduce<<<(int)(cdiv(total, 256) < 1184 ? cdiv(total, 256) : 1184), 256, 0, st>>>(part, splits, ntap, Cout, Cin, dw);
+  conv_wgrad_reduce<<<(int)(cdiv(total, 256) < 1184 ? cdiv(total, 256) : 1184), 256, 0, st>>>(part, splits, ntap, Cout, Cin, dw,
+                                                                                             dbias ? bpart : nullptr, dbias);
 }
 
 int gemm_simt_launch(const float* A, const float* B, float* C, int M, int N, int K, int batch, int64_t lda, int64_t ldb, int64_t ldc,

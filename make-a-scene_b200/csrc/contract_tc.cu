@@ -861,18 +861,10 @@ __global__ void __launch_bounds__(128, 1) mma_probe(const float* __restrict__ A,
   if (warp == 0) tmem_dealloc(tb, 64);
 }
 
-// dbias[c] = sum_split bpart[split][c]
-__global__ void bias_reduce(const float* __restrict__ bpart, int splits, int C, float* __restrict__ out) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float a = 0.f;
-  for (int s = 0; s < splits; ++s) a += bpart[(size_t)s * C + c];
-  out[c] = a;
-}
-
 }  // namespace tc
 
-void conv_wgrad_reduce_launch(const float* part, int splits, int ntap, int Cout, int Cin, float* dw, cudaStream_t st);
+void conv_wgrad_reduce_launch(const float* part, int splits, int ntap, int Cout, int Cin, float* dw, const float* bpart, float* dbias,
+                              cudaStream_t st);
 
 static bool dense_nhwc(const mas_tensor4& t) {
   return t.sc == 1 && t.sw == t.c && t.sh == t.w * t.c && t.sn == t.h * t.w * t.c;
@@ -1020,13 +1012,8 @@ static int wgrad_tc_run(tc::WParams& p, int splits, float* dw, float* dbias, voi
   dim3 grid((unsigned)(p.Cin / NT), (unsigned)(p.Cout / tc::BM), (unsigned)splits);
   tc::wgrad_tc<TAPS, PRO><<<grid, tc::WG_THREADS, smem, st>>>(p, dy_map);
   if (int e = launched("wgrad_tc")) return e;
-  conv_wgrad_reduce_launch((const float*)ws, splits, TAPS, p.Cout, p.Cin, dw, st);
-  if (int e = launched("conv_wgrad_reduce")) return e;
-  if (dbias) {
-    tc::bias_reduce<<<(int)cdiv(p.Cout, 128), 128, 0, st>>>(p.bpart, splits, p.Cout, dbias);
-    return launched("bias_reduce");
-  }
-  return MAS_OK;
+  conv_wgrad_reduce_launch((const float*)ws, splits, TAPS, p.Cout, p.Cin, dw, p.bpart, dbias, st);  // + bias partials -> dbias
+  return launched("conv_wgrad_reduce");
 }
 // dbias (may be null) is produced here too when the tensor path runs.
 int conv_wgrad_tc_launch(const float* x, mas_tensor4 xs, const float* dy, mas_tensor4 dys, float* dw, float* dbias, int mode,

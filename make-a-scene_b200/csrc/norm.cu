@@ -232,30 +232,45 @@ __global__ void gn_bwd_nc(const double* __restrict__ part, int N, int nchunks, i
   if (i >= N * C) return;
   int n = i / C, c = i % C;
   double a = 0, b = 0;
-  for (int k = 0; k < nchunks; ++k) {
-    const double* o = part + (((size_t)n * nchunks + k) * C + c) * 2;
-    a += o[0];
-    b += o[1];
+  const double2* o = reinterpret_cast<const double2*>(part) + (size_t)n * nchunks * C + c;
+  int k = 0;
+  for (; k + 7 < nchunks; k += 8) {   // eight chunks in flight (fixed order of additions)
+    double2 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = o[(size_t)(k + j) * C];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a += v[j].x; b += v[j].y; }
   }
+  for (; k < nchunks; ++k) { const double2 v = o[(size_t)k * C]; a += v.x; b += v.y; }
   nc[(size_t)i * 2 + 0] = a;
   nc[(size_t)i * 2 + 1] = b;
 }
-// stage 2 (one block; N*C <= 32*512): dgamma/dbeta and per-(n,g) A,B
-__global__ void gn_bwd_final(int N, int C, int G, const float* __restrict__ gamma, const double* __restrict__ nc,
-                             float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ AB /*[N][G][2]*/,
-                             double inv_m) {
+// stage 2: dgamma/dbeta (blocks [0, cblocks): one thread per channel, sum over images) and the per-(n,g) coefficients
+// A,B of the apply pass (remaining blocks: one thread per (image, group)).  Both read only nc, so they share a launch.
+__global__ void __launch_bounds__(128) gn_bwd_final(int N, int C, int G, const float* __restrict__ gamma, const double* __restrict__ nc,
+                                                    float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                    float* __restrict__ AB /*[N][G][2]*/, double inv_m, int cblocks) {
   const int cpg = C / G;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  if ((int)blockIdx.x < cblocks) {
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    if (c >= C) return;
     double a = 0, b = 0;
-    for (int n = 0; n < N; ++n) {
-      a += nc[((size_t)n * C + c) * 2 + 0];
-      b += nc[((size_t)n * C + c) * 2 + 1];
+    const double2* p = reinterpret_cast<const double2*>(nc) + c;
+    int n = 0;
+    for (; n + 7 < N; n += 8) {   // eight images in flight (fixed order of additions)
+      double2 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = p[(size_t)(n + k) * C];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { a += v[k].x; b += v[k].y; }
     }
+    for (; n < N; ++n) { const double2 v = p[(size_t)n * C]; a += v.x; b += v.y; }
     dgamma[c] = (float)a;
     dbeta[c] = (float)b;
-  }
-  for (int i = threadIdx.x; i < N * G; i += blockDim.x) {
-    int n = i / G, g = i % G;
+  } else {
+    const int i = (blockIdx.x - cblocks) * 128 + threadIdx.x;
+    if (i >= N * G) return;
+    const int n = i / G, g = i % G;
     double a = 0, b = 0;
     for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
       a += (double)gamma[c] * nc[((size_t)n * C + c) * 2 + 0];
@@ -662,7 +677,9 @@ int mas_gn_backward(const float* dy, const float* x, const float* mean, const fl
   if (int e = launched("gn_bwd_partial")) return e;
   gn_bwd_nc<<<(int)cdiv((int64_t)N * C, 128), 128, 0, S(stream)>>>(part, N, chunks, C, nc);
   if (int e = launched("gn_bwd_nc")) return e;
-  gn_bwd_final<<<1, 1024, 0, S(stream)>>>(N, C, G, gamma, nc, dgamma, dbeta, AB, 1.0 / ((double)HW * (C / G)));
+  const int cblocks = (int)cdiv(C, 128);
+  gn_bwd_final<<<cblocks + (int)cdiv((int64_t)N * G, 128), 128, 0, S(stream)>>>(N, C, G, gamma, nc, dgamma, dbeta, AB,
+                                                                                1.0 / ((double)HW * (C / G)), cblocks);
   if (int e = launched("gn_bwd_final")) return e;
   gn_bwd_apply<<<dim3(chunks, N), GN_THREADS, 0, S(stream)>>>(dy, x, mean, rstd, gamma, beta, AB, dx_add, dx, HW, C, G, silu);
   return launched("gn_bwd_apply");

@@ -477,10 +477,13 @@ class ResnetBlockFn(torch.autograd.Function):
         else:
             mo, ro = st_out
             ctx.mark_non_differentiable(mo, ro)
+        ctx.set_materialize_grads(False)   # no zero-fill launches for the (non-differentiable) statistics outputs
         return out, mo, ro
 
     @staticmethod
     def backward(ctx, dout, _gm, _gr):
+        if dout is None:
+            return (None,) * 13
         x, h1, a1, a2, m1, r1, m2, r2, n1w, n1b, c1w, n2w, n2b, c2w, sw = ctx.saved_tensors
         dout = nhwc(dout)
         cout, cin = c1w.shape[0], c1w.shape[1]
@@ -541,6 +544,7 @@ class AttnBlockFn(torch.autograd.Function):
         L.call("mas_attnblock_forward", x, n, hw, c, GN_GROUPS, mean, rstd, nw, nb, qw.contiguous(), qb, kw.contiguous(), kb,
                vw.contiguous(), vb, pw.contiguous(), pb, hn, qkv, P, O, out, part, _cfg["impl"], ws, ws.numel())
         ctx.save_for_backward(x, mean, rstd, hn, qkv, P, O, nw, nb, qw, kw, vw, pw)
+        ctx.set_materialize_grads(False)   # no zero-fill launches for the (non-differentiable) statistics outputs
         if part is not None:
             mo, ro = _finalize_stats(part, hw // 128, n, c, hw)
             ctx.mark_non_differentiable(mo, ro)
@@ -549,6 +553,8 @@ class AttnBlockFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout, _gm, _gr):
+        if dout is None:
+            return (None,) * 13
         x, mean, rstd, hn, qkv, P, O, nw, nb, qw, kw, vw, pw = ctx.saved_tensors
         dout = nhwc(dout)
         n, c, h, w = x.shape
