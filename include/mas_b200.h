@@ -247,6 +247,23 @@ int mas_embed3_forward(const float* t0, const int64_t* id0, const float* t1, con
 int mas_embed3_backward(const float* dout, const int64_t* id0, float* d0, const int64_t* id1, float* d1,
                         const int64_t* id2, float* d2, int64_t R, int H, int seg, int total, int off, void* stream);
 
+/* ---- Autoregressive sampling with a KV cache ---------------------------------------------
+ * The reference has no working cached path (models/transformer.py:73-115 vs :176-210; train.py never samples); the
+ * specification is its non-cached forward (transformer.py:77-103, 216-244): a decode step reproduces the logits the
+ * full causal forward gives at that position.
+ * mas_linear_small: y[r,n] = act(sum_k x[r,k] W[n,k] + b[n]) for R <= 8 rows (cond + uncond streams), strict fp32,
+ *   W [N,K] row-major (nn.Linear layout) streamed once; act 0 = none, 1 = tanh-GELU (transformer.py:11-14).
+ * mas_kv_append: k / v thirds of a fused qkv activation [R,T,3H] -> caches [R,heads,Tmax,hd] at pos0..pos0+T-1.
+ * mas_attn_decode: softmax(q k^T / sqrt(hd)) v for ONE query per (row, head) (qkv [R,3H]) over the first `len`
+ *   cached positions; ctx [R,H].  mas_cfg_mix: out = uncond + scale * (cond - uncond) (classifier-free guidance). */
+int mas_linear_small(const float* x, int64_t ldx, const float* W, const float* bias, float* y, int64_t ldy, int R, int N,
+                     int K, int act, void* stream);
+int mas_kv_append(const float* qkv, int R, int T, int heads, int hd, float* kcache, float* vcache, int Tmax, int pos0,
+                  void* stream);
+int mas_attn_decode(const float* qkv, const float* kcache, const float* vcache, float* ctx, int R, int heads, int hd,
+                    int Tmax, int len, void* stream);
+int mas_cfg_mix(const float* cond, const float* uncond, float* out, int64_t n, float scale, void* stream);
+
 /* ---- weighted BCE-with-logits (VQ-SEG loss, losses/loss_seg.py:15-22) — "next" row ------------------
  * logits/target: strided [N,H,W,C] views; pos_weight [C]; loss_out = mean over all elements. grad may be NULL. */
 int mas_bce_logits(const float* logits, mas_tensor4 ls, const float* target, mas_tensor4 ts,

@@ -87,6 +87,10 @@ _SPEC = {
     "mas_softmax_causal_forward": (_I, [_P, _P, _L, _I, _I, _P]),
     "mas_embed3_forward": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P]),
     "mas_embed3_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P]),
+    "mas_linear_small": (_I, [_P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _P]),
+    "mas_kv_append": (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _P]),
+    "mas_attn_decode": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "mas_cfg_mix": (_I, [_P, _P, _P, _L, _F, _P]),
     "mas_bce_ws_bytes": (_Z, [_T]),
     "mas_bce_logits": (_I, [_P, _T, _P, _T, _P, _P, _P, _T, _F, _P, _Z, _P]),
 }

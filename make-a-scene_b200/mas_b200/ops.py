@@ -822,6 +822,41 @@ class CausalAttentionFn(torch.autograd.Function):
         return dqkv, None
 
 
+# ---- autoregressive sampling (inference only) --------------------------------------------------
+def linear_small(x, weight, bias, act=0):
+    """nn.Linear for a handful of rows ([R<=8, K] -> [R, N]): the weight-streaming decode kernel, strict fp32.
+    act=1 fuses the tanh-GELU of MLP.lin1 (transformer.py:11-14)."""
+    _need_cuda(x)
+    x = x.contiguous()
+    R, K = x.shape
+    N = weight.shape[0]
+    y = torch.empty((R, N), dtype=torch.float32, device=x.device)
+    L.call("mas_linear_small", x, K, weight.contiguous(), bias, y, N, R, N, K, int(act))
+    return y
+
+
+def kv_append(qkv, kcache, vcache, pos0):
+    """qkv [R,T,3H] (fused q|k|v activation) -> caches [R,heads,Tmax,hd] at positions pos0..pos0+T-1."""
+    R, heads, Tmax, hd = kcache.shape
+    T = qkv.shape[1]
+    L.call("mas_kv_append", qkv.contiguous(), R, T, heads, hd, kcache, vcache, Tmax, int(pos0))
+
+
+def attn_decode(qkv, kcache, vcache, length):
+    """One query per (row, head) (qkv [R,3H]) against the first `length` cached positions -> ctx [R,H]."""
+    R, heads, Tmax, hd = kcache.shape
+    ctx = torch.empty((R, heads * hd), dtype=torch.float32, device=qkv.device)
+    L.call("mas_attn_decode", qkv.contiguous(), kcache, vcache, ctx, R, heads, hd, Tmax, int(length))
+    return ctx
+
+
+def cfg_mix(cond, uncond, scale):
+    """Classifier-free guidance on logits: uncond + scale * (cond - uncond)."""
+    out = torch.empty_like(cond)
+    L.call("mas_cfg_mix", cond.contiguous(), uncond.contiguous(), out, cond.numel(), float(scale))
+    return out
+
+
 class EmbedFn(torch.autograd.Function):
     """Token + (row, column | position) embedding sums for the text / segmentation / image segments, written straight
     into the concatenated [B, total, H] sequence (transformer.py:350-364)."""

@@ -2,8 +2,10 @@
 
 Same class names, constructor signatures, attribute names and state_dict keys (including the `transformer.mask`
 buffer). Supported configuration = the reference's defaults: cogview_pb_relax=True (a softmax-invariant shift),
-sandwich LayerNorm, no prescale, no rudalle_relax, dropout 0, no KV cache (the reference's cache path is broken:
-transformer.py:73 vs :181). Anything else raises — there is no fallback path.
+sandwich LayerNorm, no prescale, no rudalle_relax, dropout 0. The reference's `cache` / `use_cache` arguments raise
+(its cache path is broken: transformer.py:73 vs :181); autoregressive sampling with a KV cache and
+classifier-free guidance is `MakeAScene.generate` (new API, SURVEY.md 8f-3: specified by the non-cached forward).
+Anything else raises — there is no fallback path.
 """
 import math
 
@@ -162,7 +164,8 @@ class MakeAScene(nn.Module):
             module.bias.data.zero_()
             module.weight.data.fill_(1.0)
 
-    def forward(self, text_tokens, seg_tokens, img_tokens):
+    def _embed(self, text_tokens, seg_tokens, img_tokens):
+        """Token + position embeddings of the concatenated sequence, transformer.py:350-364."""
         dev = text_tokens.device
         text_range = torch.arange(self.text_length, device=dev) + (self.text_vocab_size - self.text_length)
         text_tokens = torch.where(text_tokens == 0, text_range, text_tokens)      # pad-id trick, transformer.py:350-353
@@ -177,7 +180,101 @@ class MakeAScene(nn.Module):
             segs.append((img_tokens, ar(img_tokens.shape[1]) // ip, ar(img_tokens.shape[1]) % ip, total))
             tables += [self.image_token_embedding.weight, self.image_row_embeddings.weight, self.image_col_embeddings.weight]
             total += img_tokens.shape[1]
-        emb = ops.EmbedFn.apply(segs, total, self.hidden_dim, *tables)
+        return ops.EmbedFn.apply(segs, total, self.hidden_dim, *tables)
+
+    def forward(self, text_tokens, seg_tokens, img_tokens):
+        emb = self._embed(text_tokens, seg_tokens, img_tokens)
         out, _ = self.transformer(emb)
         logits = self.to_logits[1](self.to_logits[0](out))
         return logits[:, -self.image_length - 1:-1, :]
+
+    # ---- sampling ---------------------------------------------------------------------------
+    def _prefill(self, emb, kc, vc):
+        """Full causal pass over the text+segmentation prefix with the training kernels, recording every layer's k / v."""
+        x = emb
+        heads = self.transformer.layers[0].attn.num_attn_heads
+        for li, layer in enumerate(self.transformer.layers):
+            qkv = layer.attn.qkv(layer.ln_in(x))
+            ops.kv_append(qkv, kc[li], vc[li], 0)
+            a = layer.attn.out_proj(ops.CausalAttentionFn.apply(qkv, heads))
+            x = layer.first_ln_sandwich(a, residual=x) if layer.cogview_sandwich_layernorm else x + a
+            m = layer.mlp(layer.ln_out(x))
+            x = layer.second_ln_sandwich(m, residual=x) if layer.cogview_sandwich_layernorm else x + m
+        return x[:, -1].contiguous()
+
+    def _decode_step(self, x, kc, vc, pos):
+        """One new token per row (x [R,H], absolute position pos) through all layers against the cache."""
+        for li, layer in enumerate(self.transformer.layers):
+            at, mlp = layer.attn, layer.mlp
+            qkv = ops.linear_small(layer.ln_in(x), at.qkv.weight, at.qkv.bias)
+            ops.kv_append(qkv.view(qkv.shape[0], 1, -1), kc[li], vc[li], pos)
+            a = ops.linear_small(ops.attn_decode(qkv, kc[li], vc[li], pos + 1), at.out_proj.weight, at.out_proj.bias)
+            x = layer.first_ln_sandwich(a, residual=x) if layer.cogview_sandwich_layernorm else x + a
+            m = ops.linear_small(layer.ln_out(x), mlp.lin1.weight, mlp.lin1.bias, act=1)
+            m = ops.linear_small(m, mlp.lin2.weight, mlp.lin2.bias)
+            x = layer.second_ln_sandwich(m, residual=x) if layer.cogview_sandwich_layernorm else x + m
+        return x
+
+    def _logits_of(self, hidden):
+        h = self.to_logits[0](self.transformer.final_ln(hidden))
+        return ops.linear_small(h, self.to_logits[1].weight, self.to_logits[1].bias)
+
+    @torch.no_grad()
+    def generate(self, text_tokens, seg_tokens, guidance_scale=None, uncond_text_tokens=None, temperature=1.0, top_k=None,
+                 generator=None, img_tokens=None, return_logits=False):
+        """Autoregressive sampling of the image tokens with a KV cache; optional classifier-free guidance
+        (logits = uncond + scale * (cond - uncond), the unconditional stream sees padded text; Make-A-Scene paper 3.4).
+
+        text_tokens [B,text_length], seg_tokens [B,seg_length] int64. B (x2 with guidance) <= 8 rows per call.
+        temperature 0 = greedy; top_k keeps the k most likely codes. img_tokens (optional [B,image_length]) are fed
+        instead of the sampled ones (teacher forcing — what the parity test uses). Returns tokens [B,image_length]
+        (and the per-position logits [B,image_length,V] actually sampled from when return_logits=True)."""
+        B = text_tokens.shape[0]
+        dev = text_tokens.device
+        cfg = guidance_scale is not None and float(guidance_scale) != 1.0
+        if cfg:
+            if uncond_text_tokens is None:
+                uncond_text_tokens = torch.zeros_like(text_tokens)          # all padding -> the per-position pad ids
+            text_all = torch.cat([text_tokens, uncond_text_tokens], 0)
+            seg_all = torch.cat([seg_tokens, seg_tokens], 0)
+        else:
+            text_all, seg_all = text_tokens, seg_tokens
+        R = text_all.shape[0]
+        if R > 8:
+            raise ValueError("generate: at most 8 rows per call (batch x2 with guidance)")
+        layers = self.transformer.layers
+        heads = layers[0].attn.num_attn_heads
+        hd = self.hidden_dim // heads
+        kc = [torch.empty((R, heads, self.total_length, hd), dtype=torch.float32, device=dev) for _ in layers]
+        vc = [torch.empty_like(k) for k in kc]
+        prefix = text_all.shape[1] + seg_all.shape[1]
+        logits = self._logits_of(self._prefill(self._embed(text_all, seg_all, None), kc, vc))
+        ip = self.image_tokens_per_dim
+        toks, kept = [], []
+        for t in range(self.image_length):
+            mixed = ops.cfg_mix(logits[:B], logits[B:], guidance_scale) if cfg else logits
+            if return_logits:
+                kept.append(mixed)
+            if img_tokens is not None:
+                tok = img_tokens[:, t]
+            elif not temperature:
+                tok = mixed.argmax(-1)
+            else:
+                z = mixed / float(temperature)
+                if top_k is not None:
+                    kth = torch.topk(z, int(top_k), dim=-1).values[:, -1:]
+                    z = torch.where(z < kth, torch.full_like(z, float("-inf")), z)
+                tok = torch.multinomial(torch.softmax(z, -1), 1, generator=generator).squeeze(1)
+            toks.append(tok)
+            if t == self.image_length - 1:
+                break
+            tok_all = torch.cat([tok, tok], 0) if cfg else tok
+            row = torch.full((1,), t // ip, dtype=torch.long, device=dev)
+            col = torch.full((1,), t % ip, dtype=torch.long, device=dev)
+            emb = ops.EmbedFn.apply([(tok_all.view(R, 1), row, col, 0)], 1, self.hidden_dim, self.image_token_embedding.weight,
+                                    self.image_row_embeddings.weight, self.image_col_embeddings.weight)
+            logits = self._logits_of(self._decode_step(emb.view(R, self.hidden_dim), kc, vc, prefix + t))
+        tokens = torch.stack(toks, 1)
+        if return_logits:
+            return tokens, torch.stack(kept, 1)
+        return tokens
