@@ -29,12 +29,12 @@ __global__ void __launch_bounds__(256) linear_small_kernel(const float* __restri
   for (int r = 0; r < R; ++r) acc[r] = 0.f;
   const int K4 = K >> 2;
   int k = lane;
-  for (; k + 96 < K4; k += 128) {  // four weight quads in flight per lane
-    float4 wv[4];
+  for (; k + 224 < K4; k += 256) {  // eight weight quads (128 B per lane, 4 KB per warp) in flight: the stream is latency-bound
+    float4 wv[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) wv[u] = __ldg(w4 + k + 32 * u);
+    for (int u = 0; u < 8; ++u) wv[u] = __ldg(w4 + k + 32 * u);
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < 8; ++u)
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (size_t)r * ldx) + k + 32 * u);
@@ -85,65 +85,90 @@ __global__ void kv_append_kernel(const float* __restrict__ qkv, int R, int T, in
   }
 }
 
-// block per (row, head), 128 threads; q = this token's query (row r of qkv [R, 3H]); len cached positions (incl. this one)
-__global__ void __launch_bounds__(128) attn_decode_kernel(const float* __restrict__ qkv, const float* __restrict__ kc,
-                                                          const float* __restrict__ vc, float* __restrict__ ctx, int heads, int hd,
-                                                          int Tmax, int len) {
-  extern __shared__ float sm[];  // [hd] q, [len] scores, [128] scratch, [128] partial outputs
+// block per (row, head), 256 threads; q = this token's query (row r of qkv [R, 3H]); len cached positions (incl. this one).
+// Everything is latency-bound here (a few hundred KB per block), so both passes keep many independent 16-byte loads in
+// flight: HD is a template parameter (fully unrolled dot products), the v pass is unrolled eight positions deep.
+template <int HD>
+__global__ void __launch_bounds__(256) attn_decode_kernel(const float* __restrict__ qkv, const float* __restrict__ kc,
+                                                          const float* __restrict__ vc, float* __restrict__ ctx, int heads, int Tmax,
+                                                          int len) {
+  extern __shared__ __align__(16) float sm[];  // [HD] q, [len] scores, [32] scratch, [256/(HD/4)][HD] partial outputs
+  constexpr int Q = HD / 4, GROUPS = 256 / Q;
   float* qs = sm;
-  float* sc = sm + hd;
-  float* red = sc + len;
-  float* po = red + 128;
-  const int r = blockIdx.x / heads, h = blockIdx.x % heads, H = heads * hd, t0 = threadIdx.x;
-  for (int d = t0; d < hd; d += 128) qs[d] = qkv[(size_t)r * 3 * H + h * hd + d];
+  float* sc = sm + HD;
+  float* red = sc + ((len + 3) & ~3);
+  float* po = red + 32;
+  const int r = blockIdx.x / heads, h = blockIdx.x % heads, H = heads * HD, t0 = threadIdx.x, lane = t0 & 31, warp = t0 >> 5;
+  if (t0 < HD) qs[t0] = qkv[(size_t)r * 3 * H + h * HD + t0];
   __syncthreads();
-  const float alpha = rsqrtf((float)hd);
-  const float* kb = kc + ((size_t)r * heads + h) * Tmax * hd;
-  const float* vb = vc + ((size_t)r * heads + h) * Tmax * hd;
+  const float alpha = rsqrtf((float)HD);
+  const float* kb = kc + ((size_t)r * heads + h) * Tmax * HD;
+  const float* vb = vc + ((size_t)r * heads + h) * Tmax * HD;
+  float4 q4[Q];
+#pragma unroll
+  for (int i = 0; i < Q; ++i) q4[i] = *reinterpret_cast<const float4*>(qs + 4 * i);
   float mx = -INFINITY;
-  for (int t = t0; t < len; t += 128) {
-    const float4* kr = reinterpret_cast<const float4*>(kb + (size_t)t * hd);
-    float s = 0.f;
-    for (int d4 = 0; d4 < (hd >> 2); ++d4) {
-      const float4 kv = __ldg(kr + d4);
-      s = fmaf(qs[d4 * 4 + 0], kv.x, s); s = fmaf(qs[d4 * 4 + 1], kv.y, s);
-      s = fmaf(qs[d4 * 4 + 2], kv.z, s); s = fmaf(qs[d4 * 4 + 3], kv.w, s);
+  for (int t = t0; t < len; t += 256) {
+    const float4* kr = reinterpret_cast<const float4*>(kb + (size_t)t * HD);
+    float4 kv[Q];
+#pragma unroll
+    for (int i = 0; i < Q; ++i) kv[i] = __ldg(kr + i);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+      s0 = fmaf(q4[i].x, kv[i].x, s0); s1 = fmaf(q4[i].y, kv[i].y, s1);
+      s2 = fmaf(q4[i].z, kv[i].z, s2); s3 = fmaf(q4[i].w, kv[i].w, s3);
     }
-    s *= alpha;
+    const float s = ((s0 + s1) + (s2 + s3)) * alpha;
     sc[t] = s;
     mx = fmaxf(mx, s);
   }
-  red[t0] = mx;
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
   __syncthreads();
-  for (int o = 64; o > 0; o >>= 1) {
-    if (t0 < o) red[t0] = fmaxf(red[t0], red[t0 + o]);
-    __syncthreads();
-  }
   mx = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
   __syncthreads();
   float sum = 0.f;
-  for (int t = t0; t < len; t += 128) {
+  for (int t = t0; t < len; t += 256) {
     const float e = expf(sc[t] - mx);
     sc[t] = e;
     sum += e;
   }
-  red[t0] = sum;
+  sum = warp_sum(sum);
+  if (lane == 0) red[8 + warp] = sum;
   __syncthreads();
-  for (int o = 64; o > 0; o >>= 1) {
-    if (t0 < o) red[t0] += red[t0 + o];
-    __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) tot += red[8 + w];
+  const float inv = 1.f / tot;
+  // ctx[d] = sum_t p_t v[t][d]: thread = (quad of d, one of GROUPS interleaved t ranges); 16-byte loads coalesced over d
+  const int dq = t0 % Q, g = t0 / Q;
+  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+  int t = g;
+  for (; t + 7 * GROUPS < len; t += 8 * GROUPS) {
+    float4 vv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) vv[u] = __ldg(reinterpret_cast<const float4*>(vb + (size_t)(t + u * GROUPS) * HD) + dq);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float p = sc[t + u * GROUPS];
+      o.x = fmaf(p, vv[u].x, o.x); o.y = fmaf(p, vv[u].y, o.y); o.z = fmaf(p, vv[u].z, o.z); o.w = fmaf(p, vv[u].w, o.w);
+    }
   }
-  const float inv = 1.f / red[0];
-  // ctx[d] = sum_t p_t v[t][d]: the 128 threads form 128/hd groups that split the t range; reads coalesced over d
-  const int groups = 128 / hd, d = t0 % hd, gidx = t0 / hd;
-  float o_ = 0.f;
-  for (int t = gidx; t < len; t += groups) o_ = fmaf(sc[t], __ldg(vb + (size_t)t * hd + d), o_);
-  po[gidx * hd + d] = o_;
+  for (; t < len; t += GROUPS) {
+    const float4 vv = __ldg(reinterpret_cast<const float4*>(vb + (size_t)t * HD) + dq);
+    const float p = sc[t];
+    o.x = fmaf(p, vv.x, o.x); o.y = fmaf(p, vv.y, o.y); o.z = fmaf(p, vv.z, o.z); o.w = fmaf(p, vv.w, o.w);
+  }
+  *reinterpret_cast<float4*>(po + (size_t)g * HD + 4 * dq) = o;
   __syncthreads();
-  if (t0 < hd) {
+  if (t0 < HD) {
     float v = 0.f;
-    for (int g2 = 0; g2 < groups; ++g2) v += po[g2 * hd + t0];
-    ctx[(size_t)r * H + h * hd + t0] = v * inv;
+#pragma unroll 4
+    for (int g2 = 0; g2 < GROUPS; ++g2) v += po[g2 * HD + t0];
+    ctx[(size_t)r * H + h * HD + t0] = v * inv;
   }
 }
 
@@ -155,9 +180,71 @@ __global__ void cfg_mix_kernel(const float* __restrict__ cond, const float* __re
   }
 }
 
+// K-split variant for long rows and few outputs (MLP.lin2: N = 1024, K = 4096 gives only 128 blocks of the kernel above
+// and a 16 KB latency-bound stream per warp): a block owns two outputs, four warps each split one row of W, partials are
+// folded in a fixed order (deterministic).
+template <int R>
+__global__ void __launch_bounds__(256) linear_small_ks_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ W,
+                                                              const float* __restrict__ bias, float* __restrict__ y, int64_t ldy, int N,
+                                                              int K, int act) {
+  __shared__ float part[8][R];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = blockIdx.x * 2 + (warp >> 2), slice = warp & 3;
+  const int K4 = K >> 2, per = (K4 + 3) / 4, k0 = slice * per, k1 = min(K4, k0 + per);
+  float acc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc[r] = 0.f;
+  if (n < N) {
+    const float4* w4 = reinterpret_cast<const float4*>(W + (size_t)n * K);
+    int k = k0 + lane;
+    for (; k + 224 < k1; k += 256) {
+      float4 wv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) wv[u] = __ldg(w4 + k + 32 * u);
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (size_t)r * ldx) + k + 32 * u);
+          acc[r] = fmaf(wv[u].x, xv.x, acc[r]); acc[r] = fmaf(wv[u].y, xv.y, acc[r]);
+          acc[r] = fmaf(wv[u].z, xv.z, acc[r]); acc[r] = fmaf(wv[u].w, xv.w, acc[r]);
+        }
+    }
+    for (; k < k1; k += 32) {
+      const float4 wv = __ldg(w4 + k);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (size_t)r * ldx) + k);
+        acc[r] = fmaf(wv.x, xv.x, acc[r]); acc[r] = fmaf(wv.y, xv.y, acc[r]);
+        acc[r] = fmaf(wv.z, xv.z, acc[r]); acc[r] = fmaf(wv.w, xv.w, acc[r]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc[r] = warp_sum(acc[r]);
+  if (lane == 0)
+#pragma unroll
+    for (int r = 0; r < R; ++r) part[warp][r] = acc[r];
+  __syncthreads();
+  if (threadIdx.x < 2 * R) {
+    const int o = threadIdx.x / R, r = threadIdx.x % R, nn = blockIdx.x * 2 + o;
+    if (nn < N) {
+      float v = ((part[o * 4 + 0][r] + part[o * 4 + 1][r]) + (part[o * 4 + 2][r] + part[o * 4 + 3][r])) + (bias ? __ldg(bias + nn) : 0.f);
+      if (act == 1) {
+        const float u = 0.7978845608028654f * v * (1.f + 0.044715f * v * v);
+        v = 0.5f * v * (1.f + tanhf(u));
+      }
+      y[(size_t)r * ldy + nn] = v;
+    }
+  }
+}
+
 template <int R>
 int linear_small_run(const float* x, int64_t ldx, const float* W, const float* bias, float* y, int64_t ldy, int N, int K, int act,
                      cudaStream_t st) {
+  if (K >= 2048 && N <= 2048) {
+    linear_small_ks_kernel<R><<<(int)cdiv(N, 2), 256, 0, st>>>(x, ldx, W, bias, y, ldy, N, K, act);
+    return launched("linear_small_ks");
+  }
   linear_small_kernel<R><<<(int)cdiv(N, 8), 256, 0, st>>>(x, ldx, W, bias, y, ldy, N, K, act);
   return launched("linear_small");
 }
@@ -199,11 +286,17 @@ int mas_kv_append(const float* qkv, int R, int T, int heads, int hd, float* kcac
 int mas_attn_decode(const float* qkv, const float* kcache, const float* vcache, float* ctx, int R, int heads, int hd, int Tmax, int len,
                     void* stream) {
   MAS_REQUIRE(qkv && kcache && vcache && ctx && R > 0 && heads > 0, "attn_decode: bad arguments");
-  if (hd % 4 || hd > 128 || 128 % hd) return fail(MAS_ERR_UNSUPPORTED, "attn_decode: head dim must divide 128 and be a multiple of 4 (got %d)", hd);
   if (len <= 0 || len > Tmax) return fail(MAS_ERR_INVALID_ARG, "attn_decode: cache length %d outside (0, %d]", len, Tmax);
-  const size_t smem = (size_t)(hd + len + 128 + 128) * sizeof(float);
+  const size_t smem = (size_t)(hd + ((len + 3) & ~3) + 32 + 1024) * sizeof(float);
   if (smem > 48 * 1024) return fail(MAS_ERR_UNSUPPORTED, "attn_decode: sequence too long for the single-pass kernel (%d)", len);
-  attn_decode_kernel<<<R * heads, 128, smem, S(stream)>>>(qkv, kcache, vcache, ctx, heads, hd, Tmax, len);
+  const int grid = R * heads;
+  switch (hd) {
+    case 16: attn_decode_kernel<16><<<grid, 256, smem, S(stream)>>>(qkv, kcache, vcache, ctx, heads, Tmax, len); break;
+    case 32: attn_decode_kernel<32><<<grid, 256, smem, S(stream)>>>(qkv, kcache, vcache, ctx, heads, Tmax, len); break;
+    case 64: attn_decode_kernel<64><<<grid, 256, smem, S(stream)>>>(qkv, kcache, vcache, ctx, heads, Tmax, len); break;
+    case 128: attn_decode_kernel<128><<<grid, 256, smem, S(stream)>>>(qkv, kcache, vcache, ctx, heads, Tmax, len); break;
+    default: return fail(MAS_ERR_UNSUPPORTED, "attn_decode: head dim %d (supported: 16, 32, 64, 128)", hd);
+  }
   return launched("attn_decode");
 }
 

@@ -129,6 +129,52 @@ class Transformer(nn.Module):
         return self.final_ln(x), {}
 
 
+class _GraphedDecoder:
+    """KV caches + one captured CUDA graph per image position for MakeAScene.generate(use_graphs=True).
+
+    A decode step is ~250 launches of a few microseconds each (24 layers x 10 kernels): launched from Python it is
+    host-bound (~22 us per launch). The kernels only depend on the position through launch parameters, so each position
+    gets its own graph (captured on first use, replayed in position order afterwards; the graphs share one memory pool)."""
+
+    def __init__(self, model, rows, dev):
+        layers = model.transformer.layers
+        heads = layers[0].attn.num_attn_heads
+        hd = model.hidden_dim // heads
+        self.model, self.rows = model, rows
+        self.kc = [torch.empty((rows, heads, model.total_length, hd), dtype=torch.float32, device=dev) for _ in layers]
+        self.vc = [torch.empty_like(k) for k in self.kc]
+        self.tok = torch.zeros(rows, dtype=torch.long, device=dev)
+        self.pool = torch.cuda.graph_pool_handle()
+        self.graphs, self.keep = {}, {}
+
+    def eager_step(self, t, tok_all, prefix):
+        m = self.model
+        dev, ip, R = tok_all.device, m.image_tokens_per_dim, self.rows
+        row = torch.full((1,), t // ip, dtype=torch.long, device=dev)
+        col = torch.full((1,), t % ip, dtype=torch.long, device=dev)
+        return self._body(tok_all, row, col, prefix + t)
+
+    def _body(self, tok, row, col, pos):
+        m, R = self.model, self.rows
+        emb = ops.EmbedFn.apply([(tok.view(R, 1), row, col, 0)], 1, m.hidden_dim, m.image_token_embedding.weight,
+                                m.image_row_embeddings.weight, m.image_col_embeddings.weight)
+        return m._logits_of(m._decode_step(emb.view(R, m.hidden_dim), self.kc, self.vc, pos))
+
+    def graphed_step(self, t, tok_all, prefix):
+        self.tok.copy_(tok_all)
+        if t not in self.graphs:
+            dev, ip = tok_all.device, self.model.image_tokens_per_dim
+            row = torch.full((1,), t // ip, dtype=torch.long, device=dev)
+            col = torch.full((1,), t % ip, dtype=torch.long, device=dev)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=self.pool):
+                out = self._body(self.tok, row, col, prefix + t)
+            self.graphs[t], self.keep[t] = g, (out, row, col)
+        self.graphs[t].replay()
+        return self.keep[t][0]
+
+
 class MakeAScene(nn.Module):
     def __init__(self, num_layers, hidden_dim, num_attn_heads, image_vocab_size, seg_vocab_size, text_vocab_size,
                  image_tokens_per_dim, seg_tokens_per_dim, text_length):
@@ -154,6 +200,10 @@ class MakeAScene(nn.Module):
                   self.image_col_embeddings):
             self._init_weights(m)
         self.to_logits = torch.nn.Sequential(LayerNorm(hidden_dim), Linear(hidden_dim, image_vocab_size))
+
+    def reset_sampler(self):
+        """Drops the cached KV buffers / CUDA graphs of generate(use_graphs=True)."""
+        self._sampler = None
 
     def _init_weights(self, module):
         if isinstance(module, (nn.Linear, nn.Embedding)):
@@ -221,14 +271,16 @@ class MakeAScene(nn.Module):
 
     @torch.no_grad()
     def generate(self, text_tokens, seg_tokens, guidance_scale=None, uncond_text_tokens=None, temperature=1.0, top_k=None,
-                 generator=None, img_tokens=None, return_logits=False):
+                 generator=None, img_tokens=None, return_logits=False, use_graphs=False):
         """Autoregressive sampling of the image tokens with a KV cache; optional classifier-free guidance
         (logits = uncond + scale * (cond - uncond), the unconditional stream sees padded text; Make-A-Scene paper 3.4).
 
         text_tokens [B,text_length], seg_tokens [B,seg_length] int64. B (x2 with guidance) <= 8 rows per call.
         temperature 0 = greedy; top_k keeps the k most likely codes. img_tokens (optional [B,image_length]) are fed
         instead of the sampled ones (teacher forcing — what the parity test uses). Returns tokens [B,image_length]
-        (and the per-position logits [B,image_length,V] actually sampled from when return_logits=True)."""
+        (and the per-position logits [B,image_length,V] actually sampled from when return_logits=True).
+        use_graphs: replay each position's decode step from a CUDA graph (captured at first use and kept on the module for
+        the same row count; call reset_sampler() after replacing parameter storage)."""
         B = text_tokens.shape[0]
         dev = text_tokens.device
         cfg = guidance_scale is not None and float(guidance_scale) != 1.0
@@ -242,14 +294,14 @@ class MakeAScene(nn.Module):
         R = text_all.shape[0]
         if R > 8:
             raise ValueError("generate: at most 8 rows per call (batch x2 with guidance)")
-        layers = self.transformer.layers
-        heads = layers[0].attn.num_attn_heads
-        hd = self.hidden_dim // heads
-        kc = [torch.empty((R, heads, self.total_length, hd), dtype=torch.float32, device=dev) for _ in layers]
-        vc = [torch.empty_like(k) for k in kc]
+        dec = getattr(self, "_sampler", None)
+        if dec is None or dec.rows != R or dec.tok.device != dev or not use_graphs:
+            dec = _GraphedDecoder(self, R, dev)
+            if use_graphs:
+                self._sampler = dec
+        kc, vc = dec.kc, dec.vc
         prefix = text_all.shape[1] + seg_all.shape[1]
         logits = self._logits_of(self._prefill(self._embed(text_all, seg_all, None), kc, vc))
-        ip = self.image_tokens_per_dim
         toks, kept = [], []
         for t in range(self.image_length):
             mixed = ops.cfg_mix(logits[:B], logits[B:], guidance_scale) if cfg else logits
@@ -269,11 +321,7 @@ class MakeAScene(nn.Module):
             if t == self.image_length - 1:
                 break
             tok_all = torch.cat([tok, tok], 0) if cfg else tok
-            row = torch.full((1,), t // ip, dtype=torch.long, device=dev)
-            col = torch.full((1,), t % ip, dtype=torch.long, device=dev)
-            emb = ops.EmbedFn.apply([(tok_all.view(R, 1), row, col, 0)], 1, self.hidden_dim, self.image_token_embedding.weight,
-                                    self.image_row_embeddings.weight, self.image_col_embeddings.weight)
-            logits = self._logits_of(self._decode_step(emb.view(R, self.hidden_dim), kc, vc, prefix + t))
+            logits = (dec.graphed_step if use_graphs else dec.eager_step)(t, tok_all, prefix)
         tokens = torch.stack(toks, 1)
         if return_logits:
             return tokens, torch.stack(kept, 1)

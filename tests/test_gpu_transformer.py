@@ -82,7 +82,27 @@ def test_generate_guidance_greedy_and_seeded_sampling():
     assert bool((lgb.gather(-1, b.unsqueeze(-1)).squeeze(-1) >= kth).all())
 
 
-@pytest.mark.parametrize("R,N,K,act", [(1, 37, 132, 0), (3, 64, 1024, 1), (8, 130, 4 * 257, 0), (2, 8192, 1024, 0)])
+def test_generate_with_cuda_graphs_matches_eager():
+    """generate(use_graphs=True): first call captures one graph per position, later calls replay them; both reproduce the
+    reference logits under teacher forcing and the eager path's samples under a fixed seed."""
+    m, g, dev = _load_model("tiny")
+    text, seg, img = g["text"].to(dev), g["seg"].to(dev), g["img"].to(dev)
+    for _ in range(2):                       # capture, then replay
+        toks, lg = m.generate(text, seg, img_tokens=img, return_logits=True, use_graphs=True)
+        assert bool((toks == img).all()) and rel_err(lg, g["logits"]) < 2e-3
+    other = img.flip(1).contiguous()         # different tokens through the same graphs
+    _, lg_g = m.generate(text, seg, img_tokens=other, return_logits=True, use_graphs=True)
+    _, lg_e = m.generate(text, seg, img_tokens=other, return_logits=True)
+    assert torch.equal(lg_g, lg_e)
+    a = m.generate(text, seg, guidance_scale=2.0, temperature=1.0, top_k=8, generator=torch.Generator(device=dev).manual_seed(3))
+    b = m.generate(text, seg, guidance_scale=2.0, temperature=1.0, top_k=8, generator=torch.Generator(device=dev).manual_seed(3),
+                   use_graphs=True)   # 4 rows now: a new decoder is captured
+    assert bool((a == b).all())
+    m.reset_sampler()
+
+
+@pytest.mark.parametrize("R,N,K,act", [(1, 37, 132, 0), (3, 64, 1024, 1), (8, 130, 4 * 257, 0), (2, 8192, 1024, 0),
+                                       (2, 1024, 4096, 0), (5, 37, 2052, 1), (8, 2, 4096, 0)])   # last three: K-split variant
 def test_linear_small_vs_torch(R, N, K, act):
     from mas_b200 import ops
     dev = torch.device("cuda:0")
@@ -94,6 +114,22 @@ def test_linear_small_vs_torch(R, N, K, act):
     if act:
         ref = 0.5 * ref * (1.0 + torch.tanh(0.7978845608028654 * ref * (1.0 + 0.044715 * ref * ref)))
     y = ops.linear_small(x.to(dev), w.to(dev), b.to(dev), act=act)
+    assert rel_err(y, ref.float()) < 1e-5
+
+
+@pytest.mark.parametrize("R,H,res", [(1, 1024, True), (2, 1024, False), (8, 4096, True), (3, 132, True), (64, 64, False)])
+def test_layernorm_few_rows_vs_torch(R, H, res):
+    """The block-per-row LayerNorm the decode steps use (R <= 64 rows)."""
+    from mas_b200 import ops
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(R + H)
+    x = torch.randn(R, H, generator=gen) * 3 + 0.5
+    w, b = torch.randn(H, generator=gen), torch.randn(H, generator=gen)
+    r = torch.randn(R, H, generator=gen) if res else None
+    ref = torch.nn.functional.layer_norm(x.double(), (H,), w.double(), b.double(), 1e-5)
+    if res:
+        ref = ref + r.double()
+    y = ops.LayerNormFn.apply(x.to(dev), w.to(dev), b.to(dev), r.to(dev) if res else None, 1e-5)
     assert rel_err(y, ref.float()) < 1e-5
 
 

@@ -17,6 +17,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=1)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--layers", type=int, default=24)
+ap.add_argument("--graphs", action="store_true", help="replay each position's decode step from a CUDA graph")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
@@ -28,18 +29,18 @@ B = args.batch
 text = torch.randint(1, 40000, (B, 128), device=dev)
 seg = torch.randint(0, 1024, (B, 256), device=dev)
 gen = torch.Generator(device=dev).manual_seed(1)
-m.generate(text, seg, guidance_scale=3.0, temperature=1.0, top_k=64, generator=gen)     # warm-up
+m.generate(text, seg, guidance_scale=3.0, temperature=1.0, top_k=64, generator=gen, use_graphs=args.graphs)     # warm-up (captures)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 l0 = _lib.launch_count()
 e0.record()
 for _ in range(args.reps):
-    toks = m.generate(text, seg, guidance_scale=3.0, temperature=1.0, top_k=64, generator=gen)
+    toks = m.generate(text, seg, guidance_scale=3.0, temperature=1.0, top_k=64, generator=gen, use_graphs=args.graphs)
 e1.record()
 torch.cuda.synchronize()
 sec = e0.elapsed_time(e1) * 1e-3 / args.reps
 params = sum(p.numel() for n, p in m.named_parameters() if "embedding" not in n)
 print(json.dumps({"metric": "image tokens/s, classifier-free guided sampling with KV cache", "value": B * 256 / sec, "unit": "tokens/s",
-                  "batch": B, "rows": 2 * B, "seconds_per_image": sec, "launches_per_image": (_lib.launch_count() - l0) // args.reps,
+                  "batch": B, "rows": 2 * B, "cuda_graphs": bool(args.graphs), "seconds_per_image": sec, "launches_per_image": (_lib.launch_count() - l0) // args.reps,
                   "weight_stream_gb_per_token": params * 4 / 1e9,
                   "weight_stream_gbs": params * 4 * 255 / sec / 1e9, "config": cfg}))
