@@ -36,14 +36,13 @@ class VQBASE(nn.Module):
         self.post_quant_conv = Conv2d(embed_dim, ddconfig["z_channels"], 1)
 
     def encode(self, x):
-        h = self.encoder(x)
-        h = self.quant_conv(h)
-        quant, emb_loss, info = self.quantize(h)
-        return quant, emb_loss
+        """image [B,3,H,W] -> (quantised latent [B,embed_dim,h,w], codebook loss); vqvae.py:20-24."""
+        z_q, codebook_loss, _indices = self.quantize(self.quant_conv(self.encoder(x)))
+        return z_q, codebook_loss
 
     def decode(self, quant):
-        quant = self.post_quant_conv(quant)
-        return self.decoder(quant)
+        """quantised latent -> reconstruction; vqvae.py:26-29."""
+        return self.decoder(self.post_quant_conv(quant))
 
     def decode_code(self, code_b, shape=None):
         """Reference vqvae.py:31-34 calls a non-existent `embed_code`; implemented via get_codebook_entry.
@@ -55,6 +54,6 @@ class VQBASE(nn.Module):
         return self.decode(quant_b)
 
     def forward(self, input):
-        quant, diff = self.encode(input)
-        dec = self.decode(quant)
-        return dec, diff
+        """-> (dec, diff) exactly like vqvae.py:36-39 (train.py:84 unpacks this pair)."""
+        z_q, diff = self.encode(input)
+        return self.decode(z_q), diff
