@@ -102,6 +102,8 @@ def cpu_reference_steps(steps, warmup, batch=1):
     sd.update(params)
     x = torch.rand(batch, 3, RES, RES, generator=torch.Generator().manual_seed(1234))
     times = []
+    budget = float(os.environ.get("MAS_CPU_ARM_SECONDS", "150"))   # bounded sample: a step is ~5 s on 64 host cores
+    warmup = min(warmup, 2)
     for i in range(warmup + steps):
         for p in params.values():
             p.grad = None
@@ -110,20 +112,22 @@ def cpu_reference_steps(steps, warmup, batch=1):
         O.proxy_loss(x, dec, diff).backward()
         if i >= warmup:
             times.append(time.perf_counter() - t0)
-    return batch * len(times) / sum(times), sum(times) / len(times)
+            if sum(times) > budget:
+                break
+    return batch * len(times) / sum(times), sum(times) / len(times), len(times)
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    v, sec = cpu_reference_steps(args.steps, args.warmup, batch=1)
+    v, sec, done = cpu_reference_steps(args.steps, args.warmup, batch=1)
     cores = torch.get_num_threads()
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "VQ-IMG 256x256 codebook=8192 dim=256 (BASELINE configs[1])", "sample": "1 image per step"},
             "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
-                             "sample": "%d timed fwd+bwd steps of 1 image (batch-32 workload sampled at batch 1)" % args.steps},
+                             "sample": "%d timed fwd+bwd steps of 1 image (batch-32 workload sampled at batch 1; bounded to ~150 s)" % done},
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -309,8 +313,8 @@ def main():
                     "ms_per_step": sec_e2e / args.steps * 1e3},
             "gpu_launches": int(launches), "clocks": clocks,
             "model_tflops": FLOP_PER_IMG_FWD_BWD * value / 1e12, "roofline": roof, "vq": vq}
-    if not args.no_cpu_baseline:
-        v, s = cpu_reference_steps(3, 1, batch=1)
+    if not args.no_cpu_baseline and world == 1:   # reported baseline: rank 0 at N=1 only
+        v, s, _ = cpu_reference_steps(3, 1, batch=1)
         line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
                                 "sample": "3 timed fwd+bwd steps of 1 image after 1 warm-up (%.1f s/step)" % s}
     print(json.dumps(line), flush=True)
