@@ -108,3 +108,25 @@ def test_transformer_oracle_matches_reference():
         loss.backward()
         for k, gv in g["grads"].items():
             assert rel_err(sd[k].grad, gv) < 2e-4, (tag, k)
+
+
+def test_cached_sampling_oracle_matches_reference_logits():
+    """oracle/transformer_oracle.generate_logits (KV-cached decoding, the algorithm MakeAScene.generate runs on the GPU):
+    teacher-forced it reproduces the logits of the REAL reference's non-cached forward (fixture), and guided greedy
+    decoding follows the arg-max of the mixed cond / uncond logits of two non-cached passes."""
+    from oracle import transformer_oracle as T
+    for tag in ("tiny", "wide"):
+        g = _load(f"transformer_{tag}.pt")
+        sd = {k: v.clone() for k, v in g["state_dict"].items()}
+        with torch.no_grad():
+            toks, lg = T.generate_logits(sd, g["cfg"], g["text"], g["seg"], img_tokens=g["img"])
+        assert torch.equal(toks, g["img"])
+        assert rel_err(lg, g["logits"]) < 1e-4
+    g = _load("transformer_tiny.pt")
+    sd = {k: v.clone() for k, v in g["state_dict"].items()}
+    with torch.no_grad():
+        toks, lg = T.generate_logits(sd, g["cfg"], g["text"], g["seg"], guidance_scale=2.5)
+        cond = T.make_a_scene_forward(sd, g["cfg"], g["text"], g["seg"], toks)
+        unc = T.make_a_scene_forward(sd, g["cfg"], torch.zeros_like(g["text"]), g["seg"], toks)
+    assert rel_err(lg, unc + 2.5 * (cond - unc)) < 1e-4
+    assert torch.equal(toks, lg.argmax(-1))
