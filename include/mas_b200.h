@@ -41,6 +41,8 @@ extern "C" {
 #define MAS_IMPL_AUTO 0  /* tcgen05 (TF32 operands, fp32 accumulate) when the shape is eligible, else SIMT */
 #define MAS_IMPL_SIMT 1  /* fp32 FFMA kernels (exact fp32; also the on-GPU checker for the tensor path)      */
 #define MAS_IMPL_TC 2    /* tcgen05 only; MAS_ERR_UNSUPPORTED if the shape is not eligible                   */
+#define MAS_IMPL_TC3 3   /* mas_gemm only, explicit opt-in: fp32-accurate 3xTF32 operand-split tcgen05 GEMM (staged:
+                          * no module path selects it yet; see csrc/contract_tc3.cu)                            */
 
 typedef struct mas_tensor4 {
   int64_t n, h, w, c;     /* logical extents */

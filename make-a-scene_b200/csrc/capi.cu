@@ -19,6 +19,9 @@ int gemm_tc_launch(const float* A, const float* B, float* C, int M, int N, int K
 size_t conv_wgrad_tc_ws(mas_tensor4 xs, mas_tensor4 dys, int mode);
 int conv_wgrad_tc_launch(const float* x, mas_tensor4 xs, const float* dy, mas_tensor4 dys, float* dw, float* dbias, int mode,
                          const float* gn_table, int gn_silu, void* ws, size_t ws_bytes, cudaStream_t st);
+int gemm_tc3_launch(const float* A, const float* B, float* C, int M, int N, int K, int batch, int64_t lda, int64_t ldb, int64_t ldc,
+                    int64_t sa, int64_t sb, int64_t sc, int ta, int tb, float alpha, const float* bias, const float* res,
+                    cudaStream_t st);
 size_t conv1x1_wgrad_tc_ws(int64_t M, int Cin, int Cout);
 int conv1x1_wgrad_tc_launch(const float* x, int64_t ldx, const float* dy, int64_t ldy, int64_t M, int Cin, int Cout, float* dw,
                             float* dbias, void* ws, size_t ws_bytes, cudaStream_t st);
@@ -96,6 +99,9 @@ int mas_gemm(const float* A, const float* B, float* C, int M, int N, int K, int 
              int64_t stride_a, int64_t stride_b, int64_t stride_c, int trans_a, int trans_b, float alpha, const float* bias,
              const float* residual, int impl, void* stream) {
   MAS_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && batch > 0, "gemm: bad arguments");
+  if (impl == MAS_IMPL_TC3)   // explicit opt-in only (staged kernel): never chosen by MAS_IMPL_AUTO
+    return gemm_tc3_launch(A, B, C, M, N, K, batch, lda, ldb, ldc, stride_a, stride_b, stride_c, trans_a, trans_b, alpha, bias, residual,
+                           S(stream));
   if (impl != MAS_IMPL_SIMT) {
     int e = gemm_tc_launch(A, B, C, M, N, K, batch, lda, ldb, ldc, stride_a, stride_b, stride_c, trans_a, trans_b, alpha, bias,
                            residual, S(stream));
