@@ -21,6 +21,7 @@
 // (modules.py:55-59,74-78), nn.Conv2d 1x1 (modules.py:113-117,145-164).
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 #include "mas_common.cuh"
 
@@ -865,6 +866,8 @@ __global__ void __launch_bounds__(128, 1) mma_probe(const float* __restrict__ A,
 
 void conv_wgrad_reduce_launch(const float* part, int splits, int ntap, int Cout, int Cin, float* dw, const float* bpart, float* dbias,
                               cudaStream_t st);
+int conv3x3_fprop_tc2_launch(const float* x, mas_tensor4 xs, const float* w_tc, const float* bias, const float* res, float* y,
+                             mas_tensor4 ys, int mode, const float* gn_table, int gn_silu, float* stats_part, cudaStream_t st);
 
 static bool dense_nhwc(const mas_tensor4& t) {
   return t.sc == 1 && t.sw == t.c && t.sh == t.w * t.c && t.sn == t.h * t.w * t.c;
@@ -1106,6 +1109,9 @@ int mas_conv3x3_tc_eligible(mas_tensor4 xs, mas_tensor4 ys, int mode) {
 int mas_conv3x3_fprop_tc(const float* x, mas_tensor4 xs, const float* w_tc, const float* bias, const float* residual, float* y,
                          mas_tensor4 ys, int mode, const float* gn_table, int gn_silu, float* stats_part, void* stream) {
   MAS_REQUIRE(x && w_tc && y, "conv3x3_fprop_tc: null pointer");
+  // staged cta_group::2 variant (contract_tc2.cu): explicit opt-in for validation runs only
+  static const bool two_cta = [] { const char* e = getenv("MAS_CONV_2CTA"); return e && e[0] == '1'; }();
+  if (two_cta) return conv3x3_fprop_tc2_launch(x, xs, w_tc, bias, residual, y, ys, mode, gn_table, gn_silu, stats_part, S(stream));
   return conv3x3_fprop_tc_launch(x, xs, w_tc, bias, residual, y, ys, mode, gn_table, gn_silu, stats_part, S(stream));
 }
 
