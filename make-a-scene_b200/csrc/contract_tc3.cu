@@ -6,7 +6,7 @@
 // accumulated in fp32 in tensor memory recovers fp32-level accuracy at three MMAs per K step - still ~5x the FFMA rate.
 //
 //   C[b][m,n] = alpha * sum_k opA(A[b])[m,k] * opB(B[b])[n,k]
-//   * CTA = one 128 x 128 output tile, full K, K chunks of 32; grid (N/128, ceil(M/128), batch)
+//   * CTA = one 128 x BN output tile (BN = 128, or 64 for 64-channel attention heads), full K, K chunks of 32
 //   * BOTH operands are staged by the producer warps straight from the activation tensors (no pack pass): generic loads,
 //     split into hi / lo in registers, st.shared into the K-major no-swizzle UMMA layout [k/4][row][4] (the layout the
 //     convolution kernels use for their weight operand).  Either source orientation works: [row][k] (16-byte loads along
@@ -16,13 +16,13 @@
 //     the MMAs (12 per chunk); 2-stage full/empty mbarrier ring; 128 TMEM columns.
 //
 // STATUS: staged for the next round - built and exported, selected ONLY by impl = MAS_IMPL_TC3 of mas_gemm; no module
-// path uses it until it has been validated on a B200 (tests/test_gpu_tc3.py, opt-in through MAS_EXPERIMENTAL=1).
+// path uses it until it has been validated on a B200 (tests/test_gpu_staged.py, opt-in through MAS_EXPERIMENTAL=1).
 #include "mas_common.cuh"
 
 namespace mas {
 namespace tc3 {
 
-constexpr int BM = 128, BN = 128, KC = 32, STAGES = 2;
+constexpr int BM = 128, KC = 32, STAGES = 2;   // the N tile (128 or 64: attention heads of 64) is a template parameter
 constexpr int NPROD = 256, NTHREADS = 288;   // 8 producer / epilogue warps + the MMA warp
 constexpr int SLOTS = 132;                   // row pitch of an operand plane in 16-byte units (132 % 8 == 4: conflict-free stores)
 constexpr int LBO = SLOTS * 16;              // bytes between k-quads
@@ -87,8 +87,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
          (1ull << 46);
 }
-// instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N=128
-constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
 
 struct P3 {
   const float* A;
@@ -105,7 +107,11 @@ struct Quad4 {
   float4 v[4];
 };
 
+template <int BN>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm3_tc(const P3 p) {
+  constexpr uint32_t IDESC = make_idesc(BN);
+  constexpr int TCOLS = BN < 32 ? 32 : BN;          // tensor-memory columns (power of two >= 32)
+  constexpr int B_ITEMS = BN * (KC / 4) / NPROD;    // 16-byte items of the B operand per producer thread (4 or 2)
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
@@ -128,7 +134,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm3_tc(const P3 p) {
     mbar_init(accum_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(smem_u32(tmem_slot), BN);
+  if (warp == 8) tmem_alloc(smem_u32(tmem_slot), TCOLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -139,9 +145,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm3_tc(const P3 p) {
     // item i (0..3) of this thread, per operand:
     //   k-contiguous source : quad q = item % 8 (k = 4q..4q+3), row = item / 8            -> one 16-byte store at [q][row]
     //   row-contiguous      : k = item % 32, row quad rq = item / 32 (rows 4rq..4rq+3)    -> four 4-byte stores at [k/4][row+j][k%4]
-    auto load_op = [&](const float* base, int64_t ld, int trans, int row0, int rows_total, int kc, Quad4& out) {
+    auto load_op = [&](const float* base, int64_t ld, int trans, int row0, int rows_total, int kc, Quad4& out, int nitems) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
+        if (i >= nitems) break;
         const int item = tid + i * NPROD;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (!trans) {
@@ -161,9 +168,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm3_tc(const P3 p) {
         out.v[i] = v;
       }
     };
-    auto store_op = [&](uint8_t* hi_plane, uint8_t* lo_plane, int trans, const Quad4& in) {
+    auto store_op = [&](uint8_t* hi_plane, uint8_t* lo_plane, int trans, const Quad4& in, int nitems) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
+        if (i >= nitems) break;
         const int item = tid + i * NPROD;
         const float4 v = in.v[i];
         float4 h = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
@@ -186,18 +194,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm3_tc(const P3 p) {
     int stage = 0;
     uint32_t phase = 0;
     Quad4 an, bn;
-    load_op(Ab, p.lda, p.ta, m0, p.M, 0, an);
-    load_op(Bb, p.ldb, p.tb, n0, p.N, 0, bn);
+    load_op(Ab, p.lda, p.ta, m0, p.M, 0, an, 4);
+    load_op(Bb, p.ldb, p.tb, n0, p.N, 0, bn, B_ITEMS);
     for (int kc = 0; kc < nchunks; ++kc) {
       const Quad4 a = an, b = bn;
       if (kc + 1 < nchunks) {   // next chunk's loads fly while this one is split and stored
-        load_op(Ab, p.lda, p.ta, m0, p.M, kc + 1, an);
-        load_op(Bb, p.ldb, p.tb, n0, p.N, kc + 1, bn);
+        load_op(Ab, p.lda, p.ta, m0, p.M, kc + 1, an, 4);
+        load_op(Bb, p.ldb, p.tb, n0, p.N, kc + 1, bn, B_ITEMS);
       }
       mbar_wait(empty_bar(stage), phase ^ 1);
       uint8_t* st = smem + (size_t)stage * STAGE;
-      store_op(st, st + PLANE, p.ta, a);
-      store_op(st + 2 * PLANE, st + 3 * PLANE, p.tb, b);
+      store_op(st, st + PLANE, p.ta, a, 4);
+      store_op(st + 2 * PLANE, st + 3 * PLANE, p.tb, b, B_ITEMS);
       fence_proxy_async();
       mbar_arrive(full_bar(stage));
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -210,8 +218,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm3_tc(const P3 p) {
     float* patch = reinterpret_cast<float*>(smem) + warp * (32 * EP_LD);
     const int sub_r = lane >> 3, sub_c = lane & 7;
 #pragma unroll 1
-    for (int cc = 0; cc < 2; ++cc) {
-      const int col = chalf * 64 + cc * 32;
+    for (int cc = 0; cc < BN / 64; ++cc) {          // the two warp groups split the BN columns in halves of BN/2
+      const int col = chalf * (BN / 2) + cc * 32;
       float v[32];
       tmem_ld32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)col, v);
       __syncwarp();
@@ -257,7 +265,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm3_tc(const P3 p) {
   __syncthreads();
   if (warp == 8) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, TCOLS);
   }
 }
 
@@ -273,8 +281,8 @@ int gemm_tc3_launch(const float* A, const float* B, float* C, int M, int N, int 
                     int64_t sa, int64_t sb, int64_t sc, int ta, int tb, float alpha, const float* bias, const float* res,
                     cudaStream_t st) {
   if (bias || res) return fail(MAS_ERR_UNSUPPORTED, "tc3 gemm: bias / residual epilogue not available");
-  if (N % tc3::BN || K % tc3::KC || lda % 4 || ldb % 4 || ldc % 4 || sa % 4 || sb % 4 || sc % 4 || !al16q(A) || !al16q(B) || !al16q(C))
-    return fail(MAS_ERR_UNSUPPORTED, "tc3 gemm: need N %% 128 == 0, K %% 32 == 0, pitches %% 4 == 0 and 16-byte aligned operands");
+  if (N % 64 || K % tc3::KC || lda % 4 || ldb % 4 || ldc % 4 || sa % 4 || sb % 4 || sc % 4 || !al16q(A) || !al16q(B) || !al16q(C))
+    return fail(MAS_ERR_UNSUPPORTED, "tc3 gemm: need N %% 64 == 0, K %% 32 == 0, pitches %% 4 == 0 and 16-byte aligned operands");
   if (ta && M % 4) return fail(MAS_ERR_UNSUPPORTED, "tc3 gemm: a [K][M] stored A operand needs M %% 4 == 0");
   tc3::P3 p;
   p.A = A; p.B = B; p.C = C; p.M = M; p.N = N; p.K = K;
@@ -284,12 +292,18 @@ int gemm_tc3_launch(const float* A, const float* B, float* C, int M, int N, int 
   p.alpha = alpha;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc3::gemm3_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc3::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(tc3::gemm3_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc3::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc3::gemm3_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc3::SMEM_BYTES);
     if (e != cudaSuccess) return fail(MAS_ERR_LAUNCH, "cudaFuncSetAttribute(smem=%zu): %s", tc3::SMEM_BYTES, cudaGetErrorString(e));
     configured = true;
   }
-  dim3 grid((unsigned)(N / tc3::BN), (unsigned)cdiv(M, tc3::BM), (unsigned)batch);
-  tc3::gemm3_tc<<<grid, tc3::NTHREADS, tc3::SMEM_BYTES, st>>>(p);
+  if (N % 128 == 0) {
+    dim3 grid((unsigned)(N / 128), (unsigned)cdiv(M, tc3::BM), (unsigned)batch);
+    tc3::gemm3_tc<128><<<grid, tc3::NTHREADS, tc3::SMEM_BYTES, st>>>(p);
+  } else {   // attention heads of 64 channels: P.V and the q / k / v gradients of the token transformer
+    dim3 grid((unsigned)(N / 64), (unsigned)cdiv(M, tc3::BM), (unsigned)batch);
+    tc3::gemm3_tc<64><<<grid, tc3::NTHREADS, tc3::SMEM_BYTES, st>>>(p);
+  }
   return launched("gemm3_tc");
 }
 

@@ -23,7 +23,9 @@ pytestmark = [pytest.mark.gpu,
                                                (256, 512, 256, 2, 1, 0),     # dV = P^T dO
                                                (256, 256, 512, 2, 0, 1),     # dP = dO V^T
                                                (640, 640, 64, 5, 0, 1),      # transformer head: S
-                                               (100, 128, 32, 1, 0, 1), (100, 128, 64, 2, 1, 0)])   # ragged M
+                                               (640, 64, 640, 5, 0, 0),      # transformer head: P V (N tile 64)
+                                               (640, 64, 640, 2, 1, 0),      # transformer head: dV = P^T dO
+                                               (100, 128, 32, 1, 0, 1), (100, 128, 64, 2, 1, 0), (72, 192, 96, 2, 0, 0)])   # ragged M
 def test_gemm_tc3_vs_fp64(M, N, K, batch, ta, tb):
     from mas_b200 import _lib as L
     dev = torch.device("cuda:0")
