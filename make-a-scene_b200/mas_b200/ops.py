@@ -171,14 +171,14 @@ def _packed_conv_weight(wc, weight, cout, cin, transpose, dev, prepack=False):
     key = wc.data_ptr()
     if transpose:
         hit = _dgrad_packs.pop(key, None)
-        if hit is not None and hit[0] == weight._version and hit[1].device == dev:
+        if hit is not None and hit[0] == weight._version and hit[1].device == dev and hit[2] == tuple(weight.shape):
             return hit[1]
     wt = torch.empty(9 * cout * cin, dtype=torch.float32, device=dev)
     if prepack and not transpose and cout % 128 == 0 and cin % 128 == 0:
         # forward of a training step whose backward will run the data gradient: it wants the transposed packing
         wd = torch.empty(9 * cout * cin, dtype=torch.float32, device=dev)
         L.call("mas_pack_conv3x3_tc_pair", wc, wt, wd, weight.shape[0], weight.shape[1])
-        _dgrad_packs[key] = (weight._version, wd)
+        _dgrad_packs[key] = (weight._version, wd, tuple(weight.shape))
         return wt
     L.call("mas_pack_conv3x3_tc", wc, wt, weight.shape[0], weight.shape[1], int(transpose))
     return wt
