@@ -77,3 +77,34 @@ def test_yaml_model_blocks_instantiate():
         cfg["ddconfig"]["channels"] = [32, 32, 64]  # keep the CPU test light; stale keys must be tolerated
         m = VQBASE(**cfg)
         assert m.encoder.model[0].in_channels == 159
+
+
+def test_dgrad_pack_handover_is_keyed_by_version_and_shape(monkeypatch):
+    """Host logic of ops._packed_conv_weight (no kernels run: the C-ABI call is stubbed): the data-gradient packing made
+    in the forward is handed to exactly one backward of the same, unmodified weight."""
+    import torch
+    from mas_b200 import ops
+    calls = []
+    monkeypatch.setattr(ops.L, "call", lambda name, *a: calls.append(name))
+    ops._dgrad_packs.clear()
+    w = torch.zeros(128, 128, 3, 3)
+    dev = w.device
+    ops._packed_conv_weight(w, w, 128, 128, False, dev, prepack=True)
+    assert calls == ["mas_pack_conv3x3_tc_pair"] and len(ops._dgrad_packs) == 1
+    ops._packed_conv_weight(w, w, 128, 128, True, dev)                 # backward of the same step: no packing launch
+    assert calls == ["mas_pack_conv3x3_tc_pair"] and not ops._dgrad_packs
+    ops._packed_conv_weight(w, w, 128, 128, True, dev)                 # a second backward (retained graph): repacks
+    assert calls[-1] == "mas_pack_conv3x3_tc" and len(calls) == 2
+    ops._packed_conv_weight(w, w, 128, 128, False, dev, prepack=True)
+    w.add_(1.0)                                                         # optimiser step in between: version changed
+    ops._packed_conv_weight(w, w, 128, 128, True, dev)
+    assert calls[-1] == "mas_pack_conv3x3_tc"
+    ops._packed_conv_weight(w, w, 128, 128, False, dev, prepack=True)
+    key = next(iter(ops._dgrad_packs))
+    ver, wd, _shape = ops._dgrad_packs[key]
+    ops._dgrad_packs[key] = (ver, wd, (256, 128, 3, 3))                # a different weight that reused the address
+    n = len(calls)
+    ops._packed_conv_weight(w, w, 128, 128, True, dev)
+    assert len(calls) == n + 1 and calls[-1] == "mas_pack_conv3x3_tc"
+    ops._packed_conv_weight(w, w, 64, 128, False, dev, prepack=True)    # not pair-eligible: plain packing, nothing stored
+    assert calls[-1] == "mas_pack_conv3x3_tc" and not ops._dgrad_packs
