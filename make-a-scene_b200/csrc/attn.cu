@@ -4,6 +4,8 @@
 // concatenated [3C, C] weight (forward: N = 3C; data gradient: K = 3C; weight gradient: Cout = 3C), the 1x1 convolutions
 // go to the tcgen05 row-GEMM / weight-gradient kernels when the shape is eligible, and the two batched token contractions
 // (QK^T and PV, plus their four gradients) stay strict fp32 like the reference's torch.bmm (modules.py:180,186).
+#include <stdlib.h>
+
 #include "mas_common.cuh"
 
 using namespace mas;
@@ -27,6 +29,12 @@ __global__ void cat3_kernel(const float* __restrict__ a, const float* __restrict
 }
 size_t al(size_t v) { return (v + 255) / 256 * 256; }
 bool rows_on_tc(int impl, int N, int K) { return impl != MAS_IMPL_SIMT && N % 128 == 0 && K % 32 == 0; }
+// implementation of the token contractions (QK^T, PV and their gradients): strict-fp32 FFMA kernels, or - explicit opt-in
+// for validating the staged operand-split tensor-core GEMM (contract_tc3.cu) - MAS_ATTN_TC3=1
+int bmm_impl(int impl, int HW, int C) {
+  static const bool tc3 = [] { const char* e = getenv("MAS_ATTN_TC3"); return e && e[0] == '1'; }();
+  return (tc3 && impl != MAS_IMPL_SIMT && HW % 128 == 0 && C % 128 == 0) ? MAS_IMPL_TC3 : impl;
+}
 
 struct Carver {
   char* p;
@@ -87,12 +95,12 @@ int mas_attnblock_forward(const float* x, int N, int HW, int C, int G, const flo
   }
   // S[i,j] = scale * sum_c q[i,c] k[j,c]   (w_ = bmm(q^T, k) * c^-0.5)
   if (int e = mas_gemm(qkv, qkv + c, P, HW, HW, C, N, 3 * c, 3 * c, HW, (int64_t)HW * 3 * c, (int64_t)HW * 3 * c, (int64_t)HW * HW, 0, 1,
-                       scale, nullptr, nullptr, impl, stream))
+                       scale, nullptr, nullptr, bmm_impl(impl, HW, C), stream))
     return e;
   if (int e = mas_softmax_forward(P, P, (int64_t)N * HW, HW, stream)) return e;
   // O[i,c] = sum_j P[i,j] v[j,c]
   if (int e = mas_gemm(P, qkv + 2 * c, O, HW, C, HW, N, HW, 3 * c, c, (int64_t)HW * HW, (int64_t)HW * 3 * c, (int64_t)HW * c, 0, 0, 1.f,
-                       nullptr, nullptr, impl, stream))
+                       nullptr, nullptr, bmm_impl(impl, HW, C), stream))
     return e;
   if (tc) {
     if (int e = mas_pack_gemm_tc(proj_w, wpk, C, C, 0, stream)) return e;
@@ -134,13 +142,13 @@ int mas_attnblock_backward(const float* dout, const float* x, int N, int HW, int
   if (int e = mas_conv1x1_wgrad(O, c, dout, c, M, C, C, dproj_w, dproj_b, impl, scratch, scratch_bytes, stream)) return e;
   const int64_t sP = (int64_t)HW * HW, sQ = (int64_t)HW * 3 * c, sO = (int64_t)HW * c;
   // dV[j,c] = sum_i P[i,j] dO[i,c]
-  if (int e = mas_gemm(P, dO, dqkv + 2 * c, HW, C, HW, N, HW, c, 3 * c, sP, sO, sQ, 1, 0, 1.f, nullptr, nullptr, impl, stream)) return e;
+  if (int e = mas_gemm(P, dO, dqkv + 2 * c, HW, C, HW, N, HW, c, 3 * c, sP, sO, sQ, 1, 0, 1.f, nullptr, nullptr, bmm_impl(impl, HW, C), stream)) return e;
   // dP[i,j] = sum_c dO[i,c] V[j,c]
-  if (int e = mas_gemm(dO, qkv + 2 * c, dP, HW, HW, C, N, c, 3 * c, HW, sO, sQ, sP, 0, 1, 1.f, nullptr, nullptr, impl, stream)) return e;
+  if (int e = mas_gemm(dO, qkv + 2 * c, dP, HW, HW, C, N, c, 3 * c, HW, sO, sQ, sP, 0, 1, 1.f, nullptr, nullptr, bmm_impl(impl, HW, C), stream)) return e;
   if (int e = mas_softmax_backward(P, dP, dP, (int64_t)N * HW, HW, scale, stream)) return e;  // dP <- dS (times c^-0.5)
   // dQ[i,c] = sum_j dS[i,j] K[j,c] ; dK[j,c] = sum_i dS[i,j] Q[i,c]
-  if (int e = mas_gemm(dP, qkv + c, dqkv, HW, C, HW, N, HW, 3 * c, 3 * c, sP, sQ, sQ, 0, 0, 1.f, nullptr, nullptr, impl, stream)) return e;
-  if (int e = mas_gemm(dP, qkv, dqkv + c, HW, C, HW, N, HW, 3 * c, 3 * c, sP, sQ, sQ, 1, 0, 1.f, nullptr, nullptr, impl, stream)) return e;
+  if (int e = mas_gemm(dP, qkv + c, dqkv, HW, C, HW, N, HW, 3 * c, 3 * c, sP, sQ, sQ, 0, 0, 1.f, nullptr, nullptr, bmm_impl(impl, HW, C), stream)) return e;
+  if (int e = mas_gemm(dP, qkv, dqkv + c, HW, C, HW, N, HW, 3 * c, 3 * c, sP, sQ, sQ, 1, 0, 1.f, nullptr, nullptr, bmm_impl(impl, HW, C), stream)) return e;
   // dhn = [dq dk dv] . [Wq; Wk; Wv]   (one contraction over K = 3C)
   if (tc && (3 * C) % 32 == 0) {
     cat3_kernel<<<296, 256, 0, S(stream)>>>(q_w, k_w, v_w, wcat, c * c, nullptr, nullptr, nullptr, nullptr, 0);

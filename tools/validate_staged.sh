@@ -12,6 +12,10 @@ echo "== 2. cta_group::2 convolution (contract_tc2.cu): dedicated shapes first, 
 MAS_EXPERIMENTAL=1 MAS_CONV_2CTA=1 timeout 120 python -m pytest tests/test_gpu_staged.py -m gpu -q -k cta_pair 2>&1 | tail -5
 MAS_EXPERIMENTAL=1 MAS_CONV_2CTA=1 timeout 300 python -m pytest tests -m gpu -q -x 2>&1 | tail -5
 
+echo "== 2b. AttnBlock token contractions on the 3xTF32 kernel (MAS_ATTN_TC3=1): parity suite, then step time"
+MAS_ATTN_TC3=1 timeout 300 python -m pytest tests -m gpu -q -x 2>&1 | tail -5
+MAS_ATTN_TC3=1 timeout 200 python bench.py --no-cpu-baseline --steps 4 --warmup 3 2>&1 | tail -1 | cut -c1-260
+
 echo "== 3. step time with / without the CTA-pair kernel (same box)"
 timeout 200 python bench.py --no-cpu-baseline --steps 4 --warmup 3 2>&1 | tail -1 | cut -c1-260
 MAS_CONV_2CTA=1 timeout 200 python bench.py --no-cpu-baseline --steps 4 --warmup 3 2>&1 | tail -1 | cut -c1-260
