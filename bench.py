@@ -92,42 +92,80 @@ def build_model():
     return m
 
 
-def cpu_reference_steps(steps, warmup, batch=1):
-    """The reference's algorithm on host cores: the CPU oracle (oracle/vqgan_oracle.py, kind 'port'), all threads."""
-    from oracle import vqgan_oracle as O
-    torch.manual_seed(0)
-    # identical seeded weights: build the holders on CPU (no kernels run), take their state_dict
-    sd = {k: v.detach().clone() for k, v in build_model().state_dict().items()}
-    params = {k: v.requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k}
-    sd.update(params)
+def cpu_threads():
+    """All host cores, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank)."""
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        pass
+    torch.set_num_threads(n)
+    return n
+
+
+def cpu_reference_steps(steps, warmup, batch=2):
+    """The reference's own CPU implementation of the path, all host threads, on a bounded sample of the workload (`batch`
+    images per step instead of 32). kind "reference": the UNMODIFIED reference modules staged under oracle/_ref
+    (oracle/vendor_ref.py); kind "port": the oracle restatement, when oracle/_ref is absent."""
+    from oracle import vendor_ref
+    cores = cpu_threads()
     x = torch.rand(batch, 3, RES, RES, generator=torch.Generator().manual_seed(1234))
+    if vendor_ref.available():
+        kind = "reference"
+        ref_models = vendor_ref.load_models()
+        torch.manual_seed(0)
+        m = ref_models.VQBASE(IMG_CFG, N_EMBED, EMBED_DIM, 3000, 12500)
+        with torch.no_grad():
+            m.quantize.embedding.weight.normal_()
+        m.quantize.q_counter = 10 ** 6
+        m.train()
+
+        def one():
+            m.zero_grad(set_to_none=True)
+            dec, diff = m(x)
+            ((x - dec).abs().mean() + diff).backward()
+    else:
+        kind = "port"
+        from oracle import vqgan_oracle as O
+        torch.manual_seed(0)
+        sd = {k: v.detach().clone() for k, v in build_model().state_dict().items()}   # CPU parameter holders, no kernels
+        params = {k: v.requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k}
+        sd.update(params)
+
+        def one():
+            for p in params.values():
+                p.grad = None
+            dec, diff, _ = O.vqbase_forward(sd, IMG_CFG, x)
+            O.proxy_loss(x, dec, diff).backward()
     times = []
-    budget = float(os.environ.get("MAS_CPU_ARM_SECONDS", "150"))   # bounded sample: a step is ~5 s on 64 host cores
-    warmup = min(warmup, 2)
+    budget = float(os.environ.get("MAS_CPU_ARM_SECONDS", "120"))   # bounded sample
+    warmup = min(warmup, 1)
     for i in range(warmup + steps):
-        for p in params.values():
-            p.grad = None
         t0 = time.perf_counter()
-        dec, diff, _ = O.vqbase_forward(sd, IMG_CFG, x)
-        O.proxy_loss(x, dec, diff).backward()
+        one()
         if i >= warmup:
             times.append(time.perf_counter() - t0)
             if sum(times) > budget:
                 break
-    return batch * len(times) / sum(times), sum(times) / len(times), len(times)
+    return dict(value=batch * len(times) / sum(times), sec=sum(times) / len(times), done=len(times), kind=kind, cores=cores,
+                batch=batch)
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    v, sec, done = cpu_reference_steps(args.steps, args.warmup, batch=1)
-    cores = torch.get_num_threads()
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "VQ-IMG 256x256 codebook=8192 dim=256 (BASELINE configs[1])", "sample": "1 image per step"},
-            "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
-                             "sample": "%d timed fwd+bwd steps of 1 image (batch-32 workload sampled at batch 1; bounded to ~150 s)" % done},
+    r = cpu_reference_steps(args.steps, args.warmup, batch=2)
+    v = r["value"]
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": r["done"],
+            "warmup": min(args.warmup, 1), "ms_per_step": r["sec"] * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "VQ-IMG 256x256 codebook=8192 dim=256 (BASELINE configs[1])",
+                       "sample": "%d images per step (the batch-32 workload sampled at batch %d)" % (r["batch"], r["batch"])},
+            "cpu_baseline": {"value": v, "unit": "images/s", "cores": r["cores"], "kind": r["kind"],
+                             "sample": "%d timed fwd+bwd steps of %d images (%.1f s/step; %s)" % (
+                                 r["done"], r["batch"], r["sec"],
+                                 "unmodified reference modules from oracle/_ref, stock PyTorch CPU kernels" if r["kind"] == "reference"
+                                 else "oracle port: oracle/_ref not staged")},
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -177,16 +215,41 @@ def dominant_kernel_roofline(dev, pk):
             "algorithmic_bytes_per_launch": 4.0 * BATCH * RES * RES * 256 + 4 * 128 * 128 * 9}
 
 
-def vq_metric(dev, pk):
-    """VQ argmin standalone at B=32 (8192 rows x 8192 codes x 256): algorithmic bytes (2056*R + 8,388,608) / time."""
+def ffma_peak(dev):
+    """fp32 FMA-pipe peak measured live (mas_ffma_probe, CUDA events): the roofline of the exact-fp32 VQ distance kernel."""
+    import ctypes
+    from mas_b200 import _lib as L
+    scratch = torch.empty(148 * 4 * 512, device=dev)
+    fl = ctypes.c_double(0.0)
+    fn = lambda: L.call("mas_ffma_probe", scratch, 2048, ctypes.cast(ctypes.pointer(fl), ctypes.c_void_p))
+    sec = time_kernel(fn, iters=5, warm=2)
+    return fl.value / sec / 1e12
+
+
+def vq_metric(dev, pk, sweep=True):
+    """VQ argmin standalone (BASELINE configs[2]): 16x16x256 latents against the 8192-entry codebook, batch sweep
+    1..4096 (R = 256*B rows). Per point: algorithmic bytes (2056*R + 8,388,608) / time, 4,194,304*R FLOP / time, and the
+    fraction of the live-measured fp32 FFMA peak (the kernel's bound: exact-fp32 contraction, 1,363 FLOP/B at B=32)."""
     from mas_b200 import ops
-    z = torch.randn(BATCH, 256, 16, 16, generator=torch.Generator().manual_seed(1234)).to(dev).contiguous(memory_format=torch.channels_last)
     E = torch.randn(N_EMBED, 256, generator=torch.Generator().manual_seed(4321)).to(dev)
-    sec = time_kernel(lambda: ops.VQFn.apply(z, E, 0.25), iters=10, warm=3)
-    R = BATCH * 256
-    byts = 2056.0 * R + 8388608.0
-    return {"rows": R, "ms": sec * 1e3, "gb_per_s": byts / sec / 1e9, "tflop_per_s": 4194304.0 * R / sec / 1e12,
-            "hbm_frac": byts / sec / 1e9 / pk["hbm"], "bound": "fp32 FFMA pipe (exact-fp32 contraction), not HBM"}
+    peak = ffma_peak(dev)
+    pts = []
+    batches = [1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096] if sweep else [BATCH]
+    g = torch.Generator(device=dev).manual_seed(1234)
+    for B in batches:
+        z = torch.randn(B, 256, 16, 16, generator=g, device=dev).contiguous(memory_format=torch.channels_last)
+        it = 10 if B <= 256 else (4 if B <= 1024 else 2)
+        sec = time_kernel(lambda: ops.VQFn.apply(z, E, 0.25), iters=it, warm=2)
+        R = B * 256
+        byts = 2056.0 * R + 8388608.0
+        pts.append({"batch": B, "rows": R, "ms": round(sec * 1e3, 4), "gb_per_s": round(byts / sec / 1e9, 2),
+                    "tflop_per_s": round(4194304.0 * R / sec / 1e12, 2), "ffma_frac": round(4194304.0 * R / sec / 1e12 / peak, 3),
+                    "hbm_frac": round(byts / sec / 1e9 / pk["hbm"], 4)})
+        del z
+    at32 = next(p for p in pts if p["batch"] == BATCH)
+    return {"rows": at32["rows"], "ms": at32["ms"], "gb_per_s": at32["gb_per_s"], "tflop_per_s": at32["tflop_per_s"],
+            "hbm_frac": at32["hbm_frac"], "ffma_frac": at32["ffma_frac"], "ffma_peak_tflops_measured": round(peak, 2),
+            "bound": "fp32 FFMA pipe (exact-fp32 contraction), not HBM", "sweep": pts}
 
 
 def main():
@@ -314,9 +377,9 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks,
             "model_tflops": FLOP_PER_IMG_FWD_BWD * value / 1e12, "roofline": roof, "vq": vq}
     if not args.no_cpu_baseline and world == 1:   # reported baseline: rank 0 at N=1 only
-        v, s, _ = cpu_reference_steps(3, 1, batch=1)
-        line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": "3 timed fwd+bwd steps of 1 image after 1 warm-up (%.1f s/step)" % s}
+        r = cpu_reference_steps(3, 1, batch=2)
+        line["cpu_baseline"] = {"value": r["value"], "unit": "images/s", "cores": r["cores"], "kind": r["kind"],
+                                "sample": "%d timed fwd+bwd steps of %d images after 1 warm-up (%.1f s/step)" % (r["done"], r["batch"], r["sec"])}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -41,8 +41,8 @@ extern "C" {
 #define MAS_IMPL_AUTO 0  /* tcgen05 (TF32 operands, fp32 accumulate) when the shape is eligible, else SIMT */
 #define MAS_IMPL_SIMT 1  /* fp32 FFMA kernels (exact fp32; also the on-GPU checker for the tensor path)      */
 #define MAS_IMPL_TC 2    /* tcgen05 only; MAS_ERR_UNSUPPORTED if the shape is not eligible                   */
-#define MAS_IMPL_TC3 3   /* mas_gemm only, explicit opt-in: fp32-accurate 3xTF32 operand-split tcgen05 GEMM (staged:
-                          * no module path selects it yet; see csrc/contract_tc3.cu)                            */
+#define MAS_IMPL_TC3 3   /* mas_gemm only, explicit selection: fp32-accurate 3xTF32 operand-split tcgen05 GEMM
+                          * (csrc/contract_tc3.cu; the AttnBlock token contractions run on it)                  */
 
 typedef struct mas_tensor4 {
   int64_t n, h, w, c;     /* logical extents */
@@ -53,6 +53,14 @@ int mas_version(void);
 const char* mas_last_error(void);
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
 int64_t mas_launch_count(void);
+/* ... of which kernels that issue tcgen05 tensor-core MMAs (the driver's evidence that the tensor path ran). */
+int64_t mas_tc_launch_count(void);
+
+/* Measurement aid for bench.py: runs a pure-FFMA kernel (16 independent chains per thread, 148*4 blocks of 512 threads,
+ * 128*iters FMAs per thread); *flops_out_host (HOST pointer, may be NULL) receives the FLOPs of one launch. `scratch`
+ * needs 148*4*512 floats (never written). Timed by the caller with CUDA events => the fp32 FMA-pipe peak at the
+ * clocks the GPU actually runs. */
+int mas_ffma_probe(float* scratch, int iters, double* flops_out_host, void* stream);
 
 /* ---- layout helpers (boundary only; the VQBASE path itself never transposes) ------------------- */
 int mas_copy_strided(const float* x, mas_tensor4 xs, float* y, mas_tensor4 ys, void* stream);
@@ -194,15 +202,19 @@ int mas_attnblock_backward(const float* dout, const float* x, int N, int HW, int
                            void* ws, size_t ws_bytes, void* stream);
 
 /* ---- (Sync)BatchNorm for quant_conv[1] — vqvae.py:16 ---------------------------------------------------
- * x [R, C] NHWC rows.  mas_bn_stats writes LOCAL [sum(C), sumsq(C)] as fp64 (2*C doubles); the caller
- * all-reduces those 2*C numbers (+ the row count) across ranks over NCCL, then mas_bn_finalize turns the
+ * x [R, C] NHWC rows.  mas_bn_stats writes LOCAL [sum(C), sumsq(C), R] as fp64 (2*C+1 doubles: the last one is the
+ * local row count); the caller all-reduces those 2*C+1 numbers across ranks over NCCL, then mas_bn_finalize turns the
  * global sums into mean / invstd (biased variance) and updates running_mean / running_var (unbiased,
- * momentum; either may be NULL) exactly like nn.SyncBatchNorm.  Backward: mas_bn_backward_reduce writes the
- * LOCAL [sum_dy(C), sum_dy_xhat(C)] (fp64) for the second all-reduce; mas_bn_backward_apply consumes the
- * global sums for dx and the local sums for dgamma/dbeta (DDP all-reduces parameter grads itself). */
+ * momentum; either may be NULL) exactly like nn.SyncBatchNorm; count <= 0 means "read the reduced count from
+ * stats[2*C]" (ranks with different batch sizes, no host round trip).  Backward: mas_bn_backward_reduce writes the
+ * LOCAL [sum_dy(C), sum_dy_xhat(C), R] (fp64, 2*C+1) for the second all-reduce; mas_bn_backward_apply consumes the
+ * global sums for dx (inv_count <= 0: 1 / sums_global[2*C]) and the local sums for dgamma/dbeta (DDP all-reduces
+ * parameter grads itself). */
 int mas_bn_stats(const float* x, int64_t R, int C, double* stats_out, void* stream);
 int mas_bn_finalize(const double* stats, double count, int C, float eps, float momentum, float* mean,
                     float* invstd, float* running_mean, float* running_var, void* stream);
+/* eval mode: invstd = 1/sqrt(running_var + eps) for mas_bn_apply (nn.BatchNorm2d.eval()) */
+int mas_bn_invstd(const float* running_var, float eps, float* invstd, int C, void* stream);
 int mas_bn_apply(const float* x, const float* mean, const float* invstd, const float* gamma,
                  const float* beta, float* y, int64_t R, int C, void* stream);
 int mas_bn_backward_reduce(const float* dy, const float* x, const float* mean, const float* invstd,
@@ -223,6 +235,10 @@ int mas_vq_forward(const float* z, const float* E, int64_t R, int K, int D, floa
                    float* zq_out, float* loss_out, void* ws, size_t ws_bytes, void* stream);
 /* Backward (modules.py:509-512): grad_z = g_zq + g_loss*(2/(R*D))*(z - zq);
  * grad_E[k] += g_loss*(2*beta/(R*D)) * sum_{r: idx_r = k} (e_k - z_r).  grad_E must be zeroed by the caller. */
+/* Same gather + loss + straight-through value for CALLER-SUPPLIED code indices (the argmin is skipped): teacher-forced
+ * quantisation, e.g. re-evaluating the codebook loss of stored codes (modules.py:506-512 with idx given). */
+int mas_vq_forward_given(const float* z, const float* E, const int64_t* idx_in, int64_t R, int K, int D, float beta,
+                         float* zq_out, float* loss_out, void* ws, size_t ws_bytes, void* stream);
 int mas_vq_backward(const float* g_zq, const float* g_loss, const float* z, const float* E,
                     const int64_t* idx, int64_t R, int K, int D, float beta, float* grad_z, float* grad_E,
                     void* stream);

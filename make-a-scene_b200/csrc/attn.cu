@@ -3,7 +3,8 @@
 // enqueued on the caller's stream from caller-provided buffers. The q/k/v projections run as ONE row GEMM against the
 // concatenated [3C, C] weight (forward: N = 3C; data gradient: K = 3C; weight gradient: Cout = 3C), the 1x1 convolutions
 // go to the tcgen05 row-GEMM / weight-gradient kernels when the shape is eligible, and the two batched token contractions
-// (QK^T and PV, plus their four gradients) stay strict fp32 like the reference's torch.bmm (modules.py:180,186).
+// (QK^T and PV, plus their four gradients) keep fp32-level accuracy like the reference's torch.bmm (modules.py:180,186):
+// 3xTF32 operand splitting on the tensor cores (contract_tc3.cu), or the FFMA kernel for extents off its tiles.
 #include <stdlib.h>
 
 #include "mas_common.cuh"
@@ -29,11 +30,12 @@ __global__ void cat3_kernel(const float* __restrict__ a, const float* __restrict
 }
 size_t al(size_t v) { return (v + 255) / 256 * 256; }
 bool rows_on_tc(int impl, int N, int K) { return impl != MAS_IMPL_SIMT && N % 128 == 0 && K % 32 == 0; }
-// implementation of the token contractions (QK^T, PV and their gradients): strict-fp32 FFMA kernels, or - explicit opt-in
-// for validating the staged operand-split tensor-core GEMM (contract_tc3.cu) - MAS_ATTN_TC3=1
+// implementation of the token contractions (QK^T, PV and their four gradients): the operand-split 3xTF32 tcgen05 GEMM
+// (contract_tc3.cu: fp32-level accuracy like the reference's strict-fp32 torch.bmm, validated against fp64 on B200) when the
+// extents fit its tiles, else the strict-fp32 FFMA kernel. MAS_ATTN_TC3=0 forces the FFMA kernel (A/B measurements).
 int bmm_impl(int impl, int HW, int C) {
-  static const bool tc3 = [] { const char* e = getenv("MAS_ATTN_TC3"); return e && e[0] == '1'; }();
-  return (tc3 && impl != MAS_IMPL_SIMT && HW % 128 == 0 && C % 128 == 0) ? MAS_IMPL_TC3 : impl;
+  static const bool off = [] { const char* e = getenv("MAS_ATTN_TC3"); return e && e[0] == '0'; }();
+  return (!off && impl != MAS_IMPL_SIMT && HW % 128 == 0 && C % 128 == 0) ? MAS_IMPL_TC3 : impl;
 }
 
 struct Carver {

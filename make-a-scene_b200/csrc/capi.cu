@@ -99,7 +99,7 @@ int mas_gemm(const float* A, const float* B, float* C, int M, int N, int K, int 
              int64_t stride_a, int64_t stride_b, int64_t stride_c, int trans_a, int trans_b, float alpha, const float* bias,
              const float* residual, int impl, void* stream) {
   MAS_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && batch > 0, "gemm: bad arguments");
-  if (impl == MAS_IMPL_TC3)   // explicit opt-in only (staged kernel): never chosen by MAS_IMPL_AUTO
+  if (impl == MAS_IMPL_TC3)   // explicit selection (the AttnBlock path does): never chosen by MAS_IMPL_AUTO
     return gemm_tc3_launch(A, B, C, M, N, K, batch, lda, ldb, ldc, stride_a, stride_b, stride_c, trans_a, trans_b, alpha, bias, residual,
                            S(stream));
   if (impl != MAS_IMPL_SIMT) {

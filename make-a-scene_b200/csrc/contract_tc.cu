@@ -866,8 +866,6 @@ __global__ void __launch_bounds__(128, 1) mma_probe(const float* __restrict__ A,
 
 void conv_wgrad_reduce_launch(const float* part, int splits, int ntap, int Cout, int Cin, float* dw, const float* bpart, float* dbias,
                               cudaStream_t st);
-int conv3x3_fprop_tc2_launch(const float* x, mas_tensor4 xs, const float* w_tc, const float* bias, const float* res, float* y,
-                             mas_tensor4 ys, int mode, const float* gn_table, int gn_silu, float* stats_part, cudaStream_t st);
 
 static bool dense_nhwc(const mas_tensor4& t) {
   return t.sc == 1 && t.sw == t.c && t.sh == t.w * t.c && t.sn == t.h * t.w * t.c;
@@ -906,14 +904,14 @@ int conv3x3_fprop_tc_launch(const float* x, mas_tensor4 xs, const float* w_tc, c
   // overlap the other's main loop
   constexpr int T = 2, STG = 2;
   constexpr size_t smem = tc::smem_bytes<9, 8, STG, T>();
-  static bool configured = false;
-  if (!configured) {
+  static std::atomic<uint64_t> configured{0};
+  if (first_on_device(configured)) {
     if (int e = set_smem(tc::shift_gemm_tc<9, 8, STG, T>, smem)) return e;
-    configured = true;
+    mark_device(configured);
   }
   dim3 grid((unsigned)cdiv(p.total_tiles, T), (unsigned)(Cout / tc::BN));
   tc::shift_gemm_tc<9, 8, STG, T><<<grid, tc::NTHREADS, smem, st>>>(p);
-  return launched("shift_gemm_tc<9>");
+  return launched_tc("shift_gemm_tc<9>");
 }
 
 // Row GEMM C[M,N] = alpha * A[M,K] * Wt[N,K]^T + bias + residual with PRE-PACKED weights (mas_pack_gemm_tc).
@@ -934,14 +932,14 @@ int gemm_rows_tc_launch(const float* A, int64_t lda, const float* w_tc, float* C
   p.gn_table = nullptr; p.gn_silu = 0; p.stats_part = stats_part;
   if (stats_part && (M % tc::BM || ldc != N)) return fail(MAS_ERR_UNSUPPORTED, "tc gemm: fused statistics need M %% 128 == 0 and a dense output");
   constexpr size_t smem = tc::smem_bytes<1, 32, 2, 2>();
-  static bool configured = false;
-  if (!configured) {
+  static std::atomic<uint64_t> configured{0};
+  if (first_on_device(configured)) {
     if (int e = set_smem(tc::shift_gemm_tc<1, 32, 2, 2>, smem)) return e;
-    configured = true;
+    mark_device(configured);
   }
   dim3 grid((unsigned)cdiv(p.total_tiles, 2), (unsigned)(N / tc::BN));
   tc::shift_gemm_tc<1, 32, 2, 2><<<grid, tc::NTHREADS, smem, st>>>(p);
-  return launched("shift_gemm_tc<1>");
+  return launched_tc("shift_gemm_tc<1>");
 }
 
 int gemm_tc_launch(const float*, const float*, float*, int, int, int, int, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int, int,
@@ -1005,16 +1003,16 @@ static int wgrad_tc_run(tc::WParams& p, int splits, float* dw, float* dbias, voi
   p.units_per_split = cdiv(p.total_units, splits);
   constexpr int NT = (TAPS == 9) ? tc::WG_NT : 128;
   constexpr size_t smem = (size_t)tc::WG_STAGES * ((TAPS == 9 ? 3 * 20 : 16) * NT * 16 + tc::WG_DY_STAGE) + (4 * tc::WG_STAGES + 1) * 8 + 16;
-  static bool configured = false;
-  if (!configured) {
+  static std::atomic<uint64_t> configured{0};
+  if (first_on_device(configured)) {
     if (int e = set_smem(tc::wgrad_tc<TAPS, PRO>, smem)) return e;
-    configured = true;
+    mark_device(configured);
   }
   CUtensorMap dy_map;
   if (int e = make_dy_map(&dy_map, p, TAPS)) return e;
   dim3 grid((unsigned)(p.Cin / NT), (unsigned)(p.Cout / tc::BM), (unsigned)splits);
   tc::wgrad_tc<TAPS, PRO><<<grid, tc::WG_THREADS, smem, st>>>(p, dy_map);
-  if (int e = launched("wgrad_tc")) return e;
+  if (int e = launched_tc("wgrad_tc")) return e;
   conv_wgrad_reduce_launch((const float*)ws, splits, TAPS, p.Cout, p.Cin, dw, p.bpart, dbias, st);  // + bias partials -> dbias
   return launched("conv_wgrad_reduce");
 }
@@ -1096,7 +1094,7 @@ int mas_gemm_rows_packed(const float* A, int64_t lda, const float* w_tc, float* 
 int mas_tc_probe(const float* A, const float* B, float* D, int a_src, int b_layout, uint64_t raw_desc, uint32_t raw_idesc,
                  int raw_off, void* stream) {
   tc::mma_probe<<<1, 128, 0, S(stream)>>>(A, B, D, a_src, b_layout, (unsigned long long)raw_desc, raw_idesc, raw_off);
-  return launched("mma_probe");
+  return launched_tc("mma_probe");
 }
 
 int mas_conv3x3_tc_eligible(mas_tensor4 xs, mas_tensor4 ys, int mode) {
@@ -1109,9 +1107,6 @@ int mas_conv3x3_tc_eligible(mas_tensor4 xs, mas_tensor4 ys, int mode) {
 int mas_conv3x3_fprop_tc(const float* x, mas_tensor4 xs, const float* w_tc, const float* bias, const float* residual, float* y,
                          mas_tensor4 ys, int mode, const float* gn_table, int gn_silu, float* stats_part, void* stream) {
   MAS_REQUIRE(x && w_tc && y, "conv3x3_fprop_tc: null pointer");
-  // staged cta_group::2 variant (contract_tc2.cu): explicit opt-in for validation runs only
-  static const bool two_cta = [] { const char* e = getenv("MAS_CONV_2CTA"); return e && e[0] == '1'; }();
-  if (two_cta) return conv3x3_fprop_tc2_launch(x, xs, w_tc, bias, residual, y, ys, mode, gn_table, gn_silu, stats_part, S(stream));
   return conv3x3_fprop_tc_launch(x, xs, w_tc, bias, residual, y, ys, mode, gn_table, gn_silu, stats_part, S(stream));
 }
 

@@ -290,12 +290,12 @@ int gemm_tc3_launch(const float* A, const float* B, float* C, int M, int N, int 
   p.ta = ta ? 1 : 0;        // A stored [K][M]  -> rows (m) contiguous
   p.tb = tb ? 0 : 1;        // B stored [N][K] (tb = 1) is the k-contiguous orientation; [K][N] (tb = 0) is row-contiguous
   p.alpha = alpha;
-  static bool configured = false;
-  if (!configured) {
+  static std::atomic<uint64_t> configured{0};
+  if (first_on_device(configured)) {
     cudaError_t e = cudaFuncSetAttribute(tc3::gemm3_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc3::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tc3::gemm3_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc3::SMEM_BYTES);
     if (e != cudaSuccess) return fail(MAS_ERR_LAUNCH, "cudaFuncSetAttribute(smem=%zu): %s", tc3::SMEM_BYTES, cudaGetErrorString(e));
-    configured = true;
+    mark_device(configured);
   }
   if (N % 128 == 0) {
     dim3 grid((unsigned)(N / 128), (unsigned)cdiv(M, tc3::BM), (unsigned)batch);
@@ -304,7 +304,7 @@ int gemm_tc3_launch(const float* A, const float* B, float* C, int M, int N, int 
     dim3 grid((unsigned)(N / 64), (unsigned)cdiv(M, tc3::BM), (unsigned)batch);
     tc3::gemm3_tc<64><<<grid, tc3::NTHREADS, tc3::SMEM_BYTES, st>>>(p);
   }
-  return launched("gemm3_tc");
+  return launched_tc("gemm3_tc");
 }
 
 }  // namespace mas

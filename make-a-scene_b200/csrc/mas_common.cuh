@@ -11,10 +11,26 @@ namespace mas {
 
 extern thread_local char g_err[512];
 extern std::atomic<int64_t> g_launches;
+extern std::atomic<int64_t> g_tc_launches;
 
 int fail(int code, const char* fmt, ...);
 // Checks the launch that was just enqueued (no synchronisation) and counts it.
 int launched(const char* what);
+// Same, for a kernel that issues tcgen05 MMAs (counted separately: mas_tc_launch_count).
+int launched_tc(const char* what);
+
+// cudaFuncSetAttribute is per device: true the first time a call site runs on the CURRENT device (bit d of `mask`).
+static inline bool first_on_device(std::atomic<uint64_t>& mask) {
+  int d = 0;
+  cudaGetDevice(&d);
+  const uint64_t bit = 1ull << (d & 63);
+  return !(mask.load(std::memory_order_relaxed) & bit);
+}
+static inline void mark_device(std::atomic<uint64_t>& mask) {
+  int d = 0;
+  cudaGetDevice(&d);
+  mask.fetch_or(1ull << (d & 63), std::memory_order_relaxed);
+}
 
 static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }

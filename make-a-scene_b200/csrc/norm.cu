@@ -9,6 +9,7 @@ namespace mas {
 
 thread_local char g_err[512] = {0};
 std::atomic<int64_t> g_launches{0};
+std::atomic<int64_t> g_tc_launches{0};
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -23,6 +24,11 @@ int launched(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(MAS_ERR_LAUNCH, "%s: %s", what, cudaGetErrorString(e));
   return MAS_OK;
+}
+
+int launched_tc(const char* what) {
+  g_tc_launches.fetch_add(1, std::memory_order_relaxed);
+  return launched(what);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -438,6 +444,7 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, int64_t R, int C, d
     }
     out[c] = a;
     out[C + c] = b;
+    if (c == 0) out[2 * C] = (double)R;   // local element count per channel: reduced across ranks with the sums
   }
 }
 __global__ void bn_finalize_kernel(const double* __restrict__ stats, double count, int C, float eps, float momentum,
@@ -445,6 +452,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, double coun
                                    float* __restrict__ run_var) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
+  if (count <= 0) count = stats[2 * C];   // the (all-reduced) element count travels with the sums
   double m = stats[c] / count, var = stats[C + c] / count - m * m;
   if (var < 0) var = 0;
   mean[c] = (float)m;
@@ -454,6 +462,10 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, double coun
     run_mean[c] = (float)((1.0 - momentum) * run_mean[c] + momentum * m);
     run_var[c] = (float)((1.0 - momentum) * run_var[c] + momentum * unb);
   }
+}
+__global__ void bn_invstd_kernel(const float* __restrict__ var, float eps, float* __restrict__ out, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) out[c] = (float)(1.0 / sqrt((double)var[c] + (double)eps));
 }
 __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y,
@@ -486,6 +498,7 @@ __global__ void bn_bwd_reduce_kernel(const float* __restrict__ dy, const float* 
     }
     out[c] = a;
     out[C + c] = b;
+    if (c == 0) out[2 * C] = (double)R;
   }
 }
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
@@ -493,6 +506,7 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* _
                                     const double* __restrict__ sums /*[2C] global sums*/, double inv_count,
                                     float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                     const double* __restrict__ local_sums, int64_t total, int C) {
+  if (inv_count <= 0) inv_count = 1.0 / sums[2 * C];
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(i % C);
     float xh = (x[i] - mean[c]) * invstd[c];
@@ -619,6 +633,7 @@ extern "C" {
 int mas_version(void) { return 100; }
 const char* mas_last_error(void) { return g_err; }
 int64_t mas_launch_count(void) { return g_launches.load(); }
+int64_t mas_tc_launch_count(void) { return g_tc_launches.load(); }
 
 static int gn_check(int N, int HW, int C, int G) {
   if (N <= 0 || HW <= 0 || C <= 0 || G <= 0 || C % G != 0) return fail(MAS_ERR_INVALID_ARG, "groupnorm: bad shape N=%d HW=%d C=%d G=%d", N, HW, C, G);
@@ -730,6 +745,10 @@ int mas_bn_finalize(const double* stats, double count, int C, float eps, float m
                     float* running_mean, float* running_var, void* stream) {
   bn_finalize_kernel<<<(int)cdiv(C, 128), 128, 0, S(stream)>>>(stats, count, C, eps, momentum, mean, invstd, running_mean, running_var);
   return launched("bn_finalize");
+}
+int mas_bn_invstd(const float* running_var, float eps, float* invstd, int C, void* stream) {
+  bn_invstd_kernel<<<(int)cdiv(C, 128), 128, 0, S(stream)>>>(running_var, eps, invstd, C);
+  return launched("bn_invstd");
 }
 int mas_bn_apply(const float* x, const float* mean, const float* invstd, const float* gamma, const float* beta, float* y,
                  int64_t R, int C, void* stream) {

@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(256) vq_merge_kernel(const float* __restrict__
       int i = best_idx[row * splits + s];
       if (v < bv || (v == bv && i < bi)) { bv = v; bi = i; }
     }
-    if (lane == 0) idx_out[row] = (int64_t)bi;
+    if (lane == 0 && idx_out) idx_out[row] = (int64_t)bi;
     for (int q = lane; q < (D >> 2); q += 32) {
       const float4 e = __ldg(reinterpret_cast<const float4*>(E + (size_t)bi * D) + q);
       const float4 zv = __ldg(reinterpret_cast<const float4*>(z + (size_t)row * D) + q);
@@ -204,6 +204,16 @@ __global__ void __launch_bounds__(256) vq_merge_kernel(const float* __restrict__
     for (int k = 0; k < 8; ++k) a += red_s[k];
     loss_part[blockIdx.x] = a;
   }
+}
+
+// caller-supplied code indices (int64, clamped) -> the (value, index) slot layout vq_merge_kernel reads with splits = 1
+__global__ void vq_given_indices_kernel(const int64_t* __restrict__ idx_in, int64_t R, int K, float* __restrict__ best_val,
+                                        int* __restrict__ best_idx) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  int64_t k = idx_in[r];
+  best_idx[r] = (int)(k < 0 ? 0 : (k >= K ? K - 1 : k));
+  best_val[r] = 0.f;
 }
 
 __global__ void vq_loss_final(const double* __restrict__ part, int n, double inv_count, float beta, float* __restrict__ out) {
@@ -284,11 +294,12 @@ int mas_vq_forward(const float* z, const float* E, int64_t R, int K, int D, floa
   double* part = (double*)w;
   const int blocks = (int)cdiv(R, VQ_BM), splits = vq_splits(R);
   size_t smem = ((size_t)VQ_BM * (D + 4) + 2 * VQ_BN * VQ_LDE + VQ_BM) * sizeof(float) + VQ_BM * sizeof(int);
-  static int configured_smem = 0;
-  if ((int)smem > configured_smem) {
-    cudaError_t e = cudaFuncSetAttribute(vq_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (smem > 232448) return fail(MAS_ERR_UNSUPPORTED, "vq_forward: D=%d needs %zu bytes of shared memory", D, smem);
+  static std::atomic<uint64_t> configured{0};   // per-device: the opt-in ceiling (227 KB), whatever D asks for later
+  if (first_on_device(configured)) {
+    cudaError_t e = cudaFuncSetAttribute(vq_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return fail(MAS_ERR_LAUNCH, "vq_forward: smem attr: %s", cudaGetErrorString(e));
-    configured_smem = (int)smem;
+    mark_device(configured);
   }
   vq_code_norms<<<(int)cdiv(K, 8), 256, 0, S(stream)>>>(E, K, D, ee);
   if (int e = launched("vq_code_norms")) return e;
@@ -296,6 +307,24 @@ int mas_vq_forward(const float* z, const float* E, int64_t R, int K, int D, floa
   if (int e = launched("vq_forward")) return e;
   const int mblocks = (int)cdiv(R, 8);
   vq_merge_kernel<<<mblocks, 256, 0, S(stream)>>>(z, E, bval, bidx, splits, R, D, idx_out, zq_out, part);
+  if (int e = launched("vq_merge")) return e;
+  vq_loss_final<<<1, 256, 0, S(stream)>>>(part, mblocks, 1.0 / ((double)R * D), beta, loss_out);
+  return launched("vq_loss_final");
+}
+
+int mas_vq_forward_given(const float* z, const float* E, const int64_t* idx_in, int64_t R, int K, int D, float beta,
+                         float* zq_out, float* loss_out, void* ws, size_t ws_bytes, void* stream) {
+  MAS_REQUIRE(R > 0 && K > 0 && D > 0 && D % 4 == 0, "vq_forward_given: bad shape R=%lld K=%d D=%d", (long long)R, K, D);
+  if (ws_bytes < mas_vq_ws_bytes(R, K, D)) return fail(MAS_ERR_WORKSPACE, "vq_forward_given: workspace too small");
+  char* w = (char*)ws;
+  w += a256((size_t)K * sizeof(float));
+  float* bval = (float*)w; w += a256((size_t)R * 4 * sizeof(float));
+  int* bidx = (int*)w; w += a256((size_t)R * 4 * sizeof(int));
+  double* part = (double*)w;
+  vq_given_indices_kernel<<<(int)cdiv(R, 256), 256, 0, S(stream)>>>(idx_in, R, K, bval, bidx);
+  if (int e = launched("vq_given_indices")) return e;
+  const int mblocks = (int)cdiv(R, 8);
+  vq_merge_kernel<<<mblocks, 256, 0, S(stream)>>>(z, E, bval, bidx, 1, R, D, nullptr, zq_out, part);
   if (int e = launched("vq_merge")) return e;
   vq_loss_final<<<1, 256, 0, S(stream)>>>(part, mblocks, 1.0 / ((double)R * D), beta, loss_out);
   return launched("vq_loss_final");

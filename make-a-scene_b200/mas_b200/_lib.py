@@ -30,6 +30,8 @@ _SPEC = {
     "mas_version": (_I, []),
     "mas_last_error": (ctypes.c_char_p, []),
     "mas_launch_count": (_L, []),
+    "mas_tc_launch_count": (_L, []),
+    "mas_ffma_probe": (_I, [_P, _I, _P, _P]),
     "mas_copy_strided": (_I, [_P, _T, _P, _T, _P]),
     "mas_gn_ws_bytes": (_Z, [_I, _I, _I, _I]),
     "mas_gn_stats": (_I, [_P, _I, _I, _I, _I, _F, _P, _P, _P, _Z, _P]),
@@ -72,11 +74,13 @@ _SPEC = {
     "mas_softmax_backward": (_I, [_P, _P, _P, _L, _I, _F, _P]),
     "mas_bn_stats": (_I, [_P, _L, _I, _P, _P]),
     "mas_bn_finalize": (_I, [_P, _D, _I, _F, _F, _P, _P, _P, _P, _P]),
+    "mas_bn_invstd": (_I, [_P, _F, _P, _I, _P]),
     "mas_bn_apply": (_I, [_P, _P, _P, _P, _P, _P, _L, _I, _P]),
     "mas_bn_backward_reduce": (_I, [_P, _P, _P, _P, _L, _I, _P, _P]),
     "mas_bn_backward_apply": (_I, [_P, _P, _P, _P, _P, _P, _P, _D, _P, _P, _P, _L, _I, _P]),
     "mas_vq_ws_bytes": (_Z, [_L, _I, _I]),
     "mas_vq_forward": (_I, [_P, _P, _L, _I, _I, _F, _P, _P, _P, _P, _Z, _P]),
+    "mas_vq_forward_given": (_I, [_P, _P, _P, _L, _I, _I, _F, _P, _P, _P, _Z, _P]),
     "mas_vq_backward": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _F, _P, _P, _P]),
     "mas_vq_gather": (_I, [_P, _P, _L, _I, _I, _P, _P]),
     "mas_layernorm_forward": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _F, _P]),
@@ -135,8 +139,20 @@ def stream_ptr():
 _prof = None   # when a list: (name, start_event, end_event) per call — see profile_start/profile_report
 
 
+def _device_of(args):
+    for a in args:
+        if isinstance(a, torch.Tensor) and a.is_cuda:
+            return a.device
+    return None
+
+
 def call(name, *args):
-    """Invoke an int-returning entry on the current CUDA stream; non-zero status -> RuntimeError."""
+    """Invoke an int-returning entry on the current CUDA stream of the tensors' device; non-zero status -> RuntimeError.
+    A model living on a device other than torch.cuda.current_device() is served by switching to it for the call."""
+    dev = _device_of(args)
+    if dev is not None and dev.index != torch.cuda.current_device():
+        with torch.cuda.device(dev):
+            return call(name, *args)
     lib = load()
     fn = getattr(lib, name)
     conv = [_ptr(a) for a in args]
@@ -185,6 +201,11 @@ def launch_count() -> int:
     return int(load().mas_launch_count())
 
 
+def tc_launch_count() -> int:
+    """Launches of kernels that issue tcgen05 MMAs (subset of launch_count)."""
+    return int(load().mas_tc_launch_count())
+
+
 def t4(x: torch.Tensor) -> Tensor4:
     """Describe a logical [N,C,H,W] tensor (any strides) as extents + element strides."""
     n, c, h, w = x.shape
@@ -208,3 +229,9 @@ def workspace(nbytes: int, device) -> torch.Tensor:
         buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
         _ws[key] = buf
     return buf
+
+
+def pin_workspaces():
+    """References to the current scratch buffers (a CUDA graph that recorded their addresses keeps them alive through
+    this list; workspace() replaces — never resizes in place — a buffer that is too small)."""
+    return list(_ws.values())

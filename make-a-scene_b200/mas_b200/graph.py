@@ -23,6 +23,12 @@ class GraphedStep:
     loss_fn(model, x) -> 0-dim loss.  After a call, parameter .grad tensors hold this step's gradients (static buffers,
     overwritten by the next call) and the returned loss is a static 0-dim tensor.  Construction runs `warmup` real eager
     steps on example_input first (they advance BatchNorm running statistics and the codebook counters like any step).
+
+    The optimizer runs OUTSIDE the graph, between calls.  `optimizer.zero_grad()` (set_to_none=True by default) detaches
+    the static gradient buffers from the parameters; every call re-attaches them after the replay, so
+    `gs(x); opt.step(); opt.zero_grad()` loops train exactly like eager steps.  The library's scratch buffer whose address
+    is baked into the graph is held by this object until close(): a later, larger eager call allocates a new one instead
+    of freeing the captured one under the graph.
     """
 
     def __init__(self, model, loss_fn, example_input, warmup=2):
@@ -58,6 +64,8 @@ class GraphedStep:
                 self.vq.defer_collect = False
             raise
         self.launches_per_step = L.launch_count() - l0
+        self._grads = [(p, p.grad) for p in model.parameters() if p.grad is not None]   # static buffers of the capture
+        self._ws = L.pin_workspaces()    # scratch addresses recorded in the graph stay allocated while it lives
         self._z = getattr(self.vq, "_deferred_z", None) if self.vq is not None else None
         if self.vq is not None and base.training:
             self.vq.q_counter -= 1           # the captured step was recorded, not executed
@@ -65,6 +73,9 @@ class GraphedStep:
     def __call__(self, x):
         self.static_in.copy_(x, non_blocking=True)
         self.graph.replay()
+        for p, g in self._grads:         # zero_grad(set_to_none=True) / a manual `p.grad = None` between calls
+            if p.grad is not g:
+                p.grad = g
         if self.vq is not None and _unwrap(self.model).training:
             self.vq.q_counter += 1
             if self._z is not None:
@@ -78,6 +89,8 @@ class GraphedStep:
             self.vq._deferred_z = None
         self._z = None
         self.loss = None
+        self._grads = []
+        self._ws = None
         if self.graph is not None:
             self.model.zero_grad(set_to_none=True)
             self.graph.reset()

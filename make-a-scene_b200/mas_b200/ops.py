@@ -583,15 +583,17 @@ class BatchNormFn(torch.autograd.Function):
         x = nhwc(x)
         n, c, h, w = x.shape
         R = n * h * w
-        stats = torch.empty(2 * c, dtype=torch.float64, device=x.device)
-        L.call("mas_bn_stats", x, R, c, stats)
+        # [sum(x) | sum(x^2) | row count] as fp64: ranks may hold different numbers of rows (uneven last batch), so the
+        # count is reduced with the sums like nn.SyncBatchNorm's per-rank counts (vqvae.py:16) and read on the device
+        buf = torch.empty(2 * c + 1, dtype=torch.float64, device=x.device)
+        L.call("mas_bn_stats", x, R, c, buf)
         world = 1
         if sync and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             world = dist.get_world_size()
-            dist.all_reduce(stats)
+            dist.all_reduce(buf)
         mean = torch.empty(c, dtype=torch.float32, device=x.device)
         invstd = torch.empty_like(mean)
-        L.call("mas_bn_finalize", stats, float(R * world), c, float(eps), float(momentum), mean, invstd, running_mean, running_var)
+        L.call("mas_bn_finalize", buf, 0.0, c, float(eps), float(momentum), mean, invstd, running_mean, running_var)
         y = torch.empty_like(x)
         L.call("mas_bn_apply", x, mean, invstd, weight, bias, y, R, c)
         ctx.save_for_backward(x, weight, mean, invstd)
@@ -604,7 +606,7 @@ class BatchNormFn(torch.autograd.Function):
         dy = nhwc(dy)
         n, c, h, w = x.shape
         R = n * h * w
-        local = torch.empty(2 * c, dtype=torch.float64, device=x.device)
+        local = torch.empty(2 * c + 1, dtype=torch.float64, device=x.device)
         L.call("mas_bn_backward_reduce", dy, x, mean, invstd, R, c, local)
         glob = local
         if ctx.world > 1:
@@ -613,14 +615,15 @@ class BatchNormFn(torch.autograd.Function):
         dx = torch.empty_like(x)
         dg = torch.empty_like(weight)
         db = torch.empty_like(weight)
-        L.call("mas_bn_backward_apply", dy, x, mean, invstd, weight, glob, local, 1.0 / float(R * ctx.world), dx, dg, db, R, c)
+        L.call("mas_bn_backward_apply", dy, x, mean, invstd, weight, glob, local, 0.0, dx, dg, db, R, c)
         return dx, dg, db, None, None, None, None, None
 
 
 def batchnorm_eval(x, weight, bias, running_mean, running_var, eps):
     x = nhwc(x)
     n, c, h, w = x.shape
-    invstd = torch.rsqrt(running_var + eps)
+    invstd = torch.empty_like(running_var)
+    L.call("mas_bn_invstd", running_var, float(eps), invstd, c)
     y = torch.empty_like(x)
     L.call("mas_bn_apply", x, running_mean, invstd, weight, bias, y, n * h * w, c)
     return y
@@ -658,6 +661,41 @@ class VQFn(torch.autograd.Function):
         grad_E = torch.zeros_like(E) if ctx.needs_input_grad[1] else None
         L.call("mas_vq_backward", g_zq, g_loss, z, E, idx, R, K, d, ctx.beta, grad_z, grad_E)
         return grad_z, grad_E, None
+
+
+class VQGivenFn(torch.autograd.Function):
+    """Codebook gather + loss + straight-through for caller-supplied indices (no argmin): modules.py:506-515 with
+    `min_encoding_indices` given. Same backward kernel as VQFn."""
+
+    @staticmethod
+    def forward(ctx, z, E, beta, idx):
+        z = nhwc(z)
+        n, d, h, w = z.shape
+        R, K = n * h * w, E.shape[0]
+        E = E.contiguous()
+        idx = idx.contiguous().view(-1)
+        if idx.numel() != R or idx.dtype != torch.int64:
+            raise RuntimeError("VQGivenFn: need %d int64 indices" % R)
+        zq = torch.empty_like(z)
+        loss = torch.empty((), dtype=torch.float32, device=z.device)
+        ws = L.workspace(L.query("mas_vq_ws_bytes", R, K, d), z.device)
+        L.call("mas_vq_forward_given", z, E, idx, R, K, d, float(beta), zq, loss, ws, ws.numel())
+        ctx.save_for_backward(z, E, idx)
+        ctx.beta = float(beta)
+        return zq, loss
+
+    @staticmethod
+    def backward(ctx, g_zq, g_loss):
+        z, E, idx = ctx.saved_tensors
+        n, d, h, w = z.shape
+        R, K = n * h * w, E.shape[0]
+        g_zq = nhwc(g_zq) if g_zq is not None else None
+        if g_loss is not None:
+            g_loss = g_loss.contiguous()
+        grad_z = torch.empty_like(z) if ctx.needs_input_grad[0] else None
+        grad_E = torch.zeros_like(E) if ctx.needs_input_grad[1] else None
+        L.call("mas_vq_backward", g_zq, g_loss, z, E, idx, R, K, d, ctx.beta, grad_z, grad_E)
+        return grad_z, grad_E, None, None
 
 
 def vq_gather(E, idx):

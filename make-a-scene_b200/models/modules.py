@@ -196,8 +196,9 @@ class Encoder(nn.Module):
 
 
 class Decoder(nn.Module):
-    """modules.py:337-369. `out_ch` is accepted as an alias of out_channels (conf/seg_config.yaml uses the taming key;
-    the reference silently ignores it and emits 3 channels — SURVEY.md 3.5)."""
+    """modules.py:337-369. Bug-compatible with the reference: the stale taming key `out_ch` (conf/seg_config.yaml) is
+    swallowed by **kwargs and IGNORED, so the output width is `out_channels` (default 3) — SURVEY.md 3.5. Pass
+    out_channels explicitly for the 159-channel segmentation decoder."""
 
     def __init__(self, out_channels=3, channels=[128, 128, 128, 256, 512, 512], attn_resolutions=[32], resolution=512,
                  dropout=0.0, num_res_blocks=2, z_channels=256, **kwargs):

@@ -124,6 +124,17 @@ class Transformer(nn.Module):
         # the kernels implement the causal mask directly.
         if use_cache or cache:
             raise NotImplementedError("KV cache has no kernel")
+        if attn_mask is not None:
+            S = x.shape[1]
+            am = attn_mask.to(self.mask.device, self.mask.dtype)
+            while am.dim() > 2:        # [B,1,S,S] / [1,1,S,S] -> [S,S] only if it is the same for every row
+                if am.shape[0] != 1 and not bool((am == am[:1]).all()):
+                    raise RuntimeError("per-sample attention masks have no kernel (only the causal mask is implemented)")
+                am = am[0]
+            eff = am[:S, :S] * self.mask[:S, :S]
+            if not torch.equal(eff != 0, self.mask[:S, :S] != 0):
+                raise RuntimeError("attn_mask * causal mask is not the plain causal mask: only causal attention has a kernel "
+                                   "(a padding / prefix mask would silently be ignored otherwise)")
         for layer in self.layers:
             x, _ = layer(x)
         return self.final_ln(x), {}

@@ -48,6 +48,19 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     ref_models, M, V, L, T = load_reference()
+    only = None
+    for a in sys.argv[1:]:
+        if a.startswith("--only="):
+            only = set(a[len("--only="):].split(","))
+    if only is None or "base" in only:
+        base_fixtures(ref_models, M, V, L, T)
+    if only is None or "tc" in only:
+        tensor_path_block_fixtures(M)
+    if only is None or "img256" in only:
+        img256_fixture(ref_models)
+
+
+def base_fixtures(ref_models, M, V, L, T):
 
     # ---- G1: tiny VQBASE fwd+bwd, VQ active, train mode --------------------------------------
     torch.manual_seed(0)
@@ -216,6 +229,85 @@ def main():
     torch.save(dict(pred=pred.detach().clone(), target=tgt, qloss=q, loss=lv.detach(), grad=pred.grad.clone()),
                os.path.join(OUT, "seg_loss.pt"))
     print("seg loss done")
+
+
+def tensor_path_block_fixtures(M):
+    """G7: blocks at widths / extents that the tcgen05 kernels take (Cout % 128 == 0, H % 16 == 0, W % 8 == 0), run on the
+    REAL reference modules. Weights and inputs are regenerated from seeds on both sides (oracle/seeded.py)."""
+    import torch.nn as nn
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from seeded import fill_seeded, seeded_input, sample
+    specs = {
+        "res_128_128": (lambda: M.ResnetBlock(in_channels=128, out_channels=128, dropout=0.0), (2, 128, 32, 32)),
+        "res_128_256": (lambda: M.ResnetBlock(in_channels=128, out_channels=256, dropout=0.0), (2, 128, 32, 32)),
+        "res_512_512": (lambda: M.ResnetBlock(in_channels=512, out_channels=512, dropout=0.0), (2, 512, 16, 16)),
+        "attn_512": (lambda: M.AttnBlock(512), (2, 512, 16, 16)),
+        # the AttnBlock's projection epilogue emits the statistics the following ResnetBlock's first GroupNorm consumes
+        "attn_res_512": (lambda: nn.Sequential(M.AttnBlock(512), M.ResnetBlock(in_channels=512, out_channels=512, dropout=0.0)),
+                         (2, 512, 16, 16)),
+        # ... and a ResnetBlock's conv2 epilogue emits those of the next block (res -> res -> attn chain of the decoder)
+        "res_res_attn_512": (lambda: nn.Sequential(M.ResnetBlock(in_channels=512, out_channels=512, dropout=0.0),
+                                                   M.ResnetBlock(in_channels=512, out_channels=512, dropout=0.0), M.AttnBlock(512)),
+                             (2, 512, 16, 16)),
+        "up_128": (lambda: M.Upsample(128, True), (2, 128, 16, 16)),
+        "down_128": (lambda: M.Downsample(128, True), (2, 128, 32, 32)),
+        "up_512": (lambda: M.Upsample(512, True), (1, 512, 16, 16)),
+    }
+    out = {}
+    for i, (name, (ctor, shape)) in enumerate(specs.items()):
+        mod = ctor()
+        checks = fill_seeded(mod, 100 + i)
+        x = seeded_input(shape, 200 + i, 1.5, 0.3).requires_grad_(True)
+        y = mod(x)
+        w = torch.linspace(-1, 1, y.numel()).view_as(y)
+        (y * w).sum().backward()
+        grads, norms = {}, {}
+        for k, p in mod.named_parameters():
+            norms[k] = float(p.grad.double().norm())
+            grads[k] = p.grad.clone() if p.grad.numel() <= 70000 else sample(p.grad, 8192)
+        out[name] = dict(seed_w=100 + i, seed_x=200 + i, shape=shape, param_checks=checks, y=sample(y, y.numel() // 3),
+                         y_norm=float(y.double().norm()), grad_x=sample(x.grad, x.numel() // 3),
+                         grad_x_norm=float(x.grad.double().norm()), grads=grads, grad_norms=norms)
+        print("tc block", name, "y norm", float(y.norm()))
+    torch.save(out, os.path.join(OUT, "blocks_tc.pt"))
+
+
+def img256_fixture(ref_models):
+    """G8: the img_config model at BASELINE's 256x256 (batch 2), fwd + bwd on the REAL reference."""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from seeded import sample
+    torch.manual_seed(0)
+    big = ref_models.VQBASE(IMG, 8192, 256, 3000, 12500)
+    with torch.no_grad():
+        big.quantize.embedding.weight.normal_()
+    big.quantize.q_counter = 10 ** 6
+    big.train()
+    x = torch.rand(2, 3, 256, 256, generator=torch.Generator().manual_seed(1234))
+    qc = {}
+    h1 = big.quant_conv.register_forward_hook(lambda _m, _i, o: qc.__setitem__("h", o))
+    def _h2(_m, _i, o):
+        o[0].retain_grad()
+        qc["idx"], qc["zq"] = o[2].clone(), o[0]
+    h2 = big.quantize.register_forward_hook(_h2)
+    def _h1(_m, _i, o):
+        o.retain_grad()
+        qc["h"] = o
+    h1.remove()
+    h1 = big.quant_conv.register_forward_hook(_h1)
+    dec, diff = big(x)
+    loss = (x - dec).abs().mean() + diff
+    loss.backward()
+    h1.remove(); h2.remove()
+    named = dict(big.named_parameters())
+    grad_samples = {k: sample(p.grad, 512) for k, p in named.items()}
+    torch.save(dict(ddconfig=IMG, x_seed=1234, x_shape=(2, 3, 256, 256), x_sum=float(x.double().sum()),
+                    idx=qc["idx"], quant_in=qc["h"].detach().clone(), dec_norm=float(dec.double().norm()),
+                    dec_sample=sample(dec, 16384), diff=diff.detach(), loss=loss.detach(),
+                    g_quant_in=sample(qc["h"].grad, 16384), g_quant_in_norm=float(qc["h"].grad.double().norm()),
+                    g_zq=sample(qc["zq"].grad, 16384), g_zq_norm=float(qc["zq"].grad.double().norm()),
+                    grad_norms={k: float(p.grad.double().norm()) for k, p in named.items()}, grad_samples=grad_samples),
+               os.path.join(OUT, "vqbase_img_256.pt"))
+    print("img 256 done: loss", float(loss))
 
 
 if __name__ == "__main__":
