@@ -78,8 +78,10 @@ int mas_gn_apply(const float* x, const float* mean, const float* rstd, const flo
                  void* stream);
 int mas_gn_backward(const float* dy, const float* x, const float* mean, const float* rstd,
                     const float* gamma, const float* beta, const float* dx_add, float* dx, float* dgamma,
-                    float* dbeta, float* act_out, int N, int HW, int C, int G, int silu, void* ws, size_t ws_bytes,
-                    void* stream);  /* act_out (or NULL): also writes act(GN(x)), the operand of the following weight gradient */
+                    float* dbeta, float* act_out, float* dx_amax, int N, int HW, int C, int G, int silu, void* ws,
+                    size_t ws_bytes, void* stream);
+/* act_out (or NULL): also writes act(GN(x)), the operand of the following weight gradient; dx_amax (or NULL): device
+ * scalar receiving max|dx| (what mas_amax(dx) would return), for the fp16-operand kernels that consume dx. */
 /* out = a + b (gradient of x+h where the two branches cannot be fused). */
 int mas_add(const float* a, const float* b, float* out, int64_t n, void* stream);
 /* Standalone Swish module (modules.py:194-196). */
@@ -110,6 +112,20 @@ int mas_pack_conv3x3_tc(const float* w_oihw, float* w_tc, int Cout, int Cin, int
 int mas_conv3x3_fprop_tc(const float* x, mas_tensor4 xs, const float* w_tc, const float* bias,
                          const float* residual, float* y, mas_tensor4 ys, int mode, const float* gn_table,
                          int gn_silu, float* stats_part, void* stream);
+/* fp16-operand form of the same kernel (tcgen05 kind::f16, fp32 accumulate): an fp16 significand has the 11 bits of a TF32
+ * one, so the rounding of the operands is the same as on the TF32 path, while one MMA instruction (and one byte of
+ * shared-memory operand traffic, the kernel's limiter) carries twice the FLOPs.  The narrower exponent range is handled by
+ * a power-of-two operand scale derived ON THE DEVICE from x_amax (a device scalar holding max|x|, from mas_amax; NULL = no
+ * scaling, right for post-GroupNorm activations): x*s is converted with round-to-nearest (saturating), the epilogue
+ * multiplies by 1/s, both exact.  Needs Cin % 16 == 0 on top of mas_conv3x3_tc_eligible.  w_tc16 comes from
+ * mas_pack_conv3x3_tc16: 9*Cout*Cin halves ([n_tile][k_chunk][tap][k/8][128][8]); with w_tc16_dgrad != NULL the forward
+ * packing goes to w_tc16 and the data-gradient packing (transpose = 1) to w_tc16_dgrad in one pass over the weight. */
+int mas_amax(const float* x, int64_t n, float* out, void* stream);
+int mas_pack_conv3x3_tc16(const float* w_oihw, void* w_tc16, void* w_tc16_dgrad, int Cout, int Cin, int transpose,
+                          void* stream);
+int mas_conv3x3_fprop_tc16(const float* x, mas_tensor4 xs, const void* w_tc16, const float* bias,
+                           const float* residual, float* y, mas_tensor4 ys, int mode, const float* gn_table,
+                           int gn_silu, float* stats_part, const float* x_amax, void* stream);
 /* Both packings of one weight (transpose = 0 and 1 of mas_pack_conv3x3_tc) in a single pass; Cout % 128 == Cin % 128 == 0. */
 int mas_pack_conv3x3_tc_pair(const float* w_oihw, float* w_tc_fwd, float* w_tc_dgrad, int Cout, int Cin, void* stream);
 int mas_gn_finalize_partials(const float* part, int tiles_per_image, int N, int C, int G, int64_t hw, float eps,
@@ -134,7 +150,15 @@ int mas_tc_probe(const float* A, const float* B, float* D, int a_src, int b_layo
 size_t mas_conv3x3_wgrad_ws_bytes(mas_tensor4 xs, mas_tensor4 dys, int mode);
 int mas_conv3x3_wgrad(const float* x, mas_tensor4 xs, const float* dy, mas_tensor4 dys, float* dw_oihw,
                       float* dbias, int mode, int impl, const float* gn_table, int gn_silu, void* ws,
-                      size_t ws_bytes, void* stream);  /* gn_table: x is re-activated on the fly (tensor path only) */
+                      size_t ws_bytes, void* stream);
+/* fp16-operand tensor-core form (see mas_conv3x3_fprop_tc16): dy is scaled by a power of two derived on the device from
+ * dy_amax (device scalar from mas_amax, or NULL), x (or act(GroupNorm(x)) with gn_table) is converted unscaled.
+ * MAS_ERR_UNSUPPORTED unless mas_conv3x3_wgrad_tc_eligible (dense NHWC, Cin % 32 == 0, Cout % 128 == 0, H, W % 8 == 0,
+ * mode S1 / UP).  Workspace: mas_conv3x3_wgrad_ws_bytes.  dbias (may be NULL) is produced too. */
+int mas_conv3x3_wgrad_tc_eligible(mas_tensor4 xs, mas_tensor4 dys, int mode);
+int mas_conv3x3_wgrad_tc16(const float* x, mas_tensor4 xs, const float* dy, mas_tensor4 dys, float* dw_oihw, float* dbias,
+                           int mode, const float* gn_table, int gn_silu, const float* dy_amax, void* ws, size_t ws_bytes,
+                           void* stream);  /* gn_table: x is re-activated on the fly (tensor path only) */
 /* Weight gradient of a 1x1 convolution: dw[Cout,Cin] = dy^T x over M rows (split over rows, deterministic);
  * dbias [Cout] may be NULL. x [M,Cin] and dy [M,Cout] are row-major with row pitches ldx / ldy (elements). */
 size_t mas_conv1x1_wgrad_ws_bytes(int64_t M, int Cin, int Cout);
@@ -198,8 +222,9 @@ int mas_attnblock_backward(const float* dout, const float* x, int N, int HW, int
                            const float* rstd, const float* norm_w, const float* norm_b, const float* q_w,
                            const float* k_w, const float* v_w, const float* proj_w, const float* hn,
                            const float* qkv, const float* P, const float* O, float* dx, float* dnorm_w,
-                           float* dnorm_b, float* dqkv_w, float* dqkv_b, float* dproj_w, float* dproj_b, int impl,
-                           void* ws, size_t ws_bytes, void* stream);
+                           float* dnorm_b, float* dqkv_w, float* dqkv_b, float* dproj_w, float* dproj_b,
+                           float* dx_amax /* or NULL: max|dx|, see mas_gn_backward */, int impl, void* ws,
+                           size_t ws_bytes, void* stream);
 
 /* ---- (Sync)BatchNorm for quant_conv[1] — vqvae.py:16 ---------------------------------------------------
  * x [R, C] NHWC rows.  mas_bn_stats writes LOCAL [sum(C), sumsq(C), R] as fp64 (2*C+1 doubles: the last one is the

@@ -114,8 +114,8 @@ int mas_attnblock_forward(const float* x, int N, int HW, int C, int G, const flo
 int mas_attnblock_backward(const float* dout, const float* x, int N, int HW, int C, int G, const float* mean, const float* rstd,
                            const float* norm_w, const float* norm_b, const float* q_w, const float* k_w, const float* v_w,
                            const float* proj_w, const float* hn, const float* qkv, const float* P, const float* O, float* dx,
-                           float* dnorm_w, float* dnorm_b, float* dqkv_w, float* dqkv_b, float* dproj_w, float* dproj_b, int impl,
-                           void* ws, size_t ws_bytes, void* stream) {
+                           float* dnorm_w, float* dnorm_b, float* dqkv_w, float* dqkv_b, float* dproj_w, float* dproj_b, float* dx_amax,
+                           int impl, void* ws, size_t ws_bytes, void* stream) {
   MAS_REQUIRE(dout && x && mean && rstd && norm_w && norm_b && q_w && k_w && v_w && proj_w && hn && qkv && P && O && dx && dnorm_w &&
                   dnorm_b && dqkv_w && dqkv_b && dproj_w && dproj_b,
               "attnblock_backward: null pointer");
@@ -167,7 +167,7 @@ int mas_attnblock_backward(const float* dout, const float* x, int N, int HW, int
   // [dWq; dWk; dWv] = dqkv^T . hn, biases = column sums of dqkv
   if (int e = mas_conv1x1_wgrad(hn, c, dqkv, 3 * c, M, C, 3 * C, dqkv_w, dqkv_b, impl, scratch, scratch_bytes, stream)) return e;
   // GroupNorm (no activation) backward, + dout for the residual branch
-  return mas_gn_backward(dhn, x, mean, rstd, norm_w, norm_b, dout, dx, dnorm_w, dnorm_b, nullptr, N, HW, C, G, 0, scratch, scratch_bytes,
+  return mas_gn_backward(dhn, x, mean, rstd, norm_w, norm_b, dout, dx, dnorm_w, dnorm_b, nullptr, dx_amax, N, HW, C, G, 0, scratch, scratch_bytes,
                          stream);
 }
 

@@ -21,6 +21,7 @@
 // (modules.py:55-59,74-78), nn.Conv2d 1x1 (modules.py:113-117,145-164).
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "mas_common.cuh"
@@ -93,6 +94,16 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t adesc, uin
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same, fp16 operands (11-bit significand like TF32, K = 16 per instruction: twice the FLOPs per issued MMA and per byte of
+// shared-memory operand traffic), fp32 accumulate
+__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -127,6 +138,43 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
+// instruction descriptor: D=f32, A=B=f16 (format code 0), both K-major, M=128, N
+__host__ __device__ constexpr uint32_t make_idesc_f16(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+// two floats -> packed half2 (lo = a, hi = b), round-to-nearest-even, saturating to +-65504 instead of inf
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+// power-of-two operand scale for an fp16 operand tensor from its largest magnitude (device scalar; null = 1):
+// amax * s lands in [2^14, 2^15), so the whole fp16 normal range (30 binades) sits below the largest element and
+// nothing overflows. *inv receives 1/s (exact). Zero / non-finite amax -> s = 1.
+__device__ __forceinline__ float operand_scale(const float* amax, float* inv) {
+  float s = 1.f, i = 1.f;
+  if (amax) {
+    const uint32_t b = __float_as_uint(*amax);
+    const int e = (int)((b >> 23) & 0xff);            // biased exponent of amax (0 = zero/denormal, 255 = inf/nan)
+    if (e > 0 && e < 255) {
+      int se = 127 + 14 - (e - 127);                  // biased exponent of s = 2^(14 - floor(log2 amax))
+      se = se < 1 ? 1 : (se > 254 ? 254 : se);
+      s = __uint_as_float((uint32_t)se << 23);
+      i = __uint_as_float((uint32_t)(254 - se) << 23);
+    }
+  }
+  *inv = i;
+  return s;
+}
+
+// read-only 16-byte load that also pulls the surrounding 256 bytes into L2: the K loop walks a pixel's channel vector in
+// 32/64-byte steps, so the next chunks of the same pixel hit L2 instead of paying the DRAM latency again
+__device__ __forceinline__ float4 ldg_l2pf(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::256B.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
 enum { MAP_S1 = 0, MAP_UP = 2, MAP_ZS = 3, MAP_ROWS = 4 };
 
 struct Params {
@@ -149,23 +197,30 @@ struct Params {
   // sum of squares of the stored output, [total_tiles][4][Cout/4][2] floats (null = off); reduced deterministically
   // per (image, group) by mas_gn_finalize_partials.
   float* stats_part;
+  // fp16-operand kernels: largest magnitude of x (device scalar) for the power-of-two operand scale, or null (no scaling:
+  // activations / weights sit well inside the fp16 range; gradients do not)
+  const float* x_amax;
 };
 
 // One CTA = TILES M-tiles x BN output channels, full K.
-template <int TAPS, int KC, int STAGES, int TILES>
+// F16 = false: TF32 operands (fp32 words, 4 channels per 16-byte chunk, K = 8 per MMA).
+// F16 = true : fp16 operands converted by the producers (8 channels per 16-byte chunk, K = 16 per MMA); KC still counts channels.
+template <int TAPS, int KC, int STAGES, int TILES, bool F16>
 __global__ void __launch_bounds__(NTHREADS, (TILES == 2) ? 2 : 1) shift_gemm_tc(const Params p) {
+  constexpr int EPC = F16 ? 8 : 4;                      // channels per 16-byte operand chunk
   constexpr int SLOTS = (TAPS == 9) ? 180 : 132;        // staged pixels per tile (18x10 halo | 128 rows + pad)
   constexpr int ROWP = (TAPS == 9) ? 10 : 8;            // staged pixels per image row
-  constexpr int LBO_A = SLOTS * 16;                     // bytes between k-quads of A
+  constexpr int LBO_A = SLOTS * 16;                     // bytes between k-chunks of A
   constexpr int SBO_A = ROWP * 16;                      // bytes between 8-pixel groups of A
-  constexpr int A_TILE = (KC / 4) * LBO_A;              // bytes per tile per stage
+  constexpr int A_TILE = (KC / EPC) * LBO_A;            // bytes per tile per stage
   constexpr int A_STAGE = TILES * A_TILE;
   constexpr int LBO_B = BN * 16;
-  constexpr int B_TAP = (KC / 4) * LBO_B;
+  constexpr int B_TAP = (KC / EPC) * LBO_B;
   constexpr int B_STAGE = TAPS * B_TAP;
   constexpr int STAGE = A_STAGE + B_STAGE;
-  constexpr int QUADS = KC / 4;
-  constexpr int ITEMS = TILES * SLOTS * QUADS;          // float4 items staged per K chunk
+  constexpr int QUADS = KC / EPC;
+  constexpr int ITEMS = TILES * SLOTS * QUADS;          // 16-byte operand chunks staged per K chunk
+  constexpr int LPI = F16 ? 2 : 1;                      // float4 global loads per staged chunk
   constexpr int PER_THREAD = (ITEMS + NPROD - 1) / NPROD;
   static_assert((SLOTS % 8) == 4, "A plane pitch must be 64 mod 128 bytes for conflict-free producer stores");
 
@@ -231,32 +286,39 @@ __global__ void __launch_bounds__(NTHREADS, (TILES == 2) ? 2 : 1) shift_gemm_tc(
               iy = vy >> 1; ix = vx >> 1;
             }
             if (ok) {
-              src[i] = p.x + ((int64_t)(n * p.Hin + iy) * p.Win + ix) * p.ldx + q * 4;
-              if (p.gn_table) tab[i] = p.gn_table + ((size_t)n * p.Cin + q * 4) * 2;
+              src[i] = p.x + ((int64_t)(n * p.Hin + iy) * p.Win + ix) * p.ldx + q * EPC;
+              if (p.gn_table) tab[i] = p.gn_table + ((size_t)n * p.Cin + q * EPC) * 2;
             }
           } else {
             const int64_t row = tile * BM + slot;
             if (slot >= BM) dst[i] = 0xFFFFFFFFu;  // pad slots are never read by the MMA
-            else if (row < (int64_t)p.N * p.Hout * p.Wout) src[i] = p.x + row * p.ldx + q * 4;
+            else if (row < (int64_t)p.N * p.Hout * p.Wout) src[i] = p.x + row * p.ldx + q * EPC;
           }
         }
       }
     }
     int stage = 0;
     uint32_t phase = 0;
-    float4 vn[PER_THREAD];
-    auto gload = [&](int kc, float4* v) {
+    float inv_scale = 1.f;
+    const float in_scale = F16 ? operand_scale(p.x_amax, &inv_scale) : 1.f;
+    float4 vn[PER_THREAD][LPI];
+    auto gload = [&](int kc, float4 (*v)[LPI]) {
 #pragma unroll
       for (int i = 0; i < PER_THREAD; ++i) {
-        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (src[i]) v[i] = __ldg(reinterpret_cast<const float4*>(src[i] + (size_t)kc * KC));
+#pragma unroll
+        for (int h = 0; h < LPI; ++h) {
+          v[i][h] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (src[i]) v[i][h] = ldg_l2pf(reinterpret_cast<const float4*>(src[i] + (size_t)kc * KC) + h);
+        }
       }
     };
     gload(0, vn);
     for (int kc = 0; kc < nchunks; ++kc) {
-      float4 v[PER_THREAD];
+      float4 v[PER_THREAD][LPI];
 #pragma unroll
-      for (int i = 0; i < PER_THREAD; ++i) v[i] = vn[i];
+      for (int i = 0; i < PER_THREAD; ++i)
+#pragma unroll
+        for (int h = 0; h < LPI; ++h) v[i][h] = vn[i][h];
       if (kc + 1 < nchunks) gload(kc + 1, vn);  // next chunk's global loads fly while this chunk is stored / consumed
       if (TAPS == 9) {
         if (p.gn_table) {
@@ -265,12 +327,16 @@ __global__ void __launch_bounds__(NTHREADS, (TILES == 2) ? 2 : 1) shift_gemm_tc(
 #pragma unroll
           for (int i = 0; i < PER_THREAD; ++i) {
             if (tab[i]) {
-              const float4 t0 = __ldg(reinterpret_cast<const float4*>(tab[i] + (size_t)kc * KC * 2));      // sc0 sh0 sc1 sh1
-              const float4 t1 = __ldg(reinterpret_cast<const float4*>(tab[i] + (size_t)kc * KC * 2) + 1);  // sc2 sh2 sc3 sh3
-              float a0 = fmaf(v[i].x, t0.x, t0.y), a1 = fmaf(v[i].y, t0.z, t0.w);
-              float a2 = fmaf(v[i].z, t1.x, t1.y), a3 = fmaf(v[i].w, t1.z, t1.w);
-              if (p.gn_silu) { a0 = silu_f(a0); a1 = silu_f(a1); a2 = silu_f(a2); a3 = silu_f(a3); }
-              v[i] = make_float4(a0, a1, a2, a3);
+#pragma unroll
+              for (int h = 0; h < LPI; ++h) {
+                const float4* tp = reinterpret_cast<const float4*>(tab[i] + (size_t)kc * KC * 2) + 2 * h;
+                const float4 t0 = __ldg(tp);      // sc0 sh0 sc1 sh1
+                const float4 t1 = __ldg(tp + 1);  // sc2 sh2 sc3 sh3
+                float a0 = fmaf(v[i][h].x, t0.x, t0.y), a1 = fmaf(v[i][h].y, t0.z, t0.w);
+                float a2 = fmaf(v[i][h].z, t1.x, t1.y), a3 = fmaf(v[i][h].w, t1.z, t1.w);
+                if (p.gn_silu) { a0 = silu_f(a0); a1 = silu_f(a1); a2 = silu_f(a2); a3 = silu_f(a3); }
+                v[i][h] = make_float4(a0, a1, a2, a3);
+              }
             }
           }
         }
@@ -278,12 +344,23 @@ __global__ void __launch_bounds__(NTHREADS, (TILES == 2) ? 2 : 1) shift_gemm_tc(
       mbar_wait(empty_bar(stage), phase ^ 1);
       uint8_t* a_st = smem + (size_t)stage * STAGE;
 #pragma unroll
-      for (int i = 0; i < PER_THREAD; ++i)
-        if (dst[i] != 0xFFFFFFFFu) *reinterpret_cast<float4*>(a_st + dst[i]) = v[i];
+      for (int i = 0; i < PER_THREAD; ++i) {
+        if (dst[i] != 0xFFFFFFFFu) {
+          if (F16) {
+            const float4 lo = v[i][0], hi = v[i][LPI - 1];
+            *reinterpret_cast<uint4*>(a_st + dst[i]) =
+                make_uint4(pack_h2(lo.x * in_scale, lo.y * in_scale), pack_h2(lo.z * in_scale, lo.w * in_scale),
+                           pack_h2(hi.x * in_scale, hi.y * in_scale), pack_h2(hi.z * in_scale, hi.w * in_scale));
+          } else {
+            *reinterpret_cast<float4*>(a_st + dst[i]) = v[i][0];
+          }
+        }
+      }
       fence_proxy_async();  // make the generic-proxy stores visible to the tensor core (async proxy)
       mbar_arrive(full_bar(stage));
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
+    const float alpha = p.alpha * inv_scale;
 
     // ===================== epilogue: TMEM -> registers -> smem transpose -> coalesced global stores =====================
     // A thread owns one pixel row of the accumulator (32 consecutive channels per tcgen05.ld); writing that directly
@@ -318,7 +395,7 @@ __global__ void __launch_bounds__(NTHREADS, (TILES == 2) ? 2 : 1) shift_gemm_tc(
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
           *reinterpret_cast<float4*>(patch + lane * EP_LD + j) =
-              make_float4(v[j] * p.alpha, v[j + 1] * p.alpha, v[j + 2] * p.alpha, v[j + 3] * p.alpha);
+              make_float4(v[j] * alpha, v[j + 1] * alpha, v[j + 2] * alpha, v[j + 3] * alpha);
         __syncwarp();
         float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.bias) bq = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + col + sub_c * 4));
@@ -360,7 +437,7 @@ __global__ void __launch_bounds__(NTHREADS, (TILES == 2) ? 2 : 1) shift_gemm_tc(
   } else if (warp == 8) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BN);
+      constexpr uint32_t idesc = F16 ? make_idesc_f16(BN) : make_idesc(BN);
       int stage = 0;
       uint32_t phase = 0;
       for (int kc = 0; kc < nchunks; ++kc) {
@@ -379,10 +456,11 @@ __global__ void __launch_bounds__(NTHREADS, (TILES == 2) ? 2 : 1) shift_gemm_tc(
           for (int t = 0; t < TAPS; ++t) {
             const uint32_t tapoff = (TAPS == 9) ? (uint32_t)(((t / 3) * 10 + (t % 3)) * 16) : 0u;
 #pragma unroll
-            for (int k8 = 0; k8 < KC / 8; ++k8) {
+            for (int k8 = 0; k8 < KC / (2 * EPC); ++k8) {   // one MMA = two 16-byte chunks of K (8 tf32 | 16 fp16)
               const uint64_t ad = a_base + (uint64_t)((tl * A_TILE + tapoff + k8 * 2 * LBO_A) >> 4);
               const uint64_t bd = b_base + (uint64_t)((t * B_TAP + k8 * 2 * LBO_B) >> 4);
-              mma_tf32_ss(tmem_base + (uint32_t)(tl * BN), ad, bd, idesc, (t > 0 || k8 > 0) ? 1u : acc0);
+              if (F16) mma_f16_ss(tmem_base + (uint32_t)(tl * BN), ad, bd, idesc, (t > 0 || k8 > 0) ? 1u : acc0);
+              else mma_tf32_ss(tmem_base + (uint32_t)(tl * BN), ad, bd, idesc, (t > 0 || k8 > 0) ? 1u : acc0);
             }
           }
         }
@@ -414,10 +492,10 @@ __global__ void __launch_bounds__(NTHREADS, (TILES == 2) ? 2 : 1) shift_gemm_tc(
   }
 }
 
-template <int TAPS, int KC, int STAGES, int TILES>
+template <int TAPS, int KC, int STAGES, int TILES, bool F16>
 constexpr size_t smem_bytes() {
-  constexpr int SLOTS = (TAPS == 9) ? 180 : 132;
-  return (size_t)STAGES * (TILES * (KC / 4) * SLOTS * 16 + TAPS * (KC / 4) * BN * 16) + (2 * STAGES + 1) * 8 + 16;
+  constexpr int SLOTS = (TAPS == 9) ? 180 : 132, EPC = F16 ? 8 : 4;
+  return (size_t)STAGES * (TILES * (KC / EPC) * SLOTS * 16 + TAPS * (KC / EPC) * BN * 16) + (2 * STAGES + 1) * 8 + 16;
 }
 
 // weights [Cout][Cin][TAPS] (reference layout, taps innermost) -> [n_tile][k_chunk][tap][k/4][BN][4], TF32-rounded.
@@ -439,6 +517,33 @@ __global__ void pack_weights_tc(const float* __restrict__ w, float* __restrict__
     if (!transpose) v = w[((size_t)n * Cin + k) * taps + t];
     else v = w[((size_t)k * Cin + n) * taps + (taps - 1 - t)];
     out[i] = round_tf32(v);
+  }
+}
+
+// fp16 variant of the packing: [n_tile][k_chunk][tap][k/8][BN][8 halves] (one 16-byte chunk = 8 consecutive K of one n);
+// `both` != 0 writes the forward packing to out_f AND the data-gradient packing (N = Cin, K = Cout, taps flipped) to out_d
+// in one pass over the weight; otherwise only the one selected by `transpose` goes to out_f.
+__global__ void pack_weights_tc16(const float* __restrict__ w, __half* __restrict__ out_f, __half* __restrict__ out_d, int Cout, int Cin,
+                                  int taps, int KC, int transpose, int both) {
+  const int64_t total = (int64_t)Cout * Cin * taps;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    // i enumerates the SOURCE [co][ci][tap] (coalesced reads); destinations are scattered 2-byte stores into L2
+    const int t = (int)(i % taps);
+    const int ci = (int)((i / taps) % Cin), co = (int)(i / ((int64_t)taps * Cin));
+    const __half v = __float2half_rn(w[i]);
+    auto put = [&](__half* out, int n, int k, int tt, int K) {
+      const int nchunks = K / KC, octs = KC / 8;
+      const int64_t j = (((((int64_t)(n / BN) * nchunks + k / KC) * taps + tt) * octs + (k % KC) / 8) * BN + (n % BN)) * 8 + (k % 8);
+      out[j] = v;
+    };
+    if (both) {
+      put(out_f, co, ci, t, Cin);
+      put(out_d, ci, co, taps - 1 - t, Cout);
+    } else if (!transpose) {
+      put(out_f, co, ci, t, Cin);
+    } else {
+      put(out_f, ci, co, taps - 1 - t, Cout);
+    }
   }
 }
 
@@ -493,6 +598,7 @@ struct WParams {
   int64_t total_units, units_per_split, rows, ldx, ldy;
   const float* gn_table;  // fused GroupNorm(+SiLU) prologue on x, [N][Cin][2] (sc, sh), or null (3x3 only)
   int gn_silu;
+  const float* dy_amax;   // fp16-operand kernel: max|dy| (device scalar) for the power-of-two scale of the A operand, or null
 };
 
 __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -502,6 +608,19 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ unsigned short to_h(float a) {
+  unsigned short r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(a));
+  return r;
 }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
   const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
@@ -518,8 +637,12 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 
 // TAPS == 9: 3x3 convolution (unit = 8x8 output pixels, halo 10x10).  TAPS == 1: 1x1 convolution / row GEMM
 // (unit = 64 consecutive rows, no halo).
-template <int TAPS, bool PRO>
+// F16 (3x3 only): both operands converted to fp16 on their way to the tensor core (dy scaled by a power of two from
+// p.dy_amax); a 16-byte chunk of B then holds 8 pixels = one halo row segment, one MMA (K = 16) covers two image rows
+// of the unit, and A packs two pixels per TMEM column.
+template <int TAPS, bool PRO, bool F16>
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc(const WParams p, const __grid_constant__ CUtensorMap dy_map) {
+  static_assert(!F16 || TAPS == 9, "the fp16-operand weight-gradient kernel is the 3x3 one");
   // B (the shifted operand) must be K-major with K = pixel: tests/test_gpu_tc_probe.py shows that kind::tf32 returns
   // zeros for MN-major shared-memory operands, so the halo is staged TRANSPOSED ([ci][pixel], 4 pixels per 16-byte
   // chunk) once per horizontal tap offset dx (3 copies); vertical offsets are whole-chunk K advances of the descriptor.
@@ -531,13 +654,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc(const WParams p, const
   constexpr int NT = (TAPS == 9) ? WG_NT : 128, QUADS = NT / 4;
   constexpr int SLOTS = (TAPS == 9) ? WG_SLOTS : 64;
   constexpr int COPIES = (TAPS == 9) ? 3 : 1;
-  constexpr int LBO_B = COPIES * NT * 16;                  // bytes between 4-pixel chunks
-  constexpr int B_STAGE = ((TAPS == 9) ? 20 : 16) * LBO_B; // 80 (10 halo rows x 8) or 64 pixels
+  constexpr int LBO_B = COPIES * NT * 16;                  // bytes between 16-byte chunks (4 fp32 | 8 fp16 pixels)
+  constexpr int B_STAGE = (F16 ? 10 : ((TAPS == 9) ? 20 : 16)) * LBO_B; // 80 (10 halo rows x 8) or 64 pixels
+  constexpr int A_COLS = F16 ? 32 : 64;                    // TMEM columns of one staged dy tile (64 pixels)
   constexpr int ITEMS = SLOTS * QUADS, PER_THREAD = (ITEMS + NPROD - 1) / NPROD;
   constexpr uint32_t ACC_COLS = TAPS * NT;
   constexpr int NMMA = COPIES * NT;                        // N of one MMA (96 | 128)
   // instruction descriptor: D=f32, A=tf32 (TMEM, K-major), B=tf32 K-major, M=128, N=NMMA
-  constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NMMA >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  constexpr uint32_t idesc = F16 ? make_idesc_f16(NMMA)
+                                 : ((1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NMMA >> 3) << 17) | ((uint32_t)(BM >> 4) << 24));
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* dy_smem = smem + (size_t)WG_STAGES * B_STAGE;   // [WG_STAGES][64 pixels][128 co] fp32, filled by cp.async.bulk
@@ -653,6 +778,20 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc(const WParams p, const
       for (int i = 0; i < PER_THREAD; ++i) {
         if (it_c[i] >= 0) {
           const float e[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+          if (F16) {
+            const unsigned short h[4] = {to_h(e[0]), to_h(e[1]), to_h(e[2]), to_h(e[3])};
+#pragma unroll
+            for (int dx = 0; dx < COPIES; ++dx) {
+              const int c = it_c[i] - dx;
+              if ((unsigned)c < 8u) {
+                // chunk = halo row it_r; channel 4q+j -> operand row n = (NT/4)*j + q of the dx block; 8 pixels per row
+                unsigned short* d = reinterpret_cast<unsigned short*>(b_st) + it_r[i] * (LBO_B / 2) + dx * (NT * 8) + it_q[i] * 8 + c;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) d[j * NT * 2] = h[j];
+              }
+            }
+            continue;
+          }
 #pragma unroll
           for (int dx = 0; dx < COPIES; ++dx) {
             const int c = it_c[i] - dx;
@@ -672,6 +811,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc(const WParams p, const
     }
     // ============ epilogue (warps 0-3): TAPS x [128 co x NT ci] partial sums -> workspace ============
     if (warp < 4) {
+      float inv = 1.f;
+      if (F16) operand_scale(p.dy_amax, &inv);
       mbar_wait(accum_bar, 0);
       tc_fence_after();
       const int co = co0 + warp * 32 + lane;
@@ -682,7 +823,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc(const WParams p, const
           float v[32];
           tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * NT), v);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(o + q * 4) = make_float4(v[q], v[8 + q], v[16 + q], v[24 + q]);
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(o + q * 4) = make_float4(v[q] * inv, v[8 + q] * inv, v[16 + q] * inv, v[24 + q] * inv);
         } else {
           // NT = 128: column n = 32*j + q holds channel 4q + j; gather the four j-planes, 8 quads at a time
 #pragma unroll
@@ -709,6 +851,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc(const WParams p, const
     float bsum = 0.f;
     int stage = 0;
     uint32_t phase = 0;
+    float a_inv;
+    const float a_scale = F16 ? operand_scale(p.dy_amax, &a_inv) : 1.f;
     for (int64_t u = u0; u < u1; ++u) {
       mbar_wait(fullD(stage), phase);   // implies the TMEM A stage is free too (the copy was issued after empty(stage))
       const float* dys = reinterpret_cast<const float*>(dy_smem + (size_t)stage * WG_DY_STAGE) + cl;
@@ -723,9 +867,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc(const WParams p, const
 #pragma unroll
       for (int j = 0; j < 64; ++j) bsum += v[j];
       tc_fence_after();
-      const uint32_t ta = tmem_base + ((uint32_t)(lg * 32) << 16) + ACC_COLS + (uint32_t)(stage * 64);
-      tmem_st32(ta, v);
-      tmem_st32(ta + 32, v + 32);
+      const uint32_t ta = tmem_base + ((uint32_t)(lg * 32) << 16) + ACC_COLS + (uint32_t)(stage * A_COLS);
+      if (F16) {   // two consecutive pixels (K) of this lane's channel per 32-bit TMEM column
+        float w[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) w[j] = __uint_as_float(pack_h2(v[2 * j] * a_scale, v[2 * j + 1] * a_scale));
+        tmem_st32(ta, w);
+      } else {
+        tmem_st32(ta, v);
+        tmem_st32(ta + 32, v + 32);
+      }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(fullA(stage));
@@ -764,9 +915,19 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc(const WParams p, const
         mbar_wait(fullA(stage), phase);
         tc_fence_after();
         const uint32_t b_st = smem_base + (uint32_t)stage * B_STAGE;
-        const uint32_t a_t = tmem_base + ACC_COLS + (uint32_t)(stage * 64);
+        const uint32_t a_t = tmem_base + ACC_COLS + (uint32_t)(stage * A_COLS);
         const uint64_t b_base = make_desc(b_st, LBO_B, 128);
         const uint32_t acc0 = (u > u0) ? 1u : 0u;
+        if (F16) {
+#pragma unroll
+          for (int r = 0; r < 8; r += 2) {     // K = 16 pixels = image rows (r, r+1): halo chunks r+dy, r+dy+1
+#pragma unroll
+            for (int dyy = 0; dyy < 3; ++dyy) {
+              const uint64_t bd = b_base + (uint64_t)(((r + dyy) * LBO_B) >> 4);
+              mma_f16_ts(tmem_base + (uint32_t)(dyy * NMMA), a_t + (uint32_t)(r * 4), bd, idesc, r > 0 ? 1u : acc0);
+            }
+          }
+        } else
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
 #pragma unroll
@@ -880,9 +1041,12 @@ static int set_smem(K kernel, size_t bytes) {
 }
 
 // w_tc must have been produced by mas_pack_conv3x3_tc for the matching direction.
+// f16 != 0: w_tc is the fp16 packing (mas_pack_conv3x3_tc16) and x_amax (device scalar or null) scales the A operand.
 int conv3x3_fprop_tc_launch(const float* x, mas_tensor4 xs, const float* w_tc, const float* bias, const float* res, float* y,
-                            mas_tensor4 ys, int mode, const float* gn_table, int gn_silu, float* stats_part, cudaStream_t st) {
+                            mas_tensor4 ys, int mode, const float* gn_table, int gn_silu, float* stats_part, int f16,
+                            const float* x_amax, cudaStream_t st) {
   const int Cin = (int)xs.c, Cout = (int)ys.c;
+  if (f16 && Cin % 16) return fail(MAS_ERR_UNSUPPORTED, "tc conv (fp16 operands): Cin=%d must be a multiple of 16", Cin);
   if (!(mode == MAS_CONV_S1 || mode == MAS_CONV_UP || mode == MAS_CONV_ZS)) return fail(MAS_ERR_UNSUPPORTED, "tc conv: mode %d", mode);
   if (!dense_nhwc(xs) || !dense_nhwc(ys) || Cin % 8 || Cout % tc::BN || ys.h % 16 || ys.w % 8 || !al16p(x) || !al16p(y) ||
       (res && !al16p(res)) || (bias && !al16p(bias)) || !al16p(w_tc))
@@ -899,18 +1063,25 @@ int conv3x3_fprop_tc_launch(const float* x, mas_tensor4 xs, const float* w_tc, c
   p.total_tiles = (int64_t)p.N * p.tiles_x * p.tiles_y;
   p.alpha = 1.0f;
   p.gn_table = gn_table; p.gn_silu = gn_silu; p.stats_part = stats_part;
+  p.x_amax = f16 ? x_amax : nullptr;
   if (gn_table && !al16p(gn_table)) return fail(MAS_ERR_INVALID_ARG, "tc conv: gn_table must be 16-byte aligned");
   // two co-resident CTAs per SM (2 tiles / 256 TMEM columns / 2 stages each): one CTA's epilogue and pipeline fill
   // overlap the other's main loop
   constexpr int T = 2, STG = 2;
-  constexpr size_t smem = tc::smem_bytes<9, 8, STG, T>();
+  constexpr size_t smem = tc::smem_bytes<9, 8, STG, T, false>();
+  static_assert(smem == tc::smem_bytes<9, 16, STG, T, true>(), "both operand formats stage the same bytes per K chunk");
   static std::atomic<uint64_t> configured{0};
   if (first_on_device(configured)) {
-    if (int e = set_smem(tc::shift_gemm_tc<9, 8, STG, T>, smem)) return e;
+    if (int e = set_smem(tc::shift_gemm_tc<9, 8, STG, T, false>, smem)) return e;
+    if (int e = set_smem(tc::shift_gemm_tc<9, 16, STG, T, true>, smem)) return e;
     mark_device(configured);
   }
   dim3 grid((unsigned)cdiv(p.total_tiles, T), (unsigned)(Cout / tc::BN));
-  tc::shift_gemm_tc<9, 8, STG, T><<<grid, tc::NTHREADS, smem, st>>>(p);
+  if (f16) {
+    tc::shift_gemm_tc<9, 16, STG, T, true><<<grid, tc::NTHREADS, smem, st>>>(p);
+    return launched_tc("shift_gemm_tc<9,f16>");
+  }
+  tc::shift_gemm_tc<9, 8, STG, T, false><<<grid, tc::NTHREADS, smem, st>>>(p);
   return launched_tc("shift_gemm_tc<9>");
 }
 
@@ -929,16 +1100,16 @@ int gemm_rows_tc_launch(const float* A, int64_t lda, const float* w_tc, float* C
   p.tiles_x = 1; p.tiles_y = 1;
   p.total_tiles = cdiv(M, tc::BM);
   p.alpha = alpha;
-  p.gn_table = nullptr; p.gn_silu = 0; p.stats_part = stats_part;
+  p.gn_table = nullptr; p.gn_silu = 0; p.stats_part = stats_part; p.x_amax = nullptr;
   if (stats_part && (M % tc::BM || ldc != N)) return fail(MAS_ERR_UNSUPPORTED, "tc gemm: fused statistics need M %% 128 == 0 and a dense output");
-  constexpr size_t smem = tc::smem_bytes<1, 32, 2, 2>();
+  constexpr size_t smem = tc::smem_bytes<1, 32, 2, 2, false>();
   static std::atomic<uint64_t> configured{0};
   if (first_on_device(configured)) {
-    if (int e = set_smem(tc::shift_gemm_tc<1, 32, 2, 2>, smem)) return e;
+    if (int e = set_smem(tc::shift_gemm_tc<1, 32, 2, 2, false>, smem)) return e;
     mark_device(configured);
   }
   dim3 grid((unsigned)cdiv(p.total_tiles, 2), (unsigned)(N / tc::BN));
-  tc::shift_gemm_tc<1, 32, 2, 2><<<grid, tc::NTHREADS, smem, st>>>(p);
+  tc::shift_gemm_tc<1, 32, 2, 2, false><<<grid, tc::NTHREADS, smem, st>>>(p);
   return launched_tc("shift_gemm_tc<1>");
 }
 
@@ -996,29 +1167,31 @@ static int make_dy_map(CUtensorMap* map, const tc::WParams& p, int taps) {
   return MAS_OK;
 }
 
-template <int TAPS, bool PRO>
+template <int TAPS, bool PRO, bool F16>
 static int wgrad_tc_run(tc::WParams& p, int splits, float* dw, float* dbias, void* ws, cudaStream_t st) {
   p.part = (float*)ws;
   p.bpart = dbias ? (float*)ws + (size_t)splits * TAPS * p.Cout * p.Cin : nullptr;
   p.units_per_split = cdiv(p.total_units, splits);
   constexpr int NT = (TAPS == 9) ? tc::WG_NT : 128;
-  constexpr size_t smem = (size_t)tc::WG_STAGES * ((TAPS == 9 ? 3 * 20 : 16) * NT * 16 + tc::WG_DY_STAGE) + (4 * tc::WG_STAGES + 1) * 8 + 16;
+  constexpr size_t smem = (size_t)tc::WG_STAGES * ((TAPS == 9 ? 3 * (F16 ? 10 : 20) : 16) * NT * 16 + tc::WG_DY_STAGE) + (4 * tc::WG_STAGES + 1) * 8 + 16;
   static std::atomic<uint64_t> configured{0};
   if (first_on_device(configured)) {
-    if (int e = set_smem(tc::wgrad_tc<TAPS, PRO>, smem)) return e;
+    if (int e = set_smem(tc::wgrad_tc<TAPS, PRO, F16>, smem)) return e;
     mark_device(configured);
   }
   CUtensorMap dy_map;
   if (int e = make_dy_map(&dy_map, p, TAPS)) return e;
   dim3 grid((unsigned)(p.Cin / NT), (unsigned)(p.Cout / tc::BM), (unsigned)splits);
-  tc::wgrad_tc<TAPS, PRO><<<grid, tc::WG_THREADS, smem, st>>>(p, dy_map);
+  tc::wgrad_tc<TAPS, PRO, F16><<<grid, tc::WG_THREADS, smem, st>>>(p, dy_map);
   if (int e = launched_tc("wgrad_tc")) return e;
   conv_wgrad_reduce_launch((const float*)ws, splits, TAPS, p.Cout, p.Cin, dw, p.bpart, dbias, st);  // + bias partials -> dbias
   return launched("conv_wgrad_reduce");
 }
 // dbias (may be null) is produced here too when the tensor path runs.
+bool conv_wgrad_tc_eligible(mas_tensor4 xs, mas_tensor4 dys, int mode) { return wgrad_tc_ok(xs, dys, mode); }
 int conv_wgrad_tc_launch(const float* x, mas_tensor4 xs, const float* dy, mas_tensor4 dys, float* dw, float* dbias, int mode,
-                         const float* gn_table, int gn_silu, void* ws, size_t ws_bytes, cudaStream_t st) {
+                         const float* gn_table, int gn_silu, int f16, const float* dy_amax, void* ws, size_t ws_bytes,
+                         cudaStream_t st) {
   if (!wgrad_tc_ok(xs, dys, mode) || !al16p(x) || !al16p(dy)) return fail(MAS_ERR_UNSUPPORTED, "tc wgrad: shape/layout not eligible");
   if (ws_bytes < conv_wgrad_tc_ws(xs, dys, mode)) return fail(MAS_ERR_WORKSPACE, "tc wgrad: workspace too small");
   tc::WParams p;
@@ -1028,9 +1201,10 @@ int conv_wgrad_tc_launch(const float* x, mas_tensor4 xs, const float* dy, mas_te
   p.units_x = (int)(dys.w / 8); p.units_y = (int)(dys.h / 8);
   p.total_units = (int64_t)p.N * p.units_x * p.units_y;
   p.rows = 0; p.ldx = p.Cin; p.ldy = p.Cout;
-  p.gn_table = gn_table; p.gn_silu = gn_silu;
+  p.gn_table = gn_table; p.gn_silu = gn_silu; p.dy_amax = f16 ? dy_amax : nullptr;
   const int splits = wgrad_tc_splits((dys.c / tc::BM) * (xs.c / tc::WG_NT), p.total_units);
-  return gn_table ? wgrad_tc_run<9, true>(p, splits, dw, dbias, ws, st) : wgrad_tc_run<9, false>(p, splits, dw, dbias, ws, st);
+  if (f16) return gn_table ? wgrad_tc_run<9, true, true>(p, splits, dw, dbias, ws, st) : wgrad_tc_run<9, false, true>(p, splits, dw, dbias, ws, st);
+  return gn_table ? wgrad_tc_run<9, true, false>(p, splits, dw, dbias, ws, st) : wgrad_tc_run<9, false, false>(p, splits, dw, dbias, ws, st);
 }
 static bool wgrad1_tc_ok(const float* x, int64_t ldx, const float* dy, int64_t ldy, int Cin, int Cout) {
   return Cin % 128 == 0 && Cout % tc::BM == 0 && ldx % 4 == 0 && al16p(x) && dy != nullptr && ldy >= Cout && ldy % 4 == 0 && al16p(dy);
@@ -1050,9 +1224,9 @@ int conv1x1_wgrad_tc_launch(const float* x, int64_t ldx, const float* dy, int64_
   p.units_x = 1; p.units_y = 1;
   p.total_units = cdiv(M, 64);
   p.rows = M; p.ldx = ldx; p.ldy = ldy;
-  p.gn_table = nullptr; p.gn_silu = 0;
+  p.gn_table = nullptr; p.gn_silu = 0; p.dy_amax = nullptr;
   const int splits = wgrad_tc_splits((int64_t)(Cout / tc::BM) * (Cin / 128), p.total_units);
-  return wgrad_tc_run<1, false>(p, splits, dw, dbias, ws, st);
+  return wgrad_tc_run<1, false, false>(p, splits, dw, dbias, ws, st);
 }
 
 }  // namespace mas
@@ -1074,6 +1248,18 @@ int mas_pack_conv3x3_tc_pair(const float* w_oihw, float* w_tc_fwd, float* w_tc_d
   int64_t total = (int64_t)9 * Cout * Cin;
   tc::pack_weights_tc_pair<<<(int)(cdiv(total, 256) < 2368 ? cdiv(total, 256) : 2368), 256, 0, S(stream)>>>(w_oihw, w_tc_fwd, w_tc_dgrad, Cout, Cin);
   return launched("pack_weights_tc_pair");
+}
+
+int mas_pack_conv3x3_tc16(const float* w_oihw, void* w_tc16, void* w_tc16_dgrad, int Cout, int Cin, int transpose, void* stream) {
+  // transpose selects the packing written to w_tc16 when w_tc16_dgrad is null; with w_tc16_dgrad both are produced
+  const bool both = w_tc16_dgrad != nullptr;
+  const int N = (transpose && !both) ? Cin : Cout, K = (transpose && !both) ? Cout : Cin;
+  if (N % tc::BN || K % 16 || (both && (Cin % tc::BN || Cout % 16)))
+    return fail(MAS_ERR_UNSUPPORTED, "pack_conv3x3_tc16: N must be a multiple of 128 and K of 16 (Cout=%d Cin=%d)", Cout, Cin);
+  int64_t total = (int64_t)9 * Cout * Cin;
+  tc::pack_weights_tc16<<<(int)(cdiv(total, 256) < 2368 ? cdiv(total, 256) : 2368), 256, 0, S(stream)>>>(
+      w_oihw, (__half*)w_tc16, (__half*)w_tc16_dgrad, Cout, Cin, 9, 16, transpose, both ? 1 : 0);
+  return launched("pack_weights_tc16<9>");
 }
 
 int mas_pack_gemm_tc(const float* w_nk, float* w_tc, int N, int K, int transpose, void* stream) {
@@ -1107,7 +1293,15 @@ int mas_conv3x3_tc_eligible(mas_tensor4 xs, mas_tensor4 ys, int mode) {
 int mas_conv3x3_fprop_tc(const float* x, mas_tensor4 xs, const float* w_tc, const float* bias, const float* residual, float* y,
                          mas_tensor4 ys, int mode, const float* gn_table, int gn_silu, float* stats_part, void* stream) {
   MAS_REQUIRE(x && w_tc && y, "conv3x3_fprop_tc: null pointer");
-  return conv3x3_fprop_tc_launch(x, xs, w_tc, bias, residual, y, ys, mode, gn_table, gn_silu, stats_part, S(stream));
+  return conv3x3_fprop_tc_launch(x, xs, w_tc, bias, residual, y, ys, mode, gn_table, gn_silu, stats_part, 0, nullptr, S(stream));
+}
+
+int mas_conv3x3_fprop_tc16(const float* x, mas_tensor4 xs, const void* w_tc16, const float* bias, const float* residual, float* y,
+                           mas_tensor4 ys, int mode, const float* gn_table, int gn_silu, float* stats_part, const float* x_amax,
+                           void* stream) {
+  MAS_REQUIRE(x && w_tc16 && y, "conv3x3_fprop_tc16: null pointer");
+  return conv3x3_fprop_tc_launch(x, xs, (const float*)w_tc16, bias, residual, y, ys, mode, gn_table, gn_silu, stats_part, 1, x_amax,
+                                 S(stream));
 }
 
 }  // extern "C"

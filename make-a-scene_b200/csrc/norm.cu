@@ -291,7 +291,8 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply(const float* __restri
                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            const float* __restrict__ AB, const float* __restrict__ dx_add,
-                                                           float* __restrict__ dx, int HW, int C, int G, int silu) {
+                                                           float* __restrict__ dx, int HW, int C, int G, int silu,
+                                                           unsigned int* __restrict__ dx_amax /*or null: max|dx| (float bits)*/) {
   const int U = C >> 2, n = blockIdx.y, cpg = C / G;
   const int t = threadIdx.x, u = t % U, lanes = GN_THREADS / U, pl = t / U;
   const int PIX = (HW + gridDim.x - 1) / gridDim.x;
@@ -308,6 +309,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply(const float* __restri
   const float4* dp = reinterpret_cast<const float4*>(dy + base) + u;
   const float4* ap = dx_add ? reinterpret_cast<const float4*>(dx_add + base) + u : nullptr;
   float4* op = reinterpret_cast<float4*>(dx + base) + u;
+  float amx = 0.f;   // the consumers of dx are fp16-operand tensor-core kernels: their operand scale comes from max|dx|
   auto one = [&](const float4& xv, const float4& dv, const float4& av) {
     float xi[4] = {xv.x, xv.y, xv.z, xv.w}, di[4] = {dv.x, dv.y, dv.z, dv.w}, ad[4] = {av.x, av.y, av.z, av.w}, o[4];
 #pragma unroll
@@ -317,6 +319,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply(const float* __restri
       if (silu) d *= silu_grad_f(xh * ga[k] + be[k]);
       o[k] = r[k] * (d * ga[k] - B[k] - xh * A[k]) + ad[k];
     }
+    if (dx_amax) amx = fmaxf(amx, fmaxf(fmaxf(fabsf(o[0]), fabsf(o[1])), fmaxf(fabsf(o[2]), fabsf(o[3]))));
     return make_float4(o[0], o[1], o[2], o[3]);
   };
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -331,6 +334,10 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply(const float* __restri
   for (; p < p1; p += lanes) {
     const size_t i0 = (size_t)p * U;
     op[i0] = one(__ldg(xp + i0), __ldg(dp + i0), ap ? __ldg(ap + i0) : z4);
+  }
+  if (dx_amax) {
+    amx = warp_max(amx);
+    if ((t & 31) == 0 && amx > 0.f) atomicMax(dx_amax, __float_as_uint(amx));   // order-independent: deterministic
   }
 }
 
@@ -461,6 +468,25 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, double coun
     double unb = count > 1 ? var * count / (count - 1) : var;
     run_mean[c] = (float)((1.0 - momentum) * run_mean[c] + momentum * m);
     run_var[c] = (float)((1.0 - momentum) * run_var[c] + momentum * unb);
+  }
+}
+// largest |x| of a tensor (bit pattern of a non-negative float orders like the unsigned integer): the power-of-two operand
+// scale of the fp16 tensor-core kernels is derived from it on the device. NaNs are ignored, +-inf saturates the result.
+__global__ void __launch_bounds__(256) amax_kernel(const float4* __restrict__ x, int64_t n4, const float* __restrict__ tail, int ntail,
+                                                   unsigned int* __restrict__ out) {
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(x + i);
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+  if (blockIdx.x == 0 && (int)threadIdx.x < ntail) m = fmaxf(m, fabsf(tail[threadIdx.x]));
+  m = warp_max(m);
+  __shared__ float sh[8];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 8; ++k) m = fmaxf(m, sh[k]);
+    atomicMax(out, __float_as_uint(m));
   }
 }
 __global__ void bn_invstd_kernel(const float* __restrict__ var, float eps, float* __restrict__ out, int C) {
@@ -678,8 +704,8 @@ int mas_gn_apply(const float* x, const float* mean, const float* rstd, const flo
 }
 
 int mas_gn_backward(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
-                    const float* dx_add, float* dx, float* dgamma, float* dbeta, float* act_out, int N, int HW, int C, int G, int silu,
-                    void* ws, size_t ws_bytes, void* stream) {
+                    const float* dx_add, float* dx, float* dgamma, float* dbeta, float* act_out, float* dx_amax, int N, int HW, int C,
+                    int G, int silu, void* ws, size_t ws_bytes, void* stream) {
   if (int e = gn_check(N, HW, C, G)) return e;
   if (ws_bytes < mas_gn_ws_bytes(N, HW, C, G)) return fail(MAS_ERR_WORKSPACE, "gn_backward: workspace too small");
   int chunks = gn_chunks(N, HW, C);
@@ -696,7 +722,12 @@ int mas_gn_backward(const float* dy, const float* x, const float* mean, const fl
   gn_bwd_final<<<cblocks + (int)cdiv((int64_t)N * G, 128), 128, 0, S(stream)>>>(N, C, G, gamma, nc, dgamma, dbeta, AB,
                                                                                 1.0 / ((double)HW * (C / G)), cblocks);
   if (int e = launched("gn_bwd_final")) return e;
-  gn_bwd_apply<<<dim3(chunks, N), GN_THREADS, 0, S(stream)>>>(dy, x, mean, rstd, gamma, beta, AB, dx_add, dx, HW, C, G, silu);
+  if (dx_amax) {
+    cudaError_t e = cudaMemsetAsync(dx_amax, 0, sizeof(float), S(stream));
+    if (e != cudaSuccess) return fail(MAS_ERR_LAUNCH, "gn_backward: memset: %s", cudaGetErrorString(e));
+  }
+  gn_bwd_apply<<<dim3(chunks, N), GN_THREADS, 0, S(stream)>>>(dy, x, mean, rstd, gamma, beta, AB, dx_add, dx, HW, C, G, silu,
+                                                              reinterpret_cast<unsigned int*>(dx_amax));
   return launched("gn_bwd_apply");
 }
 
@@ -745,6 +776,17 @@ int mas_bn_finalize(const double* stats, double count, int C, float eps, float m
                     float* running_mean, float* running_var, void* stream) {
   bn_finalize_kernel<<<(int)cdiv(C, 128), 128, 0, S(stream)>>>(stats, count, C, eps, momentum, mean, invstd, running_mean, running_var);
   return launched("bn_finalize");
+}
+int mas_amax(const float* x, int64_t n, float* out, void* stream) {
+  MAS_REQUIRE(x && out && n > 0, "amax: bad arguments");
+  if (reinterpret_cast<uintptr_t>(x) & 15) return fail(MAS_ERR_UNSUPPORTED, "amax: x must be 16-byte aligned");
+  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float), S(stream));
+  if (e != cudaSuccess) return fail(MAS_ERR_LAUNCH, "amax: memset: %s", cudaGetErrorString(e));
+  const int64_t n4 = n / 4;
+  const int64_t blocks = cdiv(n4 > 0 ? n4 : 1, 256 * 8);
+  amax_kernel<<<(int)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, S(stream)>>>(reinterpret_cast<const float4*>(x), n4, x + n4 * 4,
+                                                                                 (int)(n - n4 * 4), reinterpret_cast<unsigned int*>(out));
+  return launched("amax");
 }
 int mas_bn_invstd(const float* running_var, float eps, float* invstd, int C, void* stream) {
   bn_invstd_kernel<<<(int)cdiv(C, 128), 128, 0, S(stream)>>>(running_var, eps, invstd, C);

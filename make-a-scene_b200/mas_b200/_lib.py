@@ -36,7 +36,7 @@ _SPEC = {
     "mas_gn_ws_bytes": (_Z, [_I, _I, _I, _I]),
     "mas_gn_stats": (_I, [_P, _I, _I, _I, _I, _F, _P, _P, _P, _Z, _P]),
     "mas_gn_apply": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
-    "mas_gn_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _Z, _P]),
+    "mas_gn_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _Z, _P]),
     "mas_add": (_I, [_P, _P, _P, _L, _P]),
     "mas_silu_forward": (_I, [_P, _P, _L, _P]),
     "mas_silu_backward": (_I, [_P, _P, _P, _L, _P]),
@@ -47,12 +47,17 @@ _SPEC = {
     "mas_pack_conv3x3_tc": (_I, [_P, _P, _I, _I, _I, _P]),
     "mas_pack_conv3x3_tc_pair": (_I, [_P, _P, _P, _I, _I, _P]),
     "mas_conv3x3_fprop_tc": (_I, [_P, _T, _P, _P, _P, _P, _T, _I, _P, _I, _P, _P]),
+    "mas_amax": (_I, [_P, _L, _P, _P]),
+    "mas_pack_conv3x3_tc16": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "mas_conv3x3_fprop_tc16": (_I, [_P, _T, _P, _P, _P, _P, _T, _I, _P, _I, _P, _P, _P]),
     "mas_gn_finalize_partials": (_I, [_P, _I, _I, _I, _I, _L, _F, _P, _P, _P]),
     "mas_gn_table": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P]),
     "mas_pack_gemm_tc": (_I, [_P, _P, _I, _I, _I, _P]),
     "mas_gemm_rows_packed": (_I, [_P, _L, _P, _P, _L, _L, _I, _I, _F, _P, _P, _P, _P]),
     "mas_conv3x3_wgrad_ws_bytes": (_Z, [_T, _T, _I]),
     "mas_conv3x3_wgrad": (_I, [_P, _T, _P, _T, _P, _P, _I, _I, _P, _I, _P, _Z, _P]),
+    "mas_conv3x3_wgrad_tc_eligible": (_I, [_T, _T, _I]),
+    "mas_conv3x3_wgrad_tc16": (_I, [_P, _T, _P, _T, _P, _P, _I, _P, _I, _P, _P, _Z, _P]),
     "mas_conv1x1_wgrad_ws_bytes": (_Z, [_L, _I, _I]),
     "mas_conv1x1_wgrad": (_I, [_P, _L, _P, _L, _L, _I, _I, _P, _P, _I, _P, _Z, _P]),
     "mas_edge_small_cin_fprop": (_I, [_P, _T, _P, _P, _P, _T, _I, _P]),
@@ -69,7 +74,7 @@ _SPEC = {
     "mas_colsum": (_I, [_P, _T, _P, _P, _Z, _P]),
     "mas_attnblock_ws_bytes": (_Z, [_I, _I, _I, _I]),
     "mas_attnblock_forward": (_I, [_P, _I, _I, _I, _I] + [_P] * 18 + [_I, _P, _Z, _P]),
-    "mas_attnblock_backward": (_I, [_P, _P, _I, _I, _I, _I] + [_P] * 19 + [_I, _P, _Z, _P]),
+    "mas_attnblock_backward": (_I, [_P, _P, _I, _I, _I, _I] + [_P] * 20 + [_I, _P, _Z, _P]),
     "mas_softmax_forward": (_I, [_P, _P, _L, _I, _P]),
     "mas_softmax_backward": (_I, [_P, _P, _P, _L, _I, _F, _P]),
     "mas_bn_stats": (_I, [_P, _L, _I, _P, _P]),

@@ -15,7 +15,29 @@ from . import _lib as L
 GN_GROUPS = 32
 GN_EPS = 1e-6
 
-_cfg = {"impl": L.IMPL_AUTO}
+import os
+
+# "f16": fp16 operands on the 3x3 tensor-core kernels (same 11-bit significand as TF32, twice the MMA rate; operand scales
+# from a device-side amax); "tf32": TF32 operands. MAS_CONV_OPERANDS overrides the default for A/B measurements.
+_cfg = {"impl": L.IMPL_AUTO, "operands": os.environ.get("MAS_CONV_OPERANDS", "f16")}
+
+
+def set_operand_format(fmt: str):
+    """Operand format of the 3x3 convolution tensor-core kernels: "f16" (default) or "tf32"."""
+    if fmt not in ("f16", "tf32"):
+        raise ValueError(fmt)
+    _cfg["operands"] = fmt
+
+
+def get_operand_format() -> str:
+    return _cfg["operands"]
+
+
+def amax(x):
+    """max|x| as a device scalar (stays on the device: the kernels derive their power-of-two operand scale from it)."""
+    out = torch.empty(1, dtype=torch.float32, device=x.device)
+    L.call("mas_amax", x, x.numel(), out)
+    return out
 
 
 def set_impl(impl: int):
@@ -70,19 +92,39 @@ def gn_apply(x, mean, rstd, gamma, beta, silu, rtf32=False):
 
 
 def gn_backward(dy, x, mean, rstd, gamma, beta, silu, dx_add=None, want_act=False):
-    """want_act: also return act(GN(x)) (re-materialised as a by-product of the first backward pass)."""
+    """want_act: also return act(GN(x)) (re-materialised as a by-product of the first backward pass). With fp16 operands
+    selected, max|dx| is produced by the same pass and attached to dx (attach_amax) for the tensor-core kernels that
+    consume it."""
     n, c, h, w = x.shape
     dx = torch.empty_like(x)
     dg = torch.empty_like(gamma)
     db = torch.empty_like(beta)
     act = torch.empty_like(x) if want_act else None
+    am = torch.empty(1, dtype=torch.float32, device=x.device) if f16_operands() else None
     nb = L.query("mas_gn_ws_bytes", n, h * w, c, GN_GROUPS)
     ws = L.workspace(nb, x.device)
-    L.call("mas_gn_backward", dy, x, mean, rstd, gamma, beta, dx_add, dx, dg, db, act, n, h * w, c, GN_GROUPS, int(silu), ws,
+    L.call("mas_gn_backward", dy, x, mean, rstd, gamma, beta, dx_add, dx, dg, db, act, am, n, h * w, c, GN_GROUPS, int(silu), ws,
            ws.numel())
+    attach_amax(dx, am)
     if want_act:
         return dx, dg, db, act
     return dx, dg, db
+
+
+def attach_amax(t, am):
+    """Carry max|t| (device scalar produced by the kernel that wrote t) with the tensor object; autograd hands the same
+    object to the consuming Function's backward."""
+    if am is not None:
+        t._mas_amax = (am, t._version, t.data_ptr())
+    return t
+
+
+def amax_of(t):
+    """max|t| as a device scalar: the value attached by the producing kernel if t is unchanged since, else one pass."""
+    st = getattr(t, "_mas_amax", None)
+    if st is not None and st[1] == t._version and st[2] == t.data_ptr() and st[0].device == t.device:
+        return st[0]
+    return amax(t)
 
 
 def _conv_out_hw(h, w, mode):
@@ -122,7 +164,7 @@ def _finalize_stats(part, tiles_per_image, n, c, hw):
 
 
 def conv3x3_raw(x, weight, bias, residual, mode, out_nchw=False, transpose=False, table=None, silu=True, want_stats=False,
-                prepack=False):
+                prepack=False, x_amax=None):
     """y = conv3x3(x; weight) (+bias, +residual). transpose=True applies the data-gradient operand
     (taps flipped, Cin<->Cout). Dense NHWC shapes with Cin%8==0, Cout%128==0, Hout%16==0, Wout%8==0 run on the
     tcgen05 kernel; everything else (edge layers, NCHW views, small images) on the fp32 SIMT kernel.
@@ -140,12 +182,19 @@ def conv3x3_raw(x, weight, bias, residual, mode, out_nchw=False, transpose=False
     wc = weight.contiguous()
     stats = None
     if _tc_on() and not out_nchw and L.query("mas_conv3x3_tc_eligible", xs, ys, mode):
-        wt = _packed_conv_weight(wc, weight, cout, cin, transpose, x.device, prepack)
+        f16 = _cfg["operands"] == "f16" and cin % 16 == 0
+        wt = _packed_conv_weight(wc, weight, cout, cin, transpose, x.device, prepack, f16)
         part = None
         if want_stats and cout % (4 * GN_GROUPS) == 0:
             tiles = n * (ho // 16) * (wo // 8)
             part = torch.empty(tiles * cout * 2, dtype=torch.float32, device=x.device)
-        L.call("mas_conv3x3_fprop_tc", x, xs, wt, bias, residual, y, ys, mode, table, int(silu), part)
+        if f16:
+            # post-GroupNorm activations (prologue) are O(1) by construction; anything else (gradients above all) gets a
+            # power-of-two scale from its largest magnitude
+            xa = (x_amax if x_amax is not None else amax_of(x)) if table is None else None
+            L.call("mas_conv3x3_fprop_tc16", x, xs, wt, bias, residual, y, ys, mode, table, int(silu), part, xa)
+        else:
+            L.call("mas_conv3x3_fprop_tc", x, xs, wt, bias, residual, y, ys, mode, table, int(silu), part)
         if part is not None:
             stats = _finalize_stats(part, (ho // 16) * (wo // 8), n, cout, ho * wo)
     else:
@@ -161,47 +210,80 @@ def conv3x3_raw(x, weight, bias, residual, mode, out_nchw=False, transpose=False
     return y
 
 
-# data-gradient packings produced together with the forward packing (one pass over the weight), consumed by the backward
-# of the same step; keyed by storage address and checked against the tensor version, so a weight that changed in between
-# (or a second backward through a retained graph) simply repacks
-_dgrad_packs = {}
+# Packed operand images of the convolution weights, cached per parameter: a packing stays valid until the weight's version
+# counter moves (optimizer step / load_state_dict), so a training step packs every weight once (forward and data-gradient
+# images in one pass) and evaluation / gradient accumulation / the benchmark's optimizer-free steps pack nothing at all.
+# The entry holds a weak reference to the weight (identity, not storage address: the allocator reuses addresses).
+_packs = {}
 
 
-def _packed_conv_weight(wc, weight, cout, cin, transpose, dev, prepack=False):
-    key = wc.data_ptr()
-    if transpose:
-        hit = _dgrad_packs.pop(key, None)
-        if hit is not None and hit[0] == weight._version and hit[1].device == dev and hit[2] == tuple(weight.shape):
-            return hit[1]
-    wt = torch.empty(9 * cout * cin, dtype=torch.float32, device=dev)
-    if prepack and not transpose and cout % 128 == 0 and cin % 128 == 0:
+def _pack_entry(weight):
+    k = id(weight)
+    ent = _packs.get(k)
+    if ent is not None and ent[0]() is weight and ent[1] == weight._version and ent[2] == weight.data_ptr():
+        return ent[3]
+    import weakref
+    d = {}
+    _packs[k] = (weakref.ref(weight, lambda _r, k=k: _packs.pop(k, None)), weight._version, weight.data_ptr(), d)
+    return d
+
+
+def _packed_conv_weight(wc, weight, cout, cin, transpose, dev, prepack=False, f16=False):
+    ent = _pack_entry(weight)
+    key = ("d" if transpose else "f", f16)
+    hit = ent.get(key)
+    if hit is not None and hit.device == dev:
+        return hit
+    dt = torch.float16 if f16 else torch.float32
+    wt = torch.empty(9 * cout * cin, dtype=dt, device=dev)
+    pair_ok = cout % 128 == 0 and cin % 128 == 0
+    if prepack and not transpose and pair_ok:
         # forward of a training step whose backward will run the data gradient: it wants the transposed packing
-        wd = torch.empty(9 * cout * cin, dtype=torch.float32, device=dev)
-        L.call("mas_pack_conv3x3_tc_pair", wc, wt, wd, weight.shape[0], weight.shape[1])
-        _dgrad_packs[key] = (weight._version, wd, tuple(weight.shape))
-        return wt
-    L.call("mas_pack_conv3x3_tc", wc, wt, weight.shape[0], weight.shape[1], int(transpose))
+        wd = torch.empty(9 * cout * cin, dtype=dt, device=dev)
+        if f16:
+            L.call("mas_pack_conv3x3_tc16", wc, wt, wd, weight.shape[0], weight.shape[1], 0)
+        else:
+            L.call("mas_pack_conv3x3_tc_pair", wc, wt, wd, weight.shape[0], weight.shape[1])
+        ent[("d", f16)] = wd
+    elif f16:
+        L.call("mas_pack_conv3x3_tc16", wc, wt, None, weight.shape[0], weight.shape[1], int(transpose))
+    else:
+        L.call("mas_pack_conv3x3_tc", wc, wt, weight.shape[0], weight.shape[1], int(transpose))
+    ent[key] = wt
     return wt
 
 
-def conv3x3_wgrad_raw(x, dy, cout, cin, mode, want_bias=True, table=None, silu=True):
+def conv3x3_wgrad_raw(x, dy, cout, cin, mode, want_bias=True, table=None, silu=True, dy_amax=None):
     """table: x is the PRE-normalisation tensor and act(GroupNorm(x)) is recomputed while staging (tensor path only)."""
     dw = torch.empty((cout, cin, 3, 3), dtype=torch.float32, device=x.device)
     db = torch.empty(cout, dtype=torch.float32, device=x.device) if want_bias else None
     nb = L.query("mas_conv3x3_wgrad_ws_bytes", L.t4(x), L.t4(dy), mode)
     ws = L.workspace(nb, x.device)
+    if (_tc_on() and _cfg["operands"] == "f16" and wgrad_f16_on() and _is_dense_nhwc(x) and _is_dense_nhwc(dy)
+            and L.query("mas_conv3x3_wgrad_tc_eligible", L.t4(x), L.t4(dy), mode)):
+        L.call("mas_conv3x3_wgrad_tc16", x, L.t4(x), dy, L.t4(dy), dw, db, mode, table, int(silu), dy_amax if dy_amax is not None else amax_of(dy),
+               ws, ws.numel())
+        return dw, db
     L.call("mas_conv3x3_wgrad", x, L.t4(x), dy, L.t4(dy), dw, db, mode, _cfg["impl"], table, int(silu), ws, ws.numel())
     return dw, db
 
 
-def conv3x3_dgrad_raw(dy, weight, mode):
+def wgrad_f16_on():
+    return os.environ.get("MAS_WGRAD_F16", "1") != "0"
+
+
+def f16_operands():
+    return _tc_on() and _cfg["operands"] == "f16"
+
+
+def conv3x3_dgrad_raw(dy, weight, mode, dy_amax=None):
     """Data gradient of the 3x3 family: the same kernel with flipped/transposed weights (+ zero-stuffed input map for the
-    stride-2 conv, or a 2x2 sum-pool after it for the upsampling conv)."""
+    stride-2 conv, or a 2x2 sum-pool after it for the upsampling conv). dy_amax: max|dy| if the caller already has it."""
     if mode == L.CONV_S1:
-        return conv3x3_raw(dy, weight, None, None, L.CONV_S1, transpose=True)
+        return conv3x3_raw(dy, weight, None, None, L.CONV_S1, transpose=True, x_amax=dy_amax)
     if mode == L.CONV_S2:
-        return conv3x3_raw(dy, weight, None, None, L.CONV_ZS, transpose=True)
-    du = conv3x3_raw(dy, weight, None, None, L.CONV_S1, transpose=True)
+        return conv3x3_raw(dy, weight, None, None, L.CONV_ZS, transpose=True, x_amax=dy_amax)
+    du = conv3x3_raw(dy, weight, None, None, L.CONV_S1, transpose=True, x_amax=dy_amax)
     n, cin, h2, w2 = du.shape
     dx = empty_nhwc(n, cin, h2 // 2, w2 // 2, du)
     L.call("mas_sumpool2x2", du, dx, n, h2 // 2, w2 // 2, cin)
@@ -405,10 +487,12 @@ class Conv3x3Fn(torch.autograd.Function):
                 dw = torch.empty_like(weight)
                 L.call("mas_s2d_unpack_wgrad", dw9, dw, cout, cin)
         else:
+            dy = nhwc(dy)
+            am = amax_of(dy) if f16_operands() else None
             if ctx.needs_input_grad[0]:
-                dx = conv3x3_dgrad_raw(dy, weight, ctx.mode)
+                dx = conv3x3_dgrad_raw(dy, weight, ctx.mode, am)
             if want_w:
-                dw, db = conv3x3_wgrad_raw(x, dy, cout, cin, ctx.mode, ctx.has_bias)
+                dw, db = conv3x3_wgrad_raw(x, dy, cout, cin, ctx.mode, ctx.has_bias, dy_amax=am)
         if not ctx.has_bias:
             db = None
         if ctx.has_res and ctx.needs_input_grad[3]:
@@ -488,7 +572,8 @@ class ResnetBlockFn(torch.autograd.Function):
         dout = nhwc(dout)
         cout, cin = c1w.shape[0], c1w.shape[1]
         n, _, h, w = x.shape
-        d_a2 = conv3x3_dgrad_raw(dout, c2w, L.CONV_S1)
+        am_out = amax_of(dout) if f16_operands() else None   # from the producing kernel, else one pass; serves dgrad and wgrad
+        d_a2 = conv3x3_dgrad_raw(dout, c2w, L.CONV_S1, am_out)
         # fused forward never stored act(GN(.)): the GroupNorm backward re-materialises it as a by-product of its first pass
         # (cheaper than re-activating inside the weight-gradient kernel's producers: measured +0.8 ms per full-res call)
         if ctx.fused:
@@ -496,9 +581,10 @@ class ResnetBlockFn(torch.autograd.Function):
         else:
             d_h1, dn2w, dn2b = gn_backward(d_a2, h1, m2, r2, n2w, n2b, True)
         del d_a2
-        dc2w, dc2b = conv3x3_wgrad_raw(a2, dout, cout, cout, L.CONV_S1)
+        dc2w, dc2b = conv3x3_wgrad_raw(a2, dout, cout, cout, L.CONV_S1, dy_amax=am_out)
         del a2
-        d_a1 = conv3x3_dgrad_raw(d_h1, c1w, L.CONV_S1)
+        am_h1 = amax_of(d_h1) if f16_operands() else None
+        d_a1 = conv3x3_dgrad_raw(d_h1, c1w, L.CONV_S1, am_h1)
         if ctx.has_sc:
             r_ = gn_backward(d_a1, x, m1, r1, n1w, n1b, True, want_act=ctx.fused)
             dxm, dn1w, dn1b = r_[0], r_[1], r_[2]
@@ -513,7 +599,7 @@ class ResnetBlockFn(torch.autograd.Function):
                 a1 = r_[3]
             dsw = dsb = None
         del d_a1
-        dc1w, dc1b = conv3x3_wgrad_raw(a1, d_h1, cout, cin, L.CONV_S1)
+        dc1w, dc1b = conv3x3_wgrad_raw(a1, d_h1, cout, cin, L.CONV_S1, dy_amax=am_h1)
         del a1, d_h1
         return dx, None, None, dn1w, dn1b, dc1w, dc1b, dn2w, dn2b, dc2w, dc2b, dsw, dsb
 
@@ -567,9 +653,11 @@ class AttnBlockFn(torch.autograd.Function):
         dpw = torch.empty_like(pw, memory_format=torch.contiguous_format)
         dpb = torch.empty(c, dtype=torch.float32, device=dev)
         ws = L.workspace(L.query("mas_attnblock_ws_bytes", n, hw, c, GN_GROUPS), dev)
+        am = torch.empty(1, dtype=torch.float32, device=dev) if f16_operands() else None
         L.call("mas_attnblock_backward", dout, x, n, hw, c, GN_GROUPS, mean, rstd, nw, nb, qw.contiguous(), kw.contiguous(),
-               vw.contiguous(), pw.contiguous(), hn, qkv, P, O, dx, dnw, dnb, dqkv_w, dqkv_b, dpw, dpb, _cfg["impl"], ws,
+               vw.contiguous(), pw.contiguous(), hn, qkv, P, O, dx, dnw, dnb, dqkv_w, dqkv_b, dpw, dpb, am, _cfg["impl"], ws,
                ws.numel())
+        attach_amax(dx, am)
         return (dx, None, None, dnw, dnb, dqkv_w[:c], dqkv_b[:c], dqkv_w[c:2 * c], dqkv_b[c:2 * c], dqkv_w[2 * c:], dqkv_b[2 * c:],
                 dpw, dpb)
 

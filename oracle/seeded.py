@@ -35,3 +35,11 @@ def sample(t, n=512):
     if stride > 1 and stride % 2 == 0:
         stride += 1
     return f[::stride].clone(), stride
+
+
+def assert_same_fill(got, want):
+    """fill_seeded check sums agree (same names in the same order; fp64 sums up to summation-order noise)."""
+    assert list(got) == list(want), (list(got), list(want))
+    for k in got:
+        for a, b in zip(got[k], want[k]):
+            assert abs(a - b) <= 1e-9 * max(1.0, abs(b)), (k, a, b)

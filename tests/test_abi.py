@@ -79,32 +79,38 @@ def test_yaml_model_blocks_instantiate():
         assert m.encoder.model[0].in_channels == 159
 
 
-def test_dgrad_pack_handover_is_keyed_by_version_and_shape(monkeypatch):
-    """Host logic of ops._packed_conv_weight (no kernels run: the C-ABI call is stubbed): the data-gradient packing made
-    in the forward is handed to exactly one backward of the same, unmodified weight."""
+def test_weight_pack_cache_is_keyed_by_identity_and_version(monkeypatch):
+    """Host logic of ops._packed_conv_weight (no kernels run: the C-ABI call is stubbed): a weight is packed once per
+    version (forward + data-gradient images in one pass), re-used by every later forward / backward until the version
+    counter moves, and never confused with another tensor that re-uses its address or id."""
+    import gc
     import torch
     from mas_b200 import ops
     calls = []
     monkeypatch.setattr(ops.L, "call", lambda name, *a: calls.append(name))
-    ops._dgrad_packs.clear()
-    w = torch.zeros(128, 128, 3, 3)
-    dev = w.device
-    ops._packed_conv_weight(w, w, 128, 128, False, dev, prepack=True)
-    assert calls == ["mas_pack_conv3x3_tc_pair"] and len(ops._dgrad_packs) == 1
-    ops._packed_conv_weight(w, w, 128, 128, True, dev)                 # backward of the same step: no packing launch
-    assert calls == ["mas_pack_conv3x3_tc_pair"] and not ops._dgrad_packs
-    ops._packed_conv_weight(w, w, 128, 128, True, dev)                 # a second backward (retained graph): repacks
-    assert calls[-1] == "mas_pack_conv3x3_tc" and len(calls) == 2
-    ops._packed_conv_weight(w, w, 128, 128, False, dev, prepack=True)
-    w.add_(1.0)                                                         # optimiser step in between: version changed
-    ops._packed_conv_weight(w, w, 128, 128, True, dev)
-    assert calls[-1] == "mas_pack_conv3x3_tc"
-    ops._packed_conv_weight(w, w, 128, 128, False, dev, prepack=True)
-    key = next(iter(ops._dgrad_packs))
-    ver, wd, _shape = ops._dgrad_packs[key]
-    ops._dgrad_packs[key] = (ver, wd, (256, 128, 3, 3))                # a different weight that reused the address
-    n = len(calls)
-    ops._packed_conv_weight(w, w, 128, 128, True, dev)
-    assert len(calls) == n + 1 and calls[-1] == "mas_pack_conv3x3_tc"
-    ops._packed_conv_weight(w, w, 64, 128, False, dev, prepack=True)    # not pair-eligible: plain packing, nothing stored
-    assert calls[-1] == "mas_pack_conv3x3_tc" and not ops._dgrad_packs
+    ops._packs.clear()
+    for f16, pair, single in ((False, "mas_pack_conv3x3_tc_pair", "mas_pack_conv3x3_tc"),
+                              (True, "mas_pack_conv3x3_tc16", "mas_pack_conv3x3_tc16")):
+        calls.clear()
+        w = torch.zeros(128, 128, 3, 3)
+        dev = w.device
+        f1 = ops._packed_conv_weight(w, w, 128, 128, False, dev, prepack=True, f16=f16)
+        assert calls == [pair]
+        d1 = ops._packed_conv_weight(w, w, 128, 128, True, dev, f16=f16)      # backward of the same step: no packing launch
+        d2 = ops._packed_conv_weight(w, w, 128, 128, True, dev, f16=f16)      # a second backward (retained graph): still none
+        f2 = ops._packed_conv_weight(w, w, 128, 128, False, dev, prepack=True, f16=f16)   # next forward, same weights: none
+        assert calls == [pair] and d1 is d2 and f1 is f2 and d1 is not f1
+        assert f1.dtype == (torch.float16 if f16 else torch.float32)
+        w.add_(1.0)                                                         # optimiser step: version changed -> repack
+        ops._packed_conv_weight(w, w, 128, 128, True, dev, f16=f16)
+        assert calls == [pair, single]
+        ops._packed_conv_weight(w, w, 128, 128, False, dev, prepack=True, f16=f16)
+        assert len(calls) == 3
+        # not pair-eligible (Cout % 128 != 0 for the data-gradient image): plain packing of the requested image only
+        w2 = torch.zeros(128, 64, 3, 3)
+        ops._packed_conv_weight(w2, w2, 128, 64, False, dev, prepack=True, f16=f16)
+        assert calls[-1] == single
+        n_live = len(ops._packs)
+        del w, w2, f1, f2, d1, d2
+        gc.collect()
+        assert len(ops._packs) == n_live - 2                                 # entries die with their weights

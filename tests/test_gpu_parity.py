@@ -334,12 +334,12 @@ def test_tensor_path_blocks_vs_reference(name):
     outputs and gradients of the REAL reference (tests/golden/blocks_tc.pt; weights / inputs regenerated from seeds)."""
     from mas_b200 import _lib as L
     from models import modules as M
-    from oracle.seeded import fill_seeded, seeded_input
+    from oracle.seeded import assert_same_fill, fill_seeded, seeded_input
     from test_oracle import build_tc_block
     dev = _dev()
     b = _load("blocks_tc.pt")[name]
     mod = build_tc_block(name, M)
-    assert fill_seeded(mod, b["seed_w"]) == b["param_checks"]
+    assert_same_fill(fill_seeded(mod, b["seed_w"]), b["param_checks"])
     mod.to(dev)
     x = seeded_input(b["shape"], b["seed_x"], 1.5, 0.3).to(dev).requires_grad_(True)
     before = L.launch_count()

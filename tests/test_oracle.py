@@ -115,12 +115,11 @@ def test_tensor_path_blocks_oracle_matches_reference():
     restatement agrees with the REAL reference's outputs and gradients. The drop-in modules are used on the CPU as
     parameter holders only (no kernel runs): their parameter names / shapes are the reference's."""
     from models import modules as M
-    from oracle.seeded import fill_seeded, seeded_input
+    from oracle.seeded import assert_same_fill, fill_seeded, seeded_input
     blocks = _load("blocks_tc.pt")
     for name, b in blocks.items():
         mod = build_tc_block(name, M)
-        checks = fill_seeded(mod, b["seed_w"])
-        assert checks == b["param_checks"], name           # same names, same order, same values as on the reference
+        assert_same_fill(fill_seeded(mod, b["seed_w"]), b["param_checks"])   # same names, order and values as on the reference
         sd = {"m." + k: v.detach().clone().requires_grad_(True) for k, v in mod.state_dict().items()}
         x = seeded_input(b["shape"], b["seed_x"], 1.5, 0.3).requires_grad_(True)
         y = _oracle_tc_block(name, x, sd)
