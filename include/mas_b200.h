@@ -255,6 +255,12 @@ int mas_bn_backward_apply(const float* dy, const float* x, const float* mean, co
  * first-index tie-break (modules.py:501-505).  zq_out[r] = E[idx] (modules.py:506).
  * loss_out (1 float) = (1+beta) * mean((zq - z)^2)  (modules.py:509; both terms are numerically equal
  * in the forward).  The distance matrix is never materialised. */
+/* mas_vq_forward picks the arg-min with a tensor-core FILTER (csrc/vq_tc.cu: 2 x fp16 operand split, 3 MMAs per K step,
+ * the four best candidates per row) followed by an exact fp32 re-evaluation of every row whose runner-up lies within a
+ * rigorous error margin of the best candidate - the indices are those of the exact-fp32 FFMA kernel, bit for bit - when
+ * D % 32 == 0 and the latent tile fits shared memory (D <= 256); otherwise, or after mas_vq_select_path(0), the FFMA kernel
+ * evaluates every (row, code) pair.  mas_vq_select_path is process-wide (A/B measurements, tests). */
+int mas_vq_select_path(int use_tensor_core_filter);
 size_t mas_vq_ws_bytes(int64_t R, int K, int D);
 int mas_vq_forward(const float* z, const float* E, int64_t R, int K, int D, float beta, int64_t* idx_out,
                    float* zq_out, float* loss_out, void* ws, size_t ws_bytes, void* stream);

@@ -301,7 +301,10 @@ __global__ void __launch_bounds__(NTHREADS, (TILES == 2) ? 2 : 1) shift_gemm_tc(
     uint32_t phase = 0;
     float inv_scale = 1.f;
     const float in_scale = F16 ? operand_scale(p.x_amax, &inv_scale) : 1.f;
-    float4 vn[PER_THREAD][LPI];
+    // Two register sets (va, vb) hold the global loads of alternate K chunks: a set is re-issued (for chunk kc + 2) right
+    // after it has been converted and stored, so every load has TWO stage times to land instead of one - the kernel was
+    // bound by exactly that latency (ncu: long-scoreboard stalls of the producers, tensor pipe 43 % active).
+    float4 va[PER_THREAD][LPI], vb[PER_THREAD][LPI];
     auto gload = [&](int kc, float4 (*v)[LPI]) {
 #pragma unroll
       for (int i = 0; i < PER_THREAD; ++i) {
@@ -312,17 +315,10 @@ __global__ void __launch_bounds__(NTHREADS, (TILES == 2) ? 2 : 1) shift_gemm_tc(
         }
       }
     };
-    gload(0, vn);
-    for (int kc = 0; kc < nchunks; ++kc) {
-      float4 v[PER_THREAD][LPI];
-#pragma unroll
-      for (int i = 0; i < PER_THREAD; ++i)
-#pragma unroll
-        for (int h = 0; h < LPI; ++h) v[i][h] = vn[i][h];
-      if (kc + 1 < nchunks) gload(kc + 1, vn);  // next chunk's global loads fly while this chunk is stored / consumed
+    auto consume = [&](int kc, float4 (*v)[LPI]) {
       if (TAPS == 9) {
         if (p.gn_table) {
-          // fused GroupNorm (+SiLU) prologue, applied at CONSUME time so the prefetch above stays asynchronous;
+          // fused GroupNorm (+SiLU) prologue, applied at CONSUME time so the prefetches stay asynchronous;
           // the (scale, shift) pairs are L1-resident
 #pragma unroll
           for (int i = 0; i < PER_THREAD; ++i) {
@@ -359,6 +355,16 @@ __global__ void __launch_bounds__(NTHREADS, (TILES == 2) ? 2 : 1) shift_gemm_tc(
       fence_proxy_async();  // make the generic-proxy stores visible to the tensor core (async proxy)
       mbar_arrive(full_bar(stage));
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    };
+    gload(0, va);
+    if (nchunks > 1) gload(1, vb);
+    for (int kc = 0; kc < nchunks; kc += 2) {
+      consume(kc, va);
+      if (kc + 2 < nchunks) gload(kc + 2, va);
+      if (kc + 1 < nchunks) {
+        consume(kc + 1, vb);
+        if (kc + 3 < nchunks) gload(kc + 3, vb);
+      }
     }
     const float alpha = p.alpha * inv_scale;
 
@@ -849,6 +855,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc(const WParams p, const
     const int lg = warp & 3;          // TMEM lane group (warp % 4)
     const int cl = lg * 32 + lane;    // channel within the 128-wide co tile
     float bsum = 0.f;
+    const bool want_bias = p.bpart != nullptr && blockIdx.x == 0;
     int stage = 0;
     uint32_t phase = 0;
     float a_inv;
@@ -864,8 +871,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc(const WParams p, const
 #pragma unroll
         for (int j = 0; j < 64; ++j) v[j] = (u * 64 + j < p.rows) ? dys[j * 128] : 0.f;
       }
+      if (want_bias) {   // the bias gradient falls out of ONE ci-tile's pass over dy (the other ci tiles see the same dy)
 #pragma unroll
-      for (int j = 0; j < 64; ++j) bsum += v[j];
+        for (int j = 0; j < 64; ++j) bsum += v[j];
+      }
       tc_fence_after();
       const uint32_t ta = tmem_base + ((uint32_t)(lg * 32) << 16) + ACC_COLS + (uint32_t)(stage * A_COLS);
       if (F16) {   // two consecutive pixels (K) of this lane's channel per 32-bit TMEM column
@@ -882,7 +891,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc(const WParams p, const
       mbar_arrive(fullA(stage));
       if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
     }
-    if (p.bpart && blockIdx.x == 0) p.bpart[(size_t)split * p.Cout + co0 + cl] = bsum;
+    if (want_bias) p.bpart[(size_t)split * p.Cout + co0 + cl] = bsum;
   } else if (warp == 13) {
     // ============ dy TMA issuer (one thread): box [8 rows][8 pixels][128 co] (or [64 rows][128 co]) -> shared [64][128] ============
     // a tiled tensor map (cuTensorMapEncodeTiled on the host) lets ONE cp.async.bulk.tensor fetch the whole dy tile of a

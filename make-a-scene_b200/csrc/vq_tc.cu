@@ -1,0 +1,382 @@
+// Codebook argmin, tensor-core FILTER stage (modules.py:501-505).
+//
+// The reference's index is the arg-min over fp32 distances d[r,k] = fl(fl(|z_r|^2 + |e_k|^2) - 2 z_r.e_k).  The exact-fp32
+// FFMA kernel (vq.cu) reproduces that arithmetic but is bound by the FMA pipe (4.2 MFLOP per latent row).  This kernel
+// computes the R x K dot products on the tensor cores instead, to a KNOWN accuracy, and keeps per row the few smallest
+// approximate distances; vq_resolve (vq.cu) then
+//   * accepts the best code outright when the runner-up is farther than a rigorous error margin (nothing any fp32
+//     evaluation order could reorder),
+//   * re-evaluates the (at most four) candidates inside the margin with the EXACT arithmetic of the FFMA kernel, or
+//   * (more candidates than that: tie-heavy codebooks) hands the row to the FFMA kernel.
+// The indices are therefore those of the exact kernel, bit for bit, at tensor-core speed for ordinary data.
+//
+// Arithmetic: operand splitting into two fp16 numbers, x*s = h + l (h = fp16(x*s), l = fp16(x*s - h): 22 significant
+// bits; s a power of two from the tensor's largest magnitude), and three kind::f16 MMAs per K step,
+//   z.e ~= (zh.eh + zl.eh + zh.el) / (s_z s_e),   dropped term zl.el ~ 2^-22 relative,
+// accumulated in fp32 in tensor memory.
+//
+// Structure (one CTA = 128 latent rows x a contiguous range of 256-code tiles):
+//   * A (the 128 x D latent tile, both halves) is converted once and stays in shared memory for the whole sweep;
+//   * B (codes): 8 producer warps stream 32-dimension chunks of the code tile from L2 (fp32), split them in registers and
+//     store both halves in the K-major no-swizzle UMMA layout ([k/8][code][8 halves]); 2-stage full/empty mbarrier ring;
+//   * one thread issues the MMAs (M 128, N 256, K 16; 3 per K step) into one of TWO 256-column accumulators;
+//   * 4 epilogue warps (thread = latent row) drain the other accumulator meanwhile: tcgen05.ld, d~ = |e|^2 - 2 dot, sorted
+//     insertion into the row's five smallest values (four of them with their code index).
+#include <cuda_fp16.h>
+
+#include "mas_common.cuh"
+
+namespace mas {
+namespace vqtc {
+
+constexpr int BM = 128, BN = 256, KC = 32, STAGES = 2;
+constexpr int NPROD = 256, NEPI = 128, NTHREADS = NEPI + NPROD + 32;   // warps 0-3 epilogue, 4-11 producers, 12 MMA
+constexpr int PITCH_A = BM * 16 + 32;   // bytes between 8-dimension planes of A (32 B pad: conflict-free 16-byte stores)
+constexpr int PITCH_B = BN * 16 + 32;   // bytes between 8-dimension planes of a B stage half
+constexpr int B_HALF = (KC / 8) * PITCH_B;
+constexpr int B_STAGE = 2 * B_HALF;     // hi planes then lo planes
+constexpr int NCAND = 4;                // candidates kept with their index (+ one more value)
+constexpr int REC = 12;                 // floats per (row, split) record: b[5], i[4] (as int bits), pad
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
+      "%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// shared-memory matrix descriptor, K-major, no swizzle, sm_100 version field = 1 (as in contract_tc.cu)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
+         (1ull << 46);
+}
+// instruction descriptor: D = f32, A = B = f16, both K-major, M = 128, N = 256
+constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+// power-of-two scale putting the tensor's largest magnitude into [2^14, 2^15) (fp16 tops out at 65504); *inv = 1/s, exact
+__device__ __forceinline__ float split_scale(const float* amax, float* inv) {
+  float s = 1.f, i = 1.f;
+  const uint32_t b = __float_as_uint(*amax);
+  const int e = (int)((b >> 23) & 0xff);
+  if (e > 0 && e < 255) {
+    int se = 127 + 14 - (e - 127);
+    se = se < 1 ? 1 : (se > 254 ? 254 : se);
+    s = __uint_as_float((uint32_t)se << 23);
+    i = __uint_as_float((uint32_t)(254 - se) << 23);
+  }
+  *inv = i;
+  return s;
+}
+// (a, b) * s -> packed fp16 pairs (hi, lo): x*s = hi + lo up to 2^-22 relative
+__device__ __forceinline__ void split2(float a, float b, float s, uint32_t* hi, uint32_t* lo) {
+  const float as = a * s, bs = b * s;
+  const __half2 h = __floats2half2_rn(as, bs);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(as - hf.x, bs - hf.y);
+  *hi = *reinterpret_cast<const uint32_t*>(&h);
+  *lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+struct Params {
+  const float* z;      // [R, D]
+  const float* E;      // [K, D]
+  const float* ee;     // [K] |e_k|^2 (vq_code_norms: the exact kernel's values)
+  const float* z_amax; // device scalars
+  const float* e_amax;
+  float* cand;         // [R][splits][REC]
+  int64_t R;
+  int K, D, tiles_per_split;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1) vq_filter_tc(const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int planes = p.D >> 3;                       // 8-dimension planes of A
+  const int a_half = planes * PITCH_A;               // bytes of one half (hi or lo) of A
+  uint8_t* b_smem = smem + 2 * (size_t)a_half;
+  float* ee_s = reinterpret_cast<float*>(b_smem + (size_t)STAGES * B_STAGE);     // [2][BN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ee_s + 2 * BN);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  const uint32_t smem_base = smem_u32(smem), bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto accf_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
+  auto acce_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t row0 = (int64_t)blockIdx.x * BM;
+  const int ntile_all = (p.K + BN - 1) / BN;
+  const int tile_lo = blockIdx.y * p.tiles_per_split, tile_hi = min(ntile_all, tile_lo + p.tiles_per_split);
+  const int nchunk = p.D / KC;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), NPROD);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(accf_bar(b), 1);
+      mbar_init(acce_bar(b), NEPI);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 12) tmem_alloc(smem_u32(tmem_slot), 512);
+
+  float inv_z, inv_e;
+  const float s_z = split_scale(p.z_amax, &inv_z), s_e = split_scale(p.e_amax, &inv_e);
+
+  // ---- A: the latent tile, split and staged once (all warps but the MMA warp) ----
+  if (warp < 12) {
+    const int items = BM * planes;                   // 16-byte chunks per half
+    for (int it = tid; it < items; it += NEPI + NPROD) {
+      const int pl = it % planes, r = it / planes;   // consecutive threads: consecutive 32-byte pieces of one row
+      float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+      if (row0 + r < p.R) {
+        const float4* src = reinterpret_cast<const float4*>(p.z + (size_t)(row0 + r) * p.D + pl * 8);
+        v0 = __ldg(src);
+        v1 = __ldg(src + 1);
+      }
+      uint4 h, l;
+      split2(v0.x, v0.y, s_z, &h.x, &l.x);
+      split2(v0.z, v0.w, s_z, &h.y, &l.y);
+      split2(v1.x, v1.y, s_z, &h.z, &l.z);
+      split2(v1.z, v1.w, s_z, &h.w, &l.w);
+      *reinterpret_cast<uint4*>(smem + (size_t)pl * PITCH_A + r * 16) = h;
+      *reinterpret_cast<uint4*>(smem + (size_t)a_half + (size_t)pl * PITCH_A + r * 16) = l;
+    }
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ===================== epilogue: running five smallest approximate distances per row =====================
+    float b[NCAND + 1];
+    int ci[NCAND];
+#pragma unroll
+    for (int j = 0; j <= NCAND; ++j) b[j] = INFINITY;
+#pragma unroll
+    for (int j = 0; j < NCAND; ++j) ci[j] = 0;
+    const float m2 = -2.0f * inv_z * inv_e;          // dot (scaled) -> -2 z.e
+    int buf = 0;
+    uint32_t ph[2] = {0u, 0u};
+    for (int t = tile_lo; t < tile_hi; ++t) {
+      // |e|^2 of this tile -> shared (each epilogue thread brings two values)
+      float* es = ee_s + buf * BN;
+#pragma unroll
+      for (int j = 0; j < BN / NEPI; ++j) {
+        const int code = t * BN + tid + j * NEPI;
+        es[tid + j * NEPI] = code < p.K ? __ldg(p.ee + code) : INFINITY;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(accf_bar(buf), ph[buf]);
+      ph[buf] ^= 1u;
+      tc_fence_after();
+#pragma unroll 1
+      for (int cb = 0; cb < BN / 32; ++cb) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * BN + cb * 32), v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float d = fmaf(v[j], m2, es[cb * 32 + j]);     // INFINITY for codes beyond K: never inserted
+          if (d < b[NCAND]) {
+            const int code = t * BN + cb * 32 + j;
+            // sorted insertion (ascending); equal values keep the earlier code first
+            if (d < b[3]) {
+              b[4] = b[3];
+              if (d < b[2]) {
+                b[3] = b[2]; ci[3] = ci[2];
+                if (d < b[1]) {
+                  b[2] = b[1]; ci[2] = ci[1];
+                  if (d < b[0]) { b[1] = b[0]; ci[1] = ci[0]; b[0] = d; ci[0] = code; }
+                  else { b[1] = d; ci[1] = code; }
+                } else { b[2] = d; ci[2] = code; }
+              } else { b[3] = d; ci[3] = code; }
+            } else {
+              b[4] = d;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(acce_bar(buf));
+      buf ^= 1;
+    }
+    const int64_t row = row0 + warp * 32 + lane;
+    if (row < p.R) {
+      float* o = p.cand + ((size_t)row * gridDim.y + blockIdx.y) * REC;
+#pragma unroll
+      for (int j = 0; j <= NCAND; ++j) o[j] = b[j];
+#pragma unroll
+      for (int j = 0; j < NCAND; ++j) o[5 + j] = __int_as_float(ci[j]);
+    }
+  } else if (warp < 12) {
+    // ===================== producers: code chunks -> split fp16 operand planes =====================
+    const int pt = tid - NEPI;                        // 0..255
+    constexpr int ITEMS = BN * (KC / 8) / NPROD;      // 16-byte chunks per half per thread per stage (4)
+    int stage = 0;
+    uint32_t phase = 0;
+    const int nsteps = (tile_hi - tile_lo) * nchunk;
+    float4 vn[ITEMS][2];
+    auto gload = [&](int step, float4 (*v)[2]) {
+      const int t = tile_lo + step / nchunk, c = step % nchunk;
+#pragma unroll
+      for (int i = 0; i < ITEMS; ++i) {
+        const int item = pt + i * NPROD, oct = item & 3, code = item >> 2;
+        const int gcode = min(t * BN + code, p.K - 1);             // clamped copies are masked by their +inf |e|^2
+        const float4* src = reinterpret_cast<const float4*>(p.E + (size_t)gcode * p.D + c * KC + oct * 8);
+        v[i][0] = __ldg(src);
+        v[i][1] = __ldg(src + 1);
+      }
+    };
+    if (nsteps > 0) gload(0, vn);
+    for (int step = 0; step < nsteps; ++step) {
+      float4 v[ITEMS][2];
+#pragma unroll
+      for (int i = 0; i < ITEMS; ++i) { v[i][0] = vn[i][0]; v[i][1] = vn[i][1]; }
+      if (step + 1 < nsteps) gload(step + 1, vn);
+      mbar_wait(empty_bar(stage), phase ^ 1);
+      uint8_t* bs = b_smem + (size_t)stage * B_STAGE;
+#pragma unroll
+      for (int i = 0; i < ITEMS; ++i) {
+        const int item = pt + i * NPROD, oct = item & 3, code = item >> 2;
+        uint4 h, l;
+        split2(v[i][0].x, v[i][0].y, s_e, &h.x, &l.x);
+        split2(v[i][0].z, v[i][0].w, s_e, &h.y, &l.y);
+        split2(v[i][1].x, v[i][1].y, s_e, &h.z, &l.z);
+        split2(v[i][1].z, v[i][1].w, s_e, &h.w, &l.w);
+        *reinterpret_cast<uint4*>(bs + oct * PITCH_B + code * 16) = h;
+        *reinterpret_cast<uint4*>(bs + B_HALF + oct * PITCH_B + code * 16) = l;
+      }
+      fence_proxy_async();
+      mbar_arrive(full_bar(stage));
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      int stage = 0, buf = 0;
+      uint32_t phase = 0, eph[2] = {0u, 0u};
+      const uint32_t a_hi = smem_base, a_lo = smem_base + (uint32_t)a_half;
+      for (int t = tile_lo; t < tile_hi; ++t) {
+        mbar_wait(acce_bar(buf), eph[buf] ^ 1);       // the epilogue has drained this accumulator (first use: passes)
+        eph[buf] ^= 1u;
+        tc_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)(buf * BN);
+        for (int c = 0; c < nchunk; ++c) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t bst = smem_base + 2u * (uint32_t)a_half + (uint32_t)stage * B_STAGE;
+#pragma unroll
+          for (int k16 = 0; k16 < KC / 16; ++k16) {
+            const uint32_t aoff = (uint32_t)((c * (KC / 8) + k16 * 2) * PITCH_A);
+            const uint64_t ah = make_desc(a_hi + aoff, PITCH_A, 128), al = make_desc(a_lo + aoff, PITCH_A, 128);
+            const uint64_t bh = make_desc(bst + (uint32_t)(k16 * 2 * PITCH_B), PITCH_B, 128);
+            const uint64_t bl = make_desc(bst + (uint32_t)(B_HALF + k16 * 2 * PITCH_B), PITCH_B, 128);
+            mma_f16_ss(acc, ah, bh, IDESC, (c > 0 || k16 > 0) ? 1u : 0u);
+            mma_f16_ss(acc, al, bh, IDESC, 1u);
+            mma_f16_ss(acc, ah, bl, IDESC, 1u);
+          }
+          mma_commit(empty_bar(stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        mma_commit(accf_bar(buf));
+        buf ^= 1;
+      }
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+size_t filter_smem_bytes(int D) {
+  return 2 * (size_t)(D / 8) * PITCH_A + (size_t)STAGES * B_STAGE + 2 * BN * sizeof(float) + (2 * STAGES + 4) * 8 + 16;
+}
+
+}  // namespace vqtc
+
+// Host side: eligibility and launch (called from mas_vq_forward in vq.cu).
+bool vq_filter_tc_ok(int64_t R, int K, int D) {
+  return D % 32 == 0 && D >= 32 && vqtc::filter_smem_bytes(D) <= 232448 && K >= 8 && R > 0;
+}
+int vq_filter_splits(int64_t R, int K) {
+  const int64_t row_blocks = cdiv(R, vqtc::BM);
+  const int ntile = (int)cdiv(K, vqtc::BN);
+  int s = (int)(148 / row_blocks);
+  if (s < 1) s = 1;
+  if (s > ntile) s = ntile;
+  if (s > 4) s = 4;
+  return s;
+}
+int vq_filter_tc_launch(const float* z, const float* E, const float* ee, const float* z_amax, const float* e_amax, int64_t R, int K,
+                        int D, float* cand, int splits, cudaStream_t st) {
+  vqtc::Params p;
+  p.z = z; p.E = E; p.ee = ee; p.z_amax = z_amax; p.e_amax = e_amax; p.cand = cand;
+  p.R = R; p.K = K; p.D = D;
+  const int ntile = (int)cdiv(K, vqtc::BN);
+  p.tiles_per_split = (int)cdiv(ntile, splits);
+  const size_t smem = vqtc::filter_smem_bytes(D);
+  static std::atomic<uint64_t> configured{0};
+  if (first_on_device(configured)) {
+    cudaError_t e = cudaFuncSetAttribute(vqtc::vq_filter_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return fail(MAS_ERR_LAUNCH, "vq_filter_tc: smem attr: %s", cudaGetErrorString(e));
+    mark_device(configured);
+  }
+  dim3 grid((unsigned)cdiv(R, vqtc::BM), (unsigned)splits);
+  vqtc::vq_filter_tc<<<grid, vqtc::NTHREADS, smem, st>>>(p);
+  return launched_tc("vq_filter_tc");
+}
+
+}  // namespace mas

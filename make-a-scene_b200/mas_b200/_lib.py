@@ -83,6 +83,7 @@ _SPEC = {
     "mas_bn_apply": (_I, [_P, _P, _P, _P, _P, _P, _L, _I, _P]),
     "mas_bn_backward_reduce": (_I, [_P, _P, _P, _P, _L, _I, _P, _P]),
     "mas_bn_backward_apply": (_I, [_P, _P, _P, _P, _P, _P, _P, _D, _P, _P, _P, _L, _I, _P]),
+    "mas_vq_select_path": (_I, [_I]),
     "mas_vq_ws_bytes": (_Z, [_L, _I, _I]),
     "mas_vq_forward": (_I, [_P, _P, _L, _I, _I, _F, _P, _P, _P, _P, _Z, _P]),
     "mas_vq_forward_given": (_I, [_P, _P, _P, _L, _I, _I, _F, _P, _P, _P, _Z, _P]),

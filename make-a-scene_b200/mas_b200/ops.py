@@ -751,6 +751,13 @@ class VQFn(torch.autograd.Function):
         return grad_z, grad_E, None
 
 
+def vq_select_path(tensor_core_filter: bool):
+    """Codebook arg-min implementation: tensor-core filter + exact re-evaluation (default) or the all-pairs FFMA kernel."""
+    rc = L.load().mas_vq_select_path(1 if tensor_core_filter else 0)
+    if rc != 0:
+        raise RuntimeError("mas_vq_select_path failed")
+
+
 class VQGivenFn(torch.autograd.Function):
     """Codebook gather + loss + straight-through for caller-supplied indices (no argmin): modules.py:506-515 with
     `min_encoding_indices` given. Same backward kernel as VQFn."""

@@ -111,6 +111,68 @@ def test_codebook_full_size_properties():
     assert int(idx3.max()) < 4096
 
 
+@pytest.fixture
+def vq_paths():
+    from mas_b200 import ops
+    yield ops.vq_select_path
+    ops.vq_select_path(True)
+
+
+@pytest.mark.parametrize("R_img,K,D,kind", [(32, 8192, 256, "randn"), (5, 8192, 256, "randn"), (3, 1000, 64, "randn"),
+                                            (2, 512, 128, "clustered"), (2, 512, 32, "duplicated"), (2, 300, 64, "fresh"),
+                                            (4, 8192, 256, "scaled_small"), (4, 2048, 256, "scaled_big")])
+def test_codebook_tensor_core_filter_is_bit_identical_to_exact_kernel(R_img, K, D, kind, vq_paths):
+    """The tensor-core filter + exact re-evaluation path (csrc/vq_tc.cu, the default) against the all-pairs exact-fp32
+    FFMA kernel on the same inputs: identical int64 indices, identical z_q and loss - on ordinary data, on clustered /
+    duplicated / tie-heavy codebooks (every row undecided: the filter must hand them all to the exact kernel) and on
+    operands far outside the fp16 range (the power-of-two operand scales)."""
+    from mas_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(K + D + R_img)
+    E = torch.randn(K, D, generator=g)
+    z = torch.randn(R_img, D, 16, 16, generator=g)
+    if kind == "clustered":
+        j = torch.randint(0, K, (R_img * 256,), generator=g)
+        z = (E[j] + 0.3 * torch.randn(R_img * 256, D, generator=g)).view(R_img, 16, 16, D).permute(0, 3, 1, 2).contiguous()
+    elif kind == "duplicated":
+        E = torch.cat([E[:K // 2], E[:K // 2]], 0)
+    elif kind == "fresh":
+        E = (torch.rand(K, D, generator=g) * 2 - 1) / K
+    elif kind == "scaled_small":
+        E, z = E * 3e-6, z * 3e-6
+    elif kind == "scaled_big":
+        E, z = E * 4e4, z * 4e4
+    zd, Ed = z.to(dev), E.to(dev)
+    vq_paths(False)
+    zq0, loss0, idx0 = ops.VQFn.apply(zd, Ed, 0.25)
+    vq_paths(True)
+    zq1, loss1, idx1 = ops.VQFn.apply(zd, Ed, 0.25)
+    assert torch.equal(idx0, idx1), (kind, int((idx0 != idx1).sum()))
+    assert torch.equal(zq0, zq1) and float(loss0) == float(loss1)
+
+
+def test_codebook_tensor_core_filter_accuracy_and_margin():
+    """The error model of the filter (vq_margin in csrc/vq.cu): on BASELINE-sized random data the 2 x fp16 split distances
+    agree with fp64 far inside the margin, and only a small fraction of rows needs the exact re-evaluation."""
+    from mas_b200 import _lib as L, ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(11)
+    z = torch.randn(8, 256, 16, 16, generator=g)
+    E = torch.randn(8192, 256, generator=g)
+    zd, Ed = z.to(dev), E.to(dev)
+    before = L.tc_launch_count()
+    _, _, idx = ops.VQFn.apply(zd, Ed, 0.25)
+    assert L.tc_launch_count() == before + 1            # the filter kernel ran
+    zf = z.permute(0, 2, 3, 1).reshape(-1, 256).double()
+    d = (zf * zf).sum(1, keepdim=True) + (E.double() ** 2).sum(1)[None] - 2 * zf @ E.double().t()
+    top2 = d.topk(2, dim=1, largest=False).values
+    assert torch.equal(idx.cpu(), d.argmin(1)) or bool(((top2[:, 1] - top2[:, 0])[idx.cpu() != d.argmin(1)] < 1e-3).all())
+    # the margin the resolve kernel uses for this data (|z| ~ 16, |e|max ~ 18.5): a few percent of the rows fall inside it
+    margin = 2.5e-4 * zf.norm(dim=1) * E.double().norm(dim=1).max()
+    frac = float(((top2[:, 1] - top2[:, 0]) < margin).double().mean())
+    assert frac < 0.25, frac
+
+
 def test_codebook_ragged_rows():
     """R not a multiple of the 64-row tile, K not a multiple of the 128-code tile."""
     from mas_b200 import ops
