@@ -81,10 +81,18 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_model():
+SEG_CFG = dict(z_channels=256, in_channels=159, out_channels=159, channels=[128, 128, 128, 256, 512, 512], num_res_blocks=2,
+               resolution=256, attn_resolutions=[16], dropout=0.0)     # conf/seg_config.yaml (out_channels given explicitly)
+SEG_METRIC = "VQ-SEG 256^2 images/sec (enc+VQ+dec fwd+bwd, weighted BCE)"
+
+
+def build_model(workload="vqimg"):
     from models import VQBASE
     torch.manual_seed(0)
-    m = VQBASE(IMG_CFG, N_EMBED, EMBED_DIM, 3000, 12500)
+    if workload == "vqseg":
+        m = VQBASE(SEG_CFG, 1024, 256, 2000, 12500)
+    else:
+        m = VQBASE(IMG_CFG, N_EMBED, EMBED_DIM, 3000, 12500)
     with torch.no_grad():
         m.quantize.embedding.weight.normal_()
     m.quantize.q_counter = 10 ** 6
@@ -210,6 +218,29 @@ def dominant_kernel_roofline(dev, pk):
             "algorithmic_bytes_per_launch": 4.0 * BATCH * RES * RES * 256 + 4 * 128 * 128 * 9}
 
 
+def attn_metric(dev, pk):
+    """AttnBlock (modules.py:139-191) at the model's shape: batch 32, C = 512, 16x16 tokens; forward and backward of the
+    whole block (GroupNorm, q/k/v and proj_out 1x1 GEMMs on TF32 tcgen05, QK^T / PV and their four gradients on the
+    3xTF32 tcgen05 GEMM, softmax, residual, next-norm statistics). Algorithmic FLOPs per image forward: 0.671 GFLOP
+    (SURVEY.md 8d), backward = 2x; the 3xTF32 passes are not counted."""
+    from models import modules as M
+    torch.manual_seed(0)
+    blk = M.AttnBlock(512).to(dev)
+    x = torch.randn(BATCH, 512, 16, 16, device=dev).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    g = torch.randn(BATCH, 512, 16, 16, device=dev).contiguous(memory_format=torch.channels_last)
+    fwd = time_kernel(lambda: blk(x), iters=10, warm=3)
+
+    def both():
+        y = blk(x)
+        y.backward(g)
+    tot = time_kernel(both, iters=10, warm=3)
+    gf = 0.671 * BATCH
+    return {"shape": "batch 32, 256 tokens, C=512", "fwd_ms": round(fwd * 1e3, 4), "fwd_bwd_ms": round(tot * 1e3, 4),
+            "fwd_tflop_per_s": round(gf / fwd / 1e3, 1), "fwd_bwd_tflop_per_s": round(3 * gf / tot / 1e3, 1),
+            "frac_of_tf32_peak_fwd": round(gf / fwd / 1e3 / (pk["bf16"] / 2), 3), "bound": "tensor (nominal); launch / latency bound at this size",
+            "kernels": "gn_apply, shift_gemm_tc<1> (QKV, proj), gemm3_tc (QK^T, PV: 3xTF32), softmax"}
+
+
 def ffma_peak(dev):
     """fp32 FMA-pipe peak measured live (mas_ffma_probe, CUDA events): the roofline of the exact-fp32 VQ distance kernel."""
     import ctypes
@@ -277,6 +308,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="vqimg", choices=["vqimg", "vqseg"],
+                    help="vqimg: BASELINE configs[1] (the headline metric); vqseg: configs[3], 159-channel maps + weighted BCE")
     ap.add_argument("--profile", action="store_true", help="print per-entry-point CUDA-event times of one extra step")
     ap.add_argument("--graph", action="store_true",
                     help="single GPU: replay the step from one CUDA graph (mas_b200.graph.GraphedStep) instead of launching from Python")
@@ -295,18 +328,29 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     pk = peaks()
-    model = build_model().to(dev)
+    seg = args.workload == "vqseg"
+    model = build_model(args.workload).to(dev)
     net = model
     if world > 1:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
     B = args.batch
-    img_host = torch.rand(B, 3, RES, RES, generator=torch.Generator().manual_seed(1234 + rank)).pin_memory()
+    gen = torch.Generator().manual_seed(1234 + rank)
+    if seg:   # one-hot-like label maps (SURVEY.md 8d plumbing config, here at BASELINE configs[3]'s size)
+        img_host = (torch.rand(B, 159, RES, RES, generator=gen) > 0.9).float().pin_memory()
+        pos_w = torch.ones(159, device=dev)
+        pos_w[153:158] = 20
+    else:
+        img_host = torch.rand(B, 3, RES, RES, generator=gen).pin_memory()
     img_dev = img_host.to(dev)
 
     def step(img):
         net.zero_grad(set_to_none=True)
         dec, diff = net(img)
-        loss = (img - dec).abs().mean() + diff
+        if seg:
+            from mas_b200 import ops
+            loss = ops.BCELogitsFn.apply(dec, img, pos_w) + diff     # losses/loss_seg.py:15-22
+        else:
+            loss = (img - dec).abs().mean() + diff
         loss.backward()
         return loss
 
@@ -340,6 +384,9 @@ def main():
 
         def loss_fn(m, x):
             dec, diff = m(x)
+            if seg:
+                from mas_b200 import ops
+                return ops.BCELogitsFn.apply(dec, x, pos_w) + diff
             return (x - dec).abs().mean() + diff
         try:
             gs = GraphedStep(net, loss_fn, img_dev, warmup=2)
@@ -380,7 +427,23 @@ def main():
             print("  %-44s n=%4d  %9.2f ms  %5.1f%%  %7.3f ms/call" % (k, c, t, 100 * t / tot, t / c), file=sys.stderr)
         print("  total %.2f ms" % tot, file=sys.stderr)
     roof = dominant_kernel_roofline(dev, pk)
+    if seg:
+        line = {"metric": SEG_METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "%s tcgen05 operands, fp32 accumulate / storage" % _fmt(), "data": "synthetic",
+                "config": {"workload": "VQ-SEG 256x256, 159-channel maps, codebook=1024 dim=256, batch %d/GPU (BASELINE configs[3])" % B,
+                           "global_batch": B * world, "parallelism": "dp%d" % world, "launch": graph_note,
+                           "loss": "weighted BCE-with-logits (pos_weight 20 on channels 153-157) + codebook loss, kernels mas_bce_cl_*",
+                           "edge_layers": "159-channel conv_in / conv_out zero-padded to 160 / 2x128 channels on the fp16 tcgen05 kernels"},
+                "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": B * 159 * RES * RES * 4, "d2h_bytes_per_step": 4,
+                        "ms_per_step": sec_e2e / args.steps * 1e3},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
+        print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     vq = vq_metric(dev, pk)
+    attn = attn_metric(dev, pk)
     line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "%s tcgen05 operands (11-bit significand), fp32 accumulate / storage; 3xTF32 for the attention contractions; fp32 FFMA for VQ argmin and edge layers" % _fmt(),
@@ -392,7 +455,7 @@ def main():
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": B * 3 * RES * RES * 4, "d2h_bytes_per_step": 4,
                     "ms_per_step": sec_e2e / args.steps * 1e3},
             "gpu_launches": int(launches), "clocks": clocks,
-            "model_tflops": FLOP_PER_IMG_FWD_BWD * value / 1e12, "roofline": roof, "vq": vq}
+            "model_tflops": FLOP_PER_IMG_FWD_BWD * value / 1e12, "roofline": roof, "vq": vq, "attn": attn}
     if not args.no_cpu_baseline and world == 1:   # reported baseline: rank 0 at N=1 only
         r = cpu_reference_steps(3, 1, batch=2)
         line["cpu_baseline"] = {"value": r["value"], "unit": "images/s", "cores": r["cores"], "kind": r["kind"],

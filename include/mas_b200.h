@@ -65,6 +65,11 @@ int mas_ffma_probe(float* scratch, int iters, double* flops_out_host, void* stre
 /* ---- layout helpers (boundary only; the VQBASE path itself never transposes) ------------------- */
 int mas_copy_strided(const float* x, mas_tensor4 xs, float* y, mas_tensor4 ys, void* stream);
 
+/* NCHW (contiguous) -> channels-last with CP >= C channels, the extra ones zero (a 159-channel segmentation map becomes a
+ * 160-channel operand of the tensor-core convolution); y = x * g[0] with g a device scalar (a loss's upstream gradient). */
+int mas_nchw_to_nhwc_pad(const float* x_nchw, float* y_nhwc, int N, int C, int CP, int H, int W, void* stream);
+int mas_scale_by(const float* x, const float* g, float* y, int64_t n, void* stream);
+
 /* ---- GroupNorm(32, C, eps=1e-6) + optional SiLU — Normalize / nonlinearity, modules.py:35-41 ------
  * x, y: [N, HW, C] NHWC.  mean/rstd: [N*G].  silu=1 fuses x*sigmoid(x) (modules.py:122,126,194-196).
  * round_tf32=1 rounds y to TF32 (round-to-nearest) so that a following tensor-core contraction sees
@@ -154,11 +159,13 @@ int mas_conv3x3_wgrad(const float* x, mas_tensor4 xs, const float* dy, mas_tenso
 /* fp16-operand tensor-core form (see mas_conv3x3_fprop_tc16): dy is scaled by a power of two derived on the device from
  * dy_amax (device scalar from mas_amax, or NULL), x (or act(GroupNorm(x)) with gn_table) is converted unscaled.
  * MAS_ERR_UNSUPPORTED unless mas_conv3x3_wgrad_tc_eligible (dense NHWC, Cin % 32 == 0, Cout % 128 == 0, H, W % 8 == 0,
- * mode S1 / UP).  Workspace: mas_conv3x3_wgrad_ws_bytes.  dbias (may be NULL) is produced too. */
+ * mode S1 / UP).  Workspace: mas_conv3x3_wgrad_ws_bytes.  dbias (may be NULL) is produced too.
+ * cout_rows = rows of dw_oihw / dbias: dys.c normally; with dys.c % 128 != 0 (a multiple of 4) pass round_up(dys.c, 128) and
+ * buffers of that many rows - the TMA copy of dy zero-fills the missing channels and the extra rows come out zero. */
 int mas_conv3x3_wgrad_tc_eligible(mas_tensor4 xs, mas_tensor4 dys, int mode);
 int mas_conv3x3_wgrad_tc16(const float* x, mas_tensor4 xs, const float* dy, mas_tensor4 dys, float* dw_oihw, float* dbias,
-                           int mode, const float* gn_table, int gn_silu, const float* dy_amax, void* ws, size_t ws_bytes,
-                           void* stream);  /* gn_table: x is re-activated on the fly (tensor path only) */
+                           int mode, const float* gn_table, int gn_silu, const float* dy_amax, int cout_rows, void* ws,
+                           size_t ws_bytes, void* stream);  /* gn_table: x is re-activated on the fly (tensor path only) */
 /* Weight gradient of a 1x1 convolution: dw[Cout,Cin] = dy^T x over M rows (split over rows, deterministic);
  * dbias [Cout] may be NULL. x [M,Cin] and dy [M,Cout] are row-major with row pitches ldx / ldy (elements). */
 size_t mas_conv1x1_wgrad_ws_bytes(int64_t M, int Cin, int Cout);
@@ -270,6 +277,12 @@ int mas_vq_forward(const float* z, const float* E, int64_t R, int K, int D, floa
  * quantisation, e.g. re-evaluating the codebook loss of stored codes (modules.py:506-512 with idx given). */
 int mas_vq_forward_given(const float* z, const float* E, const int64_t* idx_in, int64_t R, int K, int D, float beta,
                          float* zq_out, float* loss_out, void* ws, size_t ws_bytes, void* stream);
+/* Lloyd update step for Codebook re-initialisation (modules.py:487-499, replacing the un-installed fast_pytorch_kmeans;
+ * the assignment step is mas_vq_forward): centres_new[k] = mean of the rows x[r] with idx[r] == k (an empty cluster keeps
+ * centres_old[k]); shift_out (device scalar, may be NULL) = |centres_new - centres_old|_F. */
+size_t mas_kmeans_ws_bytes(int K, int D);
+int mas_kmeans_update(const float* x, const int64_t* idx, int64_t n, int K, int D, const float* centres_old,
+                      float* centres_new, float* shift_out, void* ws, size_t ws_bytes, void* stream);
 int mas_vq_backward(const float* g_zq, const float* g_loss, const float* z, const float* E,
                     const int64_t* idx, int64_t R, int K, int D, float beta, float* grad_z, float* grad_E,
                     void* stream);
@@ -319,6 +332,15 @@ int mas_bce_logits(const float* logits, mas_tensor4 ls, const float* target, mas
                    const float* pos_weight, float* loss_out, float* grad, mas_tensor4 gs, float grad_scale,
                    void* ws, size_t ws_bytes, void* stream);
 size_t mas_bce_ws_bytes(mas_tensor4 ls);
+/* The VQ-SEG step's own layouts: logits channels-last with channel pitch CP >= C (the padded output of the decoder's last
+ * convolution), target NCHW (the data loader's maps), W % 32 == 0.  mas_bce_cl_forward: loss = mean over N*C*H*W.
+ * mas_bce_cl_backward: grad[n,h,w,c] = g[0] * dloss/dlogit (g: device scalar from autograd, NULL = 1), pad channels
+ * written as 0 - so the loss's backward runs here, not in the host framework (losses/loss_seg.py:15-22). */
+size_t mas_bce_cl_ws_bytes(int N, int H, int W);
+int mas_bce_cl_forward(const float* logits, const float* target_nchw, const float* pos_weight, int N, int C, int CP, int H,
+                       int W, float* loss_out, void* ws, size_t ws_bytes, void* stream);
+int mas_bce_cl_backward(const float* logits, const float* target_nchw, const float* pos_weight, const float* g, int N, int C,
+                        int CP, int H, int W, float* grad, void* stream);
 
 #ifdef __cplusplus
 }

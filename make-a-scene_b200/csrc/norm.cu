@@ -584,6 +584,27 @@ __global__ void copy_strided_kernel(const float* __restrict__ x, mas_tensor4 xs,
   }
 }
 
+// NCHW (contiguous) -> channels-last with CP >= C channels (the extra ones zero): block = 32 pixels of one image row, planes read
+// as 128-byte rows, transposed through shared memory, written as one contiguous 32 x CP block.  The padded copy is what lets a
+// 159-channel input run on the 16-channel K steps of the tensor-core convolution.
+__global__ void __launch_bounds__(256) nchw_to_nhwc_pad_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int CP, int H, int W) {
+  extern __shared__ float tile[];   // [C][33]
+  const int w0 = blockIdx.x * 32, h = blockIdx.y, n = blockIdx.z;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int c = ty; c < C; c += 8) tile[c * 33 + tx] = (w0 + tx < W) ? __ldg(x + (((size_t)n * C + c) * H + h) * W + w0 + tx) : 0.f;
+  __syncthreads();
+  const size_t base = (((size_t)n * H + h) * W + w0) * CP;
+  const int npx = min(32, W - w0);
+  for (int i = threadIdx.x; i < npx * CP; i += 256) {
+    const int px = i / CP, c = i - px * CP;
+    y[base + i] = c < C ? tile[c * 33 + px] : 0.f;
+  }
+}
+__global__ void scale_by_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ y, int64_t n) {
+  const float s = g[0];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] = x[i] * s;
+}
+
 __global__ void sumpool2x2_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, int C4, int64_t total4) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(i % C4);
@@ -631,6 +652,49 @@ __global__ void __launch_bounds__(256) bce_kernel(const float* __restrict__ lg, 
     __syncthreads();
   }
   if (threadIdx.x == 0) part[blockIdx.x] = red[0];
+}
+// Same loss for the layouts the VQ-SEG step actually has: logits channels-last with pitch CP >= C (the padded output of
+// the decoder's last convolution), target NCHW (the data loader's one-hot maps).  Block = 32 consecutive pixels of one image
+// row: the target tile is read plane by plane (128-byte rows) and transposed through shared memory, the logits / gradient
+// tile is one contiguous 32 x CP block.  MODE 0: loss partials.  MODE 1: gradient g * gscale * dl/dx (pad channels get 0).
+template <int MODE>
+__global__ void __launch_bounds__(256) bce_cl_kernel(const float* __restrict__ lg, const float* __restrict__ tg, const float* __restrict__ pw,
+                                                     int C, int CP, int H, int W, const float* __restrict__ g, float gscale,
+                                                     float* __restrict__ grad, double* __restrict__ part) {
+  extern __shared__ float tile[];   // [C][33]
+  const int w0 = blockIdx.x * 32, h = blockIdx.y, n = blockIdx.z;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int c = ty; c < C; c += 8) tile[c * 33 + tx] = __ldg(tg + (((size_t)n * C + c) * H + h) * W + w0 + tx);
+  __syncthreads();
+  const size_t base = (((size_t)n * H + h) * W + w0) * CP;
+  const float gs = MODE == 1 ? gscale * (g ? g[0] : 1.f) : 0.f;
+  double acc = 0;
+  for (int i = threadIdx.x; i < 32 * CP; i += 256) {
+    const int px = i / CP, c = i - px * CP;
+    if (c < C) {
+      const float x = __ldg(lg + base + i), t = tile[c * 33 + px];
+      const float coef = 1.0f + (__ldg(pw + c) - 1.0f) * t;
+      if (MODE == 0) {
+        const float sp = fmaxf(-x, 0.f) + log1pf(expf(-fabsf(x)));
+        acc += (double)((1.0f - t) * x + coef * sp);
+      } else {
+        const float sg = 1.0f / (1.0f + expf(x));
+        grad[base + i] = gs * ((1.0f - t) - coef * sg);
+      }
+    } else if (MODE == 1) {
+      grad[base + i] = 0.f;
+    }
+  }
+  if (MODE == 0) {
+    __shared__ double red[256];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+      if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) part[((size_t)n * H + h) * gridDim.x + blockIdx.x] = red[0];
+  }
 }
 __global__ void sum_final_kernel(const double* __restrict__ part, int n, double scale, float* __restrict__ out) {
   __shared__ double sh[256];
@@ -827,11 +891,44 @@ int mas_copy_strided(const float* x, mas_tensor4 xs, float* y, mas_tensor4 ys, v
   return launched("copy_strided");
 }
 
+int mas_nchw_to_nhwc_pad(const float* x_nchw, float* y_nhwc, int N, int C, int CP, int H, int W, void* stream) {
+  MAS_REQUIRE(x_nchw && y_nhwc && N > 0 && C > 0 && CP >= C && H > 0 && W > 0, "nchw_to_nhwc_pad: bad arguments");
+  if ((size_t)C * 33 * sizeof(float) > 48 * 1024) return fail(MAS_ERR_UNSUPPORTED, "nchw_to_nhwc_pad: C=%d too large", C);
+  nchw_to_nhwc_pad_kernel<<<dim3((unsigned)cdiv(W, 32), H, N), 256, (size_t)C * 33 * sizeof(float), S(stream)>>>(x_nchw, y_nhwc, C, CP, H, W);
+  return launched("nchw_to_nhwc_pad");
+}
+int mas_scale_by(const float* x, const float* g, float* y, int64_t n, void* stream) {
+  scale_by_kernel<<<ew_grid(n), 256, 0, S(stream)>>>(x, g, y, n);
+  return launched("scale_by");
+}
+
 int mas_sumpool2x2(const float* x, float* y, int N, int H, int W, int C, void* stream) {
   MAS_REQUIRE(C % 4 == 0, "sumpool2x2: C %% 4 != 0");
   int64_t total4 = (int64_t)N * H * W * (C / 4);
   sumpool2x2_kernel<<<ew_grid(total4), 256, 0, S(stream)>>>(x, y, H, W, C / 4, total4);
   return launched("sumpool2x2");
+}
+
+// channels-last logits (pitch CP) x NCHW target: loss (mean over N*C*H*W) and, separately, the gradient scaled by the
+// upstream gradient g (device scalar or NULL = 1) - nothing of the loss's backward runs in the host framework
+size_t mas_bce_cl_ws_bytes(int N, int H, int W) { return (size_t)N * H * cdiv(W, 32) * sizeof(double) + 64; }
+int mas_bce_cl_forward(const float* logits, const float* target_nchw, const float* pos_weight, int N, int C, int CP, int H, int W,
+                       float* loss_out, void* ws, size_t ws_bytes, void* stream) {
+  MAS_REQUIRE(logits && target_nchw && pos_weight && loss_out && N > 0 && C > 0 && CP >= C && W % 32 == 0, "bce_cl_forward: bad arguments");
+  if (ws_bytes < mas_bce_cl_ws_bytes(N, H, W)) return fail(MAS_ERR_WORKSPACE, "bce_cl_forward: workspace too small");
+  const int nb = N * H * (W / 32);
+  bce_cl_kernel<0><<<dim3(W / 32, H, N), 256, (size_t)C * 33 * sizeof(float), S(stream)>>>(logits, target_nchw, pos_weight, C, CP, H, W, nullptr,
+                                                                                          0.f, nullptr, (double*)ws);
+  if (int e = launched("bce_cl_loss")) return e;
+  sum_final_kernel<<<1, 256, 0, S(stream)>>>((const double*)ws, nb, 1.0 / ((double)N * C * H * W), loss_out);
+  return launched("bce_final");
+}
+int mas_bce_cl_backward(const float* logits, const float* target_nchw, const float* pos_weight, const float* g, int N, int C, int CP,
+                        int H, int W, float* grad, void* stream) {
+  MAS_REQUIRE(logits && target_nchw && pos_weight && grad && N > 0 && C > 0 && CP >= C && W % 32 == 0, "bce_cl_backward: bad arguments");
+  bce_cl_kernel<1><<<dim3(W / 32, H, N), 256, (size_t)C * 33 * sizeof(float), S(stream)>>>(
+      logits, target_nchw, pos_weight, C, CP, H, W, g, (float)(1.0 / ((double)N * C * H * W)), grad, nullptr);
+  return launched("bce_cl_grad");
 }
 
 size_t mas_bce_ws_bytes(mas_tensor4 ls) { return (size_t)cdiv(ls.n * ls.h * ls.w * ls.c, BCE_CHUNK) * sizeof(double) + 64; }

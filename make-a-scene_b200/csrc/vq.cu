@@ -15,8 +15,9 @@ namespace mas {
 // tensor-core filter stage (vq_tc.cu)
 bool vq_filter_tc_ok(int64_t R, int K, int D);
 int vq_filter_splits(int64_t R, int K);
+size_t vq_filter_pack_bytes(int K, int D);
 int vq_filter_tc_launch(const float* z, const float* E, const float* ee, const float* z_amax, const float* e_amax, int64_t R, int K,
-                        int D, float* cand, int splits, cudaStream_t st);
+                        int D, float* cand, int splits, void* pack_buf, cudaStream_t st);
 
 constexpr int VQ_BM = 64;    // latent rows per CTA
 constexpr int VQ_BN = 128;   // codes per tile
@@ -355,6 +356,41 @@ __global__ void vq_fallback_merge_kernel(const float* __restrict__ fb_val, const
   final_idx[list[j]] = bi;
 }
 
+// ---- k-means update step of the codebook re-initialisation (modules.py:487-499; the assignment step is the VQ kernel) ----
+__global__ void kmeans_accumulate_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, int64_t n, int D,
+                                         double* __restrict__ sums, int* __restrict__ cnt) {
+  const int D4 = D >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * D4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / D4;
+    const int q = (int)(i % D4);
+    const int64_t k = idx[r];
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    double* s = sums + (size_t)k * D + q * 4;   // fp64 accumulation: the order of the atomics is invisible after rounding to fp32
+    atomicAdd(s + 0, (double)v.x);
+    atomicAdd(s + 1, (double)v.y);
+    atomicAdd(s + 2, (double)v.z);
+    atomicAdd(s + 3, (double)v.w);
+    if (q == 0) atomicAdd(cnt + k, 1);
+  }
+}
+// new centre = mean of its members (an empty cluster keeps its old centre); shift2 += |new - old|^2
+__global__ void kmeans_finalize_kernel(const double* __restrict__ sums, const int* __restrict__ cnt, const float* __restrict__ old_c,
+                                       float* __restrict__ new_c, int K, int D, double* __restrict__ shift2) {
+  double acc = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)K * D; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i / D);
+    const int c = cnt[k];
+    const float o = old_c[i];
+    const float v = c > 0 ? (float)(sums[i] / (double)c) : o;
+    new_c[i] = v;
+    acc += ((double)v - o) * ((double)v - o);
+  }
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if ((threadIdx.x & 31) == 0 && acc != 0) atomicAdd(shift2, acc);
+}
+
+__global__ void kmeans_shift_kernel(const double* __restrict__ shift2, float* __restrict__ out) { out[0] = (float)sqrt(shift2[0]); }
+
 // caller-supplied code indices (int64, clamped) -> the (value, index) slot layout vq_merge_kernel reads with splits = 1
 __global__ void vq_given_indices_kernel(const int64_t* __restrict__ idx_in, int64_t R, int K, float* __restrict__ best_val,
                                         int* __restrict__ best_idx) {
@@ -444,7 +480,7 @@ size_t mas_vq_ws_bytes(int64_t R, int K, int D) {
                 a256((size_t)cdiv(R, 8) * sizeof(double)) + 256;
   if (vq_use_tc(R, K, D))   // candidate records, final indices, undecided-row list, fallback results, scalars
     base += a256((size_t)R * 4 * VQ_REC * sizeof(float)) + 2 * a256((size_t)R * sizeof(int)) +
-            2 * a256((size_t)R * VQ_FB_SPLITS * sizeof(float)) + 256;
+            2 * a256((size_t)R * VQ_FB_SPLITS * sizeof(float)) + a256(vq_filter_pack_bytes(K, D)) + 256;
   return base;
 }
 
@@ -479,6 +515,7 @@ int mas_vq_forward(const float* z, const float* E, int64_t R, int K, int D, floa
     int* list = (int*)w; w += a256((size_t)R * sizeof(int));
     float* fb_val = (float*)w; w += a256((size_t)R * VQ_FB_SPLITS * sizeof(float));
     int* fb_idx = (int*)w; w += a256((size_t)R * VQ_FB_SPLITS * sizeof(float));
+    void* pack_buf = w; w += a256(vq_filter_pack_bytes(K, D));
     float* scal = (float*)w;   // [0] max|z|  [1] max|E|  [2] max |e|^2 (bits)  [3] undecided-row count
     cudaError_t ce = cudaMemsetAsync(scal, 0, 4 * sizeof(float), S(stream));
     if (ce != cudaSuccess) return fail(MAS_ERR_LAUNCH, "vq_forward: memset: %s", cudaGetErrorString(ce));
@@ -487,7 +524,7 @@ int mas_vq_forward(const float* z, const float* E, int64_t R, int K, int D, floa
     vq_code_norms<<<(int)cdiv(K, 8), 256, 0, S(stream)>>>(E, K, D, ee, reinterpret_cast<unsigned int*>(scal + 2));
     if (int e = launched("vq_code_norms")) return e;
     const int fsplits = vq_filter_splits(R, K);
-    if (int e = vq_filter_tc_launch(z, E, ee, scal + 0, scal + 1, R, K, D, cand, fsplits, S(stream))) return e;
+    if (int e = vq_filter_tc_launch(z, E, ee, scal + 0, scal + 1, R, K, D, cand, fsplits, pack_buf, S(stream))) return e;
     vq_resolve_kernel<<<mblocks, 256, 0, S(stream)>>>(z, E, ee, cand, fsplits, R, K, D, reinterpret_cast<const unsigned int*>(scal + 2),
                                                      final_idx, list, reinterpret_cast<int*>(scal + 3));
     if (int e = launched("vq_resolve")) return e;
@@ -533,6 +570,32 @@ int mas_vq_forward_given(const float* z, const float* E, const int64_t* idx_in, 
   if (int e = launched("vq_merge")) return e;
   vq_loss_final<<<1, 256, 0, S(stream)>>>(part, mblocks, 1.0 / ((double)R * D), beta, loss_out);
   return launched("vq_loss_final");
+}
+
+size_t mas_kmeans_ws_bytes(int K, int D) { return a256((size_t)K * D * sizeof(double)) + a256((size_t)K * sizeof(int)) + 256; }
+
+int mas_kmeans_update(const float* x, const int64_t* idx, int64_t n, int K, int D, const float* centres_old, float* centres_new,
+                      float* shift_out, void* ws, size_t ws_bytes, void* stream) {
+  MAS_REQUIRE(x && idx && centres_old && centres_new && n > 0 && K > 0 && D > 0 && D % 4 == 0, "kmeans_update: bad arguments");
+  if (ws_bytes < mas_kmeans_ws_bytes(K, D)) return fail(MAS_ERR_WORKSPACE, "kmeans_update: workspace too small");
+  char* w = (char*)ws;
+  double* sums = (double*)w; w += a256((size_t)K * D * sizeof(double));
+  int* cnt = (int*)w; w += a256((size_t)K * sizeof(int));
+  double* shift2 = (double*)w;
+  cudaError_t e = cudaMemsetAsync(ws, 0, mas_kmeans_ws_bytes(K, D), S(stream));
+  if (e != cudaSuccess) return fail(MAS_ERR_LAUNCH, "kmeans_update: memset: %s", cudaGetErrorString(e));
+  const int64_t items = n * (D / 4);
+  kmeans_accumulate_kernel<<<(int)(cdiv(items, 256) < 148 * 16 ? cdiv(items, 256) : 148 * 16), 256, 0, S(stream)>>>(x, idx, n, D, sums, cnt);
+  if (int er = launched("kmeans_accumulate")) return er;
+  const int64_t tot = (int64_t)K * D;
+  kmeans_finalize_kernel<<<(int)(cdiv(tot, 256) < 148 * 8 ? cdiv(tot, 256) : 148 * 8), 256, 0, S(stream)>>>(sums, cnt, centres_old, centres_new,
+                                                                                                       K, D, shift2);
+  if (int er = launched("kmeans_finalize")) return er;
+  if (shift_out) {
+    kmeans_shift_kernel<<<1, 1, 0, S(stream)>>>(shift2, shift_out);
+    return launched("kmeans_shift");
+  }
+  return MAS_OK;
 }
 
 int mas_vq_backward(const float* g_zq, const float* g_loss, const float* z, const float* E, const int64_t* idx, int64_t R, int K,

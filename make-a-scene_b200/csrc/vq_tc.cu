@@ -17,8 +17,9 @@
 //
 // Structure (one CTA = 128 latent rows x a contiguous range of 256-code tiles):
 //   * A (the 128 x D latent tile, both halves) is converted once and stays in shared memory for the whole sweep;
-//   * B (codes): 8 producer warps stream 32-dimension chunks of the code tile from L2 (fp32), split them in registers and
-//     store both halves in the K-major no-swizzle UMMA layout ([k/8][code][8 halves]); 2-stage full/empty mbarrier ring;
+//   * B (codes): split ONCE per launch by vq_pack_codes into the exact shared-memory image of a pipeline stage
+//     ([tile][32-dim chunk][hi|lo][k/8][code][8 halves], K-major no-swizzle UMMA layout), so one thread feeds the ring with
+//     a single cp.async.bulk (33 KB, mbarrier complete_tx) per stage; 2-stage full/empty mbarrier ring;
 //   * one thread issues the MMAs (M 128, N 256, K 16; 3 per K step) into one of TWO 256-column accumulators;
 //   * 4 epilogue warps (thread = latent row) drain the other accumulator meanwhile: tcgen05.ld, d~ = |e|^2 - 2 dot, sorted
 //     insertion into the row's five smallest values (four of them with their code index).
@@ -56,6 +57,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
   } while (!done);
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -125,7 +134,7 @@ __device__ __forceinline__ void split2(float a, float b, float s, uint32_t* hi, 
 
 struct Params {
   const float* z;      // [R, D]
-  const float* E;      // [K, D]
+  const uint8_t* Epk;  // packed split codes: [ntile][D/32][B_STAGE bytes] (vq_pack_codes)
   const float* ee;     // [K] |e_k|^2 (vq_code_norms: the exact kernel's values)
   const float* z_amax; // device scalars
   const float* e_amax;
@@ -156,7 +165,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_filter_tc(const Params p) {
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), NPROD);
+      mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -257,48 +266,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_filter_tc(const Params p) {
 #pragma unroll
       for (int j = 0; j < NCAND; ++j) o[5 + j] = __int_as_float(ci[j]);
     }
-  } else if (warp < 12) {
-    // ===================== producers: code chunks -> split fp16 operand planes =====================
-    const int pt = tid - NEPI;                        // 0..255
-    constexpr int ITEMS = BN * (KC / 8) / NPROD;      // 16-byte chunks per half per thread per stage (4)
-    int stage = 0;
-    uint32_t phase = 0;
-    const int nsteps = (tile_hi - tile_lo) * nchunk;
-    float4 vn[ITEMS][2];
-    auto gload = [&](int step, float4 (*v)[2]) {
-      const int t = tile_lo + step / nchunk, c = step % nchunk;
-#pragma unroll
-      for (int i = 0; i < ITEMS; ++i) {
-        const int item = pt + i * NPROD, oct = item & 3, code = item >> 2;
-        const int gcode = min(t * BN + code, p.K - 1);             // clamped copies are masked by their +inf |e|^2
-        const float4* src = reinterpret_cast<const float4*>(p.E + (size_t)gcode * p.D + c * KC + oct * 8);
-        v[i][0] = __ldg(src);
-        v[i][1] = __ldg(src + 1);
+  } else if (warp == 4) {
+    // ===================== code-stage feeder (one thread): one bulk copy per stage =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int nsteps = (tile_hi - tile_lo) * nchunk;
+      const uint8_t* src = p.Epk + (size_t)tile_lo * nchunk * B_STAGE;
+      for (int step = 0; step < nsteps; ++step) {
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        mbar_expect_tx(full_bar(stage), B_STAGE);
+        bulk_g2s(smem_u32(b_smem) + (uint32_t)stage * B_STAGE, src + (size_t)step * B_STAGE, B_STAGE, full_bar(stage));
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-    };
-    if (nsteps > 0) gload(0, vn);
-    for (int step = 0; step < nsteps; ++step) {
-      float4 v[ITEMS][2];
-#pragma unroll
-      for (int i = 0; i < ITEMS; ++i) { v[i][0] = vn[i][0]; v[i][1] = vn[i][1]; }
-      if (step + 1 < nsteps) gload(step + 1, vn);
-      mbar_wait(empty_bar(stage), phase ^ 1);
-      uint8_t* bs = b_smem + (size_t)stage * B_STAGE;
-#pragma unroll
-      for (int i = 0; i < ITEMS; ++i) {
-        const int item = pt + i * NPROD, oct = item & 3, code = item >> 2;
-        uint4 h, l;
-        split2(v[i][0].x, v[i][0].y, s_e, &h.x, &l.x);
-        split2(v[i][0].z, v[i][0].w, s_e, &h.y, &l.y);
-        split2(v[i][1].x, v[i][1].y, s_e, &h.z, &l.z);
-        split2(v[i][1].z, v[i][1].w, s_e, &h.w, &l.w);
-        *reinterpret_cast<uint4*>(bs + oct * PITCH_B + code * 16) = h;
-        *reinterpret_cast<uint4*>(bs + B_HALF + oct * PITCH_B + code * 16) = l;
-      }
-      fence_proxy_async();
-      mbar_arrive(full_bar(stage));
-      if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
+    __syncwarp();
+  } else if (warp < 12) {
+    // warps 5-11 only helped staging A
   } else {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
@@ -347,6 +331,33 @@ size_t filter_smem_bytes(int D) {
 
 }  // namespace vqtc
 
+// Codes -> the packed, split stage images the filter streams (one pass over E per launch; the codebook changes once per
+// optimizer step).  Thread = (code, 8-dimension group); codes beyond K are zero rows (masked by their +inf |e|^2).
+__global__ void vq_pack_codes(const float* __restrict__ E, const float* __restrict__ e_amax, int K, int D, uint8_t* __restrict__ out) {
+  using namespace vqtc;
+  const int octs = D >> 3, nchunk = D / KC, ntile = (K + BN - 1) / BN;
+  const int64_t total = (int64_t)ntile * BN * octs;
+  float inv;
+  const float s_e = split_scale(e_amax, &inv);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int oc = (int)(i % octs);
+    const int64_t code = i / octs;
+    uint4 h = make_uint4(0u, 0u, 0u, 0u), l = h;
+    if (code < K) {
+      const float4* src = reinterpret_cast<const float4*>(E + (size_t)code * D + oc * 8);
+      const float4 v0 = __ldg(src), v1 = __ldg(src + 1);
+      split2(v0.x, v0.y, s_e, &h.x, &l.x);
+      split2(v0.z, v0.w, s_e, &h.y, &l.y);
+      split2(v1.x, v1.y, s_e, &h.z, &l.z);
+      split2(v1.z, v1.w, s_e, &h.w, &l.w);
+    }
+    const int t = (int)(code / BN), cl = (int)(code % BN), c = oc / (KC / 8), o = oc % (KC / 8);
+    uint8_t* dst = out + ((size_t)t * nchunk + c) * B_STAGE + (size_t)o * PITCH_B + (size_t)cl * 16;
+    *reinterpret_cast<uint4*>(dst) = h;
+    *reinterpret_cast<uint4*>(dst + B_HALF) = l;
+  }
+}
+
 // Host side: eligibility and launch (called from mas_vq_forward in vq.cu).
 bool vq_filter_tc_ok(int64_t R, int K, int D) {
   return D % 32 == 0 && D >= 32 && vqtc::filter_smem_bytes(D) <= 232448 && K >= 8 && R > 0;
@@ -360,10 +371,14 @@ int vq_filter_splits(int64_t R, int K) {
   if (s > 4) s = 4;
   return s;
 }
+size_t vq_filter_pack_bytes(int K, int D) { return (size_t)cdiv(K, vqtc::BN) * (D / vqtc::KC) * vqtc::B_STAGE; }
 int vq_filter_tc_launch(const float* z, const float* E, const float* ee, const float* z_amax, const float* e_amax, int64_t R, int K,
-                        int D, float* cand, int splits, cudaStream_t st) {
+                        int D, float* cand, int splits, void* pack_buf, cudaStream_t st) {
+  const int64_t pk_items = cdiv(K, vqtc::BN) * vqtc::BN * (D / 8);
+  vq_pack_codes<<<(int)(cdiv(pk_items, 256) < 1184 ? cdiv(pk_items, 256) : 1184), 256, 0, st>>>(E, e_amax, K, D, (uint8_t*)pack_buf);
+  if (int e = launched("vq_pack_codes")) return e;
   vqtc::Params p;
-  p.z = z; p.E = E; p.ee = ee; p.z_amax = z_amax; p.e_amax = e_amax; p.cand = cand;
+  p.z = z; p.Epk = (const uint8_t*)pack_buf; p.ee = ee; p.z_amax = z_amax; p.e_amax = e_amax; p.cand = cand;
   p.R = R; p.K = K; p.D = D;
   const int ntile = (int)cdiv(K, vqtc::BN);
   p.tiles_per_split = (int)cdiv(ntile, splits);

@@ -33,6 +33,8 @@ _SPEC = {
     "mas_tc_launch_count": (_L, []),
     "mas_ffma_probe": (_I, [_P, _I, _P, _P]),
     "mas_copy_strided": (_I, [_P, _T, _P, _T, _P]),
+    "mas_nchw_to_nhwc_pad": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "mas_scale_by": (_I, [_P, _P, _P, _L, _P]),
     "mas_gn_ws_bytes": (_Z, [_I, _I, _I, _I]),
     "mas_gn_stats": (_I, [_P, _I, _I, _I, _I, _F, _P, _P, _P, _Z, _P]),
     "mas_gn_apply": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
@@ -57,7 +59,7 @@ _SPEC = {
     "mas_conv3x3_wgrad_ws_bytes": (_Z, [_T, _T, _I]),
     "mas_conv3x3_wgrad": (_I, [_P, _T, _P, _T, _P, _P, _I, _I, _P, _I, _P, _Z, _P]),
     "mas_conv3x3_wgrad_tc_eligible": (_I, [_T, _T, _I]),
-    "mas_conv3x3_wgrad_tc16": (_I, [_P, _T, _P, _T, _P, _P, _I, _P, _I, _P, _P, _Z, _P]),
+    "mas_conv3x3_wgrad_tc16": (_I, [_P, _T, _P, _T, _P, _P, _I, _P, _I, _P, _I, _P, _Z, _P]),
     "mas_conv1x1_wgrad_ws_bytes": (_Z, [_L, _I, _I]),
     "mas_conv1x1_wgrad": (_I, [_P, _L, _P, _L, _L, _I, _I, _P, _P, _I, _P, _Z, _P]),
     "mas_edge_small_cin_fprop": (_I, [_P, _T, _P, _P, _P, _T, _I, _P]),
@@ -87,6 +89,8 @@ _SPEC = {
     "mas_vq_ws_bytes": (_Z, [_L, _I, _I]),
     "mas_vq_forward": (_I, [_P, _P, _L, _I, _I, _F, _P, _P, _P, _P, _Z, _P]),
     "mas_vq_forward_given": (_I, [_P, _P, _P, _L, _I, _I, _F, _P, _P, _P, _Z, _P]),
+    "mas_kmeans_ws_bytes": (_Z, [_I, _I]),
+    "mas_kmeans_update": (_I, [_P, _P, _L, _I, _I, _P, _P, _P, _P, _Z, _P]),
     "mas_vq_backward": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _F, _P, _P, _P]),
     "mas_vq_gather": (_I, [_P, _P, _L, _I, _I, _P, _P]),
     "mas_layernorm_forward": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _F, _P]),
@@ -102,6 +106,9 @@ _SPEC = {
     "mas_attn_decode": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "mas_cfg_mix": (_I, [_P, _P, _P, _L, _F, _P]),
     "mas_bce_ws_bytes": (_Z, [_T]),
+    "mas_bce_cl_ws_bytes": (_Z, [_I, _I, _I]),
+    "mas_bce_cl_forward": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _Z, _P]),
+    "mas_bce_cl_backward": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "mas_bce_logits": (_I, [_P, _T, _P, _T, _P, _P, _P, _T, _F, _P, _Z, _P]),
 }
 

@@ -259,11 +259,14 @@ def conv3x3_wgrad_raw(x, dy, cout, cin, mode, want_bias=True, table=None, silu=T
     db = torch.empty(cout, dtype=torch.float32, device=x.device) if want_bias else None
     nb = L.query("mas_conv3x3_wgrad_ws_bytes", L.t4(x), L.t4(dy), mode)
     ws = L.workspace(nb, x.device)
+    padded = cout != dy.shape[1]      # dw sized for round_up(channels of dy, 128): the explicit padded path of Conv3x3Fn
     if (_tc_on() and _cfg["operands"] == "f16" and wgrad_f16_on() and _is_dense_nhwc(x) and _is_dense_nhwc(dy)
-            and L.query("mas_conv3x3_wgrad_tc_eligible", L.t4(x), L.t4(dy), mode)):
+            and (padded or L.query("mas_conv3x3_wgrad_tc_eligible", L.t4(x), L.t4(dy), mode))):
         L.call("mas_conv3x3_wgrad_tc16", x, L.t4(x), dy, L.t4(dy), dw, db, mode, table, int(silu), dy_amax if dy_amax is not None else amax_of(dy),
-               ws, ws.numel())
+               cout, ws, ws.numel())
         return dw, db
+    if padded:
+        raise RuntimeError("padded weight gradient needs the fp16 tensor-core kernel")
     L.call("mas_conv3x3_wgrad", x, L.t4(x), dy, L.t4(dy), dw, db, mode, _cfg["impl"], table, int(silu), ws, ws.numel())
     return dw, db
 
@@ -291,8 +294,9 @@ def conv3x3_dgrad_raw(dy, weight, mode, dy_amax=None):
 
 
 def gemm(A, B, C, M, N, K, batch=1, lda=None, ldb=None, ldc=None, sa=0, sb=0, sc=0, ta=False, tb=False, alpha=1.0,
-         bias=None, residual=None):
-    """Pointers may be tensors or (tensor, element_offset) pairs."""
+         bias=None, residual=None, impl=None):
+    """Pointers may be tensors or (tensor, element_offset) pairs. impl: override of the global selection (L.IMPL_TC3 = the
+    fp32-accurate 3xTF32 tensor-core GEMM)."""
     def p(v):
         if isinstance(v, tuple):
             import ctypes
@@ -300,7 +304,7 @@ def gemm(A, B, C, M, N, K, batch=1, lda=None, ldb=None, ldc=None, sa=0, sb=0, sc
             return ctypes.c_void_p(t.data_ptr() + 4 * off)
         return v
     L.call("mas_gemm", p(A), p(B), p(C), M, N, K, batch, lda, ldb, ldc, sa, sb, sc, int(ta), int(tb), float(alpha), p(bias),
-           p(residual), _cfg["impl"])
+           p(residual), _cfg["impl"] if impl is None else impl)
 
 
 def gemm_w(A, lda, weight, C, ldc, M, transpose=False, alpha=1.0, bias=None, residual=None, stats_part=None):
@@ -437,6 +441,35 @@ class Conv3x3Fn(torch.autograd.Function):
             x = nhwc(x)
             y = (torch.empty((n, cout, h, w), dtype=torch.float32, device=x.device) if out_nchw else empty_nhwc(n, cout, h, w, x))
             L.call("mas_edge_small_cout_fprop", x, L.t4(x), weight.contiguous(), bias, y, L.t4(y))
+        elif (mode == L.CONV_S1 and f16_operands() and residual is None and cin % 16 != 0 and cin > 64 and cout % 128 == 0
+              and h % 16 == 0 and w % 8 == 0):
+            # channel count off the 16-wide K step of the tensor kernels (the 159-channel VQ-SEG input): zero-pad the input
+            # channels (one tiled transposing copy from the caller's NCHW maps) and the weight, run the tensor-core kernel
+            edge = 4
+            cp = _round_up(cin, 16)
+            x = pad_nhwc(x, cp)
+            wp = torch.zeros((cout, cp, 3, 3), dtype=torch.float32, device=x.device)
+            wp[:, :cin].copy_(weight.detach())
+            y = conv3x3_raw(x, wp, bias, None, L.CONV_S1)
+        elif (mode == L.CONV_S1 and f16_operands() and residual is None and cout % 128 != 0 and cout > 128 and cin % 16 == 0
+              and h % 16 == 0 and w % 8 == 0):
+            # output width off the 128-wide tile (the 159-channel VQ-SEG decoder head): the kernel runs round_up(cout, 128)
+            # channels from zero-padded weights and stores only the first round_up(cout, 4); the result is RETURNED AS A
+            # CHANNELS-LAST VIEW [N, cout, H, W] of that buffer (the weighted-BCE kernels take it as it is; `out_nchw` is
+            # not honoured here: a contiguous NCHW copy of a 1.3 GB logits tensor would cost more than the convolution)
+            edge = 5
+            x = nhwc(x)
+            cpo, ck = _round_up(cout, 4), _round_up(cout, 128)
+            wk = torch.zeros((ck, cin, 3, 3), dtype=torch.float32, device=x.device)
+            wk[:cout].copy_(weight.detach())
+            bk = torch.zeros(ck, dtype=torch.float32, device=x.device)
+            if bias is not None:
+                bk[:cout].copy_(bias.detach())
+            wt = torch.empty(9 * ck * cin, dtype=torch.float16, device=x.device)
+            L.call("mas_pack_conv3x3_tc16", wk, wt, None, ck, cin, 0)
+            full = torch.empty((n, h, w, cpo), dtype=torch.float32, device=x.device).permute(0, 3, 1, 2)
+            L.call("mas_conv3x3_fprop_tc16", x, L.t4(x), wt, bk, None, full, L.t4(full), L.CONV_S1, None, 0, None, amax_of(x))
+            y = full[:, :cout]
         elif (mode == L.CONV_S2 and _tc_on() and residual is None and not out_nchw and _is_dense_nhwc(x) and cin % 8 == 0
               and cout % 128 == 0 and h % 32 == 0 and w % 16 == 0):
             edge = 3  # stride-2 conv on the stride-1 tensor kernels through space-to-depth
@@ -479,6 +512,30 @@ class Conv3x3Fn(torch.autograd.Function):
                 db = torch.empty(cout, dtype=torch.float32, device=x.device)
                 ws = L.workspace(L.query("mas_edge_wgrad_ws_bytes", cin), x.device)
                 L.call("mas_edge_small_cout_wgrad", x, L.t4(x), dy, L.t4(dy), dw, db, ws, ws.numel())
+        elif ctx.edge == 4:
+            cp = x.shape[1]                                              # x is the zero-padded channels-last copy
+            dy = nhwc(dy)
+            am = amax_of(dy)
+            if want_w:
+                dwp, db = conv3x3_wgrad_raw(x, dy, cout, cp, L.CONV_S1, ctx.has_bias, dy_amax=am)
+                dw = dwp[:, :cin].contiguous()
+            if ctx.needs_input_grad[0]:
+                wp = torch.zeros((cout, cp, 3, 3), dtype=torch.float32, device=x.device)
+                wp[:, :cin].copy_(weight.detach())
+                dx = conv3x3_dgrad_raw(dy, wp, L.CONV_S1, am)[:, :cin]
+        elif ctx.edge == 5:
+            cpo, ck = _round_up(cout, 4), _round_up(cout, 128)
+            full = getattr(dy, "_mas_pad_base", None)                    # the loss kernel wrote the gradient padded already
+            if full is None or full.shape[1] != cpo or full.data_ptr() != dy.data_ptr() or not _is_dense_nhwc(full):
+                full = pad_nhwc(dy.contiguous() if not dy.is_contiguous() and _cl_pitch(dy) is None else dy, cpo)
+            am = amax_of(full)
+            if ctx.needs_input_grad[0]:
+                w160 = torch.zeros((cpo, cin, 3, 3), dtype=torch.float32, device=x.device)
+                w160[:cout].copy_(weight.detach())
+                dx = conv3x3_raw(full, w160, None, None, L.CONV_S1, transpose=True, x_amax=am)
+            if want_w:
+                dwk, dbk = conv3x3_wgrad_raw(x, full, ck, cin, L.CONV_S1, True, dy_amax=am)
+                dw, db = dwk[:cout].contiguous(), dbk[:cout].contiguous()
         elif ctx.edge == 3:
             if ctx.needs_input_grad[0]:
                 dx = conv3x3_dgrad_raw(nhwc(dy), weight, ctx.mode)       # zero-stuffed map on the tensor kernel
@@ -800,25 +857,81 @@ def vq_gather(E, idx):
     return out
 
 
+def _round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+def pad_nhwc(x, cp):
+    """x [N,C,H,W] -> logical [N,cp,H,W] in dense channels-last memory with channels >= C zero (cp >= C)."""
+    _need_cuda(x)
+    n, c, h, w = x.shape
+    base = torch.empty((n, h, w, cp), dtype=torch.float32, device=x.device)
+    if x.is_contiguous() and c * 33 * 4 <= 48 * 1024:
+        L.call("mas_nchw_to_nhwc_pad", x, base, n, c, cp, h, w)
+    else:
+        if cp > c:
+            base[..., c:].zero_()
+        view = base.permute(0, 3, 1, 2)[:, :c]
+        L.call("mas_copy_strided", x, L.t4(x), view, L.t4(view))
+    return base.permute(0, 3, 1, 2)
+
+
+def _cl_pitch(t):
+    """Channel pitch if t [N,C,H,W] is a channels-last view whose pixels are `pitch` floats apart (pitch >= C), else None."""
+    if t.dim() != 4 or t.stride(1) != 1:
+        return None
+    n, c, h, w = t.shape
+    pitch = t.stride(3)
+    if pitch < c or t.stride(2) != w * pitch or (n > 1 and t.stride(0) != h * w * pitch):
+        return None
+    return pitch
+
+
 class BCELogitsFn(torch.autograd.Function):
-    """binary_cross_entropy_with_logits(pos_weight) mean (losses/loss_seg.py:15-19); grad computed in the same pass."""
+    """binary_cross_entropy_with_logits(pos_weight) mean (losses/loss_seg.py:15-19). With the VQ-SEG step's own layouts
+    (channels-last logits - the padded view the decoder's last convolution returns - and an NCHW target) loss and
+    gradient are two tiled kernels and the gradient is produced directly in the padded channels-last buffer the convolution's
+    backward consumes; other layouts take the generic strided kernel. Nothing of the backward runs in torch."""
 
     @staticmethod
     def forward(ctx, logits, target, pos_weight):
         _need_cuda(logits)
-        grad = torch.empty_like(logits)
+        n, c, h, w = logits.shape
         loss = torch.empty((), dtype=torch.float32, device=logits.device)
+        cp = _cl_pitch(logits)
+        if cp is not None and target.is_contiguous() and w % 32 == 0 and c * 33 * 4 <= 48 * 1024:
+            ws = L.workspace(L.query("mas_bce_cl_ws_bytes", n, h, w), logits.device)
+            L.call("mas_bce_cl_forward", logits, target, pos_weight, n, c, cp, h, w, loss, ws, ws.numel())
+            ctx.save_for_backward(logits, target, pos_weight)
+            ctx.cp = cp
+            return loss
+        grad = torch.empty_like(logits)
         nb = L.query("mas_bce_ws_bytes", L.t4(logits))
         ws = L.workspace(nb, logits.device)
         L.call("mas_bce_logits", logits, L.t4(logits), target, L.t4(target), pos_weight, loss, grad, L.t4(grad),
                1.0 / logits.numel(), ws, ws.numel())
         ctx.save_for_backward(grad)
+        ctx.cp = None
         return loss
 
     @staticmethod
     def backward(ctx, g):
-        (grad,) = ctx.saved_tensors
-        return grad * g, None, None
+        g = g.contiguous()
+        if ctx.cp is None:
+            (grad,) = ctx.saved_tensors
+            out = torch.empty_like(grad)
+            src = grad if grad.is_contiguous() or grad.is_contiguous(memory_format=torch.channels_last) else grad.contiguous()
+            out = torch.empty_like(src)
+            L.call("mas_scale_by", src, g, out, src.numel())
+            return out, None, None
+        logits, target, pw = ctx.saved_tensors
+        n, c, h, w = logits.shape
+        base = torch.empty((n, h, w, ctx.cp), dtype=torch.float32, device=logits.device)
+        L.call("mas_bce_cl_backward", logits, target, pw, g, n, c, ctx.cp, h, w, base)
+        full = base.permute(0, 3, 1, 2)
+        grad = full[:, :c]
+        grad._mas_pad_base = full          # the padded tensor this view lives in (picked up by the convolution's backward)
+        return grad, None, None
 
 
 # ------------------------------------------------------------------------------------------------ tier 2: token transformer
@@ -901,6 +1014,15 @@ class LinearFn(torch.autograd.Function):
         return dx, dw.view(N, K), db
 
 
+def _attn_impl(S_, hd):
+    """Token-attention contractions (transformer.py:77-103): the 3xTF32 tensor-core GEMM (fp32-level accuracy, like the
+    reference's torch.matmul with TF32 off) when the extents fit its tiles (the 640-token / 64-wide heads of the paper's
+    configuration do), else the global selection."""
+    if _tc_on() and S_ % 64 == 0 and hd % 64 == 0:
+        return L.IMPL_TC3
+    return None
+
+
 class CausalAttentionFn(torch.autograd.Function):
     """softmax_causal((q / sqrt(hd)) k^T) v per (batch, head) from the fused qkv activation [B,S,3H]
     (transformer.py:77-103; head h owns columns h*hd..(h+1)*hd of each third)."""
@@ -913,17 +1035,18 @@ class CausalAttentionFn(torch.autograd.Function):
         H = H3 // 3
         hd = H // heads
         alpha = 1.0 / float(hd) ** 0.5
+        impl = _attn_impl(S_, hd)
         P = torch.empty((B, heads, S_, S_), dtype=torch.float32, device=qkv.device)
         ctxv = torch.empty((B, S_, H), dtype=torch.float32, device=qkv.device)
         for b in range(B):
             base = b * S_ * H3
             gemm((qkv, base), (qkv, base + H), (P, b * heads * S_ * S_), S_, S_, hd, batch=heads, lda=H3, ldb=H3, ldc=S_, sa=hd,
-                 sb=hd, sc=S_ * S_, tb=True, alpha=alpha)
+                 sb=hd, sc=S_ * S_, tb=True, alpha=alpha, impl=impl)
         L.call("mas_softmax_causal_forward", P, P, B * heads, S_, S_)
         for b in range(B):
             base = b * S_ * H3
             gemm((P, b * heads * S_ * S_), (qkv, base + 2 * H), (ctxv, b * S_ * H), S_, hd, S_, batch=heads, lda=S_, ldb=H3, ldc=H,
-                 sa=S_ * S_, sb=hd, sc=hd)
+                 sa=S_ * S_, sb=hd, sc=hd, impl=impl)
         ctx.save_for_backward(qkv, P)
         ctx.heads = heads
         return ctxv
@@ -937,21 +1060,23 @@ class CausalAttentionFn(torch.autograd.Function):
         H = H3 // 3
         hd = H // heads
         alpha = 1.0 / float(hd) ** 0.5
+        impl = _attn_impl(S_, hd)
         dqkv = torch.empty_like(qkv)
         dP = torch.empty_like(P)
         for b in range(B):
             base, pb, cb = b * S_ * H3, b * heads * S_ * S_, b * S_ * H
             # dV = P^T dO ; dP = dO V^T
             gemm((P, pb), (dctx, cb), (dqkv, base + 2 * H), S_, hd, S_, batch=heads, lda=S_, ldb=H, ldc=H3, sa=S_ * S_, sb=hd, sc=hd,
-                 ta=True)
+                 ta=True, impl=impl)
             gemm((dctx, cb), (qkv, base + 2 * H), (dP, pb), S_, S_, hd, batch=heads, lda=H, ldb=H3, ldc=S_, sa=hd, sb=hd,
-                 sc=S_ * S_, tb=True)
+                 sc=S_ * S_, tb=True, impl=impl)
         L.call("mas_softmax_backward", P, dP, dP, B * heads * S_, S_, alpha)     # dS (already times 1/sqrt(hd))
         for b in range(B):
             base, pb = b * S_ * H3, b * heads * S_ * S_
-            gemm((dP, pb), (qkv, base + H), (dqkv, base), S_, hd, S_, batch=heads, lda=S_, ldb=H3, ldc=H3, sa=S_ * S_, sb=hd, sc=hd)
+            gemm((dP, pb), (qkv, base + H), (dqkv, base), S_, hd, S_, batch=heads, lda=S_, ldb=H3, ldc=H3, sa=S_ * S_, sb=hd, sc=hd,
+                 impl=impl)
             gemm((dP, pb), (qkv, base), (dqkv, base + H), S_, hd, S_, batch=heads, lda=S_, ldb=H3, ldc=H3, sa=S_ * S_, sb=hd, sc=hd,
-                 ta=True)
+                 ta=True, impl=impl)
         return dqkv, None
 
 

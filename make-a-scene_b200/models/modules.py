@@ -272,12 +272,13 @@ class Codebook(nn.Module):
         if cent.shape[0] < self.codebook_size:
             cent = torch.cat([cent, self.embedding.weight.data[cent.shape[0]:]], 0)
         rows = res.contiguous().view(1, n, 1, self.codebook_dim).permute(0, 3, 1, 2)  # [1,D,n,1] channels-last view
+        resc = res.contiguous()
+        shift = torch.empty(1, dtype=torch.float32, device=res.device)
+        ws = L.workspace(L.query("mas_kmeans_ws_bytes", cent.shape[0], self.codebook_dim), res.device)
         for _ in range(iters):
-            _, _, idx = ops.VQFn.apply(rows, cent, 0.0)
-            sums = torch.zeros_like(cent).index_add_(0, idx, res)
-            cnt = torch.zeros(cent.shape[0], device=res.device).index_add_(0, idx, torch.ones(n, device=res.device))
-            new = torch.where(cnt[:, None] > 0, sums / cnt.clamp_min(1)[:, None], cent)
-            shift = (new - cent).norm()
+            _, _, idx = ops.VQFn.apply(rows, cent, 0.0)               # assignment: the VQ kernel
+            new = torch.empty_like(cent)                                # update: segmented mean + centre shift, one call
+            L.call("mas_kmeans_update", resc, idx, n, cent.shape[0], self.codebook_dim, cent, new, shift, ws, ws.numel())
             cent = new
             if float(shift) < 1e-4:
                 break

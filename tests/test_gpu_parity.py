@@ -571,6 +571,25 @@ def test_groupnorm_swish_vs_oracle(c, hw):
     assert rel_err(gn.weight.grad, sd["n.weight"].grad) < 1e-4 and rel_err(gn.bias.grad, sd["n.bias"].grad) < 1e-4
 
 
+@pytest.mark.parametrize("shape,cl", [((3, 32, 9, 7), False), ((2, 64, 8, 8), True), ((5, 7), False)])
+def test_standalone_swish_vs_torch(shape, cl):
+    """nonlinearity / Swish modules on their own (modules.py:35-37,194-196): mas_silu_forward / mas_silu_backward."""
+    from models import modules as M
+    dev = _dev()
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(*shape, generator=g) * 3
+    xo = x.clone().requires_grad_(True)
+    yo = xo * torch.sigmoid(xo)
+    (yo * _w(yo)).sum().backward()
+    xd = x.to(dev)
+    if cl:
+        xd = xd.contiguous(memory_format=torch.channels_last)
+    xd = xd.requires_grad_(True)
+    y = M.Swish()(xd) if len(shape) == 4 else M.nonlinearity(xd)
+    (y * _w(yo).to(dev)).sum().backward()
+    assert rel_err(y, yo) < 1e-6 and rel_err(xd.grad, xo.grad) < 1e-6
+
+
 @pytest.mark.parametrize("cin,cout,h,w,mode", [(3, 32, 9, 7, "s1"), (32, 3, 8, 8, "s1"), (64, 64, 16, 16, "s1"),
                                                (128, 128, 32, 32, "s1"), (128, 256, 8, 24, "s1"), (256, 128, 16, 16, "s1"),
                                                (512, 512, 16, 16, "s1"), (64, 64, 16, 16, "s2"), (128, 128, 32, 32, "s2"),
@@ -715,6 +734,102 @@ def test_seg_loss_vs_reference():
     assert rel_err(pred.grad, g["grad"]) < 1e-5
 
 
+@pytest.mark.parametrize("cin,cout,h,w", [(159, 128, 32, 32), (128, 159, 32, 64), (100, 256, 16, 16), (64, 200, 16, 24)])
+def test_conv3x3_padded_channel_counts_vs_oracle(cin, cout, h, w):
+    """Channel counts off the tensor tiles (VQ-SEG's 159-channel input / output layers): zero-padded to the 16-wide K step /
+    the 128-wide output tile inside Conv3x3Fn, run on the fp16 tcgen05 kernels; the 159-wide output comes back as a
+    channels-last view. Forward and all gradients against F.conv2d (fp32, CPU)."""
+    import torch.nn.functional as F
+    from mas_b200 import _lib as L, ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(cin + cout)
+    x = torch.randn(2, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, 3, 3, generator=g) / (3 * cin ** 0.5)
+    b = torch.randn(cout, generator=g)
+    xo, wo, bo = x.clone().requires_grad_(True), wt.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yo = F.conv2d(xo, wo, bo, padding=1)
+    (yo * _w(yo)).sum().backward()
+    xd = x.to(dev)
+    if cin % 16 == 0:
+        xd = xd.contiguous(memory_format=torch.channels_last)
+    xd, wd, bd = xd.requires_grad_(True), wt.to(dev).requires_grad_(True), b.to(dev).requires_grad_(True)
+    before = L.tc_launch_count()
+    y = ops.Conv3x3Fn.apply(xd, wd, bd, None, L.CONV_S1, False)
+    assert L.tc_launch_count() > before and y.shape == yo.shape
+    (y * _w(yo).to(dev)).sum().backward()
+    # forward and weight gradient on tensor cores (and the data gradient when its own output width fits the 128-wide tile)
+    assert L.tc_launch_count() >= before + (3 if cin % 128 == 0 else 2)
+    assert rel_err(y, yo) < TOL_FWD
+    assert rel_err(xd.grad, xo.grad) < TOL_GRAD
+    assert rel_err(wd.grad, wo.grad) < TOL_GRAD
+    assert rel_err(bd.grad, bo.grad) < 1e-4
+
+
+def test_seg_loss_fast_path_and_padded_gradient():
+    """Weighted BCE on the VQ-SEG step's layouts: channels-last logits with channel pitch 160 (the view the padded decoder
+    head returns) x NCHW target -> loss and gradient against torch's own binary_cross_entropy_with_logits on the CPU; the
+    gradient comes back as a view of a padded channels-last tensor (pad channel exactly zero), scaled by the upstream gradient."""
+    import torch.nn.functional as F
+    from mas_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(9)
+    n, c, h, w = 2, 159, 16, 64
+    lo = torch.randn(n, c, h, w, generator=g) * 2
+    tg = (torch.rand(n, c, h, w, generator=g) > 0.9).float()
+    pw = torch.ones(c)
+    pw[153:158] = 20
+    lr = lo.clone().requires_grad_(True)
+    ref = F.binary_cross_entropy_with_logits(lr.permute(0, 2, 3, 1), tg.permute(0, 2, 3, 1), pos_weight=pw)
+    (ref * 0.7).backward()
+    base = torch.zeros(n, h, w, 160, device=dev)
+    base[..., :c] = lo.permute(0, 2, 3, 1).to(dev)
+    logits = base.permute(0, 3, 1, 2)[:, :c].requires_grad_(True)
+    loss = ops.BCELogitsFn.apply(logits, tg.to(dev), pw.to(dev))
+    assert abs(float(loss) - float(ref)) < 1e-5 * abs(float(ref))
+    (loss * 0.7).backward()
+    assert rel_err(logits.grad, lr.grad) < 1e-5
+
+
+def test_vqseg_tensor_path_step_vs_oracle():
+    """Segmentation-shaped VQBASE whose 159-channel edge layers take the padded tensor-core paths (128-wide trunk, 64x64
+    one-hot-like maps): forward, weighted-BCE + codebook loss and every gradient against the CPU oracle."""
+    from mas_b200 import _lib as L, ops
+    from models import VQBASE
+    from oracle import vqgan_oracle as O
+    dev = _dev()
+    dd = dict(z_channels=64, in_channels=159, out_channels=159, channels=[128, 128], num_res_blocks=1, resolution=64,
+              attn_resolutions=[], dropout=0.0)
+    torch.manual_seed(0)
+    m = VQBASE(dd, 128, 64, 10, 100)
+    with torch.no_grad():
+        m.quantize.embedding.weight.normal_()
+    m.quantize.q_counter = 10 ** 6
+    m.train()
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    params = {k: v.requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k}
+    sd.update(params)
+    seg = (torch.rand(2, 159, 64, 64, generator=torch.Generator().manual_seed(5)) > 0.9).float()
+    dec_o, diff_o, idx_o = O.vqbase_forward(sd, dd, seg)
+    lo = O.bce_loss_with_quant(diff_o, seg, dec_o)
+    lo.backward()
+    m.to(dev)
+    pw = torch.ones(159, device=dev)
+    pw[153:158] = 20
+    segd = seg.to(dev)
+    before = L.tc_launch_count()
+    _forced_indices(m, idx_o)          # the quantiser's decision pinned to the oracle's (the VQ kernels have their own tests)
+    dec, diff = m(segd)
+    assert dec.shape == (2, 159, 64, 64) and ops._cl_pitch(dec) == 160
+    loss = ops.BCELogitsFn.apply(dec, segd, pw) + diff
+    loss.backward()
+    assert L.tc_launch_count() - before >= 20
+    assert rel_err(dec, dec_o) < 2e-3
+    assert abs(float(loss) - float(lo)) < 2e-3 * abs(float(lo))
+    named = dict(m.named_parameters())
+    for k, pr in params.items():
+        assert rel_err(named[k].grad, pr.grad) < 1e-2, k
+
+
 def test_native_library_is_the_path_that_ran():
     from mas_b200 import _lib
     assert _lib.launch_count() > 0
@@ -760,6 +875,27 @@ def test_vqseg_plumbing_three_adam_steps_vs_oracle():
         loss.backward()
         opt.step()
         assert abs(float(loss) - float(lo)) < 2e-3 * abs(float(lo)), (step, float(loss), float(lo))
+
+
+def test_kmeans_update_step_vs_torch():
+    """mas_kmeans_update (segmented mean, empty clusters keep their centre, centre shift) against index_add_ in torch."""
+    from mas_b200 import _lib as L
+    dev = _dev()
+    g = torch.Generator().manual_seed(5)
+    n, K, D = 5000, 96, 32
+    x = torch.randn(n, D, generator=g).to(dev)
+    idx = torch.randint(0, K - 6, (n,), generator=g).to(dev)          # the last six clusters stay empty
+    old = torch.randn(K, D, generator=g).to(dev)
+    new = torch.empty_like(old)
+    shift = torch.empty(1, device=dev)
+    ws = L.workspace(L.query("mas_kmeans_ws_bytes", K, D), dev)
+    L.call("mas_kmeans_update", x, idx, n, K, D, old, new, shift, ws, ws.numel())
+    sums = torch.zeros(K, D, device=dev, dtype=torch.float64).index_add_(0, idx, x.double())
+    cnt = torch.zeros(K, device=dev, dtype=torch.float64).index_add_(0, idx, torch.ones(n, device=dev, dtype=torch.float64))
+    ref = torch.where(cnt[:, None] > 0, sums / cnt.clamp_min(1)[:, None], old.double()).float()
+    assert torch.allclose(new, ref, rtol=1e-6, atol=1e-7)
+    assert torch.equal(new[K - 6:], old[K - 6:])
+    assert abs(float(shift) - float((ref - old).norm())) < 1e-4 * float((ref - old).norm())
 
 
 def test_kmeans_reinit_runs_and_reduces_quantisation_error():

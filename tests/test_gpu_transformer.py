@@ -152,3 +152,27 @@ def test_kv_append_and_attn_decode_vs_torch(heads, hd, length, tmax):
     ref = (p @ v.double()).reshape(R, H).float()
     ctx = ops.attn_decode(qkv_all[:, -1].contiguous().to(dev), kc, vc, length)
     assert rel_err(ctx, ref) < 1e-5
+
+
+def test_causal_attention_on_tensor_cores_matches_fp32_kernels():
+    """transformer.py:77-103 at the paper's extents (640 tokens, 16 heads of 64): QK^T / PV and their four gradients on the
+    3xTF32 tcgen05 GEMM against the exact-fp32 FFMA kernels (which the reference fixtures pin at small extents)."""
+    from mas_b200 import _lib as L, ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(3)
+    qkv = torch.randn(2, 640, 3 * 1024, generator=g).to(dev)
+    w = torch.randn(2, 640, 1024, generator=g).to(dev)
+    out = {}
+    for name, impl in (("tc", L.IMPL_AUTO), ("simt", L.IMPL_SIMT)):
+        ops.set_impl(impl)
+        try:
+            x = qkv.clone().requires_grad_(True)
+            before = L.tc_launch_count()
+            y = ops.CausalAttentionFn.apply(x, 16)
+            (y * w).sum().backward()
+            out[name] = (y.detach(), x.grad.detach(), L.tc_launch_count() - before)
+        finally:
+            ops.set_impl(L.IMPL_AUTO)
+    assert out["tc"][2] >= 12 and out["simt"][2] == 0
+    assert rel_err(out["tc"][0], out["simt"][0]) < 2e-5
+    assert rel_err(out["tc"][1], out["simt"][1]) < 2e-5
