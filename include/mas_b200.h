@@ -150,6 +150,9 @@ int mas_gemm_rows_packed(const float* A, int64_t lda, const float* w_tc, float* 
  * start offset are taken verbatim from raw_* and the B region holds its own word indices (address reveal). */
 int mas_tc_probe(const float* A, const float* B, float* D, int a_src, int b_layout, uint64_t raw_desc,
                  uint32_t raw_idesc, int raw_off, void* stream);
+/* fp16 address-reveal form: D[k][n] (k < 16, n < 32; D is [128][32]) = index of the half the tensor core reads for element
+ * (n, k) of a B operand described by the raw descriptor / instruction descriptor, from a region filled with 0..2047. */
+int mas_tc_probe16(float* D, uint64_t raw_desc, uint32_t raw_idesc, int raw_off, void* stream);
 /* Weight gradient, written in the reference's [Cout,Cin,3,3] layout; dbias [Cout] may be NULL.
  * x is the convolution's (already normalised+activated) input, dy the output gradient. */
 size_t mas_conv3x3_wgrad_ws_bytes(mas_tensor4 xs, mas_tensor4 dys, int mode);

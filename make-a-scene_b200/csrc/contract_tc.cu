@@ -964,14 +964,20 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc(const WParams p, const
   constexpr int NT = (TAPS == 9) ? WG_NT : 128, QUADS = NT / 4;
   constexpr int SLOTS = (TAPS == 9) ? WG_SLOTS : 64;
   constexpr int COPIES = (TAPS == 9) ? 3 : 1;
-  constexpr int LBO_B = COPIES * NT * 16;                  // bytes between 16-byte chunks (4 fp32 | 8 fp16 pixels)
-  constexpr int B_STAGE = (F16 ? 10 : ((TAPS == 9) ? 20 : 16)) * LBO_B; // 80 (10 halo rows x 8) or 64 pixels
+  constexpr int LBO_B = COPIES * NT * 16;                  // TF32: bytes between 16-byte chunks (4 pixels)
+  // fp16: kind::f16 DOES take MN-major shared-memory operands (tests/test_gpu_tc_probe.py::test_reveal_raw_f16: element (n, k)
+  // sits at (n%8)*2 + (k%8)*16 + (k/8)*LBO + (n/8)*SBO bytes), so the halo is staged UNTRANSPOSED, as planes
+  // [dx copy][ci/8][slot][8 channels]: a pixel's 8 channels are one 16-byte store per dx copy (copy dx holds the halo shifted
+  // left by dx pixels) instead of 24 two-byte stores; K groups are image rows (LBO = the 160-byte halo row), N groups are the
+  // 12 (dx, ci/8) planes (SBO = plane pitch), a vertical tap is a start-address advance of one halo row.
+  constexpr int P16 = SLOTS * 16 + 32;                     // plane pitch (32-byte skew: conflict-free 16-byte stores)
+  constexpr int B_STAGE = F16 ? 12 * P16 : ((TAPS == 9) ? 20 : 16) * LBO_B;
   constexpr int A_COLS = F16 ? 32 : 64;                    // TMEM columns of one staged dy tile (64 pixels)
   constexpr int ITEMS = SLOTS * QUADS, PER_THREAD = (ITEMS + NPROD - 1) / NPROD;
   constexpr uint32_t ACC_COLS = TAPS * NT;
   constexpr int NMMA = COPIES * NT;                        // N of one MMA (96 | 128)
   // instruction descriptor: D=f32, A=tf32 (TMEM, K-major), B=tf32 K-major, M=128, N=NMMA
-  constexpr uint32_t idesc = F16 ? make_idesc_f16(NMMA)
+  constexpr uint32_t idesc = F16 ? (make_idesc_f16(NMMA) | (1u << 16))   // bit 16: B operand MN-major
                                  : ((1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NMMA >> 3) << 17) | ((uint32_t)(BM >> 4) << 24));
 
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -1006,7 +1012,114 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc(const WParams p, const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 8) {
+  if (warp < 8 && F16) {
+    // ============ producers, fp16: x halo -> shared memory planes [dx][ci/8][slot][8 channels] (no transposition) ============
+    constexpr int OCTS = NT / 8, ITEMS16 = SLOTS * OCTS, PT16 = (ITEMS16 + NPROD - 1) / NPROD;   // 400 items, 2 per thread
+    int sl_r[PT16], sl_c[PT16], sl_o[PT16];
+#pragma unroll
+    for (int i = 0; i < PT16; ++i) {
+      const int item = tid + i * NPROD, slot = item / OCTS;
+      sl_o[i] = item % OCTS;
+      sl_r[i] = slot / 10;
+      sl_c[i] = item < ITEMS16 ? slot % 10 : -100;
+    }
+    int pux = (int)(u0 % p.units_x), puy = (int)((u0 / p.units_x) % p.units_y), pn = (int)(u0 / ((int64_t)p.units_x * p.units_y));
+    int cux = 0, cuy = 0, cn = 0;   // coordinates of the unit whose data sits in v (for the prologue's padding test)
+    auto gload16 = [&](float4 (*v)[2]) {
+      const int ux = pux, uy = puy, n = pn;
+      if (++pux == p.units_x) { pux = 0; if (++puy == p.units_y) { puy = 0; ++pn; } }
+#pragma unroll
+      for (int i = 0; i < PT16; ++i) {
+        v[i][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        v[i][1] = v[i][0];
+        if (sl_c[i] >= 0) {
+          const int vy = uy * 8 - 1 + sl_r[i], vx = ux * 8 - 1 + sl_c[i];
+          int iy = vy, ix = vx;
+          bool ok;
+          if (p.map == MAP_S1) {
+            ok = (unsigned)vy < (unsigned)p.Hin && (unsigned)vx < (unsigned)p.Win;
+          } else {  // MAP_UP
+            ok = (unsigned)vy < (unsigned)(2 * p.Hin) && (unsigned)vx < (unsigned)(2 * p.Win);
+            iy = vy >> 1; ix = vx >> 1;
+          }
+          if (ok) {
+            const float4* src = reinterpret_cast<const float4*>(p.x + ((int64_t)(n * p.Hin + iy) * p.Win + ix) * p.Cin + ci0 + sl_o[i] * 8);
+            v[i][0] = __ldg(src);
+            v[i][1] = __ldg(src + 1);
+          }
+        }
+      }
+    };
+    int stage = 0;
+    uint32_t phase = 0;
+    float4 vn[PT16][2];
+    if (u0 < u1) gload16(vn);
+    for (int64_t u = u0; u < u1; ++u) {
+      float4 v[PT16][2];
+#pragma unroll
+      for (int i = 0; i < PT16; ++i) { v[i][0] = vn[i][0]; v[i][1] = vn[i][1]; }
+      if (PRO) {
+        cux = (int)(u % p.units_x); cuy = (int)((u / p.units_x) % p.units_y); cn = (int)(u / ((int64_t)p.units_x * p.units_y));
+      }
+      if (u + 1 < u1) gload16(vn);
+      if (PRO && p.gn_table) {
+        // the convolution's input is act(GroupNorm(x)): recomputed here instead of stored; padding pixels stay exactly zero
+#pragma unroll
+        for (int i = 0; i < PT16; ++i) {
+          if (sl_c[i] >= 0) {
+            const int vy = cuy * 8 - 1 + sl_r[i], vx = cux * 8 - 1 + sl_c[i];
+            const bool ok = (p.map == MAP_S1) ? ((unsigned)vy < (unsigned)p.Hin && (unsigned)vx < (unsigned)p.Win)
+                                              : ((unsigned)vy < (unsigned)(2 * p.Hin) && (unsigned)vx < (unsigned)(2 * p.Win));
+            if (ok) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const float4* tp = reinterpret_cast<const float4*>(p.gn_table + ((size_t)cn * p.Cin + ci0 + sl_o[i] * 8 + h * 4) * 2);
+                const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1);
+                float a0 = fmaf(v[i][h].x, t0.x, t0.y), a1 = fmaf(v[i][h].y, t0.z, t0.w);
+                float a2 = fmaf(v[i][h].z, t1.x, t1.y), a3 = fmaf(v[i][h].w, t1.z, t1.w);
+                if (p.gn_silu) { a0 = silu_f(a0); a1 = silu_f(a1); a2 = silu_f(a2); a3 = silu_f(a3); }
+                v[i][h] = make_float4(a0, a1, a2, a3);
+              }
+            }
+          }
+        }
+      }
+      mbar_wait(empty(stage), phase ^ 1);
+      uint8_t* b_st = smem + (size_t)stage * B_STAGE;
+#pragma unroll
+      for (int i = 0; i < PT16; ++i) {
+        if (sl_c[i] >= 0) {
+          const uint4 h = make_uint4(pack_h2(v[i][0].x, v[i][0].y), pack_h2(v[i][0].z, v[i][0].w), pack_h2(v[i][1].x, v[i][1].y),
+                                     pack_h2(v[i][1].z, v[i][1].w));
+          const int slot = sl_r[i] * 10 + sl_c[i];
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx)
+            if (sl_c[i] >= dx) *reinterpret_cast<uint4*>(b_st + (dx * OCTS + sl_o[i]) * P16 + (slot - dx) * 16) = h;
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(fullB(stage));
+      if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+    }
+    // epilogue (warps 0-3): accumulator column t*NT + j of lane co is dW[tap t][co][ci0 + j]
+    if (warp < 4) {
+      float inv = 1.f;
+      operand_scale(p.dy_amax, &inv);
+      mbar_wait(accum_bar, 0);
+      tc_fence_after();
+      const int co = co0 + warp * 32 + lane;
+#pragma unroll 1
+      for (int t = 0; t < TAPS; ++t) {
+        float* o = p.part + (((size_t)split * TAPS + t) * p.Cout + co) * p.Cin + ci0;
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * NT), v);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(o + q * 4) = make_float4(v[4 * q] * inv, v[4 * q + 1] * inv, v[4 * q + 2] * inv, v[4 * q + 3] * inv);
+      }
+      tc_fence_before();
+    }
+  } else if (warp < 8) {
     // ============ producers: x halo / rows -> shared memory, transposed (K = pixel) ============
     int it_r[PER_THREAD], it_c[PER_THREAD], it_q[PER_THREAD];
 #pragma unroll
@@ -1232,11 +1345,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc(const WParams p, const
         const uint64_t b_base = make_desc(b_st, LBO_B, 128);
         const uint32_t acc0 = (u > u0) ? 1u : 0u;
         if (F16) {
+          const uint64_t b16 = make_desc(b_st, 160, P16);   // MN-major: LBO = K-group (halo row) pitch, SBO = N-group (plane) pitch
 #pragma unroll
-          for (int r = 0; r < 8; r += 2) {     // K = 16 pixels = image rows (r, r+1): halo chunks r+dy, r+dy+1
+          for (int r = 0; r < 8; r += 2) {     // K = 16 pixels = image rows (r, r+1) of the unit: halo rows r+dy, r+dy+1
 #pragma unroll
             for (int dyy = 0; dyy < 3; ++dyy) {
-              const uint64_t bd = b_base + (uint64_t)(((r + dyy) * LBO_B) >> 4);
+              const uint64_t bd = b16 + (uint64_t)(((r + dyy) * 160) >> 4);
               mma_f16_ts(tmem_base + (uint32_t)(dyy * NMMA), a_t + (uint32_t)(r * 4), bd, idesc, r > 0 ? 1u : acc0);
             }
           }
@@ -1324,6 +1438,43 @@ __global__ void __launch_bounds__(128, 1) mma_probe(const float* __restrict__ A,
     }
     if (a_src == 0) mma_tf32_ss(tb, make_desc(smem_u32(sa), 2048, 128), bd, idesc, 0);
     else mma_tf32_ts(tb, tb + 32, bd, idesc, 0);
+    mma_commit(smem_u32(&bar));
+  }
+  mbar_wait(smem_u32(&bar), 0);
+  tc_fence_after();
+  float v[32];
+  tmem_ld32(tb + ((uint32_t)(warp * 32) << 16), v);
+  for (int j = 0; j < 32; ++j) D[(warp * 32 + lane) * 32 + j] = v[j];
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 64);
+}
+
+// fp16 address-reveal probe: A (shared memory, K-major) selects k = m % 16 in row m; the B region (2048 halves) holds its own
+// half index; D[k][n] is therefore the index of the half the tensor core reads for element (n, k) of B under the raw shared-
+// memory descriptor / instruction descriptor supplied by the host (tests/test_gpu_tc_probe.py: MN-major conventions).
+__global__ void __launch_bounds__(128, 1) mma_probe16(float* __restrict__ D, unsigned long long raw_desc, unsigned raw_idesc, int raw_off) {
+  __shared__ __align__(1024) uint8_t sm[8192];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tslot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  __half* sa = reinterpret_cast<__half*>(sm);          // A: 128 x 16 halves, K-major [k/8][m][8]: LBO 2048, SBO 128
+  __half* sb = reinterpret_cast<__half*>(sm + 4096);   // B region: 2048 halves
+  if (tid == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(smem_u32(&tslot), 64);
+  for (int i = tid; i < 128 * 16; i += 128) {
+    const int m = i / 16, k = i % 16;
+    sa[(k / 8) * 1024 + m * 8 + (k % 8)] = __float2half((k == m % 16) ? 1.f : 0.f);
+  }
+  for (int i = tid; i < 2048; i += 128) sb[i] = __float2half((float)i);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tslot;
+  if (tid == 0) {
+    const uint64_t bd = (raw_desc & ~0x3FFFull) | (uint64_t)(((smem_u32(sb) + (uint32_t)raw_off) >> 4) & 0x3FFF);
+    mma_f16_ss(tb, make_desc(smem_u32(sa), 2048, 128), bd, raw_idesc, 0);
     mma_commit(smem_u32(&bar));
   }
   mbar_wait(smem_u32(&bar), 0);
@@ -1511,7 +1662,8 @@ static int wgrad_tc_run(tc::WParams& p, int splits, float* dw, float* dbias, voi
   p.bpart = dbias ? (float*)ws + (size_t)splits * TAPS * p.Cout * p.Cin : nullptr;
   p.units_per_split = cdiv(p.total_units, splits);
   constexpr int NT = (TAPS == 9) ? tc::WG_NT : 128;
-  constexpr size_t smem = (size_t)tc::WG_STAGES * ((TAPS == 9 ? 3 * (F16 ? 10 : 20) : 16) * NT * 16 + tc::WG_DY_STAGE) + (4 * tc::WG_STAGES + 1) * 8 + 16;
+  constexpr size_t bstage = F16 ? (size_t)12 * (tc::WG_SLOTS * 16 + 32) : (size_t)(TAPS == 9 ? 3 * 20 : 16) * NT * 16;
+  constexpr size_t smem = (size_t)tc::WG_STAGES * (bstage + tc::WG_DY_STAGE) + (4 * tc::WG_STAGES + 1) * 8 + 16;
   static std::atomic<uint64_t> configured{0};
   if (first_on_device(configured)) {
     if (int e = set_smem(tc::wgrad_tc<TAPS, PRO, F16>, smem)) return e;
@@ -1623,6 +1775,11 @@ int mas_tc_probe(const float* A, const float* B, float* D, int a_src, int b_layo
                  int raw_off, void* stream) {
   tc::mma_probe<<<1, 128, 0, S(stream)>>>(A, B, D, a_src, b_layout, (unsigned long long)raw_desc, raw_idesc, raw_off);
   return launched_tc("mma_probe");
+}
+
+int mas_tc_probe16(float* D, uint64_t raw_desc, uint32_t raw_idesc, int raw_off, void* stream) {
+  tc::mma_probe16<<<1, 128, 0, S(stream)>>>(D, (unsigned long long)raw_desc, raw_idesc, raw_off);
+  return launched_tc("mma_probe16");
 }
 
 int mas_conv3x3_tc_eligible(mas_tensor4 xs, mas_tensor4 ys, int mode) {

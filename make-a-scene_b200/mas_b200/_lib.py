@@ -45,6 +45,7 @@ _SPEC = {
     "mas_pack_conv3x3": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "mas_conv3x3_fprop": (_I, [_P, _T, _P, _P, _P, _P, _T, _I, _I, _P]),
     "mas_tc_probe": (_I, [_P, _P, _P, _I, _I, ctypes.c_uint64, ctypes.c_uint32, _I, _P]),
+    "mas_tc_probe16": (_I, [_P, ctypes.c_uint64, ctypes.c_uint32, _I, _P]),
     "mas_conv3x3_tc_eligible": (_I, [_T, _T, _I]),
     "mas_pack_conv3x3_tc": (_I, [_P, _P, _I, _I, _I, _P]),
     "mas_pack_conv3x3_tc_pair": (_I, [_P, _P, _P, _I, _I, _P]),

@@ -81,3 +81,38 @@ def test_reveal_raw(case):
     print(f"RAW {name}")
     for n in list(range(0, 9)) + [12, 16, 31]:
         print("  n=%2d:" % n, o[n].tolist())
+
+
+def _idesc16(n, b_mn, a_mn=0):
+    return (1 << 4) | ((1 << 15) if a_mn else 0) | ((1 << 16) if b_mn else 0) | ((n >> 3) << 17) | ((128 >> 4) << 24)
+
+
+RAW16 = [  # name, lbo, sbo, layout_type, b_mn, start_off
+    ("f16 K-major none (control)", 512, 128, 0, 0, 0),
+    ("f16 MN none lbo512 sbo128", 512, 128, 0, 1, 0),
+    ("f16 MN none lbo128 sbo512", 128, 512, 0, 1, 0),
+    ("f16 MN none lbo256 sbo128", 256, 128, 0, 1, 0),
+    ("f16 MN none lbo128 sbo256", 128, 256, 0, 1, 0),
+    ("f16 MN none lbo1024 sbo256", 1024, 256, 0, 1, 0),
+    ("f16 MN none lbo256 sbo1024", 256, 1024, 0, 1, 0),
+    ("f16 MN none start+16", 512, 128, 0, 1, 16),
+    ("f16 MN sw128 lbo1024 sbo1024", 1024, 1024, 2, 1, 0),
+]
+
+
+@pytest.mark.parametrize("case", RAW16, ids=[c[0] for c in RAW16])
+def test_reveal_raw_f16(case):
+    """kind::f16 shared-memory operand addressing under MN-major / K-major descriptors (prints the half index read for each
+    (n, k)); the K-major control must reproduce the layout the production kernels rely on: index = (k/8)*LBO/2 + n*8 + k%8."""
+    from mas_b200 import _lib as L
+    name, lbo, sbo, lt, b_mn, off = case
+    dev = torch.device("cuda:0")
+    D = torch.full((128, 32), float("nan"), device=dev)
+    L.call("mas_tc_probe16", D, _desc(lbo, sbo, lt), _idesc16(32, b_mn), off)
+    o = D[:16].t().cpu().long()           # [n][k]
+    print(f"RAW16 {name}")
+    for n in list(range(0, 10)) + [15, 16, 17, 31]:
+        print("  n=%2d:" % n, o[n].tolist())
+    if not b_mn:
+        want = torch.tensor([[(k // 8) * (lbo // 2) + n * 8 + (k % 8) for k in range(16)] for n in range(32)])
+        assert torch.equal(o, want)
