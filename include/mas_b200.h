@@ -83,9 +83,10 @@ int mas_gn_apply(const float* x, const float* mean, const float* rstd, const flo
                  void* stream);
 int mas_gn_backward(const float* dy, const float* x, const float* mean, const float* rstd,
                     const float* gamma, const float* beta, const float* dx_add, float* dx, float* dgamma,
-                    float* dbeta, float* act_out, float* dx_amax, int N, int HW, int C, int G, int silu, void* ws,
-                    size_t ws_bytes, void* stream);
-/* act_out (or NULL): also writes act(GN(x)), the operand of the following weight gradient; dx_amax (or NULL): device
+                    float* dbeta, void* act_out, int act_f16, float* dx_amax, int N, int HW, int C, int G, int silu,
+                    void* ws, size_t ws_bytes, void* stream);
+/* act_out (or NULL): also writes act(GN(x)), the operand of the following weight gradient - as fp32, or with act_f16 != 0
+ * as fp16 (what mas_conv3x3_wgrad_tc16(..., x_is_f16 = 1) stages without converting); dx_amax (or NULL): device
  * scalar receiving max|dx| (what mas_amax(dx) would return), for the fp16-operand kernels that consume dx. */
 /* out = a + b (gradient of x+h where the two branches cannot be fused). */
 int mas_add(const float* a, const float* b, float* out, int64_t n, void* stream);
@@ -166,9 +167,9 @@ int mas_conv3x3_wgrad(const float* x, mas_tensor4 xs, const float* dy, mas_tenso
  * cout_rows = rows of dw_oihw / dbias: dys.c normally; with dys.c % 128 != 0 (a multiple of 4) pass round_up(dys.c, 128) and
  * buffers of that many rows - the TMA copy of dy zero-fills the missing channels and the extra rows come out zero. */
 int mas_conv3x3_wgrad_tc_eligible(mas_tensor4 xs, mas_tensor4 dys, int mode);
-int mas_conv3x3_wgrad_tc16(const float* x, mas_tensor4 xs, const float* dy, mas_tensor4 dys, float* dw_oihw, float* dbias,
-                           int mode, const float* gn_table, int gn_silu, const float* dy_amax, int cout_rows, void* ws,
-                           size_t ws_bytes, void* stream);  /* gn_table: x is re-activated on the fly (tensor path only) */
+int mas_conv3x3_wgrad_tc16(const void* x, int x_is_f16, mas_tensor4 xs, const float* dy, mas_tensor4 dys, float* dw_oihw,
+                           float* dbias, int mode, const float* gn_table, int gn_silu, const float* dy_amax, int cout_rows,
+                           void* ws, size_t ws_bytes, void* stream);   /* x_is_f16: x holds fp16 (dense NHWC, no gn_table) */  /* gn_table: x is re-activated on the fly (tensor path only) */
 /* Weight gradient of a 1x1 convolution: dw[Cout,Cin] = dy^T x over M rows (split over rows, deterministic);
  * dbias [Cout] may be NULL. x [M,Cin] and dy [M,Cout] are row-major with row pitches ldx / ldy (elements). */
 size_t mas_conv1x1_wgrad_ws_bytes(int64_t M, int Cin, int Cout);

@@ -19,8 +19,8 @@ int gemm_tc_launch(const float* A, const float* B, float* C, int M, int N, int K
 size_t conv_wgrad_tc_ws(mas_tensor4 xs, mas_tensor4 dys, int mode);
 bool conv_wgrad_tc_eligible(mas_tensor4 xs, mas_tensor4 dys, int mode);
 int conv_wgrad_tc_launch(const float* x, mas_tensor4 xs, const float* dy, mas_tensor4 dys, float* dw, float* dbias, int mode,
-                         const float* gn_table, int gn_silu, int f16, const float* dy_amax, int cout_rows, void* ws, size_t ws_bytes,
-                         cudaStream_t st);
+                         const float* gn_table, int gn_silu, int f16, const float* dy_amax, int cout_rows, int x_f16, void* ws,
+                         size_t ws_bytes, cudaStream_t st);
 int gemm_tc3_launch(const float* A, const float* B, float* C, int M, int N, int K, int batch, int64_t lda, int64_t ldb, int64_t ldc,
                     int64_t sa, int64_t sb, int64_t sc, int ta, int tb, float alpha, const float* bias, const float* res,
                     cudaStream_t st);
@@ -57,7 +57,7 @@ int mas_conv3x3_wgrad(const float* x, mas_tensor4 xs, const float* dy, mas_tenso
   size_t main_bytes = align256(a > b ? a : b);
   int e = MAS_ERR_UNSUPPORTED;
   if (impl != MAS_IMPL_SIMT) {
-    e = conv_wgrad_tc_launch(x, xs, dy, dys, dw_oihw, dbias, mode, gn_table, gn_silu, 0, nullptr, (int)dys.c, ws, main_bytes, S(stream));
+    e = conv_wgrad_tc_launch(x, xs, dy, dys, dw_oihw, dbias, mode, gn_table, gn_silu, 0, nullptr, (int)dys.c, 0, ws, main_bytes, S(stream));
     if (e != MAS_OK && (e != MAS_ERR_UNSUPPORTED || impl == MAS_IMPL_TC)) return e;
     if (e == MAS_OK) return MAS_OK;  // the tensor path also produced dbias
   }
@@ -72,14 +72,14 @@ int mas_conv3x3_wgrad(const float* x, mas_tensor4 xs, const float* dy, mas_tenso
 
 int mas_conv3x3_wgrad_tc_eligible(mas_tensor4 xs, mas_tensor4 dys, int mode) { return conv_wgrad_tc_eligible(xs, dys, mode) ? 1 : 0; }
 
-int mas_conv3x3_wgrad_tc16(const float* x, mas_tensor4 xs, const float* dy, mas_tensor4 dys, float* dw_oihw, float* dbias, int mode,
-                           const float* gn_table, int gn_silu, const float* dy_amax, int cout_rows, void* ws, size_t ws_bytes,
-                           void* stream) {
+int mas_conv3x3_wgrad_tc16(const void* x, int x_is_f16, mas_tensor4 xs, const float* dy, mas_tensor4 dys, float* dw_oihw, float* dbias,
+                           int mode, const float* gn_table, int gn_silu, const float* dy_amax, int cout_rows, void* ws,
+                           size_t ws_bytes, void* stream) {
   MAS_REQUIRE(x && dy && dw_oihw, "conv3x3_wgrad_tc16: null pointer");
   if (ws_bytes < mas_conv3x3_wgrad_ws_bytes(xs, dys, mode)) return fail(MAS_ERR_WORKSPACE, "conv3x3_wgrad_tc16: workspace too small");
   size_t a = conv_wgrad_simt_ws(xs, dys, 3), b = conv_wgrad_tc_ws(xs, dys, mode);
-  return conv_wgrad_tc_launch(x, xs, dy, dys, dw_oihw, dbias, mode, gn_table, gn_silu, 1, dy_amax, cout_rows, ws, align256(a > b ? a : b),
-                              S(stream));
+  return conv_wgrad_tc_launch((const float*)x, xs, dy, dys, dw_oihw, dbias, mode, gn_table, gn_silu, 1, dy_amax, cout_rows, x_is_f16, ws,
+                              align256(a > b ? a : b), S(stream));
 }
 
 static mas_tensor4 rows_t4(int64_t M, int C, int64_t ld) {

@@ -909,6 +909,7 @@ struct WParams {
   int gn_silu;
   const float* dy_amax;   // fp16-operand kernel: max|dy| (device scalar) for the power-of-two scale of the A operand, or null
   int Cout_real;          // channels present in dy (Cout = round_up to 128: the TMA copy zero-fills the rest)
+  int x_f16;              // fp16-operand kernel: x already holds fp16 (mas_gn_backward's act_out): staged without conversion
 };
 
 __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -1043,9 +1044,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc(const WParams p, const
             iy = vy >> 1; ix = vx >> 1;
           }
           if (ok) {
-            const float4* src = reinterpret_cast<const float4*>(p.x + ((int64_t)(n * p.Hin + iy) * p.Win + ix) * p.Cin + ci0 + sl_o[i] * 8);
-            v[i][0] = __ldg(src);
-            v[i][1] = __ldg(src + 1);
+            const int64_t e = ((int64_t)(n * p.Hin + iy) * p.Win + ix) * p.Cin + ci0 + sl_o[i] * 8;
+            if (p.x_f16) {   // eight halves = the 16-byte operand chunk itself (carried in v[i][0])
+              v[i][0] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const __half*>(p.x) + e));
+            } else {
+              const float4* src = reinterpret_cast<const float4*>(p.x + e);
+              v[i][0] = __ldg(src);
+              v[i][1] = __ldg(src + 1);
+            }
           }
         }
       }
@@ -1089,8 +1095,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc(const WParams p, const
 #pragma unroll
       for (int i = 0; i < PT16; ++i) {
         if (sl_c[i] >= 0) {
-          const uint4 h = make_uint4(pack_h2(v[i][0].x, v[i][0].y), pack_h2(v[i][0].z, v[i][0].w), pack_h2(v[i][1].x, v[i][1].y),
-                                     pack_h2(v[i][1].z, v[i][1].w));
+          const uint4 h = p.x_f16 ? make_uint4(__float_as_uint(v[i][0].x), __float_as_uint(v[i][0].y), __float_as_uint(v[i][0].z),
+                                               __float_as_uint(v[i][0].w))
+                                  : make_uint4(pack_h2(v[i][0].x, v[i][0].y), pack_h2(v[i][0].z, v[i][0].w), pack_h2(v[i][1].x, v[i][1].y),
+                                               pack_h2(v[i][1].z, v[i][1].w));
           const int slot = sl_r[i] * 10 + sl_c[i];
 #pragma unroll
           for (int dx = 0; dx < 3; ++dx)
@@ -1680,8 +1688,9 @@ static int wgrad_tc_run(tc::WParams& p, int splits, float* dw, float* dbias, voi
 // dbias (may be null) is produced here too when the tensor path runs.
 bool conv_wgrad_tc_eligible(mas_tensor4 xs, mas_tensor4 dys, int mode) { return wgrad_tc_ok(xs, dys, mode); }
 int conv_wgrad_tc_launch(const float* x, mas_tensor4 xs, const float* dy, mas_tensor4 dys, float* dw, float* dbias, int mode,
-                         const float* gn_table, int gn_silu, int f16, const float* dy_amax, int cout_rows, void* ws, size_t ws_bytes,
-                         cudaStream_t st) {
+                         const float* gn_table, int gn_silu, int f16, const float* dy_amax, int cout_rows, int x_f16, void* ws,
+                         size_t ws_bytes, cudaStream_t st) {
+  if (x_f16 && (!f16 || gn_table)) return fail(MAS_ERR_INVALID_ARG, "tc wgrad: an fp16 x needs the fp16-operand kernel and no prologue");
   // cout_rows: rows of dw / dbias the caller allocated; padding (dys.c % 128 != 0) only when it equals round_up(dys.c, 128)
   const bool pad_ok = cout_rows == (int)(cdiv(dys.c, tc::BM) * tc::BM);
   if (!wgrad_tc_ok(xs, dys, mode, pad_ok) || !al16p(x) || !al16p(dy)) return fail(MAS_ERR_UNSUPPORTED, "tc wgrad: shape/layout not eligible");
@@ -1695,7 +1704,7 @@ int conv_wgrad_tc_launch(const float* x, mas_tensor4 xs, const float* dy, mas_te
   p.units_x = (int)(dys.w / 8); p.units_y = (int)(dys.h / 8);
   p.total_units = (int64_t)p.N * p.units_x * p.units_y;
   p.rows = 0; p.ldx = p.Cin; p.ldy = p.Cout_real;
-  p.gn_table = gn_table; p.gn_silu = gn_silu; p.dy_amax = f16 ? dy_amax : nullptr;
+  p.gn_table = gn_table; p.gn_silu = gn_silu; p.dy_amax = f16 ? dy_amax : nullptr; p.x_f16 = x_f16;
   const int splits = wgrad_tc_splits((p.Cout / tc::BM) * (xs.c / tc::WG_NT), p.total_units);
   if (f16) return gn_table ? wgrad_tc_run<9, true, true>(p, splits, dw, dbias, ws, st) : wgrad_tc_run<9, false, true>(p, splits, dw, dbias, ws, st);
   return gn_table ? wgrad_tc_run<9, true, false>(p, splits, dw, dbias, ws, st) : wgrad_tc_run<9, false, false>(p, splits, dw, dbias, ws, st);
@@ -1718,7 +1727,7 @@ int conv1x1_wgrad_tc_launch(const float* x, int64_t ldx, const float* dy, int64_
   p.units_x = 1; p.units_y = 1;
   p.total_units = cdiv(M, 64);
   p.rows = M; p.ldx = ldx; p.ldy = ldy;
-  p.gn_table = nullptr; p.gn_silu = 0; p.dy_amax = nullptr;
+  p.gn_table = nullptr; p.gn_silu = 0; p.dy_amax = nullptr; p.x_f16 = 0;
   const int splits = wgrad_tc_splits((int64_t)(Cout / tc::BM) * (Cin / 128), p.total_units);
   return wgrad_tc_run<1, false, false>(p, splits, dw, dbias, ws, st);
 }

@@ -38,7 +38,7 @@ _SPEC = {
     "mas_gn_ws_bytes": (_Z, [_I, _I, _I, _I]),
     "mas_gn_stats": (_I, [_P, _I, _I, _I, _I, _F, _P, _P, _P, _Z, _P]),
     "mas_gn_apply": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
-    "mas_gn_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _Z, _P]),
+    "mas_gn_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _Z, _P]),
     "mas_add": (_I, [_P, _P, _P, _L, _P]),
     "mas_silu_forward": (_I, [_P, _P, _L, _P]),
     "mas_silu_backward": (_I, [_P, _P, _P, _L, _P]),
@@ -60,7 +60,7 @@ _SPEC = {
     "mas_conv3x3_wgrad_ws_bytes": (_Z, [_T, _T, _I]),
     "mas_conv3x3_wgrad": (_I, [_P, _T, _P, _T, _P, _P, _I, _I, _P, _I, _P, _Z, _P]),
     "mas_conv3x3_wgrad_tc_eligible": (_I, [_T, _T, _I]),
-    "mas_conv3x3_wgrad_tc16": (_I, [_P, _T, _P, _T, _P, _P, _I, _P, _I, _P, _I, _P, _Z, _P]),
+    "mas_conv3x3_wgrad_tc16": (_I, [_P, _I, _T, _P, _T, _P, _P, _I, _P, _I, _P, _I, _P, _Z, _P]),
     "mas_conv1x1_wgrad_ws_bytes": (_Z, [_L, _I, _I]),
     "mas_conv1x1_wgrad": (_I, [_P, _L, _P, _L, _L, _I, _I, _P, _P, _I, _P, _Z, _P]),
     "mas_edge_small_cin_fprop": (_I, [_P, _T, _P, _P, _P, _T, _I, _P]),

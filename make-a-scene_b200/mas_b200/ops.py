@@ -91,7 +91,7 @@ def gn_apply(x, mean, rstd, gamma, beta, silu, rtf32=False):
     return y
 
 
-def gn_backward(dy, x, mean, rstd, gamma, beta, silu, dx_add=None, want_act=False):
+def gn_backward(dy, x, mean, rstd, gamma, beta, silu, dx_add=None, want_act=False, act_f16=False):
     """want_act: also return act(GN(x)) (re-materialised as a by-product of the first backward pass). With fp16 operands
     selected, max|dx| is produced by the same pass and attached to dx (attach_amax) for the tensor-core kernels that
     consume it."""
@@ -99,12 +99,13 @@ def gn_backward(dy, x, mean, rstd, gamma, beta, silu, dx_add=None, want_act=Fals
     dx = torch.empty_like(x)
     dg = torch.empty_like(gamma)
     db = torch.empty_like(beta)
-    act = torch.empty_like(x) if want_act else None
+    # act_f16: the re-materialised activation only feeds the fp16-operand weight gradient -> written as fp16 (half the bytes)
+    act = torch.empty_like(x, dtype=torch.float16 if act_f16 else torch.float32) if want_act else None
     am = torch.empty(1, dtype=torch.float32, device=x.device) if f16_operands() else None
     nb = L.query("mas_gn_ws_bytes", n, h * w, c, GN_GROUPS)
     ws = L.workspace(nb, x.device)
-    L.call("mas_gn_backward", dy, x, mean, rstd, gamma, beta, dx_add, dx, dg, db, act, am, n, h * w, c, GN_GROUPS, int(silu), ws,
-           ws.numel())
+    L.call("mas_gn_backward", dy, x, mean, rstd, gamma, beta, dx_add, dx, dg, db, act, int(act_f16 and want_act), am, n, h * w, c,
+           GN_GROUPS, int(silu), ws, ws.numel())
     attach_amax(dx, am)
     if want_act:
         return dx, dg, db, act
@@ -262,13 +263,24 @@ def conv3x3_wgrad_raw(x, dy, cout, cin, mode, want_bias=True, table=None, silu=T
     padded = cout != dy.shape[1]      # dw sized for round_up(channels of dy, 128): the explicit padded path of Conv3x3Fn
     if (_tc_on() and _cfg["operands"] == "f16" and wgrad_f16_on() and _is_dense_nhwc(x) and _is_dense_nhwc(dy)
             and (padded or L.query("mas_conv3x3_wgrad_tc_eligible", L.t4(x), L.t4(dy), mode))):
-        L.call("mas_conv3x3_wgrad_tc16", x, L.t4(x), dy, L.t4(dy), dw, db, mode, table, int(silu), dy_amax if dy_amax is not None else amax_of(dy),
-               cout, ws, ws.numel())
+        L.call("mas_conv3x3_wgrad_tc16", x, int(x.dtype == torch.float16), L.t4(x), dy, L.t4(dy), dw, db, mode, table, int(silu),
+               dy_amax if dy_amax is not None else amax_of(dy), cout, ws, ws.numel())
         return dw, db
+    if x.dtype == torch.float16:
+        raise RuntimeError("an fp16 activation can only feed the fp16-operand tensor-core weight gradient")
     if padded:
         raise RuntimeError("padded weight gradient needs the fp16 tensor-core kernel")
     L.call("mas_conv3x3_wgrad", x, L.t4(x), dy, L.t4(dy), dw, db, mode, _cfg["impl"], table, int(silu), ws, ws.numel())
     return dw, db
+
+
+def wgrad_f16_eligible(x, dout, c1w):
+    """Both convolutions of a ResnetBlock (Cin -> Cout on x's extent, Cout -> Cout) take the fp16 tensor-core weight gradient."""
+    if not (f16_operands() and wgrad_f16_on() and _is_dense_nhwc(x) and _is_dense_nhwc(dout)):
+        return False
+    n, cin, h, w = x.shape
+    cout = c1w.shape[0]
+    return cin % 32 == 0 and cout % 128 == 0 and h % 8 == 0 and w % 8 == 0
 
 
 def wgrad_f16_on():
@@ -633,8 +645,10 @@ class ResnetBlockFn(torch.autograd.Function):
         d_a2 = conv3x3_dgrad_raw(dout, c2w, L.CONV_S1, am_out)
         # fused forward never stored act(GN(.)): the GroupNorm backward re-materialises it as a by-product of its first pass
         # (cheaper than re-activating inside the weight-gradient kernel's producers: measured +0.8 ms per full-res call)
+        # the activation re-materialised for the weight gradient goes straight into an fp16 operand: write it as fp16
+        a16 = ctx.fused and wgrad_f16_eligible(x, dout, c1w)
         if ctx.fused:
-            d_h1, dn2w, dn2b, a2 = gn_backward(d_a2, h1, m2, r2, n2w, n2b, True, want_act=True)
+            d_h1, dn2w, dn2b, a2 = gn_backward(d_a2, h1, m2, r2, n2w, n2b, True, want_act=True, act_f16=a16)
         else:
             d_h1, dn2w, dn2b = gn_backward(d_a2, h1, m2, r2, n2w, n2b, True)
         del d_a2
@@ -643,14 +657,14 @@ class ResnetBlockFn(torch.autograd.Function):
         am_h1 = amax_of(d_h1) if f16_operands() else None
         d_a1 = conv3x3_dgrad_raw(d_h1, c1w, L.CONV_S1, am_h1)
         if ctx.has_sc:
-            r_ = gn_backward(d_a1, x, m1, r1, n1w, n1b, True, want_act=ctx.fused)
+            r_ = gn_backward(d_a1, x, m1, r1, n1w, n1b, True, want_act=ctx.fused, act_f16=a16)
             dxm, dn1w, dn1b = r_[0], r_[1], r_[2]
             if ctx.fused:
                 a1 = r_[3]
             dx = conv1x1_dgrad_raw(dout, sw, residual=dxm)   # dout.Wn + dx_main
             dsw, dsb = conv1x1_wgrad_raw(x, dout, n * h * w, cin, cout)
         else:
-            r_ = gn_backward(d_a1, x, m1, r1, n1w, n1b, True, dx_add=dout, want_act=ctx.fused)
+            r_ = gn_backward(d_a1, x, m1, r1, n1w, n1b, True, dx_add=dout, want_act=ctx.fused, act_f16=a16)
             dx, dn1w, dn1b = r_[0], r_[1], r_[2]
             if ctx.fused:
                 a1 = r_[3]
