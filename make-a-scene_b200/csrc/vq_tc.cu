@@ -15,12 +15,14 @@
 //   z.e ~= (zh.eh + zl.eh + zh.el) / (s_z s_e),   dropped term zl.el ~ 2^-22 relative,
 // accumulated in fp32 in tensor memory.
 //
-// Structure (one CTA = 128 latent rows x a contiguous range of 256-code tiles):
-//   * A (the 128 x D latent tile, both halves) is converted once and stays in shared memory for the whole sweep;
+// Structure (one CTA = 128 latent rows x a contiguous range of 128-code tiles):
+//   * A (the 128 x D latent tile, both halves) is converted once and stays in TENSOR MEMORY for the whole sweep (lane = row,
+//     two fp16 per column: 2 x D/2 columns), which leaves shared memory to a 12-stage ring of code stages - the first version
+//     kept A in shared memory, had room for 2 stages and was bound by the latency of the bulk copies (ncu: 14 % tensor pipe);
 //   * B (codes): split ONCE per launch by vq_pack_codes into the exact shared-memory image of a pipeline stage
 //     ([tile][32-dim chunk][hi|lo][k/8][code][8 halves], K-major no-swizzle UMMA layout), so one thread feeds the ring with
-//     a single cp.async.bulk (33 KB, mbarrier complete_tx) per stage; 2-stage full/empty mbarrier ring;
-//   * one thread issues the MMAs (M 128, N 256, K 16; 3 per K step) into one of TWO 256-column accumulators;
+//     a single cp.async.bulk (16.6 KB, mbarrier complete_tx) per stage;
+//   * one thread issues the MMAs (A from tensor memory, M 128, N 128, K 16; 3 per K step) into one of TWO 128-column accumulators;
 //   * 4 epilogue warps (thread = latent row) drain the other accumulator meanwhile: tcgen05.ld, d~ = |e|^2 - 2 dot, sorted
 //     insertion into the row's five smallest values (four of them with their code index).
 #include <cuda_fp16.h>
@@ -30,14 +32,14 @@
 namespace mas {
 namespace vqtc {
 
-constexpr int BM = 128, BN = 256, KC = 32, STAGES = 2;
-constexpr int NPROD = 256, NEPI = 128, NTHREADS = NEPI + NPROD + 32;   // warps 0-3 epilogue, 4-11 producers, 12 MMA
-constexpr int PITCH_A = BM * 16 + 32;   // bytes between 8-dimension planes of A (32 B pad: conflict-free 16-byte stores)
+constexpr int BM = 128, BN = 128, KC = 32, STAGES = 12;
+constexpr int NEPI = 128, NTHREADS = NEPI + 64;   // warps 0-3: A staging then epilogue; warp 4: code-stage feeder; warp 5: MMA issuer
 constexpr int PITCH_B = BN * 16 + 32;   // bytes between 8-dimension planes of a B stage half
 constexpr int B_HALF = (KC / 8) * PITCH_B;
-constexpr int B_STAGE = 2 * B_HALF;     // hi planes then lo planes
+constexpr int B_STAGE = 2 * B_HALF;     // hi planes then lo planes (16.6 KB)
 constexpr int NCAND = 4;                // candidates kept with their index (+ one more value)
 constexpr int REC = 12;                 // floats per (row, split) record: b[5], i[4] (as int bits), pad
+constexpr int A_COLS = 256;             // tensor-memory columns of the latent tile: D/2 for each half (D <= 256)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -85,6 +87,25 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t adesc, uint
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
+      "%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+      "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -145,9 +166,7 @@ struct Params {
 
 __global__ void __launch_bounds__(NTHREADS, 1) vq_filter_tc(const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int planes = p.D >> 3;                       // 8-dimension planes of A
-  const int a_half = planes * PITCH_A;               // bytes of one half (hi or lo) of A
-  uint8_t* b_smem = smem + 2 * (size_t)a_half;
+  uint8_t* b_smem = smem;
   float* ee_s = reinterpret_cast<float*>(b_smem + (size_t)STAGES * B_STAGE);     // [2][BN]
   uint64_t* bars = reinterpret_cast<uint64_t*>(ee_s + 2 * BN);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
@@ -162,6 +181,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_filter_tc(const Params p) {
   const int ntile_all = (p.K + BN - 1) / BN;
   const int tile_lo = blockIdx.y * p.tiles_per_split, tile_hi = min(ntile_all, tile_lo + p.tiles_per_split);
   const int nchunk = p.D / KC;
+  const int half_cols = p.D >> 1;                    // tensor-memory columns of one half of A (two fp16 per column)
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -174,36 +194,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_filter_tc(const Params p) {
     }
     fence_barrier_init();
   }
-  if (warp == 12) tmem_alloc(smem_u32(tmem_slot), 512);
-
-  float inv_z, inv_e;
-  const float s_z = split_scale(p.z_amax, &inv_z), s_e = split_scale(p.e_amax, &inv_e);
-
-  // ---- A: the latent tile, split and staged once (all warps but the MMA warp) ----
-  if (warp < 12) {
-    const int items = BM * planes;                   // 16-byte chunks per half
-    for (int it = tid; it < items; it += NEPI + NPROD) {
-      const int pl = it % planes, r = it / planes;   // consecutive threads: consecutive 32-byte pieces of one row
-      float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-      if (row0 + r < p.R) {
-        const float4* src = reinterpret_cast<const float4*>(p.z + (size_t)(row0 + r) * p.D + pl * 8);
-        v0 = __ldg(src);
-        v1 = __ldg(src + 1);
-      }
-      uint4 h, l;
-      split2(v0.x, v0.y, s_z, &h.x, &l.x);
-      split2(v0.z, v0.w, s_z, &h.y, &l.y);
-      split2(v1.x, v1.y, s_z, &h.z, &l.z);
-      split2(v1.z, v1.w, s_z, &h.w, &l.w);
-      *reinterpret_cast<uint4*>(smem + (size_t)pl * PITCH_A + r * 16) = h;
-      *reinterpret_cast<uint4*>(smem + (size_t)a_half + (size_t)pl * PITCH_A + r * 16) = l;
-    }
-    fence_proxy_async();
-  }
+  if (warp == 5) tmem_alloc(smem_u32(tmem_slot), 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+
+  float inv_z, inv_e;
+  const float s_z = split_scale(p.z_amax, &inv_z);
+  split_scale(p.e_amax, &inv_e);
+
+  // ---- A: thread = latent row (TMEM lane); 64 dimensions at a time -> 32 packed hi words + 32 packed lo words ----
+  if (warp < 4) {
+    const int64_t row = row0 + warp * 32 + lane;
+    const float4* src = reinterpret_cast<const float4*>(p.z + (size_t)(row < p.R ? row : 0) * p.D);
+    for (int d0 = 0; d0 < p.D; d0 += 64) {
+      uint32_t hi[32], lo[32];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < p.R) v = __ldg(src + (d0 >> 2) + q);
+        split2(v.x, v.y, s_z, &hi[2 * q], &lo[2 * q]);
+        split2(v.z, v.w, s_z, &hi[2 * q + 1], &lo[2 * q + 1]);
+      }
+      const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(d0 >> 1);
+      tmem_st32(ta, hi);
+      tmem_st32(ta + (uint32_t)half_cols, lo);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   if (warp < 4) {
     // ===================== epilogue: running five smallest approximate distances per row =====================
@@ -217,12 +239,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_filter_tc(const Params p) {
     int buf = 0;
     uint32_t ph[2] = {0u, 0u};
     for (int t = tile_lo; t < tile_hi; ++t) {
-      // |e|^2 of this tile -> shared (each epilogue thread brings two values)
       float* es = ee_s + buf * BN;
-#pragma unroll
-      for (int j = 0; j < BN / NEPI; ++j) {
-        const int code = t * BN + tid + j * NEPI;
-        es[tid + j * NEPI] = code < p.K ? __ldg(p.ee + code) : INFINITY;
+      {
+        const int code = t * BN + tid;
+        es[tid] = code < p.K ? __ldg(p.ee + code) : INFINITY;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       mbar_wait(accf_bar(buf), ph[buf]);
@@ -231,7 +251,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_filter_tc(const Params p) {
 #pragma unroll 1
       for (int cb = 0; cb < BN / 32; ++cb) {
         float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * BN + cb * 32), v);
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(A_COLS + buf * BN + cb * 32), v);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float d = fmaf(v[j], m2, es[cb * 32 + j]);     // INFINITY for codes beyond K: never inserted
@@ -276,37 +296,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_filter_tc(const Params p) {
       for (int step = 0; step < nsteps; ++step) {
         mbar_wait(empty_bar(stage), phase ^ 1);
         mbar_expect_tx(full_bar(stage), B_STAGE);
-        bulk_g2s(smem_u32(b_smem) + (uint32_t)stage * B_STAGE, src + (size_t)step * B_STAGE, B_STAGE, full_bar(stage));
+        bulk_g2s(smem_base + (uint32_t)stage * B_STAGE, src + (size_t)step * B_STAGE, B_STAGE, full_bar(stage));
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
     __syncwarp();
-  } else if (warp < 12) {
-    // warps 5-11 only helped staging A
   } else {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
       int stage = 0, buf = 0;
       uint32_t phase = 0, eph[2] = {0u, 0u};
-      const uint32_t a_hi = smem_base, a_lo = smem_base + (uint32_t)a_half;
       for (int t = tile_lo; t < tile_hi; ++t) {
         mbar_wait(acce_bar(buf), eph[buf] ^ 1);       // the epilogue has drained this accumulator (first use: passes)
         eph[buf] ^= 1u;
         tc_fence_after();
-        const uint32_t acc = tmem_base + (uint32_t)(buf * BN);
+        const uint32_t acc = tmem_base + (uint32_t)(A_COLS + buf * BN);
         for (int c = 0; c < nchunk; ++c) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t bst = smem_base + 2u * (uint32_t)a_half + (uint32_t)stage * B_STAGE;
+          const uint32_t bst = smem_base + (uint32_t)stage * B_STAGE;
 #pragma unroll
           for (int k16 = 0; k16 < KC / 16; ++k16) {
-            const uint32_t aoff = (uint32_t)((c * (KC / 8) + k16 * 2) * PITCH_A);
-            const uint64_t ah = make_desc(a_hi + aoff, PITCH_A, 128), al = make_desc(a_lo + aoff, PITCH_A, 128);
+            const uint32_t acol = (uint32_t)((c * KC + k16 * 16) >> 1);          // 16 dimensions = 8 columns
             const uint64_t bh = make_desc(bst + (uint32_t)(k16 * 2 * PITCH_B), PITCH_B, 128);
             const uint64_t bl = make_desc(bst + (uint32_t)(B_HALF + k16 * 2 * PITCH_B), PITCH_B, 128);
-            mma_f16_ss(acc, ah, bh, IDESC, (c > 0 || k16 > 0) ? 1u : 0u);
-            mma_f16_ss(acc, al, bh, IDESC, 1u);
-            mma_f16_ss(acc, ah, bl, IDESC, 1u);
+            mma_f16_ts(acc, tmem_base + acol, bh, IDESC, (c > 0 || k16 > 0) ? 1u : 0u);                    // zh . eh
+            mma_f16_ts(acc, tmem_base + (uint32_t)half_cols + acol, bh, IDESC, 1u);                     // zl . eh
+            mma_f16_ts(acc, tmem_base + acol, bl, IDESC, 1u);                                          // zh . el
           }
           mma_commit(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -319,14 +335,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_filter_tc(const Params p) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 12) {
+  if (warp == 5) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
 }
 
 size_t filter_smem_bytes(int D) {
-  return 2 * (size_t)(D / 8) * PITCH_A + (size_t)STAGES * B_STAGE + 2 * BN * sizeof(float) + (2 * STAGES + 4) * 8 + 16;
+  (void)D;
+  return (size_t)STAGES * B_STAGE + 2 * BN * sizeof(float) + (2 * STAGES + 4) * 8 + 16;
 }
 
 }  // namespace vqtc
@@ -360,7 +377,7 @@ __global__ void vq_pack_codes(const float* __restrict__ E, const float* __restri
 
 // Host side: eligibility and launch (called from mas_vq_forward in vq.cu).
 bool vq_filter_tc_ok(int64_t R, int K, int D) {
-  return D % 32 == 0 && D >= 32 && vqtc::filter_smem_bytes(D) <= 232448 && K >= 8 && R > 0;
+  return D % 64 == 0 && D >= 64 && D <= 2 * vqtc::A_COLS && K >= 8 && R > 0;   // latent tile: two fp16 halves in 256 TMEM columns
 }
 int vq_filter_splits(int64_t R, int K) {
   const int64_t row_blocks = cdiv(R, vqtc::BM);

@@ -2,7 +2,7 @@
 set -u
 cd "$(dirname "$0")/.."
 O=gpurun_out; mkdir -p $O
-timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | grep -v Warning | tail -12
+timeout 300 python -m pytest tests -m gpu -q -x 2>&1 | grep -v Warning | tail -12
 timeout 400 python bench.py --no-cpu-baseline --steps 4 --warmup 3 --profile > $O/q_bench.json 2> $O/q_prof.log
 python - <<PY
 import json
