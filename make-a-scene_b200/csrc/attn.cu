@@ -11,6 +11,11 @@
 
 using namespace mas;
 
+namespace mas {
+bool attn_core_fused_ok(int HW, int C);
+int attn_core_fused_launch(const float* qkv, const float* amax, float* P, float* O, int N, int HW, int C, float scale, cudaStream_t st);
+}
+
 namespace {
 __global__ void cat3_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c, float* __restrict__ out,
                             int64_t n, const float* __restrict__ ba, const float* __restrict__ bb, const float* __restrict__ bc,
@@ -95,6 +100,13 @@ int mas_attnblock_forward(const float* x, int N, int HW, int C, int G, const flo
     for (int i = 0; i < 3; ++i)
       if (int e = mas_gemm(hn, ws_[i], qkv + i * c, (int)M, C, C, 1, c, c, 3 * c, 0, 0, 0, 0, 1, 1.f, bs_[i], nullptr, impl, stream)) return e;
   }
+  // fused core (attn_fused.cu): S = scale q k^T in tensor memory -> softmax in registers -> P (TMEM A operand) -> O = P v
+  static const bool fused_off = [] { const char* e = getenv("MAS_ATTN_FUSED"); return e && e[0] == '0'; }();
+  if (!fused_off && impl != MAS_IMPL_SIMT && attn_core_fused_ok(HW, C)) {
+    float* amax = wpk;   // scratch: the packed QKV weight is dead once the QKV GEMM is enqueued (stream order), proj re-packs later
+    if (int e = mas_amax(qkv, M * 3 * c, amax, stream)) return e;
+    if (int e = attn_core_fused_launch(qkv, amax, P, O, N, HW, C, scale, S(stream))) return e;
+  } else {
   // S[i,j] = scale * sum_c q[i,c] k[j,c]   (w_ = bmm(q^T, k) * c^-0.5)
   if (int e = mas_gemm(qkv, qkv + c, P, HW, HW, C, N, 3 * c, 3 * c, HW, (int64_t)HW * 3 * c, (int64_t)HW * 3 * c, (int64_t)HW * HW, 0, 1,
                        scale, nullptr, nullptr, bmm_impl(impl, HW, C), stream))
@@ -104,6 +116,7 @@ int mas_attnblock_forward(const float* x, int N, int HW, int C, int G, const flo
   if (int e = mas_gemm(P, qkv + 2 * c, O, HW, C, HW, N, HW, 3 * c, c, (int64_t)HW * HW, (int64_t)HW * 3 * c, (int64_t)HW * c, 0, 0, 1.f,
                        nullptr, nullptr, bmm_impl(impl, HW, C), stream))
     return e;
+  }
   if (tc) {
     if (int e = mas_pack_gemm_tc(proj_w, wpk, C, C, 0, stream)) return e;
     return mas_gemm_rows_packed(O, c, wpk, out, c, M, C, C, 1.f, proj_b, x, stats_part, stream);

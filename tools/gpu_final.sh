@@ -4,18 +4,15 @@ set -u
 cd "$(dirname "$0")/.."
 O=gpurun_out; mkdir -p $O
 TAG=${1:-final}
-timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -6
+timeout 400 python -m pytest tests -m gpu -q 2>&1 | tail -6
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
 timeout 600 python bench.py --steps 6 --warmup 3 --profile > $O/${TAG}_bench.json 2> $O/${TAG}_prof.log
-tail -1 $O/${TAG}_bench.json > profiles/r02_bench_n1.json
 timeout 600 python bench.py --workload vqseg --steps 4 --warmup 3 > $O/${TAG}_seg.json 2> $O/${TAG}_seg.err
-tail -1 $O/${TAG}_seg.json > profiles/r02_bench_vqseg_n1.json
-cp $O/${TAG}_prof.log profiles/r02_step_profile_batch32.log
 python - <<PY
 import json
-d=json.loads(open("profiles/r02_bench_n1.json").read())
+d=json.loads(open("$O/${TAG}_bench.json").read().strip().splitlines()[-1])
 print({k:d[k] for k in ("value","ms_per_step","gpu_launches")}, "e2e",d["e2e"]["value"], "roofline",d["roofline"]["ms_per_launch"], d["roofline"]["frac"], d["clocks"], d.get("cpu_baseline"))
 v=d["vq"]; print({k:v[k] for k in v if k not in ("sweep","kernel","bound","all_pairs_ffma_kernel")}); print(d["attn"])
-s=json.loads(open("profiles/r02_bench_vqseg_n1.json").read()); print("vqseg", s["value"], s["ms_per_step"], s["e2e"])
+s=json.loads(open("$O/${TAG}_seg.json").read().strip().splitlines()[-1]); print("vqseg", s["value"], s["ms_per_step"], s["e2e"])
 PY
 timeout 300 ncu --set full --clock-control none -k regex:"vq_filter_tc|vq_resolve|vq_pack_codes" -c 3 -o $O/r02_vq2 python tools/prof_kernels.py vq > $O/r02_vq2.log 2>&1; tail -1 $O/r02_vq2.log
