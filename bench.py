@@ -224,8 +224,8 @@ def dominant_kernel_roofline(dev, pk):
 
 def attn_metric(dev, pk):
     """AttnBlock (modules.py:139-191) at the model's shape: batch 32, C = 512, 16x16 tokens; forward and backward of the
-    whole block (GroupNorm, q/k/v and proj_out 1x1 GEMMs on TF32 tcgen05, QK^T / PV and their four gradients on the
-    3xTF32 tcgen05 GEMM, softmax, residual, next-norm statistics). Algorithmic FLOPs per image forward: 0.671 GFLOP
+    whole block (GroupNorm, q/k/v and proj_out 1x1 GEMMs on TF32 tcgen05, the fused QK^T -> softmax -> PV core, the four
+    gradients of the two contractions on the 3xTF32 tcgen05 GEMM, residual, next-norm statistics). Algorithmic FLOPs per image forward: 0.671 GFLOP
     (SURVEY.md 8d), backward = 2x; the 3xTF32 passes are not counted."""
     from models import modules as M
     torch.manual_seed(0)
@@ -242,7 +242,8 @@ def attn_metric(dev, pk):
     return {"shape": "batch 32, 256 tokens, C=512", "fwd_ms": round(fwd * 1e3, 4), "fwd_bwd_ms": round(tot * 1e3, 4),
             "fwd_tflop_per_s": round(gf / fwd / 1e3, 1), "fwd_bwd_tflop_per_s": round(3 * gf / tot / 1e3, 1),
             "frac_of_tf32_peak_fwd": round(gf / fwd / 1e3 / (pk["bf16"] / 2), 3), "bound": "tensor (nominal); launch / latency bound at this size",
-            "kernels": "gn_apply, shift_gemm_tc<1> (QKV, proj), gemm3_tc (QK^T, PV: 3xTF32), softmax"}
+            "kernels": "gn_apply, shift_gemm_tc<1> (QKV, proj; TF32), attn_core_fwd (fused QK^T -> softmax -> PV, 2 x fp16 split); "
+                       "backward: gemm3_tc (3xTF32) x4, softmax_bwd, wgrad_tc<1>, shift_gemm_tc<1>"}
 
 
 def ffma_peak(dev):

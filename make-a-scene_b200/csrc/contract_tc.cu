@@ -1,4 +1,5 @@
-// tcgen05 (5th-gen tensor core) contraction kernels for sm_100a: TF32 operands, fp32 accumulation in TMEM.
+// tcgen05 (5th-gen tensor core) contraction kernels for sm_100a: fp16 operands (3x3 family; same 11-bit significand as TF32,
+// power-of-two operand scales derived on the device) or TF32 operands (1x1 row GEMM, A/B switch), fp32 accumulation in TMEM.
 //
 //   conv3x3 family / row GEMM as a "shift-GEMM":
 //     D[m, n] = sum_{tap} sum_{k} A[slot(m) + shift(tap), k] * B_tap[n, k]
@@ -7,15 +8,17 @@
 //     group stride (SBO) is the pitch of one staged image row.  The 3x3 taps are then NINE MMAs over the SAME
 //     staged halo (18 x 10 pixels): only the descriptor start address moves by (ty*10+tx)*16 B.  The input is
 //     staged once per K chunk instead of nine times (no im2col, in memory or in shared memory).
-//   * A operand: staged by 256 producer threads (generic loads -> st.shared, K-major "interleaved" no-swizzle
-//     layout [k/4][slot][4 floats]) so that upsample (x2 nearest), zero-stuffing (stride-2 data gradient) and,
-//     later, the GroupNorm+SiLU prologue are just a different slot->pixel map / register transform.
+//   * A operand: staged by 256 producer threads (generic loads -> convert -> st.shared, K-major "interleaved" no-swizzle
+//     layout [k/8][slot][8 halves] | [k/4][slot][4 floats]) so that upsample (x2 nearest), zero-stuffing (stride-2 data
+//     gradient) and the GroupNorm+SiLU prologue are just a different slot->pixel map / register transform.
 //   * B operand (weights): pre-packed in global memory in the exact shared-memory image and pulled in with ONE
 //     cp.async.bulk (TMA bulk copy, mbarrier complete_tx) per stage.
-//   * four M tiles (512 pixels) share every weight stage: 4 x 128 fp32 accumulator columns = all 512 TMEM
-//     columns; weight traffic from L2 drops 4x.
-//   * warp roles: warps 0-7 producers then epilogue (tcgen05.ld -> bias/residual -> global), warp 8 = single-thread
-//     MMA issuer (+TMEM alloc/dealloc), warp 9 = bulk-copy issuer.  smem full/empty mbarrier ring, 3 stages.
+//   * two co-resident CTAs per SM, two M tiles (256 pixels, 256 TMEM columns) and a 2-stage ring each: one CTA's epilogue /
+//     pipeline fill overlaps the other's main loop.  warps 0-7 producers then epilogue (tcgen05.ld -> smem transpose ->
+//     bias / residual / GroupNorm statistics -> global), warp 8 = single-thread MMA issuer (+TMEM alloc/dealloc), warp 9 =
+//     bulk-copy issuer; full/empty mbarrier ring.  shift_gemm_p16 is the persistent one-CTA-per-SM variant (opt-in).
+//   * wgrad_tc: the weight gradient (K = pixels): dy through TMA -> tensor memory (TS mode), the activation halo as an
+//     MN-major fp16 operand (untransposed) or a transposed TF32 one.
 //
 // Reference call sites replaced: nn.Conv2d 3x3 (modules.py:93-104), Upsample/Downsample data paths
 // (modules.py:55-59,74-78), nn.Conv2d 1x1 (modules.py:113-117,145-164).

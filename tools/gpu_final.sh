@@ -15,4 +15,5 @@ print({k:d[k] for k in ("value","ms_per_step","gpu_launches")}, "e2e",d["e2e"]["
 v=d["vq"]; print({k:v[k] for k in v if k not in ("sweep","kernel","bound","all_pairs_ffma_kernel")}); print(d["attn"])
 s=json.loads(open("$O/${TAG}_seg.json").read().strip().splitlines()[-1]); print("vqseg", s["value"], s["ms_per_step"], s["e2e"])
 PY
-timeout 300 ncu --set full --clock-control none -k regex:"vq_filter_tc|vq_resolve|vq_pack_codes" -c 3 -o $O/r02_vq2 python tools/prof_kernels.py vq > $O/r02_vq2.log 2>&1; tail -1 $O/r02_vq2.log
+timeout 300 ncu --set full --clock-control none -k regex:"vq_filter_tc|vq_resolve|vq_pack_codes" -c 3 -f -o $O/r02_vq3 python tools/prof_kernels.py vq > $O/r02_vq3.log 2>&1; tail -1 $O/r02_vq3.log
+timeout 300 ncu --set full --clock-control none -k regex:"attn_core_fwd" -c 1 -f -o $O/r02_attnf python tools/prof_kernels.py attn > $O/r02_attnf.log 2>&1; tail -1 $O/r02_attnf.log
