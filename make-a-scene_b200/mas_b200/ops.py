@@ -444,7 +444,9 @@ class Conv3x3Fn(torch.autograd.Function):
         cout, cin = weight.shape[0], weight.shape[1]
         n, _, h, w = x.shape
         edge = 0
-        if mode == L.CONV_S1 and residual is None and cin == 3 and cout > 4:
+        tc_pad_in = (mode == L.CONV_S1 and f16_operands() and residual is None and cout % 128 == 0 and h % 16 == 0 and w % 8 == 0
+                     and (cin % 16 != 0) and (cin > 64 or cin <= 4))
+        if mode == L.CONV_S1 and residual is None and cin == 3 and cout > 4 and not tc_pad_in:
             edge = 1
             y = empty_nhwc(n, cout, h, w, x)
             L.call("mas_edge_small_cin_fprop", x, L.t4(x), weight.contiguous(), bias, y, L.t4(y), 0)
@@ -453,12 +455,12 @@ class Conv3x3Fn(torch.autograd.Function):
             x = nhwc(x)
             y = (torch.empty((n, cout, h, w), dtype=torch.float32, device=x.device) if out_nchw else empty_nhwc(n, cout, h, w, x))
             L.call("mas_edge_small_cout_fprop", x, L.t4(x), weight.contiguous(), bias, y, L.t4(y))
-        elif (mode == L.CONV_S1 and f16_operands() and residual is None and cin % 16 != 0 and cin > 64 and cout % 128 == 0
-              and h % 16 == 0 and w % 8 == 0):
-            # channel count off the 16-wide K step of the tensor kernels (the 159-channel VQ-SEG input): zero-pad the input
-            # channels (one tiled transposing copy from the caller's NCHW maps) and the weight, run the tensor-core kernel
+        elif tc_pad_in:
+            # channel count off the 16-wide K step of the tensor kernels (the 159-channel VQ-SEG maps; the 3-channel image of
+            # conv_in, where 10x padded FLOPs on the tensor cores still beat the FFMA edge kernel 4x): zero-pad the input channels
+            # (one tiled transposing copy from the caller's NCHW tensor) and the weight, run the tensor-core kernels
             edge = 4
-            cp = _round_up(cin, 16)
+            cp = _round_up(cin, 32)          # 32: the weight-gradient kernel's input-channel tile
             x = pad_nhwc(x, cp)
             wp = torch.zeros((cout, cp, 3, 3), dtype=torch.float32, device=x.device)
             wp[:, :cin].copy_(weight.detach())
