@@ -73,7 +73,7 @@ int mas_scale_by(const float* x, const float* g, float* y, int64_t n, void* stre
 /* ---- GroupNorm(32, C, eps=1e-6) + optional SiLU — Normalize / nonlinearity, modules.py:35-41 ------
  * x, y: [N, HW, C] NHWC.  mean/rstd: [N*G].  silu=1 fuses x*sigmoid(x) (modules.py:122,126,194-196).
  * round_tf32=1 rounds y to TF32 (round-to-nearest) so that a following tensor-core contraction sees
- * correctly rounded operands.  Backward: dx = GN/SiLU input gradient (+ dx_add elementwise when not NULL, which
+ * correctly rounded operands; round_tf32=2: y receives fp16 values (N*HW*C halves: the shadow mas_conv3x3_fprop_tc16h reads).  Backward: dx = GN/SiLU input gradient (+ dx_add elementwise when not NULL, which
  * folds the residual-branch gradient of ResnetBlock/AttnBlock, modules.py:136,191); dgamma/dbeta are overwritten. */
 size_t mas_gn_ws_bytes(int N, int HW, int C, int G);
 int mas_gn_stats(const float* x, int N, int HW, int C, int G, float eps, float* mean, float* rstd,
@@ -132,6 +132,18 @@ int mas_pack_conv3x3_tc16(const float* w_oihw, void* w_tc16, void* w_tc16_dgrad,
 int mas_conv3x3_fprop_tc16(const float* x, mas_tensor4 xs, const void* w_tc16, const float* bias,
                            const float* residual, float* y, mas_tensor4 ys, int mode, const float* gn_table,
                            int gn_silu, float* stats_part, const float* x_amax, void* stream);
+/* TMA-fed form of the fp16-operand 3x3 stride-1 convolution (csrc/conv_tma.cu; nn.Conv2d 3x3, modules.py:93-104, forward and
+ * data gradient): the A operand is read by the copy engine from an fp16 channels-last "shadow" x_f16 [N][H][W][Cin] of the
+ * (already activated) input - written by mas_gn_apply(round_tf32 = 2), mas_gn_backward(dx_f16) or mas_to_half - so no thread
+ * of the kernel touches the operands.  x_amax: the device scalar the shadow's power-of-two scale was derived from (NULL for an
+ * unscaled shadow).  Eligible: dense NHWC, Cin % 64 == 0, H % 16 == 0, W % 8 == 0, Cout % 4 == 0 (weights / bias packed for
+ * round_up(Cout, 128) rows).  Same packed weights (mas_pack_conv3x3_tc16), residual and GroupNorm-statistics epilogues as
+ * mas_conv3x3_fprop_tc16.  mas_to_half: y = fp16(x * s), s = the power-of-two operand scale of *amax (NULL: 1). */
+int mas_conv3x3_tc16h_eligible(mas_tensor4 xs, mas_tensor4 ys);
+int mas_conv3x3_fprop_tc16h(const void* x_f16, mas_tensor4 xs, const void* w_tc16, const float* bias,
+                            const float* residual, float* y, mas_tensor4 ys, float* stats_part,
+                            const float* x_amax, void* stream);
+int mas_to_half(const float* x, void* y_f16, int64_t n, const float* amax, void* stream);
 /* Both packings of one weight (transpose = 0 and 1 of mas_pack_conv3x3_tc) in a single pass; Cout % 128 == Cin % 128 == 0. */
 int mas_pack_conv3x3_tc_pair(const float* w_oihw, float* w_tc_fwd, float* w_tc_dgrad, int Cout, int Cin, void* stream);
 int mas_gn_finalize_partials(const float* part, int tiles_per_image, int N, int C, int G, int64_t hw, float eps,

@@ -141,6 +141,27 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const float* __res
     return o;
   };
   int p = p0 + pl;
+  if (rtf32 == 2) {
+    // fp16 output: the channels-last "shadow" the TMA-fed convolution kernel reads (conv_tma.cu); 8 bytes per channel quad
+    uint2* hp = reinterpret_cast<uint2*>(reinterpret_cast<__half*>(y) + (size_t)n * HW * C) + u;
+    rtf32 = 0;
+    auto h4 = [&](const float4& v) {
+      uint2 h;
+      const float a0 = f(v.x, 0), a1 = f(v.y, 1), a2 = f(v.z, 2), a3 = f(v.w, 3);
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h.x) : "f"(a1), "f"(a0));
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h.y) : "f"(a3), "f"(a2));
+      return h;
+    };
+    for (; p + 3 * lanes < p1; p += 4 * lanes) {
+      float4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = __ldg(xp + (size_t)(p + k * lanes) * U);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) hp[(size_t)(p + k * lanes) * U] = h4(v[k]);
+    }
+    for (; p < p1; p += lanes) hp[(size_t)p * U] = h4(__ldg(xp + (size_t)p * U));
+    return;
+  }
   for (; p + 3 * lanes < p1; p += 4 * lanes) {
     float4 v[4];
 #pragma unroll

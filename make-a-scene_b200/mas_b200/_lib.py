@@ -53,6 +53,9 @@ _SPEC = {
     "mas_amax": (_I, [_P, _L, _P, _P]),
     "mas_pack_conv3x3_tc16": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "mas_conv3x3_fprop_tc16": (_I, [_P, _T, _P, _P, _P, _P, _T, _I, _P, _I, _P, _P, _P]),
+    "mas_conv3x3_tc16h_eligible": (_I, [_T, _T]),
+    "mas_conv3x3_fprop_tc16h": (_I, [_P, _T, _P, _P, _P, _P, _T, _P, _P, _P]),
+    "mas_to_half": (_I, [_P, _P, _L, _P, _P]),
     "mas_gn_finalize_partials": (_I, [_P, _I, _I, _I, _I, _L, _F, _P, _P, _P]),
     "mas_gn_table": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P]),
     "mas_pack_gemm_tc": (_I, [_P, _P, _I, _I, _I, _P]),

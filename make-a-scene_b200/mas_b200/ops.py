@@ -211,6 +211,49 @@ def conv3x3_raw(x, weight, bias, residual, mode, out_nchw=False, transpose=False
     return y
 
 
+def conv_tma_on():
+    """TMA-fed fp16 convolution kernel (csrc/conv_tma.cu) for stride-1 3x3 layers whose input has an fp16 shadow."""
+    return f16_operands() and os.environ.get("MAS_CONV_TMA", "1") != "0"
+
+
+def conv_h_eligible(n, cin, h, w, cout):
+    return conv_tma_on() and cin % 64 == 0 and cout % 128 == 0 and h % 16 == 0 and w % 8 == 0
+
+
+def to_half(x, x_amax=None):
+    """fp16 channels-last shadow of x (scaled by the power-of-two operand scale of *x_amax when given)."""
+    if not _is_dense_nhwc(x):
+        raise RuntimeError("to_half expects a dense channels-last tensor")
+    y = torch.empty_like(x, dtype=torch.float16)
+    L.call("mas_to_half", x, y, x.numel(), x_amax)
+    return y
+
+
+def gn_apply_f16(x, mean, rstd, gamma, beta, silu):
+    """act(GroupNorm(x)) written as the fp16 channels-last shadow the TMA-fed convolution reads (values are O(1): unscaled)."""
+    n, c, h, w = x.shape
+    y = torch.empty_like(x, dtype=torch.float16)
+    L.call("mas_gn_apply", x, mean, rstd, gamma, beta, y, n, h * w, c, GN_GROUPS, int(silu), 2)
+    return y
+
+
+def conv3x3_h_raw(x16, weight, bias, residual, transpose=False, want_stats=False, prepack=False, x_amax=None):
+    """Stride-1 conv3x3 of an fp16 channels-last shadow on the TMA-fed tcgen05 kernel (fp32 output, same epilogues as
+    conv3x3_raw). x_amax: the device scalar the shadow was scaled with (None: unscaled)."""
+    n, _, h, w = x16.shape
+    cout = weight.shape[1] if transpose else weight.shape[0]
+    cin = weight.shape[0] if transpose else weight.shape[1]
+    y = empty_nhwc(n, cout, h, w, x16)
+    wt = _packed_conv_weight(weight.contiguous(), weight, cout, cin, transpose, x16.device, prepack, True)
+    part = None
+    if want_stats and cout % (4 * GN_GROUPS) == 0:
+        part = torch.empty(n * (h // 16) * (w // 8) * cout * 2, dtype=torch.float32, device=x16.device)
+    L.call("mas_conv3x3_fprop_tc16h", x16, L.t4(x16), wt, bias, residual, y, L.t4(y), part, x_amax)
+    if want_stats:
+        return y, (_finalize_stats(part, (h // 16) * (w // 8), n, cout, h * w) if part is not None else None)
+    return y
+
+
 # Packed operand images of the convolution weights, cached per parameter: a packing stays valid until the weight's version
 # counter moves (optimizer step / load_state_dict), so a training step packs every weight once (forward and data-gradient
 # images in one pass) and evaluation / gradient accumulation / the benchmark's optimizer-free steps pack nothing at all.
@@ -610,8 +653,21 @@ class ResnetBlockFn(torch.autograd.Function):
             mean_in, rstd_in = gn_stats(x)
         m1, r1 = mean_in, rstd_in
         fused = conv_tc_eligible(x, cout, L.CONV_S1) and cin % 8 == 0 and cout % (4 * GN_GROUPS) == 0
+        # shadow mode: act(GN(.)) is written ONCE as an fp16 channels-last tensor (half the bytes of the fp32 activation the
+        # unfused path stores), the convolutions read it through the copy engine (conv_tma.cu) and the backward pass feeds the
+        # same tensor to the weight-gradient kernel instead of re-materialising it
+        hmode = (fused and conv_h_eligible(n, cin, h, w, cout) and conv_h_eligible(n, cout, h, w, cout)
+                 and wgrad_f16_on() and cin % 32 == 0)
         sc = x if sw is None else conv1x1_raw(x, sw, sb)
-        if fused:
+        if hmode:
+            a1 = gn_apply_f16(x, m1, r1, n1w, n1b, True)
+            h1, st2 = conv3x3_h_raw(a1, c1w, c1b, None, want_stats=True, prepack=ctx.needs_input_grad[0])
+            m2, r2 = st2
+            a2 = gn_apply_f16(h1, m2, r2, n2w, n2b, True)
+            out, st_out = conv3x3_h_raw(a2, c2w, c2b, sc, want_stats=True, prepack=any(ctx.needs_input_grad))
+            if not any(ctx.needs_input_grad):
+                a1 = a2 = None
+        elif fused:
             t1 = gn_table(m1, r1, n1w, n1b, n, cin)
             h1, st2 = conv3x3_raw(x, c1w, c1b, None, L.CONV_S1, table=t1, want_stats=True, prepack=ctx.needs_input_grad[0])
             m2, r2 = st2
@@ -626,7 +682,7 @@ class ResnetBlockFn(torch.autograd.Function):
             out = conv3x3_raw(a2, c2w, c2b, sc, L.CONV_S1, prepack=any(ctx.needs_input_grad))
             st_out = None
         ctx.save_for_backward(x, h1, a1, a2, m1, r1, m2, r2, n1w, n1b, c1w, n2w, n2b, c2w, sw)
-        ctx.has_sc, ctx.fused = sw is not None, fused
+        ctx.has_sc, ctx.fused = sw is not None, fused and not hmode   # shadow mode keeps a1 / a2 like the unfused path
         if st_out is None:
             mo = ro = None
         else:

@@ -53,6 +53,15 @@ def variants(B, C, H, Co=None):
             ops.conv3x3_wgrad_raw(x, dy, Co, C, L.CONV_S1, dy_amax=dya)
         out[fmt + "_plain"], out[fmt + "_pro"], out[fmt + "_dgrad"], out[fmt + "_wgrad"] = f_plain, f_pro, f_dgrad, f_wgrad
     out["amax"] = lambda: ops.amax(x)
+    if C % 64 == 0 and Co % 128 == 0:
+        ops.set_operand_format("f16")
+        x16 = ops.to_half(x)
+        dy16 = ops.to_half(dy, dya)
+        out["tma_plain"] = lambda: ops.conv3x3_h_raw(x16, w, b, None)
+        out["tma_stats"] = lambda: ops.conv3x3_h_raw(x16, w, b, x if C == Co else None, want_stats=True)
+        out["tma_dgrad"] = lambda: ops.conv3x3_h_raw(dy16, w, None, None, transpose=True, x_amax=dya)
+        out["gn_apply16"] = lambda: ops.gn_apply_f16(x, m, r, g, be, True)
+        out["to_half"] = lambda: ops.to_half(x)
     return out
 
 
@@ -70,6 +79,6 @@ if __name__ == "__main__":
         print("shape B%d C%d->%d @%d  (%.1f GFLOP)" % (B, C, Co, H, gf))
         for k, fn in v.items():
             ms = bench(fn)
-            print("  %-12s %8.3f ms  %7.1f TFLOP/s" % (k, ms, gf / ms if k != "amax" else 0))
+            print("  %-12s %8.3f ms  %7.1f TFLOP/s" % (k, ms, gf / ms if k not in ("amax", "gn_apply16", "to_half") else 0))
         del v
         torch.cuda.empty_cache()
