@@ -83,11 +83,14 @@ int mas_gn_apply(const float* x, const float* mean, const float* rstd, const flo
                  void* stream);
 int mas_gn_backward(const float* dy, const float* x, const float* mean, const float* rstd,
                     const float* gamma, const float* beta, const float* dx_add, float* dx, float* dgamma,
-                    float* dbeta, void* act_out, int act_f16, float* dx_amax, int N, int HW, int C, int G, int silu,
-                    void* ws, size_t ws_bytes, void* stream);
+                    float* dbeta, void* act_out, int act_f16, float* dx_amax, const float* add_amax, void* dx_f16,
+                    float* dx_bound, int N, int HW, int C, int G, int silu, void* ws, size_t ws_bytes, void* stream);
 /* act_out (or NULL): also writes act(GN(x)), the operand of the following weight gradient - as fp32, or with act_f16 != 0
  * as fp16 (what mas_conv3x3_wgrad_tc16(..., x_is_f16 = 1) stages without converting); dx_amax (or NULL): device
- * scalar receiving max|dx| (what mas_amax(dx) would return), for the fp16-operand kernels that consume dx. */
+ * scalar receiving max|dx| (what mas_amax(dx) would return), for the fp16-operand kernels that consume dx.  dx_f16 (or NULL): also write dx as an fp16 channels-last
+ * shadow for mas_conv3x3_fprop_tc16h, scaled by the power of two derived from *dx_bound - a rigorous bound on max|dx| that
+ * is known before the apply pass: rstd*(max|dy*silu'*gamma| + |B| + max|xhat|*|A|) over (image, group), the two maxima
+ * collected by the first pass, plus *add_amax = max|dx_add| (required with dx_add); dx_bound is written for the consumer. */
 /* out = a + b (gradient of x+h where the two branches cannot be fused). */
 int mas_add(const float* a, const float* b, float* out, int64_t n, void* stream);
 /* Standalone Swish module (modules.py:194-196). */
@@ -177,7 +180,9 @@ int mas_conv3x3_wgrad(const float* x, mas_tensor4 xs, const float* dy, mas_tenso
  * MAS_ERR_UNSUPPORTED unless mas_conv3x3_wgrad_tc_eligible (dense NHWC, Cin % 32 == 0, Cout % 128 == 0, H, W % 8 == 0,
  * mode S1 / UP).  Workspace: mas_conv3x3_wgrad_ws_bytes.  dbias (may be NULL) is produced too.
  * cout_rows = rows of dw_oihw / dbias: dys.c normally; with dys.c % 128 != 0 (a multiple of 4) pass round_up(dys.c, 128) and
- * buffers of that many rows - the TMA copy of dy zero-fills the missing channels and the extra rows come out zero. */
+ * buffers of that many rows - the TMA copy of dy zero-fills the missing channels and the extra rows come out zero.  x_is_f16 carries operand flags: bit 0 - x holds fp16
+ * (mas_gn_apply(round_tf32 = 2) / mas_gn_backward(act_f16)); bit 1 - dy is the fp16 shadow written by mas_gn_backward(dx_f16),
+ * already scaled by the power of two of *dy_amax (= that call's dx_bound). */
 int mas_conv3x3_wgrad_tc_eligible(mas_tensor4 xs, mas_tensor4 dys, int mode);
 int mas_conv3x3_wgrad_tc16(const void* x, int x_is_f16, mas_tensor4 xs, const float* dy, mas_tensor4 dys, float* dw_oihw,
                            float* dbias, int mode, const float* gn_table, int gn_silu, const float* dy_amax, int cout_rows,

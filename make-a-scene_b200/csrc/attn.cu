@@ -180,7 +180,7 @@ int mas_attnblock_backward(const float* dout, const float* x, int N, int HW, int
   // [dWq; dWk; dWv] = dqkv^T . hn, biases = column sums of dqkv
   if (int e = mas_conv1x1_wgrad(hn, c, dqkv, 3 * c, M, C, 3 * C, dqkv_w, dqkv_b, impl, scratch, scratch_bytes, stream)) return e;
   // GroupNorm (no activation) backward, + dout for the residual branch
-  return mas_gn_backward(dhn, x, mean, rstd, norm_w, norm_b, dout, dx, dnorm_w, dnorm_b, nullptr, 0, dx_amax, N, HW, C, G, 0, scratch, scratch_bytes,
+  return mas_gn_backward(dhn, x, mean, rstd, norm_w, norm_b, dout, dx, dnorm_w, dnorm_b, nullptr, 0, dx_amax, nullptr, nullptr, nullptr, N, HW, C, G, 0, scratch, scratch_bytes,
                          stream);
 }
 

@@ -773,6 +773,7 @@ struct WParams {
   const float* dy_amax;   // fp16-operand kernel: max|dy| (device scalar) for the power-of-two scale of the A operand, or null
   int Cout_real;          // channels present in dy (Cout = round_up to 128: the TMA copy zero-fills the rest)
   int x_f16;              // fp16-operand kernel: x already holds fp16 (mas_gn_backward's act_out): staged without conversion
+  int dy_f16;             // fp16-operand kernel: dy is the fp16 shadow (mas_gn_backward's dx_f16), already scaled by operand_scale(*dy_amax)
 };
 
 __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -1151,6 +1152,25 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc(const WParams p, const
     for (int64_t u = u0; u < u1; ++u) {
       mbar_wait(fullD(stage), phase);   // implies the TMEM A stage is free too (the copy was issued after empty(stage))
       const float* dys = reinterpret_cast<const float*>(dy_smem + (size_t)stage * WG_DY_STAGE) + cl;
+      if (F16 && p.dy_f16) {
+        // fp16 shadow: the staged tile is [64 pixels][128 channels] halves, already scaled: two pixels of this lane's channel
+        // are packed into a column as they are (no multiply, no conversion, half the shared-memory bytes)
+        const unsigned short* dh = reinterpret_cast<const unsigned short*>(dy_smem + (size_t)stage * WG_DY_STAGE) + cl;
+        float w[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const uint32_t lo = dh[(2 * j) * 128], hi = dh[(2 * j + 1) * 128];
+          w[j] = __uint_as_float(lo | (hi << 16));
+          if (want_bias) bsum += __half2float(__ushort_as_half((unsigned short)lo)) + __half2float(__ushort_as_half((unsigned short)hi));
+        }
+        tc_fence_after();
+        tmem_st32(tmem_base + ((uint32_t)(lg * 32) << 16) + ACC_COLS + (uint32_t)(stage * A_COLS), w);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(fullA(stage));
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+        continue;
+      }
       float v[64];
       if (TAPS == 9) {
 #pragma unroll
@@ -1179,7 +1199,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc(const WParams p, const
       mbar_arrive(fullA(stage));
       if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
     }
-    if (want_bias) p.bpart[(size_t)split * p.Cout + co0 + cl] = bsum;
+    if (want_bias) p.bpart[(size_t)split * p.Cout + co0 + cl] = (F16 && p.dy_f16) ? bsum * a_inv : bsum;
   } else if (warp == 13) {
     // ============ dy TMA issuer (one thread): box [8 rows][8 pixels][128 co] (or [64 rows][128 co]) -> shared [64][128] ============
     // a tiled tensor map (cuTensorMapEncodeTiled on the host) lets ONE cp.async.bulk.tensor fetch the whole dy tile of a
@@ -1190,7 +1210,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc(const WParams p, const
       for (int64_t u = u0; u < u1; ++u) {
         const uint32_t dst = smem_u32(dy_smem) + (uint32_t)stage * WG_DY_STAGE;
         mbar_wait(empty(stage), phase ^ 1);
-        mbar_expect_tx(fullD(stage), WG_DY_STAGE);
+        mbar_expect_tx(fullD(stage), (F16 && p.dy_f16) ? WG_DY_STAGE / 2 : WG_DY_STAGE);
         if (TAPS == 9) {
           const int ux = (int)(u % p.units_x), uy = (int)((u / p.units_x) % p.units_y);
           const int n = (int)(u / ((int64_t)p.units_x * p.units_y));
@@ -1511,11 +1531,12 @@ static int make_dy_map(CUtensorMap* map, const tc::WParams& p, int taps) {
   if (!enc) return fail(MAS_ERR_LAUNCH, "cuTensorMapEncodeTiled entry point not available");
   CUresult r;
   if (taps == 9) {
+    const cuuint64_t eb = p.dy_f16 ? 2 : 4;
     cuuint64_t dims[4] = {(cuuint64_t)p.Cout_real, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
-    cuuint64_t strides[3] = {(cuuint64_t)p.Cout_real * 4, (cuuint64_t)p.W * p.Cout_real * 4, (cuuint64_t)p.H * p.W * p.Cout_real * 4};
+    cuuint64_t strides[3] = {(cuuint64_t)p.Cout_real * eb, (cuuint64_t)p.W * p.Cout_real * eb, (cuuint64_t)p.H * p.W * p.Cout_real * eb};
     cuuint32_t box[4] = {128, 8, 8, 1}, es[4] = {1, 1, 1, 1};
-    r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)p.dy, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    r = enc(map, p.dy_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)p.dy, dims, strides, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   } else {
     cuuint64_t dims[2] = {(cuuint64_t)p.Cout_real, (cuuint64_t)p.rows};
     cuuint64_t strides[1] = {(cuuint64_t)p.ldy * 4};
@@ -1553,7 +1574,10 @@ bool conv_wgrad_tc_eligible(mas_tensor4 xs, mas_tensor4 dys, int mode) { return 
 int conv_wgrad_tc_launch(const float* x, mas_tensor4 xs, const float* dy, mas_tensor4 dys, float* dw, float* dbias, int mode,
                          const float* gn_table, int gn_silu, int f16, const float* dy_amax, int cout_rows, int x_f16, void* ws,
                          size_t ws_bytes, cudaStream_t st) {
+  const int dy_f16 = (x_f16 >> 1) & 1;   // operand flags: bit 0 = x holds fp16, bit 1 = dy is the scaled fp16 shadow
+  x_f16 &= 1;
   if (x_f16 && (!f16 || gn_table)) return fail(MAS_ERR_INVALID_ARG, "tc wgrad: an fp16 x needs the fp16-operand kernel and no prologue");
+  if (dy_f16 && (!f16 || !dy_amax || dys.c % 8)) return fail(MAS_ERR_INVALID_ARG, "tc wgrad: an fp16 dy needs the fp16-operand kernel, its scale source and Cout %% 8 == 0");
   // cout_rows: rows of dw / dbias the caller allocated; padding (dys.c % 128 != 0) only when it equals round_up(dys.c, 128)
   const bool pad_ok = cout_rows == (int)(cdiv(dys.c, tc::BM) * tc::BM);
   if (!wgrad_tc_ok(xs, dys, mode, pad_ok) || !al16p(x) || !al16p(dy)) return fail(MAS_ERR_UNSUPPORTED, "tc wgrad: shape/layout not eligible");
@@ -1567,7 +1591,7 @@ int conv_wgrad_tc_launch(const float* x, mas_tensor4 xs, const float* dy, mas_te
   p.units_x = (int)(dys.w / 8); p.units_y = (int)(dys.h / 8);
   p.total_units = (int64_t)p.N * p.units_x * p.units_y;
   p.rows = 0; p.ldx = p.Cin; p.ldy = p.Cout_real;
-  p.gn_table = gn_table; p.gn_silu = gn_silu; p.dy_amax = f16 ? dy_amax : nullptr; p.x_f16 = x_f16;
+  p.gn_table = gn_table; p.gn_silu = gn_silu; p.dy_amax = f16 ? dy_amax : nullptr; p.x_f16 = x_f16; p.dy_f16 = dy_f16;
   const int splits = wgrad_tc_splits((p.Cout / tc::BM) * (xs.c / tc::WG_NT), p.total_units);
   if (f16) return gn_table ? wgrad_tc_run<9, true, true>(p, splits, dw, dbias, ws, st) : wgrad_tc_run<9, false, true>(p, splits, dw, dbias, ws, st);
   return gn_table ? wgrad_tc_run<9, true, false>(p, splits, dw, dbias, ws, st) : wgrad_tc_run<9, false, false>(p, splits, dw, dbias, ws, st);
@@ -1590,7 +1614,7 @@ int conv1x1_wgrad_tc_launch(const float* x, int64_t ldx, const float* dy, int64_
   p.units_x = 1; p.units_y = 1;
   p.total_units = cdiv(M, 64);
   p.rows = M; p.ldx = ldx; p.ldy = ldy;
-  p.gn_table = nullptr; p.gn_silu = 0; p.dy_amax = nullptr; p.x_f16 = 0;
+  p.gn_table = nullptr; p.gn_silu = 0; p.dy_amax = nullptr; p.x_f16 = 0; p.dy_f16 = 0;
   const int splits = wgrad_tc_splits((int64_t)(Cout / tc::BM) * (Cin / 128), p.total_units);
   return wgrad_tc_run<1, false, false>(p, splits, dw, dbias, ws, st);
 }

@@ -7,6 +7,7 @@
 #include <stdlib.h>
 
 #include "mas_common.cuh"
+#include "tc_ptx.cuh"
 
 namespace mas {
 
@@ -182,7 +183,8 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_partial(const float* __rest
                                                              int HW, int C, int G, int silu,
                                                              double* __restrict__ part /*[N][chunks][C][2]*/,
                                                              float* __restrict__ act_out /*or null: also write act(GN(x))*/,
-                                                             int act_f16 /*act_out holds fp16 (the fp16-operand weight gradient's input)*/) {
+                                                             int act_f16 /*act_out holds fp16 (the fp16-operand weight gradient's input)*/,
+                                                             unsigned int* __restrict__ mx /*or null: [0] max|dy*silu'*gamma|, [1] max|xhat| (float bits)*/) {
   extern __shared__ double sm[];
   const int U = C >> 2, n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x, cpg = C / G;
   const int t = threadIdx.x, u = t % U, lanes = GN_THREADS / U, pl = t / U;
@@ -205,6 +207,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_partial(const float* __rest
   uint2* ap16 = (act_out && act_f16) ? reinterpret_cast<uint2*>(reinterpret_cast<__half*>(act_out) + (size_t)n * HW * C) + u : nullptr;
   // the activation act(GN(x)) (needed by the weight-gradient kernel, never stored in the forward) is re-materialised here
   // as a by-product: x is being read anyway, so this replaces a separate read+write pass by one extra write
+  float tmd = 0.f, tmx = 0.f;   // running max|d*gamma| and max|xhat|: the inputs of the rigorous bound on |dx| (gn_bwd_final)
   auto accum = [&](const float4& xv, const float4& dv, size_t idx) {
     float xi[4] = {xv.x, xv.y, xv.z, xv.w}, di[4] = {dv.x, dv.y, dv.z, dv.w}, ao[4];
 #pragma unroll
@@ -216,6 +219,8 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_partial(const float* __rest
       ao[k] = silu ? silu_f(uu) : uu;
       f1[k] = fmaf(d, xh, f1[k]);
       f2[k] += d;
+      tmd = fmaxf(tmd, fabsf(d * ga[k]));
+      tmx = fmaxf(tmx, fabsf(xh));
     }
     if (ap) ap[idx] = make_float4(ao[0], ao[1], ao[2], ao[3]);
     if (ap16) {   // round-to-nearest, saturating: the conversion the weight-gradient producers would apply anyway
@@ -262,6 +267,14 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_partial(const float* __rest
     o[0] = a;
     o[1] = b;
   }
+  if (mx) {
+    tmd = warp_max(tmd);
+    tmx = warp_max(tmx);
+    if ((t & 31) == 0) {   // non-negative floats order like their bit patterns; order-independent: deterministic
+      atomicMax(mx, __float_as_uint(tmd));
+      atomicMax(mx + 1, __float_as_uint(tmx));
+    }
+  }
 }
 
 // backward finalize, stage 1: per (n,c) sums over chunks
@@ -287,7 +300,8 @@ __global__ void gn_bwd_nc(const double* __restrict__ part, int N, int nchunks, i
 // A,B of the apply pass (remaining blocks: one thread per (image, group)).  Both read only nc, so they share a launch.
 __global__ void __launch_bounds__(128) gn_bwd_final(int N, int C, int G, const float* __restrict__ gamma, const double* __restrict__ nc,
                                                     float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                    float* __restrict__ AB /*[N][G][2]*/, double inv_m, int cblocks) {
+                                                    float* __restrict__ AB /*[N][G][2]*/, double inv_m, int cblocks,
+                                                    const float* __restrict__ rstd, unsigned int* __restrict__ mx /*or null*/) {
   const int cpg = C / G;
   if ((int)blockIdx.x < cblocks) {
     const int c = blockIdx.x * 128 + threadIdx.x;
@@ -316,6 +330,12 @@ __global__ void __launch_bounds__(128) gn_bwd_final(int N, int C, int G, const f
     }
     AB[i * 2 + 0] = (float)(a * inv_m);
     AB[i * 2 + 1] = (float)(b * inv_m);
+    if (mx) {
+      // dx = rstd*(d*gamma - B - xhat*A) (+ dx_add): |dx - dx_add| <= rstd*(max|d*gamma| + |B| + max|xhat|*|A|) for every
+      // element of this (image, group); the maximum over (image, group) lands in mx[2]
+      const float bnd = rstd[i] * (__uint_as_float(mx[0]) + fabsf((float)(b * inv_m)) + __uint_as_float(mx[1]) * fabsf((float)(a * inv_m)));
+      atomicMax(mx + 2, __float_as_uint(bnd));
+    }
   }
 }
 
@@ -324,8 +344,25 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply(const float* __restri
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            const float* __restrict__ AB, const float* __restrict__ dx_add,
                                                            float* __restrict__ dx, int HW, int C, int G, int silu,
-                                                           unsigned int* __restrict__ dx_amax /*or null: max|dx| (float bits)*/) {
+                                                           unsigned int* __restrict__ dx_amax /*or null: max|dx| (float bits)*/,
+                                                           __half* __restrict__ dx16 /*or null: fp16 shadow of dx, scaled*/,
+                                                           const unsigned int* __restrict__ mx, const float* __restrict__ add_amax,
+                                                           float* __restrict__ dx_bound /*the magnitude the shadow's scale derives from*/) {
   const int U = C >> 2, n = blockIdx.y, cpg = C / G;
+  // shadow scale: a power of two from a rigorous bound on max|dx| (known BEFORE this pass, unlike max|dx| itself); every
+  // block derives the same value, block (0, 0) publishes it for the convolution that reads the shadow
+  __shared__ float sh_bound;
+  float sscale = 1.f;
+  if (dx16) {
+    if (threadIdx.x == 0) {
+      const float bnd = __uint_as_float(mx[2]) * 1.01f + (add_amax ? *add_amax : 0.f);
+      sh_bound = bnd;
+      if (blockIdx.x == 0 && blockIdx.y == 0) *dx_bound = bnd;
+    }
+    __syncthreads();
+    float inv_unused;
+    sscale = tc::operand_scale(&sh_bound, &inv_unused);
+  }
   const int t = threadIdx.x, u = t % U, lanes = GN_THREADS / U, pl = t / U;
   const int PIX = (HW + gridDim.x - 1) / gridDim.x;
   const int p0 = blockIdx.x * PIX, p1 = min(HW, p0 + PIX);
@@ -340,7 +377,14 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply(const float* __restri
   const float4* xp = reinterpret_cast<const float4*>(x + base) + u;
   const float4* dp = reinterpret_cast<const float4*>(dy + base) + u;
   const float4* ap = dx_add ? reinterpret_cast<const float4*>(dx_add + base) + u : nullptr;
-  float4* op = reinterpret_cast<float4*>(dx + base) + u;
+  float4* op = dx ? reinterpret_cast<float4*>(dx + base) + u : nullptr;   // null: only the fp16 shadow is wanted
+  uint2* hp = dx16 ? reinterpret_cast<uint2*>(dx16 + base) + u : nullptr;
+  auto h4 = [&](const float4& v) {
+    uint2 h;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h.x) : "f"(v.y * sscale), "f"(v.x * sscale));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h.y) : "f"(v.w * sscale), "f"(v.z * sscale));
+    return h;
+  };
   float amx = 0.f;   // the consumers of dx are fp16-operand tensor-core kernels: their operand scale comes from max|dx|
   auto one = [&](const float4& xv, const float4& dv, const float4& av) {
     float xi[4] = {xv.x, xv.y, xv.z, xv.w}, di[4] = {dv.x, dv.y, dv.z, dv.w}, ad[4] = {av.x, av.y, av.z, av.w}, o[4];
@@ -360,12 +404,15 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply(const float* __restri
     const size_t i0 = (size_t)p * U, i1 = (size_t)(p + lanes) * U;
     float4 x0 = __ldg(xp + i0), x1 = __ldg(xp + i1), d0 = __ldg(dp + i0), d1 = __ldg(dp + i1);
     float4 a0 = ap ? __ldg(ap + i0) : z4, a1 = ap ? __ldg(ap + i1) : z4;
-    op[i0] = one(x0, d0, a0);
-    op[i1] = one(x1, d1, a1);
+    const float4 o0 = one(x0, d0, a0), o1 = one(x1, d1, a1);
+    if (op) { op[i0] = o0; op[i1] = o1; }
+    if (hp) { hp[i0] = h4(o0); hp[i1] = h4(o1); }
   }
   for (; p < p1; p += lanes) {
     const size_t i0 = (size_t)p * U;
-    op[i0] = one(__ldg(xp + i0), __ldg(dp + i0), ap ? __ldg(ap + i0) : z4);
+    const float4 o0 = one(__ldg(xp + i0), __ldg(dp + i0), ap ? __ldg(ap + i0) : z4);
+    if (op) op[i0] = o0;
+    if (hp) hp[i0] = h4(o0);
   }
   if (dx_amax) {
     amx = warp_max(amx);
@@ -800,33 +847,43 @@ int mas_gn_apply(const float* x, const float* mean, const float* rstd, const flo
 }
 
 int mas_gn_backward(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
-                    const float* dx_add, float* dx, float* dgamma, float* dbeta, void* act_out, int act_f16, float* dx_amax, int N, int HW,
-                    int C, int G, int silu, void* ws, size_t ws_bytes, void* stream) {
+                    const float* dx_add, float* dx, float* dgamma, float* dbeta, void* act_out, int act_f16, float* dx_amax,
+                    const float* add_amax, void* dx_f16, float* dx_bound, int N, int HW, int C, int G, int silu, void* ws,
+                    size_t ws_bytes, void* stream) {
   if (int e = gn_check(N, HW, C, G)) return e;
+  if (!dx && !dx_f16) return fail(MAS_ERR_INVALID_ARG, "gn_backward: dx may only be NULL when dx_f16 is given");
+  if (dx_f16 && (!dx_bound || (dx_add && !add_amax)))
+    return fail(MAS_ERR_INVALID_ARG, "gn_backward: the fp16 shadow of dx needs dx_bound (and add_amax with dx_add)");
   if (ws_bytes < mas_gn_ws_bytes(N, HW, C, G)) return fail(MAS_ERR_WORKSPACE, "gn_backward: workspace too small");
   int chunks = gn_chunks(N, HW, C);
   double* part = (double*)ws;
   double* nc = part + (size_t)N * chunks * C * 2;
   float* AB = (float*)(nc + (size_t)N * C * 2);
+  unsigned int* mx = dx_f16 ? reinterpret_cast<unsigned int*>(AB + (size_t)N * G * 2) : nullptr;   // 3 words (inside the +256 slack)
+  if (mx) {
+    cudaError_t e = cudaMemsetAsync(mx, 0, 3 * sizeof(unsigned int), S(stream));
+    if (e != cudaSuccess) return fail(MAS_ERR_LAUNCH, "gn_backward: memset: %s", cudaGetErrorString(e));
+  }
   int lanes = GN_THREADS / (C / 4);
   size_t smem = (size_t)lanes * C * 2 * sizeof(double);
   // (A single-kernel form - pass 1, per-image hand-over through an arrival counter, pass 2 on the same chunk hoping for L2 hits -
   //  was built and measured: 22.0 vs 18.2 ms per step for all GroupNorm backwards, and its spin-wait hung on small shapes; removed.)
   gn_bwd_partial<<<dim3(chunks, N), GN_THREADS, smem, S(stream)>>>(dy, x, mean, rstd, gamma, beta, HW, C, G, silu, part, (float*)act_out,
-                                                                   act_f16);
+                                                                   act_f16, mx);
   if (int e = launched("gn_bwd_partial")) return e;
   gn_bwd_nc<<<(int)cdiv((int64_t)N * C, 128), 128, 0, S(stream)>>>(part, N, chunks, C, nc);
   if (int e = launched("gn_bwd_nc")) return e;
   const int cblocks = (int)cdiv(C, 128);
   gn_bwd_final<<<cblocks + (int)cdiv((int64_t)N * G, 128), 128, 0, S(stream)>>>(N, C, G, gamma, nc, dgamma, dbeta, AB,
-                                                                                1.0 / ((double)HW * (C / G)), cblocks);
+                                                                                1.0 / ((double)HW * (C / G)), cblocks, rstd, mx);
   if (int e = launched("gn_bwd_final")) return e;
   if (dx_amax) {
     cudaError_t e = cudaMemsetAsync(dx_amax, 0, sizeof(float), S(stream));
     if (e != cudaSuccess) return fail(MAS_ERR_LAUNCH, "gn_backward: memset: %s", cudaGetErrorString(e));
   }
   gn_bwd_apply<<<dim3(chunks, N), GN_THREADS, 0, S(stream)>>>(dy, x, mean, rstd, gamma, beta, AB, dx_add, dx, HW, C, G, silu,
-                                                              reinterpret_cast<unsigned int*>(dx_amax));
+                                                              reinterpret_cast<unsigned int*>(dx_amax), reinterpret_cast<__half*>(dx_f16), mx,
+                                                              add_amax, dx_bound);
   return launched("gn_bwd_apply");
 }
 

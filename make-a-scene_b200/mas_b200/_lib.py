@@ -38,7 +38,7 @@ _SPEC = {
     "mas_gn_ws_bytes": (_Z, [_I, _I, _I, _I]),
     "mas_gn_stats": (_I, [_P, _I, _I, _I, _I, _F, _P, _P, _P, _Z, _P]),
     "mas_gn_apply": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
-    "mas_gn_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _Z, _P]),
+    "mas_gn_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _Z, _P]),
     "mas_add": (_I, [_P, _P, _P, _L, _P]),
     "mas_silu_forward": (_I, [_P, _P, _L, _P]),
     "mas_silu_backward": (_I, [_P, _P, _P, _L, _P]),

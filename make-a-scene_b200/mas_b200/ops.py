@@ -91,25 +91,48 @@ def gn_apply(x, mean, rstd, gamma, beta, silu, rtf32=False):
     return y
 
 
-def gn_backward(dy, x, mean, rstd, gamma, beta, silu, dx_add=None, want_act=False, act_f16=False):
+def gn_backward(dy, x, mean, rstd, gamma, beta, silu, dx_add=None, want_act=False, act_f16=False, shadow=False, add_amax=None,
+                shadow_only=False):
     """want_act: also return act(GN(x)) (re-materialised as a by-product of the first backward pass). With fp16 operands
     selected, max|dx| is produced by the same pass and attached to dx (attach_amax) for the tensor-core kernels that
-    consume it."""
+    consume it. shadow: dx is also written as an fp16 channels-last tensor scaled by a power of two from a rigorous bound on
+    max|dx| (attached: shadow_of) - the operand the TMA-fed data-gradient convolution reads; add_amax = max|dx_add|.
+    shadow_only: the fp32 dx is not written at all; the first return value is then the (shadow, scale source) pair."""
     n, c, h, w = x.shape
-    dx = torch.empty_like(x)
+    shadow = shadow or shadow_only
+    dx = None if shadow_only else torch.empty_like(x)
     dg = torch.empty_like(gamma)
     db = torch.empty_like(beta)
     # act_f16: the re-materialised activation only feeds the fp16-operand weight gradient -> written as fp16 (half the bytes)
     act = torch.empty_like(x, dtype=torch.float16 if act_f16 else torch.float32) if want_act else None
-    am = torch.empty(1, dtype=torch.float32, device=x.device) if f16_operands() else None
+    am = torch.empty(1, dtype=torch.float32, device=x.device) if (f16_operands() and not shadow_only) else None
+    dx16 = bound = None
+    if shadow:
+        dx16 = torch.empty_like(x, dtype=torch.float16)
+        bound = torch.empty(1, dtype=torch.float32, device=x.device)
+        if dx_add is not None and add_amax is None:
+            add_amax = amax_of(dx_add)
     nb = L.query("mas_gn_ws_bytes", n, h * w, c, GN_GROUPS)
     ws = L.workspace(nb, x.device)
-    L.call("mas_gn_backward", dy, x, mean, rstd, gamma, beta, dx_add, dx, dg, db, act, int(act_f16 and want_act), am, n, h * w, c,
-           GN_GROUPS, int(silu), ws, ws.numel())
-    attach_amax(dx, am)
+    L.call("mas_gn_backward", dy, x, mean, rstd, gamma, beta, dx_add, dx, dg, db, act, int(act_f16 and want_act), am,
+           add_amax if shadow else None, dx16, bound, n, h * w, c, GN_GROUPS, int(silu), ws, ws.numel())
+    if shadow_only:
+        dx = (dx16, bound)
+    else:
+        attach_amax(dx, am)
+        if shadow:
+            dx._mas_shadow = (dx16, bound, dx._version, dx.data_ptr())
     if want_act:
         return dx, dg, db, act
     return dx, dg, db
+
+
+def shadow_of(t):
+    """(fp16 shadow, scale source) attached by the kernel that wrote t, if t is unchanged since; else None."""
+    st = getattr(t, "_mas_shadow", None)
+    if st is not None and st[2] == t._version and st[3] == t.data_ptr() and st[0].device == t.device and st[0].shape == t.shape:
+        return st[0], st[1]
+    return None
 
 
 def attach_amax(t, am):
@@ -306,11 +329,14 @@ def conv3x3_wgrad_raw(x, dy, cout, cin, mode, want_bias=True, table=None, silu=T
     padded = cout != dy.shape[1]      # dw sized for round_up(channels of dy, 128): the explicit padded path of Conv3x3Fn
     if (_tc_on() and _cfg["operands"] == "f16" and wgrad_f16_on() and _is_dense_nhwc(x) and _is_dense_nhwc(dy)
             and (padded or L.query("mas_conv3x3_wgrad_tc_eligible", L.t4(x), L.t4(dy), mode))):
-        L.call("mas_conv3x3_wgrad_tc16", x, int(x.dtype == torch.float16), L.t4(x), dy, L.t4(dy), dw, db, mode, table, int(silu),
+        flags = int(x.dtype == torch.float16) | (2 if dy.dtype == torch.float16 else 0)   # bit 1: dy is a scaled fp16 shadow
+        if dy.dtype == torch.float16 and dy_amax is None:
+            raise RuntimeError("an fp16 output-gradient shadow needs the device scalar its scale was derived from")
+        L.call("mas_conv3x3_wgrad_tc16", x, flags, L.t4(x), dy, L.t4(dy), dw, db, mode, table, int(silu),
                dy_amax if dy_amax is not None else amax_of(dy), cout, ws, ws.numel())
         return dw, db
-    if x.dtype == torch.float16:
-        raise RuntimeError("an fp16 activation can only feed the fp16-operand tensor-core weight gradient")
+    if x.dtype == torch.float16 or dy.dtype == torch.float16:
+        raise RuntimeError("fp16 operands can only feed the fp16-operand tensor-core weight gradient")
     if padded:
         raise RuntimeError("padded weight gradient needs the fp16 tensor-core kernel")
     L.call("mas_conv3x3_wgrad", x, L.t4(x), dy, L.t4(dy), dw, db, mode, _cfg["impl"], table, int(silu), ws, ws.numel())
@@ -645,7 +671,7 @@ class ResnetBlockFn(torch.autograd.Function):
     Returns (out, mean, rstd): the statistics of `out` for the following block's first GroupNorm (or None)."""
 
     @staticmethod
-    def forward(ctx, x, mean_in, rstd_in, n1w, n1b, c1w, c1b, n2w, n2b, c2w, c2b, sw, sb):
+    def forward(ctx, x, mean_in, rstd_in, n1w, n1b, c1w, c1b, n2w, n2b, c2w, c2b, sw, sb, dx_shadow=False):
         x = nhwc(x)
         n, cin, h, w = x.shape
         cout = c1w.shape[0]
@@ -683,6 +709,7 @@ class ResnetBlockFn(torch.autograd.Function):
             st_out = None
         ctx.save_for_backward(x, h1, a1, a2, m1, r1, m2, r2, n1w, n1b, c1w, n2w, n2b, c2w, sw)
         ctx.has_sc, ctx.fused = sw is not None, fused and not hmode   # shadow mode keeps a1 / a2 like the unfused path
+        ctx.hmode, ctx.dx_shadow = hmode, bool(dx_shadow) and hmode and sw is None
         if st_out is None:
             mo = ro = None
         else:
@@ -694,26 +721,41 @@ class ResnetBlockFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout, _gm, _gr):
         if dout is None:
-            return (None,) * 13
+            return (None,) * 14
         x, h1, a1, a2, m1, r1, m2, r2, n1w, n1b, c1w, n2w, n2b, c2w, sw = ctx.saved_tensors
         dout = nhwc(dout)
         cout, cin = c1w.shape[0], c1w.shape[1]
         n, _, h, w = x.shape
         am_out = amax_of(dout) if f16_operands() else None   # from the producing kernel, else one pass; serves dgrad and wgrad
-        d_a2 = conv3x3_dgrad_raw(dout, c2w, L.CONV_S1, am_out)
+        hmode = ctx.hmode and conv_tma_on()
+        sh_out = shadow_of(dout) if hmode else None
+        if sh_out is not None:
+            # dout was written by a GroupNorm backward together with its fp16 shadow: pure TMA + MMA data gradient
+            d_a2 = conv3x3_h_raw(sh_out[0], c2w, None, None, transpose=True, x_amax=sh_out[1])
+        else:
+            d_a2 = conv3x3_dgrad_raw(dout, c2w, L.CONV_S1, am_out)
         # fused forward never stored act(GN(.)): the GroupNorm backward re-materialises it as a by-product of its first pass
         # (cheaper than re-activating inside the weight-gradient kernel's producers: measured +0.8 ms per full-res call)
         # the activation re-materialised for the weight gradient goes straight into an fp16 operand: write it as fp16
         a16 = ctx.fused and wgrad_f16_eligible(x, dout, c1w)
+        sh_h1 = None
         if ctx.fused:
             d_h1, dn2w, dn2b, a2 = gn_backward(d_a2, h1, m2, r2, n2w, n2b, True, want_act=True, act_f16=a16)
+        elif hmode:
+            # the gradient of conv1's output only feeds conv1's data and weight gradients: it exists as an fp16 shadow only
+            sh_h1, dn2w, dn2b = gn_backward(d_a2, h1, m2, r2, n2w, n2b, True, shadow_only=True)
         else:
             d_h1, dn2w, dn2b = gn_backward(d_a2, h1, m2, r2, n2w, n2b, True)
         del d_a2
         dc2w, dc2b = conv3x3_wgrad_raw(a2, dout, cout, cout, L.CONV_S1, dy_amax=am_out)
         del a2
-        am_h1 = amax_of(d_h1) if f16_operands() else None
-        d_a1 = conv3x3_dgrad_raw(d_h1, c1w, L.CONV_S1, am_h1)
+        if sh_h1 is not None:
+            d_h1, am_h1 = sh_h1
+            d_a1 = conv3x3_h_raw(d_h1, c1w, None, None, transpose=True, x_amax=am_h1)
+        else:
+            am_h1 = amax_of(d_h1) if f16_operands() else None
+            d_a1 = conv3x3_dgrad_raw(d_h1, c1w, L.CONV_S1, am_h1)
+        del sh_h1
         if ctx.has_sc:
             r_ = gn_backward(d_a1, x, m1, r1, n1w, n1b, True, want_act=ctx.fused, act_f16=a16)
             dxm, dn1w, dn1b = r_[0], r_[1], r_[2]
@@ -722,7 +764,8 @@ class ResnetBlockFn(torch.autograd.Function):
             dx = conv1x1_dgrad_raw(dout, sw, residual=dxm)   # dout.Wn + dx_main
             dsw, dsb = conv1x1_wgrad_raw(x, dout, n * h * w, cin, cout)
         else:
-            r_ = gn_backward(d_a1, x, m1, r1, n1w, n1b, True, dx_add=dout, want_act=ctx.fused, act_f16=a16)
+            r_ = gn_backward(d_a1, x, m1, r1, n1w, n1b, True, dx_add=dout, want_act=ctx.fused, act_f16=a16,
+                             shadow=ctx.dx_shadow and hmode, add_amax=am_out)
             dx, dn1w, dn1b = r_[0], r_[1], r_[2]
             if ctx.fused:
                 a1 = r_[3]
@@ -730,7 +773,7 @@ class ResnetBlockFn(torch.autograd.Function):
         del d_a1
         dc1w, dc1b = conv3x3_wgrad_raw(a1, d_h1, cout, cin, L.CONV_S1, dy_amax=am_h1)
         del a1, d_h1
-        return dx, None, None, dn1w, dn1b, dc1w, dc1b, dn2w, dn2b, dc2w, dc2b, dsw, dsb
+        return dx, None, None, dn1w, dn1b, dc1w, dc1b, dn2w, dn2b, dc2w, dc2b, dsw, dsb, None
 
 
 class AttnBlockFn(torch.autograd.Function):

@@ -123,9 +123,14 @@ class ResnetBlock(nn.Module):
             return self.conv2(h, residual=self.conv_shortcut(x))
         sc = self.nin_shortcut if self.in_channels != self.out_channels else None
         st = ops.take_stats(x)   # GroupNorm statistics emitted by the producing kernel's epilogue, if any
+        # x produced by another ResnetBlock: its backward will read our dx through the TMA-fed data-gradient convolution, so
+        # our GroupNorm backward also writes dx as an fp16 shadow (ops.gn_backward(shadow=True))
+        from_res = bool(getattr(x, "_mas_res_out", False))
         out, mo, ro = ops.ResnetBlockFn.apply(x, st[0], st[1], self.norm1.weight, self.norm1.bias, self.conv1.weight,
                                               self.conv1.bias, self.norm2.weight, self.norm2.bias, self.conv2.weight,
-                                              self.conv2.bias, None if sc is None else sc.weight, None if sc is None else sc.bias)
+                                              self.conv2.bias, None if sc is None else sc.weight, None if sc is None else sc.bias,
+                                              from_res)
+        out._mas_res_out = True
         return ops.attach_stats(out, mo, ro)
 
 

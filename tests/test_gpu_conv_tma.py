@@ -92,3 +92,60 @@ def test_gn_apply_f16_shadow():
         a16 = ops.gn_apply_f16(x, m, r, gamma, beta, silu)
         assert a16.dtype == torch.float16 and a16.stride() == a.stride()
         assert torch.equal(a16, a.half())
+
+
+@pytest.mark.parametrize("with_add", [False, True])
+def test_gn_backward_shadow_scale_is_a_rigorous_bound(with_add):
+    """The fp16 shadow of dx is scaled from a bound on max|dx| that must (a) hold and (b) not waste the fp16 range."""
+    import math
+    from mas_b200 import ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(5)
+    ops.set_operand_format("f16")
+    n, c, h, w = 2, 128, 32, 16
+    x = _cl((torch.randn(n, c, h, w, generator=g) * 1.7 + 0.3).to(dev))
+    x[0, 5, 3, 3] = 40.0                      # an outlier: large |xhat|
+    dy = _cl((torch.randn(n, c, h, w, generator=g) * 2e-6).to(dev))
+    add = _cl((torch.randn(n, c, h, w, generator=g) * 5e-6).to(dev)) if with_add else None
+    gamma, beta = (torch.randn(c, generator=g) * 0.5 + 1).to(dev), (torch.randn(c, generator=g) * 0.1).to(dev)
+    m, r = ops.gn_stats(x)
+    dx, dg, db = ops.gn_backward(dy, x, m, r, gamma, beta, True, dx_add=add, shadow=True)
+    dx_ref, dg_ref, db_ref = ops.gn_backward(dy, x, m, r, gamma, beta, True, dx_add=add)
+    assert torch.equal(dx, dx_ref) and torch.equal(dg, dg_ref) and torch.equal(db, db_ref)
+    sh = ops.shadow_of(dx)
+    assert sh is not None
+    dx16, bound = sh
+    amax = dx.abs().max().item()
+    b = bound.item()
+    print("bound / amax = %.2f" % (b / amax))
+    assert b >= amax and b / amax < 64.0
+    s = 2.0 ** (14 - math.floor(math.log2(b)))
+    want = (dx.double() * s).half()
+    assert torch.equal(dx16, want.to(dx16.dtype))
+    assert torch.isfinite(dx16.float()).all()
+    assert ops.amax_of(dx).item() == pytest.approx(amax, rel=0, abs=0)
+
+
+def test_wgrad_from_fp16_gradient_shadow():
+    """Weight gradient fed by the scaled fp16 shadow of dy (and the fp16 activation) against the fp32-dy call and F.conv2d."""
+    from mas_b200 import _lib as L, ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(13)
+    ops.set_operand_format("f16")
+    n, cin, cout, h, w = 2, 64, 128, 32, 16
+    x = _cl(torch.randn(n, cin, h, w, generator=g).to(dev))
+    dy = _cl((torch.randn(n, cout, h, w, generator=g) * 3e-6).to(dev))
+    am = ops.amax(dy)
+    bound = am * 1.7          # any magnitude >= max|dy| is a valid scale source
+    dy16 = ops.to_half(dy, bound)
+    x16 = ops.to_half(x)
+    dw, db = ops.conv3x3_wgrad_raw(x16, dy16, cout, cin, L.CONV_S1, dy_amax=bound)
+    dw0, db0 = ops.conv3x3_wgrad_raw(x16, dy, cout, cin, L.CONV_S1, dy_amax=bound)
+    assert torch.equal(dw, dw0)          # same fp16 operands (same scale), same accumulation
+    xr = x.clone().requires_grad_(True)
+    wr = torch.zeros(cout, cin, 3, 3, device=dev, requires_grad=True)
+    br = torch.zeros(cout, device=dev, requires_grad=True)
+    F.conv2d(xr, wr, br, padding=1).backward(dy)
+    assert (dw - wr.grad).abs().max().item() / wr.grad.abs().max().item() < 3e-3
+    assert (db - br.grad).abs().max().item() / br.grad.abs().max().item() < 1e-3
+    assert (db0 - br.grad).abs().max().item() / br.grad.abs().max().item() < 1e-5
