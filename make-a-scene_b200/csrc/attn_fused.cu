@@ -82,6 +82,17 @@ __device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uin
       ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// one lane of the (converged) warp: true for exactly one thread.  The MMA-issuing warps run their loops warp-uniformly (operand
+// descriptors stay in uniform registers) and only the issue itself is predicated on this.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -330,8 +341,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_core_fwd(const Params p) {
       }
     }
   } else {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    {
       int stage = 0;
       uint32_t phase = 0;
       constexpr uint32_t idesc1 = idesc_f16(HW, false);
@@ -339,20 +350,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_core_fwd(const Params p) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         const uint32_t st = smem_base + (uint32_t)stage * STAGE;
+        if (elect_one()) {
 #pragma unroll
-        for (int k16 = 0; k16 < KC / 16; ++k16) {
-          const uint64_t qh = make_desc(st + (uint32_t)(k16 * 2 * PITCH_Q), PITCH_Q, 128);
-          const uint64_t ql = make_desc(st + (uint32_t)(Q_HALF + k16 * 2 * PITCH_Q), PITCH_Q, 128);
-          const uint64_t kh = make_desc(st + (uint32_t)(2 * Q_HALF + k16 * 2 * PITCH_K), PITCH_K, 128);
-          const uint64_t kl = make_desc(st + (uint32_t)(2 * Q_HALF + K_HALF + k16 * 2 * PITCH_K), PITCH_K, 128);
-          mma_f16_ss(tmem_base, qh, kh, idesc1, (c > 0 || k16 > 0) ? 1u : 0u);
-          mma_f16_ss(tmem_base, ql, kh, idesc1, 1u);
-          mma_f16_ss(tmem_base, qh, kl, idesc1, 1u);
+          for (int k16 = 0; k16 < KC / 16; ++k16) {
+            const uint64_t qh = make_desc(st + (uint32_t)(k16 * 2 * PITCH_Q), PITCH_Q, 128);
+            const uint64_t ql = make_desc(st + (uint32_t)(Q_HALF + k16 * 2 * PITCH_Q), PITCH_Q, 128);
+            const uint64_t kh = make_desc(st + (uint32_t)(2 * Q_HALF + k16 * 2 * PITCH_K), PITCH_K, 128);
+            const uint64_t kl = make_desc(st + (uint32_t)(2 * Q_HALF + K_HALF + k16 * 2 * PITCH_K), PITCH_K, 128);
+            mma_f16_ss(tmem_base, qh, kh, idesc1, (c > 0 || k16 > 0) ? 1u : 0u);
+            mma_f16_ss(tmem_base, ql, kh, idesc1, 1u);
+            mma_f16_ss(tmem_base, qh, kl, idesc1, 1u);
+          }
+          mma_commit(empty_bar(stage));
+          if (c == nchunk1 - 1) mma_commit(s_full);
         }
-        mma_commit(empty_bar(stage));
+        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      mma_commit(s_full);
       mbar_wait(p_ready, 0);
       tc_fence_after();
       constexpr uint32_t idesc2 = idesc_f16(NV, true);
@@ -366,23 +380,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_core_fwd(const Params p) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t st = smem_base + (uint32_t)stage * STAGE;
+          if (elect_one()) {
 #pragma unroll
-          for (int k16 = 0; k16 < KC / 16; ++k16) {
-            const uint32_t acol = (uint32_t)((c * KC + k16 * 16) >> 1);
-            // MN-major B: K groups (8 keys) are 128 bytes apart inside a plane, N groups are the planes
-            const uint64_t vh = make_desc(st + (uint32_t)(k16 * 256), 128, PITCH_V);
-            const uint64_t vl = make_desc(st + (uint32_t)(V_HALF + k16 * 256), 128, PITCH_V);
-            mma_f16_ts(tmem_base, tmem_base + 256 + acol, vh, idesc2, (c > 0 || k16 > 0) ? 1u : 0u);
-            mma_f16_ts(tmem_base, tmem_base + 256 + phalf_cols + acol, vh, idesc2, 1u);
-            mma_f16_ts(tmem_base, tmem_base + 256 + acol, vl, idesc2, 1u);
+            for (int k16 = 0; k16 < KC / 16; ++k16) {
+              const uint32_t acol = (uint32_t)((c * KC + k16 * 16) >> 1);
+              // MN-major B: K groups (8 keys) are 128 bytes apart inside a plane, N groups are the planes
+              const uint64_t vh = make_desc(st + (uint32_t)(k16 * 256), 128, PITCH_V);
+              const uint64_t vl = make_desc(st + (uint32_t)(V_HALF + k16 * 256), 128, PITCH_V);
+              mma_f16_ts(tmem_base, tmem_base + 256 + acol, vh, idesc2, (c > 0 || k16 > 0) ? 1u : 0u);
+              mma_f16_ts(tmem_base, tmem_base + 256 + phalf_cols + acol, vh, idesc2, 1u);
+              mma_f16_ts(tmem_base, tmem_base + 256 + acol, vl, idesc2, 1u);
+            }
+            mma_commit(empty_bar(stage));
+            if (c == nchunk2 - 1) mma_commit(o_full);
           }
-          mma_commit(empty_bar(stage));
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        mma_commit(o_full);
       }
     }
-    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();

@@ -308,8 +308,9 @@ __global__ void __launch_bounds__(NTHREADS, (TILES == 2) ? 2 : 1) shift_gemm_tc(
     }
     tc_fence_before();
   } else if (warp == 8) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer =====================
+    // warp-uniform loop (descriptors stay in uniform registers), one elected lane issues: see conv_tma.cu
+    {
       constexpr uint32_t idesc = F16 ? make_idesc_f16(BN) : make_idesc(BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -317,32 +318,33 @@ __global__ void __launch_bounds__(NTHREADS, (TILES == 2) ? 2 : 1) shift_gemm_tc(
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         // one base descriptor per operand per stage; every MMA of the stage is (base + compile-time constant): the
-        // start-address field is the low 14 bits (address >> 4) and never carries out for < 256 KB of shared memory, so
-        // the single issuing thread spends one add per operand per MMA instead of re-encoding descriptors.
+        // start-address field is the low 14 bits (address >> 4) and never carries out for < 256 KB of shared memory
         const uint32_t a_st = smem_base + (uint32_t)stage * STAGE;
         const uint64_t a_base = make_desc(a_st, LBO_A, SBO_A);
         const uint64_t b_base = make_desc(a_st + A_STAGE, LBO_B, 128);
         const uint32_t acc0 = (kc > 0) ? 1u : 0u;
+        if (elect_one()) {
 #pragma unroll
-        for (int tl = 0; tl < TILES; ++tl) {
+          for (int tl = 0; tl < TILES; ++tl) {
 #pragma unroll
-          for (int t = 0; t < TAPS; ++t) {
-            const uint32_t tapoff = (TAPS == 9) ? (uint32_t)(((t / 3) * 10 + (t % 3)) * 16) : 0u;
+            for (int t = 0; t < TAPS; ++t) {
+              const uint32_t tapoff = (TAPS == 9) ? (uint32_t)(((t / 3) * 10 + (t % 3)) * 16) : 0u;
 #pragma unroll
-            for (int k8 = 0; k8 < KC / (2 * EPC); ++k8) {   // one MMA = two 16-byte chunks of K (8 tf32 | 16 fp16)
-              const uint64_t ad = a_base + (uint64_t)((tl * A_TILE + tapoff + k8 * 2 * LBO_A) >> 4);
-              const uint64_t bd = b_base + (uint64_t)((t * B_TAP + k8 * 2 * LBO_B) >> 4);
-              if (F16) mma_f16_ss(tmem_base + (uint32_t)(tl * BN), ad, bd, idesc, (t > 0 || k8 > 0) ? 1u : acc0);
-              else mma_tf32_ss(tmem_base + (uint32_t)(tl * BN), ad, bd, idesc, (t > 0 || k8 > 0) ? 1u : acc0);
+              for (int k8 = 0; k8 < KC / (2 * EPC); ++k8) {   // one MMA = two 16-byte chunks of K (8 tf32 | 16 fp16)
+                const uint64_t ad = a_base + (uint64_t)((tl * A_TILE + tapoff + k8 * 2 * LBO_A) >> 4);
+                const uint64_t bd = b_base + (uint64_t)((t * B_TAP + k8 * 2 * LBO_B) >> 4);
+                if (F16) mma_f16_ss(tmem_base + (uint32_t)(tl * BN), ad, bd, idesc, (t > 0 || k8 > 0) ? 1u : acc0);
+                else mma_tf32_ss(tmem_base + (uint32_t)(tl * BN), ad, bd, idesc, (t > 0 || k8 > 0) ? 1u : acc0);
+              }
             }
           }
+          mma_commit(empty_bar(stage));  // frees the smem stage when these MMAs have read it
+          if (kc == nchunks - 1) mma_commit(accum_bar);  // all accumulators complete
         }
-        mma_commit(empty_bar(stage));  // frees the smem stage when these MMAs have read it
+        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      mma_commit(accum_bar);  // all accumulators complete
     }
-    __syncwarp();
   } else {
     // ===================== weight bulk-copy issuer (one thread) =====================
     if (lane == 0) {
@@ -601,8 +603,8 @@ __global__ void __launch_bounds__(P_NTHREADS, 1) shift_gemm_p16(const Params p) 
       buf ^= 1;
     }
   } else if (warp == 12) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    {
       constexpr uint32_t idesc = make_idesc_f16(BN);
       int stage = 0, buf = 0;
       uint32_t phase = 0, eph[2] = {0u, 0u};
@@ -618,24 +620,26 @@ __global__ void __launch_bounds__(P_NTHREADS, 1) shift_gemm_p16(const Params p) 
           const uint64_t a_base = make_desc(a_st, LBO_A, SBO_A);
           const uint64_t b_base = make_desc(a_st + A_STAGE, LBO_B, 128);
           const uint32_t acc0 = (kc > 0) ? 1u : 0u;
+          if (elect_one()) {
 #pragma unroll
-          for (int tl = 0; tl < TILES; ++tl) {
+            for (int tl = 0; tl < TILES; ++tl) {
 #pragma unroll
-            for (int t = 0; t < TAPS; ++t) {
-              const uint32_t tapoff = (uint32_t)(((t / 3) * 10 + (t % 3)) * 16);
-              const uint64_t ad = a_base + (uint64_t)((tl * A_TILE + tapoff) >> 4);
-              const uint64_t bd = b_base + (uint64_t)((t * B_TAP) >> 4);
-              mma_f16_ss(acc + (uint32_t)(tl * BN), ad, bd, idesc, t > 0 ? 1u : acc0);
+              for (int t = 0; t < TAPS; ++t) {
+                const uint32_t tapoff = (uint32_t)(((t / 3) * 10 + (t % 3)) * 16);
+                const uint64_t ad = a_base + (uint64_t)((tl * A_TILE + tapoff) >> 4);
+                const uint64_t bd = b_base + (uint64_t)((t * B_TAP) >> 4);
+                mma_f16_ss(acc + (uint32_t)(tl * BN), ad, bd, idesc, t > 0 ? 1u : acc0);
+              }
             }
+            mma_commit(empty_bar(stage));
+            if (kc == nchunks - 1) mma_commit(accf_bar(buf));
           }
-          mma_commit(empty_bar(stage));
+          __syncwarp();
           if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
         }
-        mma_commit(accf_bar(buf));
         buf ^= 1;
       }
     }
-    __syncwarp();
   } else {
     // ===================== weight bulk-copy issuer (one thread) =====================
     if (lane == 0) {
@@ -775,40 +779,6 @@ struct WParams {
   int x_f16;              // fp16-operand kernel: x already holds fp16 (mas_gn_backward's act_out): staged without conversion
   int dy_f16;             // fp16-operand kernel: dy is the fp16 shadow (mas_gn_backward's dx_f16), already scaled by operand_scale(*dy_amax)
 };
-
-__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ unsigned short to_h(float a) {
-  unsigned short r;
-  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(a));
-  return r;
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
-  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
-      "%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
-      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
-      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
-      "r"(r[31])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // TAPS == 9: 3x3 convolution (unit = 8x8 output pixels, halo 10x10).  TAPS == 1: 1x1 convolution / row GEMM
 // (unit = 64 consecutive rows, no halo).
@@ -1224,7 +1194,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc(const WParams p, const
     __syncwarp();
   } else {
     // ============ MMA issuer ============
-    if (lane == 0) {
+    // the whole warp walks the loop (warp-uniform control flow keeps descriptors in uniform registers: the single-thread form
+    // spent ~23 instructions per MMA on vector adds and R2UR moves and could not run ahead of the tensor pipe); one elected
+    // lane issues the MMAs and the commits
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int64_t u = u0; u < u1; ++u) {
@@ -1234,33 +1207,38 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc(const WParams p, const
         const uint32_t b_st = smem_base + (uint32_t)stage * B_STAGE;
         const uint32_t a_t = tmem_base + ACC_COLS + (uint32_t)(stage * A_COLS);
         const uint64_t b_base = make_desc(b_st, LBO_B, 128);
+        const uint64_t b16 = make_desc(b_st, 160, P16);   // MN-major: LBO = K-group (halo row) pitch, SBO = N-group (plane) pitch
         const uint32_t acc0 = (u > u0) ? 1u : 0u;
-        if (F16) {
-          const uint64_t b16 = make_desc(b_st, 160, P16);   // MN-major: LBO = K-group (halo row) pitch, SBO = N-group (plane) pitch
+        if (elect_one()) {
+          if (F16) {
 #pragma unroll
-          for (int r = 0; r < 8; r += 2) {     // K = 16 pixels = image rows (r, r+1) of the unit: halo rows r+dy, r+dy+1
+            for (int r = 0; r < 8; r += 2) {     // K = 16 pixels = image rows (r, r+1) of the unit: halo rows r+dy, r+dy+1
 #pragma unroll
-            for (int dyy = 0; dyy < 3; ++dyy) {
-              const uint64_t bd = b16 + (uint64_t)(((r + dyy) * 160) >> 4);
-              mma_f16_ts(tmem_base + (uint32_t)(dyy * NMMA), a_t + (uint32_t)(r * 4), bd, idesc, r > 0 ? 1u : acc0);
+              for (int dyy = 0; dyy < 3; ++dyy) {
+                const uint64_t bd = b16 + (uint64_t)(((r + dyy) * 160) >> 4);
+                mma_f16_ts(tmem_base + (uint32_t)(dyy * NMMA), a_t + (uint32_t)(r * 4), bd, idesc, r > 0 ? 1u : acc0);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+#pragma unroll
+              for (int dyy = 0; dyy < ((TAPS == 9) ? 3 : 1); ++dyy) {
+                // image row r + dy starts at chunk 2*(r+dy) (8 pixels = 2 chunks); the three dx taps are the N blocks
+                const uint64_t bd = b_base + (uint64_t)(((r + dyy) * 2 * LBO_B) >> 4);
+                mma_tf32_ts(tmem_base + (uint32_t)(dyy * NMMA), a_t + (uint32_t)(r * 8), bd, idesc, r > 0 ? 1u : acc0);
+              }
             }
           }
-        } else
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-#pragma unroll
-          for (int dyy = 0; dyy < ((TAPS == 9) ? 3 : 1); ++dyy) {
-            // image row r + dy starts at chunk 2*(r+dy) (8 pixels = 2 chunks); the three dx taps are the N blocks
-            const uint64_t bd = b_base + (uint64_t)(((r + dyy) * 2 * LBO_B) >> 4);
-            mma_tf32_ts(tmem_base + (uint32_t)(dyy * NMMA), a_t + (uint32_t)(r * 8), bd, idesc, r > 0 ? 1u : acc0);
-          }
+          mma_commit(empty(stage));
+          if (u + 1 == u1) mma_commit(accum_bar);
         }
-        mma_commit(empty(stage));
+        __syncwarp();
         if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
       }
-      mma_commit(accum_bar);
+      if (u0 >= u1 && elect_one()) mma_commit(accum_bar);   // empty split: nothing was issued, the epilogue still waits
+      __syncwarp();
     }
-    __syncwarp();
   }
   __syncthreads();
   if (warp == 12) {
@@ -1509,11 +1487,17 @@ static int wgrad_tc_splits(int64_t cps, int64_t units) {
   const int64_t ups = cdiv(units, s);
   return (int)cdiv(units, ups);  // every split owns at least one unit
 }
+size_t conv_wgrad_t16_ws(mas_tensor4 xs, mas_tensor4 dys);   // conv_tma.cu: the shadow-fed kernel splits differently
+bool conv_wgrad_t16_ok(mas_tensor4 xs, mas_tensor4 dys);
+int conv_wgrad_t16_launch(const void* x16, mas_tensor4 xs, const void* dy16, mas_tensor4 dys, float* dw, float* dbias,
+                          const float* dy_amax, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t conv_wgrad_tc_ws(mas_tensor4 xs, mas_tensor4 dys, int mode) {
   if (!wgrad_tc_ok(xs, dys, mode, true)) return 0;
   const int64_t coutk = cdiv(dys.c, tc::BM) * tc::BM;
   size_t splits = wgrad_tc_splits((coutk / tc::BM) * (xs.c / tc::WG_NT), dys.n * (dys.h / 8) * (dys.w / 8));
-  return splits * 9 * (size_t)coutk * xs.c * sizeof(float) + splits * (size_t)coutk * sizeof(float) + 256;
+  const size_t a = splits * 9 * (size_t)coutk * xs.c * sizeof(float) + splits * (size_t)coutk * sizeof(float) + 256;
+  const size_t b = mode == MAS_CONV_S1 ? conv_wgrad_t16_ws(xs, dys) : 0;
+  return a > b ? a : b;
 }
 PFN_cuTensorMapEncodeTiled tensor_map_encoder() {   // also used by conv_tma.cu
   static PFN_cuTensorMapEncodeTiled fn = nullptr;
@@ -1578,6 +1562,11 @@ int conv_wgrad_tc_launch(const float* x, mas_tensor4 xs, const float* dy, mas_te
   x_f16 &= 1;
   if (x_f16 && (!f16 || gn_table)) return fail(MAS_ERR_INVALID_ARG, "tc wgrad: an fp16 x needs the fp16-operand kernel and no prologue");
   if (dy_f16 && (!f16 || !dy_amax || dys.c % 8)) return fail(MAS_ERR_INVALID_ARG, "tc wgrad: an fp16 dy needs the fp16-operand kernel, its scale source and Cout %% 8 == 0");
+  // both operands as fp16 shadows: the pure TMA + MMA kernel (conv_tma.cu); MAS_WGRAD_TMA=0 keeps the register-staged one
+  static const bool tma_off = [] { const char* e = getenv("MAS_WGRAD_TMA"); return e && e[0] == '0'; }();
+  if (f16 && x_f16 && dy_f16 && mode == MAS_CONV_S1 && !gn_table && !tma_off && conv_wgrad_t16_ok(xs, dys) &&
+      cout_rows == (int)(cdiv(dys.c, tc::BM) * tc::BM))
+    return conv_wgrad_t16_launch(x, xs, dy, dys, dw, dbias, dy_amax, ws, ws_bytes, st);
   // cout_rows: rows of dw / dbias the caller allocated; padding (dys.c % 128 != 0) only when it equals round_up(dys.c, 128)
   const bool pad_ok = cout_rows == (int)(cdiv(dys.c, tc::BM) * tc::BM);
   if (!wgrad_tc_ok(xs, dys, mode, pad_ok) || !al16p(x) || !al16p(dy)) return fail(MAS_ERR_UNSUPPORTED, "tc wgrad: shape/layout not eligible");

@@ -67,6 +67,17 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t adesc, uin
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// one lane of the (converged) warp: true for exactly one thread.  The MMA-issuing warps run their loops warp-uniformly (operand
+// descriptors stay in uniform registers) and only the issue itself is predicated on this.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -238,8 +249,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm3_tc(const P3 p) {
     }
     tc_fence_before();
   } else {
-    // ---------------- MMA issuer ----------------
-    if (lane == 0) {
+    // ---------------- MMA issuer (warp-uniform loop, one elected lane issues) ----------------
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int kc = 0; kc < nchunks; ++kc) {
@@ -248,19 +259,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm3_tc(const P3 p) {
         const uint32_t st = smem_base + (uint32_t)stage * STAGE;
         const uint64_t a_hi = make_desc(st, LBO, 128), a_lo = make_desc(st + PLANE, LBO, 128);
         const uint64_t b_hi = make_desc(st + 2 * PLANE, LBO, 128), b_lo = make_desc(st + 3 * PLANE, LBO, 128);
+        if (elect_one()) {
 #pragma unroll
-        for (int k8 = 0; k8 < KC / 8; ++k8) {
-          const uint64_t ko = (uint64_t)((k8 * 2 * LBO) >> 4);
-          mma_tf32_ss(tmem_base, a_hi + ko, b_hi + ko, IDESC, (kc > 0 || k8 > 0) ? 1u : 0u);
-          mma_tf32_ss(tmem_base, a_lo + ko, b_hi + ko, IDESC, 1u);
-          mma_tf32_ss(tmem_base, a_hi + ko, b_lo + ko, IDESC, 1u);
+          for (int k8 = 0; k8 < KC / 8; ++k8) {
+            const uint64_t ko = (uint64_t)((k8 * 2 * LBO) >> 4);
+            mma_tf32_ss(tmem_base, a_hi + ko, b_hi + ko, IDESC, (kc > 0 || k8 > 0) ? 1u : 0u);
+            mma_tf32_ss(tmem_base, a_lo + ko, b_hi + ko, IDESC, 1u);
+            mma_tf32_ss(tmem_base, a_hi + ko, b_lo + ko, IDESC, 1u);
+          }
+          mma_commit(empty_bar(stage));
+          if (kc == nchunks - 1) mma_commit(accum_bar);
         }
-        mma_commit(empty_bar(stage));
+        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      mma_commit(accum_bar);
+      if (nchunks == 0 && elect_one()) mma_commit(accum_bar);
+      __syncwarp();
     }
-    __syncwarp();
   }
   __syncthreads();
   if (warp == 8) {

@@ -211,8 +211,11 @@ __global__ void __launch_bounds__(T_THREADS, 1) shift_gemm_t16(const HParams p, 
       buf ^= 1;
     }
   } else if (warp == T_EPI_WARPS) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer =====================
+    // The whole warp walks the loop (warp-uniform control flow keeps the operand descriptors in uniform registers: one add
+    // per descriptor per MMA instead of a 64-bit vector add + five R2UR moves - the single-thread form spent ~23 instructions
+    // per MMA and could not run ahead of the tensor pipe); one elected lane issues the MMAs and commits.
+    {
       constexpr uint32_t idesc = make_idesc_f16(TALL ? 256 : BN);
       int as = 0, bs = 0, buf = 0;
       uint32_t aph = 0, bph = 0, eph[2] = {0u, 0u};
@@ -230,31 +233,30 @@ __global__ void __launch_bounds__(T_THREADS, 1) shift_gemm_t16(const HParams p, 
             mbar_wait(bfull(bs), bph);
             tc_fence_after();
             const uint64_t wd0 = make_desc(b_base + (uint32_t)bs * T_BSTAGE, LBO_B, 128);
+            const uint64_t xds = xd0 + (uint64_t)((sub * 32) >> 4);
             const uint32_t acc0 = (c > 0 || sub > 0) ? 1u : 0u;
+            if (elect_one()) {
 #pragma unroll
-            for (int t = 0; t < TAPS; ++t) {
-              const uint32_t tapoff = (uint32_t)(((t / 3) * 10 + (t % 3)) * 128);
-              const uint64_t wd = wd0 + (uint64_t)((t * B_TAP) >> 4);
-              const uint64_t xd = xd0 + (uint64_t)((tapoff + sub * 32) >> 4);
-              // D^T = W x X^T: weights on the M side, pixels on the N side
-              if (TALL) {
+              for (int t = 0; t < TAPS; ++t) {
+                const uint32_t tapoff = (uint32_t)(((t / 3) * 10 + (t % 3)) * 128);
+                const uint64_t wd = wd0 + (uint64_t)((t * B_TAP) >> 4);
+                const uint64_t xd = xds + (uint64_t)(tapoff >> 4);
+                // D^T = W x X^T: weights on the M side, pixels on the N side
                 mma_f16_ss(acc, wd, xd, idesc, t > 0 ? 1u : acc0);
-              } else {
-                mma_f16_ss(acc, wd, xd, idesc, t > 0 ? 1u : acc0);
-                mma_f16_ss(acc + 128u, wd, xd + (uint64_t)(T_ATILE >> 4), idesc, t > 0 ? 1u : acc0);
+                if (!TALL) mma_f16_ss(acc + 128u, wd, xd + (uint64_t)(T_ATILE >> 4), idesc, t > 0 ? 1u : acc0);
               }
+              mma_commit(bempty(bs));
+              if (sub == 3) mma_commit(aempty(as));
+              if (sub == 3 && c == achunks - 1) mma_commit(accf(buf));
             }
-            mma_commit(bempty(bs));
+            __syncwarp();
             if (++bs == T_BSTAGES) { bs = 0; bph ^= 1; }
           }
-          mma_commit(aempty(as));
           if (++as == T_ASTAGES) { as = 0; aph ^= 1; }
         }
-        mma_commit(accf(buf));
         buf ^= 1;
       }
     }
-    __syncwarp();
   } else {
     // ===================== copy issuer (one thread): halos by tensor map, weight stages by bulk copy =====================
     if (lane == 0) {
@@ -294,6 +296,176 @@ __global__ void __launch_bounds__(T_THREADS, 1) shift_gemm_t16(const HParams p, 
 
 constexpr size_t t16_smem_bytes() {
   return 1024 + (size_t)T_ASTAGES * T_ASTAGE + (size_t)T_BSTAGES * T_BSTAGE + (2 * T_ASTAGES + 2 * T_BSTAGES + 4) * 8 + 16;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Weight gradient of the 3x3 stride-1 convolution from the two fp16 shadows (activation x16, output gradient dy16 - already
+// scaled), dW[tap][co][ci] = sum_pixels dy[p][co] * x[p + tap][ci]; the reduction runs over PIXELS, so both operands are
+// "MN-major" in memory (channels contiguous, pixels strided):
+//   * A = dy^T in tensor memory (TS mode): the dy tile of a unit (8 x 8 pixels x 128 co, one tensor-map copy) is moved
+//     shared -> registers -> TMEM by four loader warps, two pixels per 32-bit column, lane = co (the transpose is free);
+//   * B = the activation halo exactly as the copy engine lands it under the 128-byte swizzle: [row][pixel][64 ci] with 128-byte
+//     pixel rows, read as an MN-major operand (K groups = image rows of 8 pixels, SBO = the 1280-byte halo row; probe:
+//     tools/probe_mn128.py).  A tap is a descriptor start shift (dx * 128 B); no producer warps, no dx copies;
+//   * a CTA owns one kernel ROW (3 horizontal taps) of a 128 co x NCI ci block: 3 x NCI accumulator columns, N = 64 MMAs
+//     (two per tap and K step for NCI = 128), K = 16 pixels = two image rows of the unit;
+//   * split-K over the units; partial sums (and the bias gradient from the dy loaders) go to the caller's workspace in the
+//     layout conv_wgrad_reduce expects.
+constexpr int WT_STAGES = 4;
+constexpr int WT_XATOM = 8 * 10 * 128;      // 8 halo rows x 10 pixels x 128 B (64 channels)
+constexpr int WT_DY = 64 * 128 * 2;         // 64 pixels x 128 co halves
+constexpr int WT_THREADS = 6 * 32;
+
+struct WTParams {
+  float* part;      // [splits][9][Cout][Cin]
+  float* bpart;     // [splits][Cout] or null
+  int N, H, W, Cin, Cout;
+  int units_x, units_y;
+  int64_t total_units, units_per_split;
+  const float* dy_amax;   // the magnitude dy16's power-of-two scale was derived from
+};
+
+template <int NCI>
+__global__ void __launch_bounds__(WT_THREADS, 1) wgrad_t16(const WTParams p, const __grid_constant__ CUtensorMap x_map,
+                                                          const __grid_constant__ CUtensorMap dy_map) {
+  constexpr int XB = (NCI / 64) * WT_XATOM, STAGE = XB + WT_DY;
+  constexpr uint32_t ACC_COLS = 3 * NCI, A_COLS = 32;
+  static_assert(ACC_COLS + WT_STAGES * A_COLS <= 512, "tensor memory budget");
+  constexpr uint32_t idesc = make_idesc_f16(64) | (1u << 16);   // B operand MN-major
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_base = smem_u32(smem_raw);
+  const uint32_t smem_base = (raw_base + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - raw_base);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)WT_STAGES * STAGE);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * WT_STAGES + 1);
+  const uint32_t bar_base = smem_u32(bars);
+  auto fullD = [&](int s) { return bar_base + 8u * s; };                      // copies of the stage have landed
+  auto fullA = [&](int s) { return bar_base + 8u * (WT_STAGES + s); };        // dy^T of the stage is in tensor memory
+  auto empty = [&](int s) { return bar_base + 8u * (2 * WT_STAGES + s); };    // the MMAs of the stage have completed
+  const uint32_t accum_bar = bar_base + 8u * (3 * WT_STAGES);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int dyy = blockIdx.x % 3, ci0 = (blockIdx.x / 3) * NCI, co0 = blockIdx.y * BM, split = blockIdx.z;
+  const int64_t u0 = (int64_t)split * p.units_per_split;
+  const int64_t u1 = min(p.total_units, u0 + p.units_per_split);
+
+  if (tid == 0) {
+    for (int s = 0; s < WT_STAGES; ++s) { mbar_init(fullD(s), 1); mbar_init(fullA(s), 128); mbar_init(empty(s), 1); }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ============ dy loaders, then epilogue ============
+    const int cl = warp * 32 + lane;          // channel within the co tile = TMEM lane
+    float a_inv;
+    operand_scale(p.dy_amax, &a_inv);
+    float bsum = 0.f;
+    const bool want_bias = p.bpart != nullptr && blockIdx.x == 0;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int64_t u = u0; u < u1; ++u) {
+      mbar_wait(fullD(stage), phase);
+      const unsigned short* dh = reinterpret_cast<const unsigned short*>(smem + (size_t)stage * STAGE + XB) + cl;
+      float w[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const uint32_t lo = dh[(2 * j) * 128], hi = dh[(2 * j + 1) * 128];
+        w[j] = __uint_as_float(lo | (hi << 16));
+        if (want_bias) bsum += __half2float(__ushort_as_half((unsigned short)lo)) + __half2float(__ushort_as_half((unsigned short)hi));
+      }
+      tc_fence_after();
+      tmem_st32(tmem_base + ((uint32_t)(warp * 32) << 16) + ACC_COLS + (uint32_t)(stage * A_COLS), w);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(fullA(stage));
+      if (++stage == WT_STAGES) { stage = 0; phase ^= 1; }
+    }
+    if (want_bias) p.bpart[(size_t)split * p.Cout + co0 + cl] = bsum * a_inv;
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int dx = 0; dx < 3; ++dx) {
+      float* o = p.part + (((size_t)split * 9 + dyy * 3 + dx) * p.Cout + co0 + cl) * p.Cin + ci0;
+#pragma unroll 1
+      for (int cb = 0; cb < NCI / 32; ++cb) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(dx * NCI + cb * 32), v);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(o + cb * 32 + q * 4) =
+              make_float4(v[4 * q] * a_inv, v[4 * q + 1] * a_inv, v[4 * q + 2] * a_inv, v[4 * q + 3] * a_inv);
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 4) {
+    // ============ MMA issuer (warp-uniform loop, one elected lane issues) ============
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int64_t u = u0; u < u1; ++u) {
+      mbar_wait(fullA(stage), phase);     // implies fullD: the halo of the stage has landed too
+      tc_fence_after();
+      const uint32_t xs = smem_base + (uint32_t)stage * STAGE;
+      const uint32_t a_t = tmem_base + ACC_COLS + (uint32_t)(stage * A_COLS);
+      // MN-major, 128-byte swizzle: K groups (8 pixels = one image row of the unit) are SBO = 1280 B apart
+      const uint64_t xd0 = (uint64_t)((xs >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1280 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+      const uint32_t acc0 = (u > u0) ? 1u : 0u;
+      if (elect_one()) {
+#pragma unroll
+        for (int r = 0; r < 8; r += 2) {          // K = 16 pixels: image rows r, r + 1 of the unit
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+            for (int hf = 0; hf < NCI / 64; ++hf) {
+              const uint64_t xd = xd0 + (uint64_t)((hf * WT_XATOM + r * 1280 + dx * 128) >> 4);
+              mma_f16_ts(tmem_base + (uint32_t)(dx * NCI + hf * 64), a_t + (uint32_t)(r * 4), xd, idesc, r > 0 ? 1u : acc0);
+            }
+          }
+        }
+        mma_commit(empty(stage));
+        if (u + 1 == u1) mma_commit(accum_bar);
+      }
+      __syncwarp();
+      if (++stage == WT_STAGES) { stage = 0; phase ^= 1; }
+    }
+    if (u0 >= u1 && elect_one()) mma_commit(accum_bar);
+    __syncwarp();
+  } else {
+    // ============ copy issuer (one thread): dy tile + activation halo rows of this kernel row ============
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t u = u0; u < u1; ++u) {
+        const int ux = (int)(u % p.units_x), uy = (int)((u / p.units_x) % p.units_y);
+        const int n = (int)(u / ((int64_t)p.units_x * p.units_y));
+        const uint32_t dst = smem_base + (uint32_t)stage * STAGE;
+        mbar_wait(empty(stage), phase ^ 1);
+        mbar_expect_tx(fullD(stage), STAGE);
+#pragma unroll
+        for (int hf = 0; hf < NCI / 64; ++hf)
+          tma_load_4d(dst + (uint32_t)(hf * WT_XATOM), &x_map, ci0 + hf * 64, ux * 8 - 1, uy * 8 + dyy - 1, n, fullD(stage));
+        tma_load_4d(dst + XB, &dy_map, co0, ux * 8, uy * 8, n, fullD(stage));
+        if (++stage == WT_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int NCI>
+constexpr size_t wt_smem_bytes() {
+  return 1024 + (size_t)WT_STAGES * ((NCI / 64) * WT_XATOM + WT_DY) + (3 * WT_STAGES + 1) * 8 + 16;
 }
 
 // fp32 -> fp16 shadow (optionally scaled by the power-of-two operand scale of *amax): plain vectorised copy
@@ -363,6 +535,78 @@ int conv3x3_fprop_tma16_launch(const void* x16, mas_tensor4 xs, const void* w_tc
   if (tall) tc::shift_gemm_t16<true><<<g, tc::T_THREADS, smem, st>>>(p, map);
   else tc::shift_gemm_t16<false><<<g, tc::T_THREADS, smem, st>>>(p, map);
   return launched_tc(tall ? "shift_gemm_t16<tall>" : "shift_gemm_t16<pair>");
+}
+
+void conv_wgrad_reduce_launch(const float* part, int splits, int ntap, int Cout, int Cin, float* dw, const float* bpart, float* dbias,
+                              cudaStream_t st);   // contract_simt.cu
+
+static int wt_splits(int64_t cps, int64_t units) {
+  int64_t s = 148 / cps;
+  if (s < 1) s = 1;
+  if (s > units) s = units;
+  const int64_t ups = cdiv(units, s);
+  return (int)cdiv(units, ups);
+}
+bool conv_wgrad_t16_ok(mas_tensor4 xs, mas_tensor4 dys) {
+  return dense_nhwc4(xs) && dense_nhwc4(dys) && xs.c % 64 == 0 && dys.c % 8 == 0 && dys.h % 8 == 0 && dys.w % 8 == 0 && xs.h == dys.h &&
+         xs.w == dys.w && xs.n == dys.n;
+}
+size_t conv_wgrad_t16_ws(mas_tensor4 xs, mas_tensor4 dys) {
+  if (!conv_wgrad_t16_ok(xs, dys)) return 0;
+  const int64_t coutk = cdiv(dys.c, tc::BM) * tc::BM;
+  const int nci = xs.c % 128 == 0 ? 128 : 64;
+  const size_t splits = wt_splits((coutk / tc::BM) * (xs.c / nci) * 3, dys.n * (dys.h / 8) * (dys.w / 8));
+  return splits * 9 * (size_t)coutk * xs.c * sizeof(float) + splits * (size_t)coutk * sizeof(float) + 256;
+}
+// x16: fp16 activation shadow; dy16: fp16 output-gradient shadow scaled by operand_scale(*dy_amax); dw/dbias sized for
+// round_up(dys.c, 128) output channels (the copy engine zero-fills the channels dy does not have).
+int conv_wgrad_t16_launch(const void* x16, mas_tensor4 xs, const void* dy16, mas_tensor4 dys, float* dw, float* dbias,
+                          const float* dy_amax, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!conv_wgrad_t16_ok(xs, dys) || !dy_amax) return fail(MAS_ERR_UNSUPPORTED, "tma wgrad: shape/layout not eligible");
+  if (ws_bytes < conv_wgrad_t16_ws(xs, dys)) return fail(MAS_ERR_WORKSPACE, "tma wgrad: workspace too small");
+  tc::WTParams p;
+  p.N = (int)xs.n; p.H = (int)xs.h; p.W = (int)xs.w; p.Cin = (int)xs.c; p.Cout = (int)(cdiv(dys.c, tc::BM) * tc::BM);
+  p.units_x = (int)(dys.w / 8); p.units_y = (int)(dys.h / 8);
+  p.total_units = (int64_t)p.N * p.units_x * p.units_y;
+  p.dy_amax = dy_amax;
+  const int nci = p.Cin % 128 == 0 ? 128 : 64;
+  const int splits = wt_splits((int64_t)(p.Cout / tc::BM) * (p.Cin / nci) * 3, p.total_units);
+  p.units_per_split = cdiv(p.total_units, splits);
+  p.part = (float*)ws;
+  p.bpart = dbias ? (float*)ws + (size_t)splits * 9 * p.Cout * p.Cin : nullptr;
+
+  PFN_cuTensorMapEncodeTiled enc = tensor_map_encoder();
+  if (!enc) return fail(MAS_ERR_LAUNCH, "cuTensorMapEncodeTiled entry point not available");
+  CUtensorMap xmap, dmap;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)xs.c, (cuuint64_t)xs.w, (cuuint64_t)xs.h, (cuuint64_t)xs.n};
+    cuuint64_t strides[3] = {(cuuint64_t)xs.c * 2, (cuuint64_t)xs.w * xs.c * 2, (cuuint64_t)xs.h * xs.w * xs.c * 2};
+    cuuint32_t box[4] = {64, 10, 8, 1}, es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x16), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(MAS_ERR_LAUNCH, "cuTensorMapEncodeTiled (wgrad halo map) failed (%d)", (int)r);
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)dys.c, (cuuint64_t)dys.w, (cuuint64_t)dys.h, (cuuint64_t)dys.n};
+    cuuint64_t strides[3] = {(cuuint64_t)dys.c * 2, (cuuint64_t)dys.w * dys.c * 2, (cuuint64_t)dys.h * dys.w * dys.c * 2};
+    cuuint32_t box[4] = {128, 8, 8, 1}, es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&dmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(dy16), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(MAS_ERR_LAUNCH, "cuTensorMapEncodeTiled (wgrad dy map) failed (%d)", (int)r);
+  }
+  static std::atomic<uint64_t> configured{0};
+  if (first_on_device(configured)) {
+    cudaError_t e = cudaFuncSetAttribute(tc::wgrad_t16<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::wt_smem_bytes<128>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::wgrad_t16<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::wt_smem_bytes<64>());
+    if (e != cudaSuccess) return fail(MAS_ERR_LAUNCH, "cudaFuncSetAttribute(wgrad_t16): %s", cudaGetErrorString(e));
+    mark_device(configured);
+  }
+  dim3 grid((unsigned)((p.Cin / nci) * 3), (unsigned)(p.Cout / tc::BM), (unsigned)splits);
+  if (nci == 128) tc::wgrad_t16<128><<<grid, tc::WT_THREADS, tc::wt_smem_bytes<128>(), st>>>(p, xmap, dmap);
+  else tc::wgrad_t16<64><<<grid, tc::WT_THREADS, tc::wt_smem_bytes<64>(), st>>>(p, xmap, dmap);
+  if (int e = launched_tc("wgrad_t16")) return e;
+  conv_wgrad_reduce_launch((const float*)ws, splits, 9, p.Cout, p.Cin, dw, p.bpart, dbias, st);
+  return launched("conv_wgrad_reduce");
 }
 
 int to_half_launch(const float* x, void* y, int64_t n, const float* amax, cudaStream_t st) {

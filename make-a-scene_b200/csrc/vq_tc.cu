@@ -106,6 +106,17 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// one lane of the (converged) warp: true for exactly one thread.  The MMA-issuing warps run their loops warp-uniformly (operand
+// descriptors stay in uniform registers) and only the issue itself is predicated on this.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -302,8 +313,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_filter_tc(const Params p) {
     }
     __syncwarp();
   } else {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    {
       int stage = 0, buf = 0;
       uint32_t phase = 0, eph[2] = {0u, 0u};
       for (int t = tile_lo; t < tile_hi; ++t) {
@@ -315,23 +326,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_filter_tc(const Params p) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t bst = smem_base + (uint32_t)stage * B_STAGE;
+          if (elect_one()) {
 #pragma unroll
-          for (int k16 = 0; k16 < KC / 16; ++k16) {
-            const uint32_t acol = (uint32_t)((c * KC + k16 * 16) >> 1);          // 16 dimensions = 8 columns
-            const uint64_t bh = make_desc(bst + (uint32_t)(k16 * 2 * PITCH_B), PITCH_B, 128);
-            const uint64_t bl = make_desc(bst + (uint32_t)(B_HALF + k16 * 2 * PITCH_B), PITCH_B, 128);
-            mma_f16_ts(acc, tmem_base + acol, bh, IDESC, (c > 0 || k16 > 0) ? 1u : 0u);                    // zh . eh
-            mma_f16_ts(acc, tmem_base + (uint32_t)half_cols + acol, bh, IDESC, 1u);                     // zl . eh
-            mma_f16_ts(acc, tmem_base + acol, bl, IDESC, 1u);                                          // zh . el
+            for (int k16 = 0; k16 < KC / 16; ++k16) {
+              const uint32_t acol = (uint32_t)((c * KC + k16 * 16) >> 1);          // 16 dimensions = 8 columns
+              const uint64_t bh = make_desc(bst + (uint32_t)(k16 * 2 * PITCH_B), PITCH_B, 128);
+              const uint64_t bl = make_desc(bst + (uint32_t)(B_HALF + k16 * 2 * PITCH_B), PITCH_B, 128);
+              mma_f16_ts(acc, tmem_base + acol, bh, IDESC, (c > 0 || k16 > 0) ? 1u : 0u);                    // zh . eh
+              mma_f16_ts(acc, tmem_base + (uint32_t)half_cols + acol, bh, IDESC, 1u);                     // zl . eh
+              mma_f16_ts(acc, tmem_base + acol, bl, IDESC, 1u);                                          // zh . el
+            }
+            mma_commit(empty_bar(stage));
+            if (c == nchunk - 1) mma_commit(accf_bar(buf));
           }
-          mma_commit(empty_bar(stage));
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        mma_commit(accf_bar(buf));
         buf ^= 1;
       }
     }
-    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();

@@ -747,8 +747,11 @@ class ResnetBlockFn(torch.autograd.Function):
         else:
             d_h1, dn2w, dn2b = gn_backward(d_a2, h1, m2, r2, n2w, n2b, True)
         del d_a2
-        dc2w, dc2b = conv3x3_wgrad_raw(a2, dout, cout, cout, L.CONV_S1, dy_amax=am_out)
-        del a2
+        if sh_out is not None and a2.dtype == torch.float16:
+            dc2w, dc2b = conv3x3_wgrad_raw(a2, sh_out[0], cout, cout, L.CONV_S1, dy_amax=sh_out[1])   # both operands as fp16 shadows
+        else:
+            dc2w, dc2b = conv3x3_wgrad_raw(a2, dout, cout, cout, L.CONV_S1, dy_amax=am_out)
+        del a2, sh_out
         if sh_h1 is not None:
             d_h1, am_h1 = sh_h1
             d_a1 = conv3x3_h_raw(d_h1, c1w, None, None, transpose=True, x_amax=am_h1)

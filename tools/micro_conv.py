@@ -60,6 +60,7 @@ def variants(B, C, H, Co=None):
         out["tma_plain"] = lambda: ops.conv3x3_h_raw(x16, w, b, None)
         out["tma_stats"] = lambda: ops.conv3x3_h_raw(x16, w, b, x if C == Co else None, want_stats=True)
         out["tma_dgrad"] = lambda: ops.conv3x3_h_raw(dy16, w, None, None, transpose=True, x_amax=dya)
+        out["wgrad16"] = lambda: ops.conv3x3_wgrad_raw(x16, dy16, Co, C, L.CONV_S1, dy_amax=dya)   # both operands as fp16 shadows
         out["gn_apply16"] = lambda: ops.gn_apply_f16(x, m, r, g, be, True)
         out["to_half"] = lambda: ops.to_half(x)
     return out
