@@ -197,29 +197,58 @@ def time_kernel(fn, iters=5, warm=2):
 
 
 def dominant_kernel_roofline(dev, pk):
-    """conv3x3 128->128 @256x256, batch 32 (47.7% of the step's FLOPs): M=2,097,152 N=128 K=1152, timed as the model runs it
-    (plain launch: bias, no prologue; operand format = ops.get_operand_format(); weights packed once and cached)."""
+    """The kernel with the largest share of the step: the 3x3 convolution on its dominant layer, conv3x3 128->128 @256x256,
+    batch 32 (M=2,097,152 N=128 K=1152; 47.7% of the step's FLOPs run on this layer shape), launched as the model launches it:
+    the TMA-fed fp16-operand kernel shift_gemm_t16 reading the fp16 activation shadow (forward / data gradient; bias epilogue),
+    weights packed once. `others`: the shadow-fed weight-gradient kernel on the same layer and, when the TMA path is off or the
+    operand format is not f16, the register-staged kernel. Achieved = algorithmic FLOPs / CUDA-event time."""
     from mas_b200 import _lib as L, ops
     x = torch.randn(BATCH, 128, RES, RES, device=dev).contiguous(memory_format=torch.channels_last)
     w = torch.randn(128, 128, 3, 3, device=dev) * 0.03
     b = torch.zeros(128, device=dev)
+    flops = 2.0 * BATCH * RES * RES * 128 * 128 * 9
     tc = ops.get_impl() != L.IMPL_SIMT and ops.conv_tc_eligible(x, 128, L.CONV_S1)
     fmt = ops.get_operand_format() if tc else "fp32"
-    xa = ops.amax(x) if fmt == "f16" else None
-    fn = lambda: ops.conv3x3_raw(x, w, b, None, L.CONV_S1, x_amax=xa)
-    kname = {"f16": "shift_gemm_tc<9,f16> (tcgen05 kind::f16 operands, fp32 accumulate)", "tf32": "shift_gemm_tc<9> (tcgen05 TF32)",
-             "fp32": "conv_fprop_simt (fp32 FFMA)"}[fmt] + " conv3x3 128->128 @256^2 x32"
-    sec = time_kernel(fn, iters=6, warm=3)
-    flops = 2.0 * BATCH * RES * RES * 128 * 128 * 9
-    ach = flops / sec / 1e12
     traffic = None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("conv3x3_128_128_256_bytes_per_launch")
-    return {"kernel": kname, "bound": "tensor", "achieved": ach, "peak": pk["bf16"],
-            "unit": "TFLOP/s", "frac": ach / pk["bf16"], "traffic": traffic, "peak_source": pk["src"] + " bf16 burst (fp16 runs at the bf16 rate)",
-            "ms_per_launch": sec * 1e3, "operands": fmt,
-            "algorithmic_bytes_per_launch": 4.0 * BATCH * RES * RES * 256 + 4 * 128 * 128 * 9}
+    tj = json.load(open(tp)) if os.path.exists(tp) else {}
+    others = []
+
+    def entry(name, sec, alg_bytes, tkey):
+        ach = flops / sec / 1e12
+        return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": ach / pk["bf16"],
+                "traffic": tj.get(tkey), "ms_per_launch": sec * 1e3, "algorithmic_bytes_per_launch": alg_bytes}
+
+    wbytes = 2 * 128 * 128 * 9
+    if fmt == "f16" and ops.conv_tma_on():
+        x16 = ops.to_half(x)
+        y = torch.empty_like(x)
+        wt = ops._packed_conv_weight(w, w, 128, 128, False, dev, False, True)
+        fn = lambda: L.call("mas_conv3x3_fprop_tc16h", x16, L.t4(x16), wt, b, None, y, L.t4(y), None, None)
+        main = entry("shift_gemm_t16 (TMA-fed tcgen05 kind::f16, fp32 accumulate) conv3x3 128->128 @256^2 x32",
+                     time_kernel(fn, iters=6, warm=3), 2.0 * BATCH * RES * RES * 128 + 4.0 * BATCH * RES * RES * 128 + wbytes,
+                     "conv3x3_tma_128_128_256_bytes_per_launch")
+        dy = torch.randn(BATCH, 128, RES, RES, device=dev).contiguous(memory_format=torch.channels_last) * 1e-6
+        am = ops.amax(dy)
+        dy16 = ops.to_half(dy, am)
+        del dy
+        gfn = lambda: ops.conv3x3_wgrad_raw(x16, dy16, 128, 128, L.CONV_S1, dy_amax=am)
+        others.append(entry("wgrad_t16 + reduction (weight gradient from the fp16 shadows) conv3x3 128->128 @256^2 x32",
+                            time_kernel(gfn, iters=6, warm=3), 2 * 2.0 * BATCH * RES * RES * 128 + 4.0 * 128 * 128 * 9,
+                            "wgrad_t16_128_128_256_bytes_per_launch"))
+        del x16, y, dy16
+    xa = ops.amax(x) if fmt == "f16" else None
+    fn = lambda: ops.conv3x3_raw(x, w, b, None, L.CONV_S1, x_amax=xa)
+    kname = {"f16": "shift_gemm_tc<9,f16> (register-staged fp16 operands; strided / upsampling / unshadowed layers)",
+             "tf32": "shift_gemm_tc<9> (tcgen05 TF32)", "fp32": "conv_fprop_simt (fp32 FFMA)"}[fmt] + " conv3x3 128->128 @256^2 x32"
+    staged = entry(kname, time_kernel(fn, iters=6, warm=3), 4.0 * BATCH * RES * RES * 256 + 4 * 128 * 128 * 9,
+                   "conv3x3_128_128_256_bytes_per_launch")
+    if fmt == "f16" and ops.conv_tma_on():
+        others.append(staged)
+    else:
+        main = staged
+    main.update({"peak_source": pk["src"] + " bf16 burst (fp16 runs at the bf16 rate)", "operands": fmt, "others": others})
+    return main
 
 
 def attn_metric(dev, pk):
@@ -316,6 +345,8 @@ def main():
     ap.add_argument("--workload", default="vqimg", choices=["vqimg", "vqseg"],
                     help="vqimg: BASELINE configs[1] (the headline metric); vqseg: configs[3], 159-channel maps + weighted BCE")
     ap.add_argument("--profile", action="store_true", help="print per-entry-point CUDA-event times of one extra step")
+    ap.add_argument("--step-only", action="store_true",
+                    help="skip the per-kernel blocks (roofline / VQ sweep / AttnBlock / CPU baseline): launch-list captures under ncu")
     ap.add_argument("--graph", action="store_true",
                     help="single GPU: replay the step from one CUDA graph (mas_b200.graph.GraphedStep) instead of launching from Python")
     args = ap.parse_args()
@@ -431,6 +462,10 @@ def main():
         for k, (c, t) in sorted(rep.items(), key=lambda kv: -kv[1][1]):
             print("  %-44s n=%4d  %9.2f ms  %5.1f%%  %7.3f ms/call" % (k, c, t, 100 * t / tot, t / c), file=sys.stderr)
         print("  total %.2f ms" % tot, file=sys.stderr)
+    if args.step_only:
+        print(json.dumps({"metric": METRIC, "value": value, "ms_per_step": sec / args.steps * 1e3, "gpu_launches": int(launches),
+                          "step_only": True}), flush=True)
+        return
     roof = dominant_kernel_roofline(dev, pk)
     if seg:
         line = {"metric": SEG_METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

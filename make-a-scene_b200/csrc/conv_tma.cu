@@ -51,6 +51,7 @@ struct HParams {
   int64_t units;          // work units of 256 pixels: 32 x 8 tiles (TALL) or pairs of consecutive 16 x 8 tiles
   float* stats_part;   // GroupNorm-statistics epilogue (see shift_gemm_tc), or null
   const float* x_amax; // amax the shadow's power-of-two scale was derived from (null: unscaled shadow)
+  int res_prefetch;    // pull the next item's residual tile towards L2 from the epilogue warps
 };
 
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t sbo_bytes) {
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) shift_gemm_t16(const HParams p, 
       const bool st_ok = ch < p.Cstore;
       const float bv = (p.bias && st_ok) ? __ldg(p.bias + ch) : 0.f;
       const int64_t pix0 = ((int64_t)n_img * p.H + ty_ * 16) * p.W + tx_ * 8;
-      if (p.res) {
+      if (p.res && p.res_prefetch) {
         // pull the NEXT item's residual tile towards L2 while this one is being written (one 128-byte line per pixel and warp)
         const int64_t nitem = item + gridDim.x;
         int nn, nty, ntx;
@@ -504,6 +505,7 @@ int conv3x3_fprop_tma16_launch(const void* x16, mas_tensor4 xs, const void* w_tc
   p.N = (int)xs.n; p.H = (int)xs.h; p.W = (int)xs.w; p.Cin = (int)xs.c; p.Cout = Cout; p.Cstore = Cstore; p.ldy = Cstore;
   p.tiles_x = (int)(ys.w / 8); p.tiles_y = (int)(ys.h / 16);
   p.stats_part = stats_part; p.x_amax = x_amax;
+  { const char* e = getenv("MAS_TMA_RES_PREFETCH"); p.res_prefetch = (e && e[0] == '0') ? 0 : 1; }
   const bool tall = ys.h % 32 == 0;
   const int64_t tiles = (int64_t)p.N * p.tiles_x * p.tiles_y;
   p.units = tall ? tiles / 2 : cdiv(tiles, 2);

@@ -729,6 +729,10 @@ class ResnetBlockFn(torch.autograd.Function):
         am_out = amax_of(dout) if f16_operands() else None   # from the producing kernel, else one pass; serves dgrad and wgrad
         hmode = ctx.hmode and conv_tma_on()
         sh_out = shadow_of(dout) if hmode else None
+        if hmode and sh_out is None and am_out is not None:
+            # dout comes from a kernel that does not write shadows (head of a chain of blocks): one conversion pass feeds both
+            # the data gradient and the weight gradient of conv2 (cheaper than their register-staged forms)
+            sh_out = (to_half(dout, am_out), am_out)
         if sh_out is not None:
             # dout was written by a GroupNorm backward together with its fp16 shadow: pure TMA + MMA data gradient
             d_a2 = conv3x3_h_raw(sh_out[0], c2w, None, None, transpose=True, x_amax=sh_out[1])

@@ -15,5 +15,8 @@ print({k:d[k] for k in ("value","ms_per_step","gpu_launches")}, "e2e",d["e2e"]["
 v=d["vq"]; print({k:v[k] for k in v if k not in ("sweep","kernel","bound","all_pairs_ffma_kernel")}); print(d["attn"])
 s=json.loads(open("$O/${TAG}_seg.json").read().strip().splitlines()[-1]); print("vqseg", s["value"], s["ms_per_step"], s["e2e"])
 PY
-timeout 300 ncu --set full --clock-control none -k regex:"vq_filter_tc|vq_resolve|vq_pack_codes" -c 3 -f -o $O/r02_vq3 python tools/prof_kernels.py vq > $O/r02_vq3.log 2>&1; tail -1 $O/r02_vq3.log
-timeout 300 ncu --set full --clock-control none -k regex:"attn_core_fwd" -c 1 -f -o $O/r02_attnf python tools/prof_kernels.py attn > $O/r02_attnf.log 2>&1; tail -1 $O/r02_attnf.log
+# ncu --set full of the production convolution kernels on the dominant layer, and the launch list of one step
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"shift_gemm_t16|wgrad_t16" -c 6 -f -o $O/r02_conv4 \
+  python tools/micro_conv.py one tma_plain tma_stats wgrad16 > $O/r02_conv4.log 2>&1; tail -1 $O/r02_conv4.log
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 9000 --csv --log-file $O/r02_launches2.csv \
+  python bench.py --no-cpu-baseline --steps 1 --warmup 1 --step-only > $O/r02_launch_bench2.log 2>&1; tail -1 $O/r02_launch_bench2.log | cut -c1-200
