@@ -14,8 +14,8 @@
 //   * operand roles are swapped (D^T = W x X^T: the packed weights are the M-side operand, the pixels the N side), so a TMEM
 //     lane is an output channel and a column a pixel: the epilogue's 32 lanes store 32 consecutive channels of one pixel -
 //     a full 128-byte line per instruction without a shared-memory transpose; bias and GroupNorm statistics are per-thread;
-//   * two accumulator sets in tensor memory (2 x 256 columns): eight epilogue warps drain set b (bias / residual, whose
-//     next tile they prefetch into L2 / GroupNorm-statistics epilogue) while the MMAs of the next item fill set b^1;
+//   * two accumulator sets in tensor memory (2 x 256 columns): eight epilogue warps drain set b (bias / residual /
+//     GroupNorm-statistics epilogue) while the MMAs of the next item fill set b^1;
 //   * warps 0-7 epilogue, warp 8 MMA issuer, warp 9 copy issuer: no thread of the CTA touches the operands.
 //
 // Reference call sites replaced: nn.Conv2d 3x3 stride 1 (modules.py:93-104) forward and its data gradient.
@@ -51,7 +51,6 @@ struct HParams {
   int64_t units;          // work units of 256 pixels: 32 x 8 tiles (TALL) or pairs of consecutive 16 x 8 tiles
   float* stats_part;   // GroupNorm-statistics epilogue (see shift_gemm_tc), or null
   const float* x_amax; // amax the shadow's power-of-two scale was derived from (null: unscaled shadow)
-  int res_prefetch;    // pull the next item's residual tile towards L2 from the epilogue warps
 };
 
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t sbo_bytes) {
@@ -140,22 +139,10 @@ __global__ void __launch_bounds__(T_THREADS, 1) shift_gemm_t16(const HParams p, 
       const bool st_ok = ch < p.Cstore;
       const float bv = (p.bias && st_ok) ? __ldg(p.bias + ch) : 0.f;
       const int64_t pix0 = ((int64_t)n_img * p.H + ty_ * 16) * p.W + tx_ * 8;
-      if (p.res && p.res_prefetch) {
-        // pull the NEXT item's residual tile towards L2 while this one is being written (one 128-byte line per pixel and warp)
-        const int64_t nitem = item + gridDim.x;
-        int nn, nty, ntx;
-        if (nitem < nitems && unit_tile<TALL>(p, nitem / n_tiles, hf, nn, nty, ntx)) {
-          const int nch = (int)(nitem % n_tiles) * BN + quarter * 32;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int m = k * 32 + lane;
-            const int64_t pix = ((int64_t)nn * p.H + nty * 16 + (m >> 3)) * p.W + ntx * 8 + (m & 7);
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res + pix * p.ldy + nch));
-          }
-        }
-      }
       // residual: the 32 loads of a 32-pixel batch are issued ONE BATCH AHEAD (the first before the accumulator is even
-      // waited for), so 32 KB per SM are in flight - the epilogue was bound by this latency, not by the stores
+      // waited for), so 32 KB per SM are in flight - the epilogue was bound by this latency, not by the stores.  (An L2
+      // prefetch of the next item's residual tile on top of this measured SLOWER - 0.66 vs 0.61 ms - and fetched 44 % of the
+      // residual twice: the output stream evicts the prefetched lines.)
       const int rs = p.W * (int)p.ldy, ps = (int)p.ldy;      // element strides of an image row / a pixel (tile-local: fits int)
       const int64_t base0 = pix0 * p.ldy + ch;
       const bool use_res = p.res != nullptr && live && st_ok;
@@ -505,7 +492,6 @@ int conv3x3_fprop_tma16_launch(const void* x16, mas_tensor4 xs, const void* w_tc
   p.N = (int)xs.n; p.H = (int)xs.h; p.W = (int)xs.w; p.Cin = (int)xs.c; p.Cout = Cout; p.Cstore = Cstore; p.ldy = Cstore;
   p.tiles_x = (int)(ys.w / 8); p.tiles_y = (int)(ys.h / 16);
   p.stats_part = stats_part; p.x_amax = x_amax;
-  { const char* e = getenv("MAS_TMA_RES_PREFETCH"); p.res_prefetch = (e && e[0] == '0') ? 0 : 1; }
   const bool tall = ys.h % 32 == 0;
   const int64_t tiles = (int64_t)p.N * p.tiles_x * p.tiles_y;
   p.units = tall ? tiles / 2 : cdiv(tiles, 2);

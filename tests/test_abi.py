@@ -114,3 +114,27 @@ def test_weight_pack_cache_is_keyed_by_identity_and_version(monkeypatch):
         del w, w2, f1, f2, d1, d2
         gc.collect()
         assert len(ops._packs) == n_live - 2                                 # entries die with their weights
+
+
+def test_shadow_and_amax_attachments_follow_the_tensor_version():
+    """ops.shadow_of / ops.amax_of only trust what a producing kernel attached while the tensor is unchanged since (same
+    version counter, same storage address, same device and shape): host-side bookkeeping of the fp16 operand shadows."""
+    import torch
+    from mas_b200 import ops
+    t = torch.zeros(2, 8, 4, 4).contiguous(memory_format=torch.channels_last)
+    sh16 = torch.zeros_like(t, dtype=torch.float16)
+    bound = torch.ones(1)
+    assert ops.shadow_of(t) is None
+    t._mas_shadow = (sh16, bound, t._version, t.data_ptr())
+    got = ops.shadow_of(t)
+    assert got is not None and got[0] is sh16 and got[1] is bound
+    t.add_(1.0)                                   # in-place update: the shadow no longer describes the tensor
+    assert ops.shadow_of(t) is None
+    u = torch.zeros(2, 8, 4, 4).contiguous(memory_format=torch.channels_last)
+    u._mas_shadow = (torch.zeros(2, 8, 2, 2, dtype=torch.float16), bound, u._version, u.data_ptr())
+    assert ops.shadow_of(u) is None               # shape mismatch
+    am = torch.ones(1)
+    ops.attach_amax(u, am)
+    assert getattr(u, "_mas_amax")[0] is am
+    u.mul_(2.0)
+    assert getattr(u, "_mas_amax")[1] != u._version
