@@ -18,5 +18,7 @@ PY
 # ncu --set full of the production convolution kernels on the dominant layer, and the launch list of one step
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"shift_gemm_t16|wgrad_t16" -c 6 -f -o $O/r02_conv4 \
   python tools/micro_conv.py one tma_plain tma_stats wgrad16 > $O/r02_conv4.log 2>&1; tail -1 $O/r02_conv4.log
+if [ "${2:-}" = "launches" ]; then   # ~8 GPU-minutes: every launch of four steps serialised under ncu
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 9000 --csv --log-file $O/r02_launches2.csv \
   python bench.py --no-cpu-baseline --steps 1 --warmup 1 --step-only > $O/r02_launch_bench2.log 2>&1; tail -1 $O/r02_launch_bench2.log | cut -c1-200
+fi
