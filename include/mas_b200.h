@@ -222,6 +222,13 @@ int mas_sumpool2x2(const float* x, float* y, int N, int H, int W, int C, void* s
 int mas_gemm(const float* A, const float* B, float* C, int M, int N, int K, int batch, int64_t lda,
              int64_t ldb, int64_t ldc, int64_t stride_a, int64_t stride_b, int64_t stride_c, int trans_a,
              int trans_b, float alpha, const float* bias, const float* residual, int impl, void* stream);
+/* Two-level batch: outer x batch matrices, matrix (o, i) at o * outer_stride_? + i * stride_? - the heads of a fused
+ * [B, S, 3H] q|k|v activation (transformer.py:77-103) in ONE launch on the 3xTF32 kernel (impl = MAS_IMPL_TC3, outer * batch
+ * <= 65535); other impl values run one mas_gemm per outer index.  No bias / residual. */
+int mas_gemm_batched2(const float* A, const float* B, float* C, int M, int N, int K, int outer, int batch, int64_t lda,
+                      int64_t ldb, int64_t ldc, int64_t outer_stride_a, int64_t outer_stride_b, int64_t outer_stride_c,
+                      int64_t stride_a, int64_t stride_b, int64_t stride_c, int trans_a, int trans_b, float alpha, int impl,
+                      void* stream);
 /* Column sums of a strided [N,H,W,C] view (bias gradients): out[c] = sum_{n,h,w} x[n,h,w,c]. Deterministic. */
 size_t mas_colsum_ws_bytes(mas_tensor4 t);
 int mas_colsum(const float* x, mas_tensor4 t, float* out, void* ws, size_t ws_bytes, void* stream);
@@ -329,6 +336,14 @@ int mas_embed3_forward(const float* t0, const int64_t* id0, const float* t1, con
                        const int64_t* id2, float* out, int64_t R, int H, int seg, int total, int off, void* stream);
 int mas_embed3_backward(const float* dout, const int64_t* id0, float* d0, const int64_t* id1, float* d1,
                         const int64_t* id2, float* d2, int64_t R, int H, int seg, int total, int off, void* stream);
+/* Token cross-entropy, train.py:150-153 (F.cross_entropy(logits.view(-1, V), img_token.view(-1)), mean reduction):
+ * logits [R, V] with row pitch ld, target int64 [R] (outside [0, V): row ignored like ignore_index).  forward writes the
+ * per-row losses, the per-row logsumexp (kept for the backward) and out[0] = mean loss, out[1] = counted rows.
+ * backward: dlogits[r, c] = (softmax(logits_r)[c] - [c == target_r]) * dloss[0] / out[1]; dlogits may alias logits. */
+int mas_ce_forward(const float* logits, int64_t ld, const int64_t* target, float* loss_rows, float* lse, float* out,
+                   int64_t R, int V, void* stream);
+int mas_ce_backward(const float* logits, int64_t ld, const int64_t* target, const float* lse, const float* stat,
+                    const float* dloss, float* dlogits, int64_t ldd, int64_t R, int V, void* stream);
 
 /* ---- Autoregressive sampling with a KV cache ---------------------------------------------
  * The reference has no working cached path (models/transformer.py:73-115 vs :176-210; train.py never samples); the
@@ -346,6 +361,11 @@ int mas_kv_append(const float* qkv, int R, int T, int heads, int hd, float* kcac
 int mas_attn_decode(const float* qkv, const float* kcache, const float* vcache, float* ctx, int R, int heads, int hd,
                     int Tmax, int len, void* stream);
 int mas_cfg_mix(const float* cond, const float* uncond, float* out, int64_t n, float scale, void* stream);
+/* Token draw of the sampler (replaces the div / topk / where / softmax / multinomial chain of generate()): per row,
+ * z = logits / temperature, entries below the top_k-th largest value dropped (top_k <= 0 or >= V: none), p = softmax(z),
+ * tokens[r] = first index whose running sum of p exceeds u[r] (u in [0,1): caller-supplied uniforms, device floats). */
+int mas_sample_topk(const float* logits, int64_t ld, int R, int V, float temperature, int top_k, const float* u,
+                    int64_t* tokens, void* stream);
 
 /* ---- weighted BCE-with-logits (VQ-SEG loss, losses/loss_seg.py:15-22) — "next" row ------------------
  * logits/target: strided [N,H,W,C] views; pos_weight [C]; loss_out = mean over all elements. grad may be NULL. */

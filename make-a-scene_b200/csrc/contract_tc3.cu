@@ -15,8 +15,8 @@
 //   * warps 0-7 produce then run the epilogue (tcgen05.ld -> smem patch -> coalesced 16-byte stores), warp 8 lane 0 issues
 //     the MMAs (12 per chunk); 2-stage full/empty mbarrier ring; 128 TMEM columns.
 //
-// STATUS: staged for the next round - built and exported, selected ONLY by impl = MAS_IMPL_TC3 of mas_gemm; no module
-// path uses it until it has been validated on a B200 (tests/test_gpu_staged.py, opt-in through MAS_EXPERIMENTAL=1).
+// Selected by impl = MAS_IMPL_TC3 of mas_gemm / mas_gemm_batched2: the AttnBlock backward and the token transformer's attention
+// contractions run on it (tests/test_gpu_gemm3.py, tests/test_gpu_transformer.py).
 #include "mas_common.cuh"
 
 namespace mas {
@@ -111,6 +111,10 @@ struct P3 {
   int64_t lda, ldb, ldc, sa, sb, sc;
   int ta, tb;   // 0: operand stored [row][k] (k contiguous); 1: stored [k][row] (rows contiguous)
   float alpha;
+  // two-level batch: blockIdx.z = outer * inner + i -> offsets outer * s?2 + i * s? (attention heads inside a fused
+  // [B, S, 3H] activation: outer = batch element, inner = head).  inner = batch, s?2 = 0 for the plain batched form.
+  int inner;
+  int64_t sa2, sb2, sc2;
 };
 
 // One operand of one K chunk: 128 rows x 32 k = 1024 quads, four per producer thread; returns them split into hi / lo.
@@ -132,9 +136,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm3_tc(const P3 p) {
   const uint32_t accum_bar = bar_base + 8u * (2 * STAGES);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
-  const float* Ab = p.A + (int64_t)blockIdx.z * p.sa;
-  const float* Bb = p.B + (int64_t)blockIdx.z * p.sb;
-  float* Cb = p.C + (int64_t)blockIdx.z * p.sc;
+  const int zo = (int)blockIdx.z / p.inner, zi = (int)blockIdx.z - zo * p.inner;
+  const float* Ab = p.A + (int64_t)zo * p.sa2 + (int64_t)zi * p.sa;
+  const float* Bb = p.B + (int64_t)zo * p.sb2 + (int64_t)zi * p.sb;
+  float* Cb = p.C + (int64_t)zo * p.sc2 + (int64_t)zi * p.sc;
   const int nchunks = p.K / KC;
 
   if (tid == 0) {
@@ -292,9 +297,20 @@ static inline bool al16q(const void* p) { return (reinterpret_cast<uintptr_t>(p)
 
 // C[b] = alpha * opA(A[b]) . opB(B[b])^T, fp32-accurate on the tensor cores.  ta / tb as in mas_gemm: trans_a = 1 means A is
 // stored [K][M]; trans_b = 1 means B is stored [N][K] (k contiguous), trans_b = 0 means B is stored [K][N].
+int gemm_tc3_launch2(const float* A, const float* B, float* C, int M, int N, int K, int outer, int batch, int64_t lda, int64_t ldb,
+                     int64_t ldc, int64_t sa2, int64_t sb2, int64_t sc2, int64_t sa, int64_t sb, int64_t sc, int ta, int tb, float alpha,
+                     const float* bias, const float* res, cudaStream_t st);
 int gemm_tc3_launch(const float* A, const float* B, float* C, int M, int N, int K, int batch, int64_t lda, int64_t ldb, int64_t ldc,
                     int64_t sa, int64_t sb, int64_t sc, int ta, int tb, float alpha, const float* bias, const float* res,
                     cudaStream_t st) {
+  return gemm_tc3_launch2(A, B, C, M, N, K, 1, batch, lda, ldb, ldc, 0, 0, 0, sa, sb, sc, ta, tb, alpha, bias, res, st);
+}
+// outer x batch matrices: matrix (o, i) lives at o * s?2 + i * s?
+int gemm_tc3_launch2(const float* A, const float* B, float* C, int M, int N, int K, int outer, int batch, int64_t lda, int64_t ldb,
+                     int64_t ldc, int64_t sa2, int64_t sb2, int64_t sc2, int64_t sa, int64_t sb, int64_t sc, int ta, int tb, float alpha,
+                     const float* bias, const float* res, cudaStream_t st) {
+  if (outer < 1 || batch < 1 || (int64_t)outer * batch > 65535) return fail(MAS_ERR_UNSUPPORTED, "tc3 gemm: outer * batch must be in [1, 65535]");
+  if (sa2 % 4 || sb2 % 4 || sc2 % 4) return fail(MAS_ERR_UNSUPPORTED, "tc3 gemm: outer strides must be multiples of 4 elements");
   if (bias || res) return fail(MAS_ERR_UNSUPPORTED, "tc3 gemm: bias / residual epilogue not available");
   if (N % 64 || K % tc3::KC || lda % 4 || ldb % 4 || ldc % 4 || sa % 4 || sb % 4 || sc % 4 || !al16q(A) || !al16q(B) || !al16q(C))
     return fail(MAS_ERR_UNSUPPORTED, "tc3 gemm: need N %% 64 == 0, K %% 32 == 0, pitches %% 4 == 0 and 16-byte aligned operands");
@@ -305,6 +321,8 @@ int gemm_tc3_launch(const float* A, const float* B, float* C, int M, int N, int 
   p.ta = ta ? 1 : 0;        // A stored [K][M]  -> rows (m) contiguous
   p.tb = tb ? 0 : 1;        // B stored [N][K] (tb = 1) is the k-contiguous orientation; [K][N] (tb = 0) is row-contiguous
   p.alpha = alpha;
+  p.inner = batch; p.sa2 = sa2; p.sb2 = sb2; p.sc2 = sc2;
+  const int zdim = outer * batch;
   static std::atomic<uint64_t> configured{0};
   if (first_on_device(configured)) {
     cudaError_t e = cudaFuncSetAttribute(tc3::gemm3_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc3::SMEM_BYTES);
@@ -313,10 +331,10 @@ int gemm_tc3_launch(const float* A, const float* B, float* C, int M, int N, int 
     mark_device(configured);
   }
   if (N % 128 == 0) {
-    dim3 grid((unsigned)(N / 128), (unsigned)cdiv(M, tc3::BM), (unsigned)batch);
+    dim3 grid((unsigned)(N / 128), (unsigned)cdiv(M, tc3::BM), (unsigned)zdim);
     tc3::gemm3_tc<128><<<grid, tc3::NTHREADS, tc3::SMEM_BYTES, st>>>(p);
   } else {   // attention heads of 64 channels: P.V and the q / k / v gradients of the token transformer
-    dim3 grid((unsigned)(N / 64), (unsigned)cdiv(M, tc3::BM), (unsigned)batch);
+    dim3 grid((unsigned)(N / 64), (unsigned)cdiv(M, tc3::BM), (unsigned)zdim);
     tc3::gemm3_tc<64><<<grid, tc3::NTHREADS, tc3::SMEM_BYTES, st>>>(p);
   }
   return launched_tc("gemm3_tc");

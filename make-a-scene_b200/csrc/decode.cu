@@ -180,6 +180,99 @@ __global__ void cfg_mix_kernel(const float* __restrict__ cond, const float* __re
   }
 }
 
+// Token draw (Make-A-Scene paper 3.4 / generate()): z = logits / temperature, keep the top_k largest (all values equal to the
+// k-th largest are kept, like `z < kth -> -inf`), p = softmax(z), token = inverse CDF of p at u (first index whose running
+// sum exceeds u * total).  Block per row.  The k-th largest value is found by a 4-pass radix select on order-preserving keys.
+__device__ __forceinline__ uint32_t order_key(float f) {
+  const uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__global__ void __launch_bounds__(256) sample_topk_kernel(const float* __restrict__ logits, int64_t ld, int V, float temperature, int top_k,
+                                                          const float* __restrict__ u, int64_t* __restrict__ tok) {
+  __shared__ int hist[256];
+  __shared__ uint32_t s_prefix;
+  __shared__ int s_remaining;
+  __shared__ float red[8];
+  __shared__ float csum[256];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const float* x = logits + (int64_t)blockIdx.x * ld;
+  uint32_t thr = 0;                                   // keys >= thr are kept
+  if (top_k > 0 && top_k < V) {
+    uint32_t prefix = 0, mask = 0;
+    int remaining = top_k;
+    for (int pass = 3; pass >= 0; --pass) {
+      const int shift = pass * 8;
+      hist[t] = 0;
+      __syncthreads();
+      for (int c = t; c < V; c += 256) {
+        const uint32_t key = order_key(x[c] / temperature);
+        if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
+      }
+      __syncthreads();
+      if (t == 0) {
+        int rem = remaining, b = 255;
+        for (; b > 0; --b) {
+          const int cnt = hist[b];
+          if (cnt >= rem) break;
+          rem -= cnt;
+        }
+        s_prefix = prefix | ((uint32_t)b << shift);
+        s_remaining = rem;
+      }
+      __syncthreads();
+      prefix = s_prefix;
+      remaining = s_remaining;
+      mask |= 0xFFu << shift;
+      __syncthreads();
+    }
+    thr = prefix;
+  }
+  float mx = -INFINITY;
+  for (int c = t; c < V; c += 256) mx = fmaxf(mx, x[c] / temperature);
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+  // contiguous chunks per thread so that the running sum follows the index order
+  const int per = (V + 255) / 256, c0 = t * per, c1 = min(V, c0 + per);
+  float loc = 0.f;
+  for (int c = c0; c < c1; ++c) {
+    const float z = x[c] / temperature;
+    if (order_key(z) >= thr) loc += expf(z - mx);
+  }
+  csum[t] = loc;
+  __syncthreads();
+  if (t == 0) {
+    float total = 0.f;
+    for (int j = 0; j < 256; ++j) total += csum[j];
+    const float target = u[blockIdx.x] * total;
+    float run = 0.f;
+    int j = 0, last_chunk = 0;
+    for (; j < 256; ++j) {
+      if (csum[j] > 0.f) last_chunk = j;
+      if (run + csum[j] > target) break;
+      run += csum[j];
+    }
+    if (j == 256) {              // rounding pushed the target to the total: the last kept entry
+      j = last_chunk;
+      run = -INFINITY;
+    }
+    int pick = -1, last_kept = -1;
+    const int a0 = j * per, a1 = min(V, a0 + per);
+    for (int c = a0; c < a1; ++c) {
+      const float z = x[c] / temperature;
+      if (order_key(z) >= thr) {
+        last_kept = c;
+        run += expf(z - mx);
+        if (run > target) { pick = c; break; }
+      }
+    }
+    tok[blockIdx.x] = (int64_t)(pick >= 0 ? pick : last_kept);
+  }
+}
+
 // K-split variant for long rows and few outputs (MLP.lin2: N = 1024, K = 4096 gives only 128 blocks of the kernel above
 // and a 16 KB latency-bound stream per warp): a block owns two outputs, four warps each split one row of W, partials are
 // folded in a fixed order (deterministic).
@@ -304,6 +397,14 @@ int mas_cfg_mix(const float* cond, const float* uncond, float* out, int64_t n, f
   MAS_REQUIRE(cond && uncond && out && n > 0, "cfg_mix: bad arguments");
   cfg_mix_kernel<<<(int)(cdiv(n, 256) < 1184 ? cdiv(n, 256) : 1184), 256, 0, S(stream)>>>(cond, uncond, out, n, scale);
   return launched("cfg_mix");
+}
+
+int mas_sample_topk(const float* logits, int64_t ld, int R, int V, float temperature, int top_k, const float* u, int64_t* tokens,
+                    void* stream) {
+  MAS_REQUIRE(logits && u && tokens && R > 0 && V > 0 && ld >= V, "sample_topk: bad arguments");
+  if (!(temperature > 0.f)) return fail(MAS_ERR_INVALID_ARG, "sample_topk: temperature must be > 0 (greedy decoding: top_k = 1)");
+  sample_topk_kernel<<<R, 256, 0, S(stream)>>>(logits, ld, V, temperature, top_k, u, tokens);
+  return launched("sample_topk");
 }
 
 }  // extern "C"

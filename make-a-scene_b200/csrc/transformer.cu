@@ -226,6 +226,86 @@ __global__ void embed3_bwd_kernel(const float* __restrict__ dout, const int64_t*
   }
 }
 
+// ---------------------------------------------------------------------------------------------------- cross-entropy
+// train.py:150-153: F.cross_entropy(logits.view(-1, V), img_token.view(-1)) (mean over rows).  Block per row: max, then
+// sum of exp, loss_r = logsumexp - x[target]; the row's logsumexp is kept for the backward.  A target outside [0, V) marks
+// an ignored row (F.cross_entropy's ignore_index = -100): zero loss, zero gradient, not counted in the mean.
+__device__ __forceinline__ float block_max_256(float v, float* red) {
+  v = warp_max(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) r = fmaxf(r, red[w]);
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) r += red[w];
+  __syncthreads();
+  return r;
+}
+__global__ void __launch_bounds__(256) ce_fwd_kernel(const float* __restrict__ logits, int64_t ld, const int64_t* __restrict__ target,
+                                                     float* __restrict__ loss_rows, float* __restrict__ lse, int V) {
+  __shared__ float red[8];
+  const int64_t row = blockIdx.x;
+  const float* x = logits + row * ld;
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < V; c += 256) mx = fmaxf(mx, x[c]);
+  mx = block_max_256(mx, red);
+  float s = 0.f;
+  for (int c = threadIdx.x; c < V; c += 256) s += expf(x[c] - mx);
+  s = block_sum_256(s, red);
+  if (threadIdx.x == 0) {
+    const float l = mx + logf(s);
+    const int64_t t = target[row];
+    lse[row] = l;
+    loss_rows[row] = (t >= 0 && t < V) ? l - x[t] : 0.f;
+  }
+}
+// out[0] = mean of the counted rows' losses (fp64 totals, fixed order), out[1] = number of counted rows
+__global__ void __launch_bounds__(256) ce_reduce_kernel(const float* __restrict__ loss_rows, const int64_t* __restrict__ target, int64_t R,
+                                                        int V, float* __restrict__ out) {
+  __shared__ double sd[256];
+  __shared__ int sn[256];
+  double a = 0.0;
+  int n = 0;
+  for (int64_t r = threadIdx.x; r < R; r += 256) {
+    const int64_t t = target[r];
+    if (t >= 0 && t < V) { a += (double)loss_rows[r]; ++n; }
+  }
+  sd[threadIdx.x] = a;
+  sn[threadIdx.x] = n;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) { sd[threadIdx.x] += sd[threadIdx.x + o]; sn[threadIdx.x] += sn[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out[0] = sn[0] > 0 ? (float)(sd[0] / (double)sn[0]) : 0.f;
+    out[1] = (float)sn[0];
+  }
+}
+// dlogits[r, c] = (softmax(x_r)[c] - [c == t_r]) * dloss / count   (zero rows for ignored targets)
+__global__ void __launch_bounds__(256) ce_bwd_kernel(const float* __restrict__ logits, int64_t ld, const int64_t* __restrict__ target,
+                                                     const float* __restrict__ lse, const float* __restrict__ stat,
+                                                     const float* __restrict__ dloss, float* __restrict__ dlogits, int64_t ldd, int V) {
+  const int64_t row = blockIdx.x;
+  const int64_t t = target[row];
+  const bool on = t >= 0 && t < V;
+  const float cnt = stat[1];
+  const float g = on && cnt > 0.f ? dloss[0] / cnt : 0.f;
+  const float l = lse[row];
+  const float* x = logits + row * ld;
+  float* d = dlogits + row * ldd;
+  for (int c = threadIdx.x; c < V; c += 256) d[c] = on ? (expf(x[c] - l) - (c == (int)t ? 1.f : 0.f)) * g : 0.f;
+}
+
 static inline int ew_grid2(int64_t n) {
   int64_t b = cdiv(n, 256);
   return (int)(b < 148 * 16 ? (b < 1 ? 1 : b) : 148 * 16);
@@ -288,6 +368,21 @@ int mas_embed3_backward(const float* dout, const int64_t* id0, float* d0, const 
   MAS_REQUIRE(dout && id0 && d0 && R > 0 && H > 0 && seg > 0, "embed3_backward: bad arguments");
   embed3_bwd_kernel<<<(unsigned)R, 128, 0, S(stream)>>>(dout, id0, d0, id1, d1, id2, d2, R, H, seg, total, off);
   return launched("embed3_bwd");
+}
+
+int mas_ce_forward(const float* logits, int64_t ld, const int64_t* target, float* loss_rows, float* lse, float* out, int64_t R, int V,
+                   void* stream) {
+  MAS_REQUIRE(logits && target && loss_rows && lse && out && R > 0 && V > 0 && ld >= V, "ce_forward: bad arguments");
+  ce_fwd_kernel<<<(unsigned)R, 256, 0, S(stream)>>>(logits, ld, target, loss_rows, lse, V);
+  if (int e = launched("ce_fwd")) return e;
+  ce_reduce_kernel<<<1, 256, 0, S(stream)>>>(loss_rows, target, R, V, out);
+  return launched("ce_reduce");
+}
+int mas_ce_backward(const float* logits, int64_t ld, const int64_t* target, const float* lse, const float* stat, const float* dloss,
+                    float* dlogits, int64_t ldd, int64_t R, int V, void* stream) {
+  MAS_REQUIRE(logits && target && lse && stat && dloss && dlogits && R > 0 && V > 0 && ld >= V && ldd >= V, "ce_backward: bad arguments");
+  ce_bwd_kernel<<<(unsigned)R, 256, 0, S(stream)>>>(logits, ld, target, lse, stat, dloss, dlogits, ldd, V);
+  return launched("ce_bwd");
 }
 
 }  // extern "C"

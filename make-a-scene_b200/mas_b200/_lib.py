@@ -109,6 +109,10 @@ _SPEC = {
     "mas_kv_append": (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _P]),
     "mas_attn_decode": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "mas_cfg_mix": (_I, [_P, _P, _P, _L, _F, _P]),
+    "mas_sample_topk": (_I, [_P, _L, _I, _I, _F, _I, _P, _P, _P]),
+    "mas_ce_forward": (_I, [_P, _L, _P, _P, _P, _P, _L, _I, _P]),
+    "mas_ce_backward": (_I, [_P, _L, _P, _P, _P, _P, _P, _L, _L, _I, _P]),
+    "mas_gemm_batched2": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _L, _L, _L, _L, _L, _L, _L, _L, _L, _I, _I, _F, _I, _P]),
     "mas_bce_ws_bytes": (_Z, [_T]),
     "mas_bce_cl_ws_bytes": (_Z, [_I, _I, _I]),
     "mas_bce_cl_forward": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _Z, _P]),

@@ -1145,9 +1145,24 @@ def _attn_impl(S_, hd):
     return None
 
 
+def gemm2(A, B, C, M, N, K, outer, batch, lda, ldb, ldc, osa, osb, osc, sa, sb, sc, ta=False, tb=False, alpha=1.0, impl=None):
+    """outer x batch matrices in one call (mas_gemm_batched2): matrix (o, i) at o * os? + i * s?. Pointers as in gemm()."""
+    import ctypes
+
+    def at(v, o):
+        t, off = v if isinstance(v, tuple) else (v, 0)
+        return ctypes.c_void_p(t.data_ptr() + 4 * (off + o))
+    step = max(1, 65535 // batch)        # grid.z limit of the single-launch kernel
+    for o0 in range(0, outer, step):
+        n = min(step, outer - o0)
+        L.call("mas_gemm_batched2", at(A, o0 * osa), at(B, o0 * osb), at(C, o0 * osc), M, N, K, n, batch, lda, ldb, ldc, osa, osb, osc,
+               sa, sb, sc, int(ta), int(tb), float(alpha), _cfg["impl"] if impl is None else impl)
+
+
 class CausalAttentionFn(torch.autograd.Function):
     """softmax_causal((q / sqrt(hd)) k^T) v per (batch, head) from the fused qkv activation [B,S,3H]
-    (transformer.py:77-103; head h owns columns h*hd..(h+1)*hd of each third)."""
+    (transformer.py:77-103; head h owns columns h*hd..(h+1)*hd of each third). Every contraction is ONE launch over all
+    (batch element, head) pairs (two-level batch strides: the heads are column slices of the fused activation)."""
 
     @staticmethod
     def forward(ctx, qkv, heads):
@@ -1160,15 +1175,13 @@ class CausalAttentionFn(torch.autograd.Function):
         impl = _attn_impl(S_, hd)
         P = torch.empty((B, heads, S_, S_), dtype=torch.float32, device=qkv.device)
         ctxv = torch.empty((B, S_, H), dtype=torch.float32, device=qkv.device)
-        for b in range(B):
-            base = b * S_ * H3
-            gemm((qkv, base), (qkv, base + H), (P, b * heads * S_ * S_), S_, S_, hd, batch=heads, lda=H3, ldb=H3, ldc=S_, sa=hd,
-                 sb=hd, sc=S_ * S_, tb=True, alpha=alpha, impl=impl)
+        SS = S_ * S_
+        # S = alpha q k^T
+        gemm2(qkv, (qkv, H), P, S_, S_, hd, B, heads, H3, H3, S_, S_ * H3, S_ * H3, heads * SS, hd, hd, SS, tb=True, alpha=alpha,
+              impl=impl)
         L.call("mas_softmax_causal_forward", P, P, B * heads, S_, S_)
-        for b in range(B):
-            base = b * S_ * H3
-            gemm((P, b * heads * S_ * S_), (qkv, base + 2 * H), (ctxv, b * S_ * H), S_, hd, S_, batch=heads, lda=S_, ldb=H3, ldc=H,
-                 sa=S_ * S_, sb=hd, sc=hd, impl=impl)
+        # ctx = P v
+        gemm2(P, (qkv, 2 * H), ctxv, S_, hd, S_, B, heads, S_, H3, H, heads * SS, S_ * H3, S_ * H, SS, hd, hd, impl=impl)
         ctx.save_for_backward(qkv, P)
         ctx.heads = heads
         return ctxv
@@ -1185,21 +1198,63 @@ class CausalAttentionFn(torch.autograd.Function):
         impl = _attn_impl(S_, hd)
         dqkv = torch.empty_like(qkv)
         dP = torch.empty_like(P)
-        for b in range(B):
-            base, pb, cb = b * S_ * H3, b * heads * S_ * S_, b * S_ * H
-            # dV = P^T dO ; dP = dO V^T
-            gemm((P, pb), (dctx, cb), (dqkv, base + 2 * H), S_, hd, S_, batch=heads, lda=S_, ldb=H, ldc=H3, sa=S_ * S_, sb=hd, sc=hd,
-                 ta=True, impl=impl)
-            gemm((dctx, cb), (qkv, base + 2 * H), (dP, pb), S_, S_, hd, batch=heads, lda=H, ldb=H3, ldc=S_, sa=hd, sb=hd,
-                 sc=S_ * S_, tb=True, impl=impl)
+        SS = S_ * S_
+        oq, op_, oc = S_ * H3, heads * SS, S_ * H
+        # dV = P^T dO ; dP = dO V^T
+        gemm2(P, dctx, (dqkv, 2 * H), S_, hd, S_, B, heads, S_, H, H3, op_, oc, oq, SS, hd, hd, ta=True, impl=impl)
+        gemm2(dctx, (qkv, 2 * H), dP, S_, S_, hd, B, heads, H, H3, S_, oc, oq, op_, hd, hd, SS, tb=True, impl=impl)
         L.call("mas_softmax_backward", P, dP, dP, B * heads * S_, S_, alpha)     # dS (already times 1/sqrt(hd))
-        for b in range(B):
-            base, pb = b * S_ * H3, b * heads * S_ * S_
-            gemm((dP, pb), (qkv, base + H), (dqkv, base), S_, hd, S_, batch=heads, lda=S_, ldb=H3, ldc=H3, sa=S_ * S_, sb=hd, sc=hd,
-                 impl=impl)
-            gemm((dP, pb), (qkv, base), (dqkv, base + H), S_, hd, S_, batch=heads, lda=S_, ldb=H3, ldc=H3, sa=S_ * S_, sb=hd, sc=hd,
-                 ta=True, impl=impl)
+        # dQ = dS K ; dK = dS^T Q
+        gemm2(dP, (qkv, H), dqkv, S_, hd, S_, B, heads, S_, H3, H3, op_, oq, oq, SS, hd, hd, impl=impl)
+        gemm2(dP, qkv, (dqkv, H), S_, hd, S_, B, heads, S_, H3, H3, op_, oq, oq, SS, hd, hd, ta=True, impl=impl)
         return dqkv, None
+
+
+class CrossEntropyFn(torch.autograd.Function):
+    """F.cross_entropy(logits.view(-1, V), target.view(-1)) (mean; train.py:150-153) on mas_ce_forward / mas_ce_backward.
+    logits [..., V] fp32 (last dim contiguous), target int64 [...]; targets outside [0, V) are ignored rows."""
+
+    @staticmethod
+    def forward(ctx, logits, target):
+        _need_cuda(logits)
+        V = logits.shape[-1]
+        lg = logits.reshape(-1, V)
+        if lg.stride(-1) != 1:
+            lg = lg.contiguous()
+        tg = target.reshape(-1).to(torch.int64).contiguous()
+        R = lg.shape[0]
+        if tg.numel() != R:
+            raise ValueError("cross_entropy: %d logit rows vs %d targets" % (R, tg.numel()))
+        rows = torch.empty(R, dtype=torch.float32, device=lg.device)
+        lse = torch.empty(R, dtype=torch.float32, device=lg.device)
+        out = torch.empty(2, dtype=torch.float32, device=lg.device)
+        L.call("mas_ce_forward", lg, lg.stride(0), tg, rows, lse, out, R, V)
+        ctx.save_for_backward(lg, tg, lse, out)
+        ctx.shape = logits.shape
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, dloss):
+        lg, tg, lse, out = ctx.saved_tensors
+        R, V = lg.shape
+        d = torch.empty((R, V), dtype=torch.float32, device=lg.device)
+        L.call("mas_ce_backward", lg, lg.stride(0), tg, lse, out, dloss.contiguous().to(torch.float32), d, V, R, V)
+        return d.view(ctx.shape), None
+
+
+def cross_entropy(logits, target):
+    return CrossEntropyFn.apply(logits, target)
+
+
+def sample_topk(logits, temperature, top_k, u):
+    """One token per row of logits [R,V]: softmax(logits / temperature) restricted to the top_k entries, drawn by inverse CDF
+    at the caller's uniforms u [R] (device fp32 in [0,1))."""
+    _need_cuda(logits)
+    logits = logits.contiguous()
+    R, V = logits.shape
+    tok = torch.empty(R, dtype=torch.int64, device=logits.device)
+    L.call("mas_sample_topk", logits, V, R, V, float(temperature), int(top_k) if top_k else 0, u.contiguous(), tok)
+    return tok
 
 
 # ---- autoregressive sampling (inference only; SURVEY.md 8f-3) --------------------------------------------------

@@ -244,10 +244,18 @@ class MakeAScene(nn.Module):
         return ops.EmbedFn.apply(segs, total, self.hidden_dim, *tables)
 
     def forward(self, text_tokens, seg_tokens, img_tokens):
+        """Logits [B, image_length, V] predicting every image token from its prefix (transformer.py:366-378). The reference
+        computes to_logits over all 640 positions and slices afterwards; LayerNorm and Linear act row by row, so slicing the
+        hidden states first gives the same values (and the same, zero, gradient for the dropped rows) at 40 % of the work."""
         emb = self._embed(text_tokens, seg_tokens, img_tokens)
         out, _ = self.transformer(emb)
-        logits = self.to_logits[1](self.to_logits[0](out))
-        return logits[:, -self.image_length - 1:-1, :]
+        out = out[:, -self.image_length - 1:-1, :].contiguous()
+        return self.to_logits[1](self.to_logits[0](out))
+
+    def loss(self, text_tokens, seg_tokens, img_tokens):
+        """train.py:150-153 in one call: F.cross_entropy(forward(...).view(-1, V), img_tokens.view(-1)) on the fused
+        cross-entropy kernels (mas_ce_forward / mas_ce_backward: no log-softmax tensor, the gradient is written once)."""
+        return ops.cross_entropy(self.forward(text_tokens, seg_tokens, img_tokens), img_tokens)
 
     # ---- sampling (SURVEY.md 8f-3) ---------------------------------------------------------------------------
     def _prefill(self, emb, kc, vc):
@@ -322,12 +330,12 @@ class MakeAScene(nn.Module):
                 tok = img_tokens[:, t]
             elif not temperature:
                 tok = mixed.argmax(-1)
-            else:
-                z = mixed / float(temperature)
-                if top_k is not None:
-                    kth = torch.topk(z, int(top_k), dim=-1).values[:, -1:]
-                    z = torch.where(z < kth, torch.full_like(z, float("-inf")), z)
-                tok = torch.multinomial(torch.softmax(z, -1), 1, generator=generator).squeeze(1)
+            else:   # temperature, top-k filter, softmax and the draw in one kernel; torch only supplies the uniforms
+                if generator is not None and generator.device.type != dev.type:
+                    u = torch.rand(B, generator=generator).to(dev)
+                else:
+                    u = torch.rand(B, device=dev, generator=generator)
+                tok = ops.sample_topk(mixed, float(temperature), top_k, u)
             toks.append(tok)
             if t == self.image_length - 1:
                 break

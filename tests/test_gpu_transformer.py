@@ -176,3 +176,76 @@ def test_causal_attention_on_tensor_cores_matches_fp32_kernels():
     assert out["tc"][2] >= 12 and out["simt"][2] == 0
     assert rel_err(out["tc"][0], out["simt"][0]) < 2e-5
     assert rel_err(out["tc"][1], out["simt"][1]) < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------ fused cross-entropy / sampler
+@pytest.mark.parametrize("R,V,pitch", [(7, 33, 33), (512, 8192, 8192), (64, 1000, 1024)])
+def test_cross_entropy_vs_torch(R, V, pitch):
+    """mas_ce_forward / mas_ce_backward against F.cross_entropy (fp64 on the CPU): loss, gradient, ignored rows, row pitch."""
+    from mas_b200 import ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(R + V)
+    full = torch.randn(R, pitch, generator=g) * 3
+    tgt = torch.randint(0, V, (R,), generator=g)
+    tgt[R // 3] = -100                                      # F.cross_entropy's default ignore_index
+    ref_in = full[:, :V].double().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(ref_in, tgt)
+    (ref * 1.7).backward()
+    x = full.to(dev)[:, :V].requires_grad_(True)            # a strided view when pitch > V
+    loss = ops.cross_entropy(x, tgt.to(dev))
+    (loss * 1.7).backward()
+    assert abs(float(loss) - float(ref)) < 1e-5 * max(1.0, abs(float(ref)))
+    assert rel_err(x.grad, ref_in.grad.float()) < 1e-5
+    assert float(x.grad[R // 3].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("tag", ["tiny", "wide"])
+def test_make_a_scene_loss_entry_matches_reference(tag):
+    """MakeAScene.loss (forward + fused cross-entropy) against the REAL reference's loss and gradients (train.py:150-153)."""
+    from models.transformer import MakeAScene
+    g = torch.load(os.path.join(GOLDEN, f"transformer_{tag}.pt"), weights_only=False)
+    dev = torch.device("cuda:0")
+    m = MakeAScene(**g["cfg"])
+    m.load_state_dict(g["state_dict"])
+    m.to(dev)
+    m.device = dev
+    loss = m.loss(g["text"].to(dev), g["seg"].to(dev), g["img"].to(dev))
+    assert abs(float(loss) - float(g["loss"])) < 1e-3 * max(1.0, float(g["loss"]))
+    loss.backward()
+    named = dict(m.named_parameters())
+    for k, gv in g["grads"].items():
+        assert rel_err(named[k].grad, gv) < 5e-3, (tag, k)
+
+
+def test_sample_topk_kernel():
+    """mas_sample_topk: greedy when top_k = 1, the inverse CDF of the top-k softmax at the caller's uniforms otherwise,
+    and the right distribution over many rows."""
+    from mas_b200 import ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(11)
+    lg = torch.randn(8, 8192, generator=g) * 2
+    u = torch.rand(8, generator=g)
+    tok = ops.sample_topk(lg.to(dev), 0.8, 1, u.to(dev)).cpu()
+    assert torch.equal(tok, lg.argmax(-1))
+    for k in (5, 100, None):
+        tok = ops.sample_topk(lg.to(dev), 0.8, k, u.to(dev)).cpu()
+        z = lg.double() / 0.8
+        if k is not None:
+            kth = z.topk(k, -1).values[:, -1:]
+            z = torch.where(z < kth, torch.full_like(z, float("-inf")), z)
+        cdf = torch.softmax(z, -1).cumsum(-1)
+        for r in range(8):
+            t = int(tok[r])
+            assert z[r, t] > float("-inf")
+            lo = float(cdf[r, t - 1]) if t > 0 else 0.0
+            assert lo - 1e-5 <= float(u[r]) <= float(cdf[r, t]) + 1e-5, (k, r, t)
+    # distribution: 20000 rows of the same 50 logits, top 10
+    row = torch.randn(50, generator=g)
+    R = 20000
+    tok = ops.sample_topk(row.expand(R, 50).contiguous().to(dev), 1.3, 10, torch.rand(R, generator=g).to(dev)).cpu()
+    z = row.double() / 1.3
+    keep = z >= z.topk(10).values[-1]
+    p = torch.softmax(torch.where(keep, z, torch.full_like(z, float("-inf"))), -1)
+    freq = torch.bincount(tok, minlength=50).double() / R
+    assert float(freq[~keep].sum()) == 0.0
+    assert float((freq - p).abs().max()) < 5 * float((p * (1 - p) / R).sqrt().max())
