@@ -325,6 +325,11 @@ int mas_vq_gather(const float* E, const int64_t* idx, int64_t R, int K, int D, f
  * contractions go through mas_gemm_rows_packed / mas_gemm / mas_conv1x1_wgrad. */
 int mas_layernorm_forward(const float* x, const float* gamma, const float* beta, const float* residual, float* y,
                           float* mean, float* rstd, int64_t R, int H, float eps, void* stream);
+/* Two chained LayerNorms of a decode step (inference, R <= 64 rows): y1 = residual + LN1(x) (residual may be NULL) and
+ * y2 = LN2(y1) - the sandwich LayerNorm and the next sub-layer's input LayerNorm (transformer.py:183-208) in one launch. */
+int mas_layernorm2_forward(const float* x, const float* gamma1, const float* beta1, const float* residual, float* y1,
+                           const float* gamma2, const float* beta2, float* y2, int64_t R, int H, float eps1, float eps2,
+                           void* stream);
 size_t mas_layernorm_ws_bytes(int64_t R, int H);
 int mas_layernorm_backward(const float* dy, const float* x, const float* mean, const float* rstd,
                            const float* gamma, float* dx, float* dgamma, float* dbeta, int64_t R, int H, void* ws,
@@ -360,6 +365,10 @@ int mas_kv_append(const float* qkv, int R, int T, int heads, int hd, float* kcac
                   void* stream);
 int mas_attn_decode(const float* qkv, const float* kcache, const float* vcache, float* ctx, int R, int heads, int hd,
                     int Tmax, int len, void* stream);
+/* mas_attn_decode with the cache append folded in: the k / v thirds of qkv [R,3H] are stored at position pos and the query
+ * attends over positions 0..pos (one launch per layer instead of mas_kv_append + mas_attn_decode). */
+int mas_attn_decode_append(const float* qkv, float* kcache, float* vcache, float* ctx, int R, int heads, int hd, int Tmax,
+                           int pos, void* stream);
 int mas_cfg_mix(const float* cond, const float* uncond, float* out, int64_t n, float scale, void* stream);
 /* Token draw of the sampler (replaces the div / topk / where / softmax / multinomial chain of generate()): per row,
  * z = logits / temperature, entries below the top_k-th largest value dropped (top_k <= 0 or >= V: none), p = softmax(z),

@@ -88,18 +88,34 @@ __global__ void kv_append_kernel(const float* __restrict__ qkv, int R, int T, in
 // block per (row, head), 256 threads; q = this token's query (row r of qkv [R, 3H]); len cached positions (incl. this one).
 // Everything is latency-bound here (a few hundred KB per block), so both passes keep many independent 16-byte loads in
 // flight: HD is a template parameter (fully unrolled dot products), the v pass is unrolled eight positions deep.
-template <int HD>
-__global__ void __launch_bounds__(256) attn_decode_kernel(const float* __restrict__ qkv, const float* __restrict__ kc,
-                                                          const float* __restrict__ vc, float* __restrict__ ctx, int heads, int Tmax,
-                                                          int len) {
-  extern __shared__ __align__(16) float sm[];  // [HD] q, [len] scores, [32] scratch, [256/(HD/4)][HD] partial outputs
+// APPEND: the token's own k / v (the k and v thirds of its qkv row) are written to the caches at position len-1 by this
+// kernel (no separate mas_kv_append launch) and enter the attention from shared memory - the freshly written cache lines are
+// never read back here (the cache loads use the read-only path).
+template <int HD, bool APPEND>
+__global__ void __launch_bounds__(256) attn_decode_kernel(const float* __restrict__ qkv, float* __restrict__ kc, float* __restrict__ vc,
+                                                          float* __restrict__ ctx, int heads, int Tmax, int len) {
+  extern __shared__ __align__(16) float sm[];  // [HD] q, [len] scores, [32] scratch, [256/(HD/4)][HD] partial outputs, [2 HD] own k, v
   constexpr int Q = HD / 4, GROUPS = 256 / Q;
   float* qs = sm;
   float* sc = sm + HD;
   float* red = sc + ((len + 3) & ~3);
   float* po = red + 32;
+  float* ks = po + GROUPS * HD;
+  float* vs = ks + HD;
   const int r = blockIdx.x / heads, h = blockIdx.x % heads, H = heads * HD, t0 = threadIdx.x, lane = t0 & 31, warp = t0 >> 5;
-  if (t0 < HD) qs[t0] = qkv[(size_t)r * 3 * H + h * HD + t0];
+  const int lenc = APPEND ? len - 1 : len;     // positions read from the cache
+  if (t0 < HD) {
+    const float* tokrow = qkv + (size_t)r * 3 * H + h * HD + t0;
+    qs[t0] = tokrow[0];
+    if (APPEND) {
+      const float kv = tokrow[H], vv = tokrow[2 * H];
+      ks[t0] = kv;
+      vs[t0] = vv;
+      const size_t dst = (((size_t)r * heads + h) * Tmax + (len - 1)) * HD + t0;
+      kc[dst] = kv;
+      vc[dst] = vv;
+    }
+  }
   __syncthreads();
   const float alpha = rsqrtf((float)HD);
   const float* kb = kc + ((size_t)r * heads + h) * Tmax * HD;
@@ -108,7 +124,7 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(const float* __restric
 #pragma unroll
   for (int i = 0; i < Q; ++i) q4[i] = *reinterpret_cast<const float4*>(qs + 4 * i);
   float mx = -INFINITY;
-  for (int t = t0; t < len; t += 256) {
+  for (int t = t0; t < lenc; t += 256) {
     const float4* kr = reinterpret_cast<const float4*>(kb + (size_t)t * HD);
     float4 kv[Q];
 #pragma unroll
@@ -121,6 +137,18 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(const float* __restric
     }
     const float s = ((s0 + s1) + (s2 + s3)) * alpha;
     sc[t] = s;
+    mx = fmaxf(mx, s);
+  }
+  if (APPEND && t0 == 255) {   // the token itself: k from shared memory, same summation order as above
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+      const float4 kv = *reinterpret_cast<const float4*>(ks + 4 * i);
+      s0 = fmaf(q4[i].x, kv.x, s0); s1 = fmaf(q4[i].y, kv.y, s1);
+      s2 = fmaf(q4[i].z, kv.z, s2); s3 = fmaf(q4[i].w, kv.w, s3);
+    }
+    const float s = ((s0 + s1) + (s2 + s3)) * alpha;
+    sc[len - 1] = s;
     mx = fmaxf(mx, s);
   }
   mx = warp_max(mx);
@@ -147,7 +175,7 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(const float* __restric
   const int dq = t0 % Q, g = t0 / Q;
   float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
   int t = g;
-  for (; t + 7 * GROUPS < len; t += 8 * GROUPS) {
+  for (; t + 7 * GROUPS < lenc; t += 8 * GROUPS) {
     float4 vv[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) vv[u] = __ldg(reinterpret_cast<const float4*>(vb + (size_t)(t + u * GROUPS) * HD) + dq);
@@ -157,9 +185,14 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(const float* __restric
       o.x = fmaf(p, vv[u].x, o.x); o.y = fmaf(p, vv[u].y, o.y); o.z = fmaf(p, vv[u].z, o.z); o.w = fmaf(p, vv[u].w, o.w);
     }
   }
-  for (; t < len; t += GROUPS) {
+  for (; t < lenc; t += GROUPS) {
     const float4 vv = __ldg(reinterpret_cast<const float4*>(vb + (size_t)t * HD) + dq);
     const float p = sc[t];
+    o.x = fmaf(p, vv.x, o.x); o.y = fmaf(p, vv.y, o.y); o.z = fmaf(p, vv.z, o.z); o.w = fmaf(p, vv.w, o.w);
+  }
+  if (APPEND && g == 0) {
+    const float4 vv = *reinterpret_cast<const float4*>(vs + 4 * dq);
+    const float p = sc[len - 1];
     o.x = fmaf(p, vv.x, o.x); o.y = fmaf(p, vv.y, o.y); o.z = fmaf(p, vv.z, o.z); o.w = fmaf(p, vv.w, o.w);
   }
   *reinterpret_cast<float4*>(po + (size_t)g * HD + 4 * dq) = o;
@@ -376,21 +409,36 @@ int mas_kv_append(const float* qkv, int R, int T, int heads, int hd, float* kcac
   return launched("kv_append");
 }
 
-int mas_attn_decode(const float* qkv, const float* kcache, const float* vcache, float* ctx, int R, int heads, int hd, int Tmax, int len,
-                    void* stream) {
+static int attn_decode_run(const float* qkv, float* kcache, float* vcache, float* ctx, int R, int heads, int hd, int Tmax, int len,
+                           bool append, void* stream) {
   MAS_REQUIRE(qkv && kcache && vcache && ctx && R > 0 && heads > 0, "attn_decode: bad arguments");
   if (len <= 0 || len > Tmax) return fail(MAS_ERR_INVALID_ARG, "attn_decode: cache length %d outside (0, %d]", len, Tmax);
-  const size_t smem = (size_t)(hd + ((len + 3) & ~3) + 32 + 1024) * sizeof(float);
+  const size_t smem = (size_t)(hd + ((len + 3) & ~3) + 32 + 1024 + 2 * hd) * sizeof(float);
   if (smem > 48 * 1024) return fail(MAS_ERR_UNSUPPORTED, "attn_decode: sequence too long for the single-pass kernel (%d)", len);
   const int grid = R * heads;
+#define MAS_AD(HD_)                                                                                                        \
+  if (append) attn_decode_kernel<HD_, true><<<grid, 256, smem, S(stream)>>>(qkv, kcache, vcache, ctx, heads, Tmax, len); \
+  else attn_decode_kernel<HD_, false><<<grid, 256, smem, S(stream)>>>(qkv, kcache, vcache, ctx, heads, Tmax, len)
   switch (hd) {
-    case 16: attn_decode_kernel<16><<<grid, 256, smem, S(stream)>>>(qkv, kcache, vcache, ctx, heads, Tmax, len); break;
-    case 32: attn_decode_kernel<32><<<grid, 256, smem, S(stream)>>>(qkv, kcache, vcache, ctx, heads, Tmax, len); break;
-    case 64: attn_decode_kernel<64><<<grid, 256, smem, S(stream)>>>(qkv, kcache, vcache, ctx, heads, Tmax, len); break;
-    case 128: attn_decode_kernel<128><<<grid, 256, smem, S(stream)>>>(qkv, kcache, vcache, ctx, heads, Tmax, len); break;
+    case 16: MAS_AD(16); break;
+    case 32: MAS_AD(32); break;
+    case 64: MAS_AD(64); break;
+    case 128: MAS_AD(128); break;
     default: return fail(MAS_ERR_UNSUPPORTED, "attn_decode: head dim %d (supported: 16, 32, 64, 128)", hd);
   }
-  return launched("attn_decode");
+#undef MAS_AD
+  return launched(append ? "attn_decode_append" : "attn_decode");
+}
+
+int mas_attn_decode(const float* qkv, const float* kcache, const float* vcache, float* ctx, int R, int heads, int hd, int Tmax, int len,
+                    void* stream) {
+  return attn_decode_run(qkv, const_cast<float*>(kcache), const_cast<float*>(vcache), ctx, R, heads, hd, Tmax, len, false, stream);
+}
+
+int mas_attn_decode_append(const float* qkv, float* kcache, float* vcache, float* ctx, int R, int heads, int hd, int Tmax, int pos,
+                           void* stream) {
+  if (pos < 0 || pos >= Tmax) return fail(MAS_ERR_INVALID_ARG, "attn_decode_append: position %d outside the cache (%d)", pos, Tmax);
+  return attn_decode_run(qkv, kcache, vcache, ctx, R, heads, hd, Tmax, pos + 1, true, stream);
 }
 
 int mas_cfg_mix(const float* cond, const float* uncond, float* out, int64_t n, float scale, void* stream) {

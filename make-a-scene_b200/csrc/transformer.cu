@@ -72,6 +72,87 @@ __global__ void __launch_bounds__(256) layernorm_fwd_block_kernel(const float* _
   }
 }
 
+// Two chained LayerNorms of a decode step in one launch (inference): y1 = res + LN1(x) (the sandwich LayerNorm with its
+// residual, transformer.py:183-208; res may be null) and y2 = LN2(y1) (the next sub-layer's input norm / final_ln).  Same
+// row-in-registers scheme and the same two-pass statistics as layernorm_fwd_block_kernel, applied twice.
+__device__ __forceinline__ void ln_row_stats_256(const float4 (&v)[4], int Q, int H, float eps, float (*red)[8], float* m_out, float* rs_out) {
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  s = warp_sum(s);
+  if (lane == 0) red[0][warp] = s;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) tot += red[0][w];
+  const float m = tot / (float)H;
+  float qd = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (t + 256 * i < Q) {
+      const float a = v[i].x - m, b = v[i].y - m, c = v[i].z - m, d = v[i].w - m;
+      qd = fmaf(a, a, qd); qd = fmaf(b, b, qd); qd = fmaf(c, c, qd); qd = fmaf(d, d, qd);
+    }
+  qd = warp_sum(qd);
+  if (lane == 0) red[1][warp] = qd;
+  __syncthreads();
+  float tq = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) tq += red[1][w];
+  *m_out = m;
+  *rs_out = rsqrtf(tq / (float)H + eps);
+  __syncthreads();      // red[] is reused by the second normalisation
+}
+__global__ void __launch_bounds__(256) layernorm2_fwd_block_kernel(const float* __restrict__ x, const float* __restrict__ g1,
+                                                                   const float* __restrict__ b1, const float* __restrict__ res,
+                                                                   float* __restrict__ y1, const float* __restrict__ g2,
+                                                                   const float* __restrict__ b2, float* __restrict__ y2, int H, float eps1,
+                                                                   float eps2) {
+  __shared__ float red[2][8];
+  const int64_t row = blockIdx.x;
+  const int t = threadIdx.x, Q = H >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * H);
+  float4 v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int q = t + 256 * i;
+    v[i] = q < Q ? __ldg(xr + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float m, rs;
+  ln_row_stats_256(v, Q, H, eps1, red, &m, &rs);
+  const float4* r4 = res ? reinterpret_cast<const float4*>(res + row * H) : nullptr;
+  float4* o1 = reinterpret_cast<float4*>(y1 + row * H);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int q = t + 256 * i;
+    if (q < Q) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(g1) + q), b = __ldg(reinterpret_cast<const float4*>(b1) + q);
+      float4 o = make_float4((v[i].x - m) * rs * g.x + b.x, (v[i].y - m) * rs * g.y + b.y, (v[i].z - m) * rs * g.z + b.z,
+                             (v[i].w - m) * rs * g.w + b.w);
+      if (r4) {
+        const float4 r = __ldg(r4 + q);
+        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+      }
+      o1[q] = o;
+      v[i] = o;
+    } else {
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  ln_row_stats_256(v, Q, H, eps2, red, &m, &rs);
+  float4* o2 = reinterpret_cast<float4*>(y2 + row * H);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int q = t + 256 * i;
+    if (q < Q) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(g2) + q), b = __ldg(reinterpret_cast<const float4*>(b2) + q);
+      o2[q] = make_float4((v[i].x - m) * rs * g.x + b.x, (v[i].y - m) * rs * g.y + b.y, (v[i].z - m) * rs * g.z + b.z,
+                          (v[i].w - m) * rs * g.w + b.w);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------- LayerNorm (warp per row)
 __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                      const float* __restrict__ res, float* __restrict__ y, float* __restrict__ mean,
@@ -327,6 +408,16 @@ int mas_layernorm_forward(const float* x, const float* gamma, const float* beta,
   }
   layernorm_fwd_kernel<<<(unsigned)cdiv(R, 8), 256, 0, S(stream)>>>(x, gamma, beta, residual, y, mean, rstd, R, H, eps);
   return launched("layernorm_fwd");
+}
+int mas_layernorm2_forward(const float* x, const float* gamma1, const float* beta1, const float* residual, float* y1,
+                           const float* gamma2, const float* beta2, float* y2, int64_t R, int H, float eps1, float eps2, void* stream) {
+  MAS_REQUIRE(x && gamma1 && beta1 && y1 && gamma2 && beta2 && y2 && R > 0 && H > 0, "layernorm2_forward: bad arguments");
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (!(R <= 64 && H % 4 == 0 && H <= 4096 && al16(x) && al16(y1) && al16(y2) && al16(gamma1) && al16(beta1) && al16(gamma2) &&
+        al16(beta2) && (!residual || al16(residual))))
+    return fail(MAS_ERR_UNSUPPORTED, "layernorm2_forward: needs R <= 64, H %% 4 == 0, H <= 4096 and 16-byte aligned operands");
+  layernorm2_fwd_block_kernel<<<(unsigned)R, 256, 0, S(stream)>>>(x, gamma1, beta1, residual, y1, gamma2, beta2, y2, H, eps1, eps2);
+  return launched("layernorm2_fwd_block");
 }
 size_t mas_layernorm_ws_bytes(int64_t R, int H) { return (size_t)cdiv(R, LN_ROWS) * H * 2 * sizeof(double) + 64; }
 int mas_layernorm_backward(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, float* dx,

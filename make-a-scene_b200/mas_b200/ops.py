@@ -1285,6 +1285,26 @@ def attn_decode(qkv, kcache, vcache, length):
     return ctx
 
 
+def attn_decode_append(qkv, kcache, vcache, pos):
+    """attn_decode with the cache append folded in: stores this token's k / v (qkv [R,3H]) at position pos, attends over
+    positions 0..pos -> ctx [R,H]."""
+    R, heads, Tmax, hd = kcache.shape
+    ctx = torch.empty((R, heads * hd), dtype=torch.float32, device=qkv.device)
+    L.call("mas_attn_decode_append", qkv.contiguous(), kcache, vcache, ctx, R, heads, hd, Tmax, int(pos))
+    return ctx
+
+
+def layernorm2(x, ln1, residual, ln2):
+    """(y1, y2) = (residual + ln1(x), ln2(y1)) for a few rows [R,H] in one launch (inference; nn.LayerNorm modules)."""
+    _need_cuda(x)
+    x = x.contiguous()
+    R, H = x.shape
+    y1, y2 = torch.empty_like(x), torch.empty_like(x)
+    L.call("mas_layernorm2_forward", x, ln1.weight, ln1.bias, None if residual is None else residual.contiguous(), y1, ln2.weight,
+           ln2.bias, y2, R, H, float(ln1.eps), float(ln2.eps))
+    return y1, y2
+
+
 def cfg_mix(cond, uncond, scale):
     """Classifier-free guidance on logits: uncond + scale * (cond - uncond)."""
     out = torch.empty_like(cond)

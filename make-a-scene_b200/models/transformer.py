@@ -169,7 +169,7 @@ class _GraphedDecoder:
         m, R = self.model, self.rows
         emb = ops.EmbedFn.apply([(tok.view(R, 1), row, col, 0)], 1, m.hidden_dim, m.image_token_embedding.weight,
                                 m.image_row_embeddings.weight, m.image_col_embeddings.weight)
-        return m._logits_of(m._decode_step(emb.view(R, m.hidden_dim), self.kc, self.vc, pos))
+        return m._logits_of(m._decode_step(emb.view(R, m.hidden_dim), self.kc, self.vc, pos), normed=True)
 
     def graphed_step(self, t, tok_all, prefix):
         self.tok.copy_(tok_all)
@@ -272,7 +272,26 @@ class MakeAScene(nn.Module):
         return x[:, -1].contiguous()
 
     def _decode_step(self, x, kc, vc, pos):
-        """One new token per row (x [R,H], absolute position pos) through all layers against the cache."""
+        """One new token per row (x [R,H], absolute position pos) through all layers against the cache; returns
+        final_ln(hidden). Seven launches per layer: qkv, attention (+ cache append), out_proj, the sandwich LayerNorm chained
+        with the next input LayerNorm (mas_layernorm2_forward), lin1 (+GELU), lin2, the second chained pair."""
+        layers = self.transformer.layers
+        if not all(l.cogview_sandwich_layernorm for l in layers) or x.shape[-1] % 4 or x.shape[-1] > 4096:
+            return self.transformer.final_ln(self._decode_step_plain(x, kc, vc, pos))
+        y = layers[0].ln_in(x)
+        for li, layer in enumerate(layers):
+            at, mlp = layer.attn, layer.mlp
+            qkv = ops.linear_small(y, at.qkv.weight, at.qkv.bias)
+            a = ops.linear_small(ops.attn_decode_append(qkv, kc[li], vc[li], pos), at.out_proj.weight, at.out_proj.bias)
+            x, y = ops.layernorm2(a, layer.first_ln_sandwich, x, layer.ln_out)        # x + LN(a), then the MLP's input norm
+            m = ops.linear_small(y, mlp.lin1.weight, mlp.lin1.bias, act=1)
+            m = ops.linear_small(m, mlp.lin2.weight, mlp.lin2.bias)
+            nxt = layers[li + 1].ln_in if li + 1 < len(layers) else self.transformer.final_ln
+            x, y = ops.layernorm2(m, layer.second_ln_sandwich, x, nxt)
+        return y
+
+    def _decode_step_plain(self, x, kc, vc, pos):
+        """The unfused form (configurations without the sandwich LayerNorm); returns the hidden state before final_ln."""
         for li, layer in enumerate(self.transformer.layers):
             at, mlp = layer.attn, layer.mlp
             qkv = ops.linear_small(layer.ln_in(x), at.qkv.weight, at.qkv.bias)
@@ -284,8 +303,10 @@ class MakeAScene(nn.Module):
             x = layer.second_ln_sandwich(m, residual=x) if layer.cogview_sandwich_layernorm else x + m
         return x
 
-    def _logits_of(self, hidden):
-        h = self.to_logits[0](self.transformer.final_ln(hidden))
+    def _logits_of(self, hidden, normed=False):
+        """to_logits on hidden states [R,H]; normed: final_ln has been applied already (decode steps)."""
+        f = hidden if normed else self.transformer.final_ln(hidden)
+        h = self.to_logits[0](f)
         return ops.linear_small(h, self.to_logits[1].weight, self.to_logits[1].bias)
 
     @torch.no_grad()

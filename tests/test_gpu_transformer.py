@@ -152,6 +152,37 @@ def test_kv_append_and_attn_decode_vs_torch(heads, hd, length, tmax):
     ref = (p @ v.double()).reshape(R, H).float()
     ctx = ops.attn_decode(qkv_all[:, -1].contiguous().to(dev), kc, vc, length)
     assert rel_err(ctx, ref) < 1e-5
+    # the fused form: the token's k / v are appended by the attention kernel itself
+    kc2 = torch.zeros_like(kc)
+    vc2 = torch.zeros_like(vc)
+    ops.kv_append(qkv_all[:, :length - 1].to(dev), kc2, vc2, 0)
+    ctx2 = ops.attn_decode_append(qkv_all[:, -1].contiguous().to(dev), kc2, vc2, length - 1)
+    assert torch.equal(kc2, kc) and torch.equal(vc2, vc)
+    assert rel_err(ctx2, ref) < 1e-5 and rel_err(ctx2, ctx) < 1e-6
+
+
+@pytest.mark.parametrize("R,H,res", [(1, 1024, True), (2, 1024, False), (8, 4096, True), (3, 132, True)])
+def test_layernorm_pair_vs_torch(R, H, res):
+    """mas_layernorm2_forward: y1 = residual + LN1(x), y2 = LN2(y1) (the two chained LayerNorms of a decode step)."""
+    from mas_b200 import ops
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(7 * R + H)
+    x = torch.randn(R, H, generator=gen) * 3 + 0.5
+    ln1, ln2 = torch.nn.LayerNorm(H, eps=1e-5), torch.nn.LayerNorm(H, eps=1e-5)
+    with torch.no_grad():
+        for ln in (ln1, ln2):
+            ln.weight.copy_(torch.randn(H, generator=gen))
+            ln.bias.copy_(torch.randn(H, generator=gen))
+    r = torch.randn(R, H, generator=gen) if res else None
+    with torch.no_grad():
+        ref1 = ln1.double()(x.double())
+        if res:
+            ref1 = ref1 + r.double()
+        ref2 = ln2.double()(ref1)
+    ln1.float().to(dev)
+    ln2.float().to(dev)
+    y1, y2 = ops.layernorm2(x.to(dev), ln1, r.to(dev) if res else None, ln2)
+    assert rel_err(y1, ref1.float()) < 1e-5 and rel_err(y2, ref2.float()) < 1e-5
 
 
 def test_causal_attention_on_tensor_cores_matches_fp32_kernels():
