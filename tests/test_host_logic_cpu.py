@@ -94,6 +94,156 @@ class Emu:
         D[...] = np.where(ok[:, None], p * g, 0.0)
 
 
+def _emu_more():
+    """The remaining entries of the token transformer (training and cached decoding), same conventions."""
+
+    def vec(p, n):
+        return _f32(_addr(p), n)
+
+    def ln(x, g, b, eps):
+        m = x.mean(-1, keepdims=True)
+        v = ((x - m) ** 2).mean(-1, keepdims=True)
+        return (x - m) / np.sqrt(v + eps) * g + b, m[:, 0], 1.0 / np.sqrt(v[:, 0] + eps)
+
+    def gelu(v):
+        return 0.5 * v * (1.0 + np.tanh(0.7978845608028654 * v * (1.0 + 0.044715 * v * v)))
+
+    def mas_gemm(self, A, B, C, M, N, K, batch, lda, ldb, ldc, sa, sb, sc, ta, tb, alpha, bias, residual, impl):
+        for i in range(batch):
+            Am = _mat(_addr(A) + 4 * i * sa, M, K, lda, bool(ta)).astype(np.float64)
+            Bm = _mat(_addr(B) + 4 * i * sb, N, K, ldb, not bool(tb)).astype(np.float64)
+            out = alpha * (Am @ Bm.T)
+            if bias is not None:
+                out = out + vec(bias, N).astype(np.float64)[None, :]
+            if residual is not None:
+                out = out + _mat(_addr(residual) + 4 * i * sc, M, N, ldc, False)
+            _mat(_addr(C) + 4 * i * sc, M, N, ldc, False)[...] = out
+
+    def mas_layernorm_forward(self, x, gamma, beta, residual, y, mean, rstd, R, H, eps):
+        X = vec(x, R * H).reshape(R, H).astype(np.float64)
+        o, m, rs = ln(X, vec(gamma, H).astype(np.float64), vec(beta, H).astype(np.float64), eps)
+        if residual is not None:
+            o = o + vec(residual, R * H).reshape(R, H)
+        vec(y, R * H).reshape(R, H)[...] = o
+        vec(mean, R)[...] = m
+        vec(rstd, R)[...] = rs
+
+    def mas_layernorm_backward(self, dy, x, mean, rstd, gamma, dx, dgamma, dbeta, R, H, ws, ws_bytes):
+        D = vec(dy, R * H).reshape(R, H).astype(np.float64)
+        X = vec(x, R * H).reshape(R, H).astype(np.float64)
+        xh = (X - vec(mean, R).astype(np.float64)[:, None]) * vec(rstd, R).astype(np.float64)[:, None]
+        g = D * vec(gamma, H).astype(np.float64)
+        vec(dx, R * H).reshape(R, H)[...] = vec(rstd, R).astype(np.float64)[:, None] * (
+            g - g.mean(-1, keepdims=True) - xh * (g * xh).mean(-1, keepdims=True))
+        if dgamma is not None:
+            vec(dgamma, H)[...] = (D * xh).sum(0)
+            vec(dbeta, H)[...] = D.sum(0)
+
+    def mas_gelu_forward(self, x, y, n):
+        vec(y, n)[...] = gelu(vec(x, n).astype(np.float64))
+
+    def mas_gelu_backward(self, dy, x, dx, n):
+        v = vec(x, n).astype(np.float64)
+        t = np.tanh(0.7978845608028654 * v * (1.0 + 0.044715 * v * v))
+        du = 0.7978845608028654 * (1.0 + 3 * 0.044715 * v * v)
+        vec(dx, n)[...] = vec(dy, n) * (0.5 * (1 + t) + 0.5 * v * (1 - t * t) * du)
+
+    def mas_embed3_forward(self, t0, id0, t1, id1, t2, id2, out, R, H, seg, total, off):
+        i0 = _i64(_addr(id0), R)
+        i1 = _i64(_addr(id1), seg) if t1 is not None else None
+        i2 = _i64(_addr(id2), seg) if t2 is not None else None
+        rows = max(R // seg, 1) * total
+        O = vec(out, rows * H).reshape(rows, H)
+        for r in range(R):
+            v = _f32(_addr(t0) + 4 * int(i0[r]) * H, H).astype(np.float64)
+            if i1 is not None:
+                v = v + _f32(_addr(t1) + 4 * int(i1[r % seg]) * H, H)
+            if i2 is not None:
+                v = v + _f32(_addr(t2) + 4 * int(i2[r % seg]) * H, H)
+            O[(r // seg) * total + off + r % seg] = v
+
+    def mas_embed3_backward(self, dout, id0, d0, id1, d1, id2, d2, R, H, seg, total, off):
+        i0 = _i64(_addr(id0), R)
+        rows = max(R // seg, 1) * total
+        D = vec(dout, rows * H).reshape(rows, H)
+        for r in range(R):
+            g = D[(r // seg) * total + off + r % seg]
+            _f32(_addr(d0) + 4 * int(i0[r]) * H, H)[...] += g
+            if d1 is not None:
+                _f32(_addr(d1) + 4 * int(_i64(_addr(id1), seg)[r % seg]) * H, H)[...] += g
+            if d2 is not None:
+                _f32(_addr(d2) + 4 * int(_i64(_addr(id2), seg)[r % seg]) * H, H)[...] += g
+
+    def mas_conv1x1_wgrad(self, x, ldx, dy, ldy, M, cin, cout, dw, db, impl, ws, ws_bytes):
+        X = _mat(_addr(x), M, cin, ldx, False).astype(np.float64)
+        D = _mat(_addr(dy), M, cout, ldy, False).astype(np.float64)
+        vec(dw, cout * cin).reshape(cout, cin)[...] = D.T @ X
+        if db is not None:
+            vec(db, cout)[...] = D.sum(0)
+
+    def mas_linear_small(self, x, ldx, W, bias, y, ldy, R, N, K, act):
+        X = _mat(_addr(x), R, K, ldx, False).astype(np.float64)
+        Wm = vec(W, N * K).reshape(N, K).astype(np.float64)
+        o = X @ Wm.T
+        if bias is not None:
+            o = o + vec(bias, N)[None, :]
+        _mat(_addr(y), R, N, ldy, False)[...] = gelu(o) if act == 1 else o
+
+    def mas_kv_append(self, qkv, R, T, heads, hd, kc, vc, Tmax, pos0):
+        H = heads * hd
+        Q = vec(qkv, R * T * 3 * H).reshape(R, T, 3, heads, hd)
+        K_ = vec(kc, R * heads * Tmax * hd).reshape(R, heads, Tmax, hd)
+        V_ = vec(vc, R * heads * Tmax * hd).reshape(R, heads, Tmax, hd)
+        K_[:, :, pos0:pos0 + T] = Q[:, :, 1].transpose(0, 2, 1, 3)
+        V_[:, :, pos0:pos0 + T] = Q[:, :, 2].transpose(0, 2, 1, 3)
+
+    def mas_attn_decode(self, qkv, kc, vc, ctx, R, heads, hd, Tmax, length):
+        H = heads * hd
+        q = vec(qkv, R * 3 * H).reshape(R, 3, heads, hd)[:, 0].astype(np.float64)
+        K_ = vec(kc, R * heads * Tmax * hd).reshape(R, heads, Tmax, hd)[:, :, :length].astype(np.float64)
+        V_ = vec(vc, R * heads * Tmax * hd).reshape(R, heads, Tmax, hd)[:, :, :length].astype(np.float64)
+        s = np.einsum("rhd,rhtd->rht", q, K_) / np.sqrt(hd)
+        p = np.exp(s - s.max(-1, keepdims=True))
+        p = p / p.sum(-1, keepdims=True)
+        vec(ctx, R * H).reshape(R, heads, hd)[...] = np.einsum("rht,rhtd->rhd", p, V_)
+
+    def mas_attn_decode_append(self, qkv, kc, vc, ctx, R, heads, hd, Tmax, pos):
+        self.mas_kv_append(qkv, R, 1, heads, hd, kc, vc, Tmax, pos)
+        self.mas_attn_decode(qkv, kc, vc, ctx, R, heads, hd, Tmax, pos + 1)
+
+    def mas_layernorm2_forward(self, x, g1, b1, residual, y1, g2, b2, y2, R, H, eps1, eps2):
+        X = vec(x, R * H).reshape(R, H).astype(np.float64)
+        o, _, _ = ln(X, vec(g1, H).astype(np.float64), vec(b1, H).astype(np.float64), eps1)
+        if residual is not None:
+            o = o + vec(residual, R * H).reshape(R, H)
+        vec(y1, R * H).reshape(R, H)[...] = o
+        o2, _, _ = ln(vec(y1, R * H).reshape(R, H).astype(np.float64), vec(g2, H).astype(np.float64), vec(b2, H).astype(np.float64), eps2)
+        vec(y2, R * H).reshape(R, H)[...] = o2
+
+    def mas_cfg_mix(self, cond, uncond, out, n, scale):
+        u = vec(uncond, n).astype(np.float64)
+        vec(out, n)[...] = u + scale * (vec(cond, n) - u)
+
+    def mas_sample_topk(self, logits, ld, R, V, temperature, top_k, u, tokens):
+        Z = _mat(_addr(logits), R, V, ld, False).astype(np.float64) / temperature
+        uu = vec(u, R)
+        out = _i64(_addr(tokens), R)
+        for r in range(R):
+            z = Z[r].copy()
+            if 0 < top_k < V:
+                z[z < np.sort(z)[-top_k]] = -np.inf
+            p = np.exp(z - z.max())
+            c = np.cumsum(p)
+            out[r] = min(int(np.searchsorted(c, uu[r] * c[-1], side="right")), V - 1)
+
+    for k, v in list(locals().items()):
+        if k.startswith("mas_"):
+            setattr(Emu, k, v)
+
+
+_emu_more()
+
+
 @pytest.fixture
 def emu(monkeypatch):
     from mas_b200 import ops
@@ -101,6 +251,8 @@ def emu(monkeypatch):
     monkeypatch.setattr(ops.L, "call", e)
     monkeypatch.setattr(ops, "_need_cuda", lambda x: None)
     monkeypatch.setattr(ops, "_tc_on", lambda: False)
+    monkeypatch.setattr(ops.L, "query", lambda name, *a: 256)
+    monkeypatch.setattr(torch.cuda, "graph_pool_handle", lambda: None)
     return e
 
 
@@ -158,3 +310,57 @@ def test_cross_entropy_unit(emu, pitch):
     (ref * 0.5).backward()
     assert abs(float(loss) - float(ref)) < 1e-6
     assert torch.allclose(x.grad.double(), r.grad, atol=1e-6)
+
+
+def _tiny_model():
+    import os
+    from conftest import GOLDEN
+    from models.transformer import MakeAScene
+    g = torch.load(os.path.join(GOLDEN, "transformer_tiny.pt"), weights_only=False)
+    m = MakeAScene(**g["cfg"])
+    m.load_state_dict(g["state_dict"])
+    m.device = torch.device("cpu")
+    return m, g
+
+
+def test_make_a_scene_host_logic_against_reference_fixture(emu):
+    """The whole drop-in module above an emulated C-ABI reproduces the REAL reference's logits, loss and gradients
+    (tests/golden/transformer_tiny.pt): everything models/transformer.py and the autograd units do between kernel calls."""
+    from conftest import rel_err
+    m, g = _tiny_model()
+    logits = m(g["text"], g["seg"], g["img"])
+    assert rel_err(logits, g["logits"]) < 1e-5
+    loss = m.loss(g["text"], g["seg"], g["img"])
+    assert abs(float(loss.detach()) - float(g["loss"])) < 1e-5
+    loss.backward()
+    named = dict(m.named_parameters())
+    for k, gv in g["grads"].items():
+        assert rel_err(named[k].grad, gv) < 1e-4, k
+    assert "mas_ce_forward" in emu.names and "mas_ce_backward" in emu.names
+
+
+def test_generate_host_logic_against_reference_fixture(emu):
+    """KV-cached decoding (prefill, fused append + attention, chained LayerNorm pairs, guidance mix, sampler entry) above the
+    emulated C-ABI: teacher-forced logits == the reference's non-cached logits; launches per decoded token as designed."""
+    from conftest import rel_err
+    m, g = _tiny_model()
+    m.eval()
+    toks, lg = m.generate(g["text"], g["seg"], img_tokens=g["img"], return_logits=True)
+    assert torch.equal(toks, g["img"]) and rel_err(lg, g["logits"]) < 1e-5
+    layers = len(m.transformer.layers)
+    steps = m.image_length - 1
+    assert emu.names.count("mas_attn_decode_append") == layers * steps
+    assert emu.names.count("mas_layernorm2_forward") == 2 * layers * steps
+    assert emu.names.count("mas_kv_append") == layers                       # the prefill only
+    # guidance: logits = uncond + s (cond - uncond), both streams through one decode pass
+    with torch.no_grad():
+        cond = m(g["text"], g["seg"], g["img"])
+        uncond = m(torch.zeros_like(g["text"]), g["seg"], g["img"])
+    _, lg2 = m.generate(g["text"], g["seg"], guidance_scale=2.5, img_tokens=g["img"], return_logits=True)
+    assert rel_err(lg2, uncond + 2.5 * (cond - uncond)) < 1e-5
+    # sampling: seeded, top-k respected
+    gen = torch.Generator().manual_seed(5)
+    a, la = m.generate(g["text"], g["seg"], temperature=0.9, top_k=3, generator=gen, return_logits=True)
+    kth = la.topk(3, dim=-1).values[..., -1]
+    assert bool((la.gather(-1, a.unsqueeze(-1)).squeeze(-1) >= kth).all())
+    assert "mas_sample_topk" in emu.names
