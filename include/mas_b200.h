@@ -341,6 +341,13 @@ int mas_embed3_forward(const float* t0, const int64_t* id0, const float* t1, con
                        const int64_t* id2, float* out, int64_t R, int H, int seg, int total, int off, void* stream);
 int mas_embed3_backward(const float* dout, const int64_t* id0, float* d0, const int64_t* id1, float* d1,
                         const int64_t* id2, float* d2, int64_t R, int H, int seg, int total, int off, void* stream);
+/* Causal self-attention core of the token transformer, fused (transformer.py:77-103; csrc/attn_causal.cu): per (sequence,
+ * head, 128-query tile) S = q k^T * scale in tensor memory -> causal softmax in registers -> P (written once, [B,heads,S,S],
+ * zeros above the diagonal: the backward reads it) -> ctx = P v accumulated in tensor memory.  qkv [B,S,3*heads*hd] fused
+ * q|k|v, ctx [B,S,heads*hd], amax = device scalar max|qkv| (mas_amax).  Needs hd == 64 and S % 128 == 0
+ * (MAS_ERR_UNSUPPORTED otherwise: the caller runs the GEMM / softmax sequence).  2 x fp16 operand split = fp32-level accuracy. */
+int mas_attn_causal_forward(const float* qkv, const float* amax, float* P, float* ctx, int B, int S, int heads, int hd,
+                            float scale, void* stream);
 /* Token cross-entropy, train.py:150-153 (F.cross_entropy(logits.view(-1, V), img_token.view(-1)), mean reduction):
  * logits [R, V] with row pitch ld, target int64 [R] (outside [0, V): row ignored like ignore_index).  forward writes the
  * per-row losses, the per-row logsumexp (kept for the backward) and out[0] = mean loss, out[1] = counted rows.

@@ -1159,6 +1159,12 @@ def gemm2(A, B, C, M, N, K, outer, batch, lda, ldb, ldc, osa, osb, osc, sa, sb, 
                sa, sb, sc, int(ta), int(tb), float(alpha), _cfg["impl"] if impl is None else impl)
 
 
+def attn_causal_fused_on(S_, hd):
+    """The fused tcgen05 forward core (csrc/attn_causal.cu): head dim 64, S % 128 == 0, tensor path enabled.
+    MAS_ATTN_FUSED=0 selects the GEMM / softmax / GEMM sequence instead."""
+    return _tc_on() and hd == 64 and S_ % 128 == 0 and S_ >= 128 and os.environ.get("MAS_ATTN_FUSED", "1") != "0"
+
+
 class CausalAttentionFn(torch.autograd.Function):
     """softmax_causal((q / sqrt(hd)) k^T) v per (batch, head) from the fused qkv activation [B,S,3H]
     (transformer.py:77-103; head h owns columns h*hd..(h+1)*hd of each third). Every contraction is ONE launch over all
@@ -1176,12 +1182,16 @@ class CausalAttentionFn(torch.autograd.Function):
         P = torch.empty((B, heads, S_, S_), dtype=torch.float32, device=qkv.device)
         ctxv = torch.empty((B, S_, H), dtype=torch.float32, device=qkv.device)
         SS = S_ * S_
-        # S = alpha q k^T
-        gemm2(qkv, (qkv, H), P, S_, S_, hd, B, heads, H3, H3, S_, S_ * H3, S_ * H3, heads * SS, hd, hd, SS, tb=True, alpha=alpha,
-              impl=impl)
-        L.call("mas_softmax_causal_forward", P, P, B * heads, S_, S_)
-        # ctx = P v
-        gemm2(P, (qkv, 2 * H), ctxv, S_, hd, S_, B, heads, S_, H3, H, heads * SS, S_ * H3, S_ * H, SS, hd, hd, impl=impl)
+        if attn_causal_fused_on(S_, hd):
+            # scores, causal softmax and P v in one kernel per (sequence, head, 128-query tile); P is written once for the backward
+            L.call("mas_attn_causal_forward", qkv, amax(qkv), P, ctxv, B, S_, heads, hd, alpha)
+        else:
+            # S = alpha q k^T
+            gemm2(qkv, (qkv, H), P, S_, S_, hd, B, heads, H3, H3, S_, S_ * H3, S_ * H3, heads * SS, hd, hd, SS, tb=True, alpha=alpha,
+                  impl=impl)
+            L.call("mas_softmax_causal_forward", P, P, B * heads, S_, S_)
+            # ctx = P v
+            gemm2(P, (qkv, 2 * H), ctxv, S_, hd, S_, B, heads, S_, H3, H, heads * SS, S_ * H3, S_ * H, SS, hd, hd, impl=impl)
         ctx.save_for_backward(qkv, P)
         ctx.heads = heads
         return ctxv

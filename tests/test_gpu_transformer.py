@@ -185,7 +185,7 @@ def test_layernorm_pair_vs_torch(R, H, res):
     assert rel_err(y1, ref1.float()) < 1e-5 and rel_err(y2, ref2.float()) < 1e-5
 
 
-def test_causal_attention_on_tensor_cores_matches_fp32_kernels():
+def test_causal_attention_on_tensor_cores_matches_fp32_kernels(monkeypatch):
     """transformer.py:77-103 at the paper's extents (640 tokens, 16 heads of 64): QK^T / PV and their four gradients on the
     3xTF32 tcgen05 GEMM against the exact-fp32 FFMA kernels (which the reference fixtures pin at small extents)."""
     from mas_b200 import _lib as L, ops
@@ -194,6 +194,7 @@ def test_causal_attention_on_tensor_cores_matches_fp32_kernels():
     qkv = torch.randn(2, 640, 3 * 1024, generator=g).to(dev)
     w = torch.randn(2, 640, 1024, generator=g).to(dev)
     out = {}
+    monkeypatch.setenv("MAS_ATTN_FUSED", "0")      # the GEMM / softmax / GEMM sequence (the fused core has its own test below)
     for name, impl in (("tc", L.IMPL_AUTO), ("simt", L.IMPL_SIMT)):
         ops.set_impl(impl)
         try:
@@ -204,7 +205,7 @@ def test_causal_attention_on_tensor_cores_matches_fp32_kernels():
             out[name] = (y.detach(), x.grad.detach(), L.tc_launch_count() - before)
         finally:
             ops.set_impl(L.IMPL_AUTO)
-    assert out["tc"][2] >= 12 and out["simt"][2] == 0
+    assert out["tc"][2] == 6 and out["simt"][2] == 0     # one launch per contraction over all (sequence, head) pairs
     assert rel_err(out["tc"][0], out["simt"][0]) < 2e-5
     assert rel_err(out["tc"][1], out["simt"][1]) < 2e-5
 
@@ -280,3 +281,36 @@ def test_sample_topk_kernel():
     freq = torch.bincount(tok, minlength=50).double() / R
     assert float(freq[~keep].sum()) == 0.0
     assert float((freq - p).abs().max()) < 5 * float((p * (1 - p) / R).sqrt().max())
+
+
+@pytest.mark.parametrize("B,S,heads", [(1, 128, 1), (2, 640, 16), (3, 256, 2)])
+def test_fused_causal_attention_core_matches_fp32_kernels(B, S, heads, monkeypatch):
+    """csrc/attn_causal.cu (scores -> causal softmax -> P v in one tcgen05 kernel, 2 x fp16 operand split) against the
+    exact-fp32 FFMA sequence: ctx, the saved probabilities (incl. the zeros above the diagonal) and the gradients."""
+    from mas_b200 import _lib as L, ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(S + heads)
+    qkv = (torch.randn(B, S, 3 * heads * 64, generator=g) * 1.5).to(dev)
+    w = torch.randn(B, S, heads * 64, generator=g).to(dev)
+    out = {}
+    for name, impl, fused in (("fused", L.IMPL_AUTO, "1"), ("gemm", L.IMPL_AUTO, "0"), ("simt", L.IMPL_SIMT, "0")):
+        monkeypatch.setenv("MAS_ATTN_FUSED", fused)
+        ops.set_impl(impl)
+        try:
+            x = qkv.clone().requires_grad_(True)
+            before = L.launch_count()
+            y = ops.CausalAttentionFn.apply(x, heads)
+            fwd_launches = L.launch_count() - before
+            P = y.grad_fn.saved_tensors[1].clone()
+            (y * w).sum().backward()
+            out[name] = (y.detach(), x.grad.detach(), P, fwd_launches)
+        finally:
+            ops.set_impl(L.IMPL_AUTO)
+    assert out["fused"][3] == 2 and out["gemm"][3] == 3        # amax + the fused core vs GEMM, softmax, GEMM
+    for other in ("simt", "gemm"):
+        assert rel_err(out["fused"][0], out[other][0]) < 2e-5, other
+        assert rel_err(out["fused"][2], out[other][2]) < 2e-5, other
+        assert rel_err(out["fused"][1], out[other][1]) < 2e-5, other
+    P = out["fused"][2]
+    assert float(P.triu(1).abs().max()) == 0.0
+    assert float((P.sum(-1) - 1).abs().max()) < 1e-5

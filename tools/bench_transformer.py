@@ -19,6 +19,7 @@ ap.add_argument("--batch", type=int, default=8)
 ap.add_argument("--steps", type=int, default=4)
 ap.add_argument("--warmup", type=int, default=2)
 ap.add_argument("--layers", type=int, default=24)
+ap.add_argument("--profile", action="store_true", help="per-entry-point CUDA-event times of one extra step (stderr)")
 ap.add_argument("--torch-ce", action="store_true", help="F.cross_entropy on the logits instead of MakeAScene.loss (A/B of the fused entry)")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
@@ -56,6 +57,14 @@ for _ in range(args.steps):
 e1.record()
 torch.cuda.synchronize()
 sec = e0.elapsed_time(e1) * 1e-3 / args.steps
+if args.profile:
+    _lib.profile_start()
+    step()
+    rep = _lib.profile_report()
+    tot = sum(t for _, t in rep.values())
+    for k, (c, t) in sorted(rep.items(), key=lambda kv: -kv[1][1])[:24]:
+        print("  %-36s n=%4d  %8.2f ms  %5.1f%%  %7.3f ms/call" % (k, c, t, 100 * t / tot, t / c), file=sys.stderr)
+    print("  total %.2f ms in %d calls" % (tot, sum(c for c, _ in rep.values())), file=sys.stderr)
 S, H, L, V = 640, 1024, args.layers, 8192
 lin = 2 * S * (12 * H * H) * L + 2 * 256 * H * V           # Linear layers, forward, per sequence
 att = 2 * 2 * S * S * H * L                                # QK^T and PV over the full (masked) square, forward
@@ -64,4 +73,5 @@ print(json.dumps({"metric": "token transformer training step (fwd + cross-entrop
                   "model_tflops": 3 * (lin + att) * B / sec / 1e12, "gpu_launches_per_step": (_lib.launch_count() - l0) // args.steps,
                   "tcgen05_launches_per_step": (_lib.tc_launch_count() - t0) // args.steps,
                   "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,
+                  "attention": "fused core (attn_causal_fwd)" if os.environ.get("MAS_ATTN_FUSED", "1") != "0" else "GEMM / softmax / GEMM",
                   "loss_entry": "F.cross_entropy (torch)" if args.torch_ce else "MakeAScene.loss (mas_ce_*)", "config": cfg}))
