@@ -160,6 +160,14 @@ int mas_pack_gemm_tc(const float* w_nk, float* w_tc, int N, int K, int transpose
 int mas_gemm_rows_packed(const float* A, int64_t lda, const float* w_tc, float* C, int64_t ldc, int64_t M, int N,
                          int K, float alpha, const float* bias, const float* residual, float* stats_part,
                          void* stream);  /* stats_part as above with 128-row tiles: [M/128][4][N/4][2] */
+/* Row GEMM on fp16 operands read by the copy engine (csrc/gemm_tma.cu; nn.Linear forward / data gradient, transformer.py:17-56):
+ * y[M,N] = alpha * x[M,K] . W^T (+bias +residual), x_f16 a dense [M,K] fp16 copy of x (mas_to_half, scaled by the power-of-two
+ * operand scale of *x_amax when x_amax != NULL: the epilogue undoes it), w_tc16 from mas_pack_gemm_tc16 (transpose=1 packs W^T:
+ * the data gradient dx = dy . W).  Needs K % 64 == 0; output features padded to 128 inside the packed image (N % 128 == 0 for
+ * the packer).  fp16 operands carry the same 11-bit significand as the TF32 path; fp32 accumulate. */
+int mas_pack_gemm_tc16(const float* w_nk, void* w_tc16, int N, int K, int transpose, void* stream);
+int mas_gemm_rows_f16(const void* x_f16, int64_t M, int K, const void* w_tc16, float* y, int64_t ldy, int N, const float* bias,
+                      const float* residual, const float* x_amax, float alpha, void* stream);
 /* Diagnostic: one tcgen05.mma D[128x32] = A[128x8].B[32x8]^T with A from shared memory (a_src=0) or tensor memory
  * (a_src=1) and B K-major (b_layout=0) or MN-major (1; 2 = LBO/SBO fields swapped). Used by the tests to pin the
  * descriptor conventions the production kernels rely on. b_layout=99: B descriptor bits / instruction descriptor /

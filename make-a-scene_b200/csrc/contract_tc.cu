@@ -1641,6 +1641,19 @@ int mas_pack_conv3x3_tc16(const float* w_oihw, void* w_tc16, void* w_tc16_dgrad,
   return launched("pack_weights_tc16<9>");
 }
 
+int mas_pack_gemm_tc16(const float* w_nk, void* w_tc16, int N, int K, int transpose, void* stream) {
+  // fp16 image for mas_gemm_rows_f16 (gemm_tma.cu): [n_tile][k/16][2][128][8 halves]; w_nk: [N_out][K_in] row-major
+  // (nn.Linear / 1x1 convolution weight); transpose=1 packs the data-gradient operand W^T
+  if (!w_nk || !w_tc16 || N <= 0 || K <= 0) return fail(MAS_ERR_INVALID_ARG, "pack_gemm_tc16: bad arguments");
+  const int Nn = transpose ? K : N, Kk = transpose ? N : K;
+  if (Nn % tc::BN || Kk % 64)
+    return fail(MAS_ERR_UNSUPPORTED, "pack_gemm_tc16: output features (%d) must be a multiple of 128 and the contraction (%d) of 64", Nn, Kk);
+  const int64_t total = (int64_t)N * K;
+  tc::pack_weights_tc16<<<(int)(cdiv(total, 256) < 2368 ? cdiv(total, 256) : 2368), 256, 0, S(stream)>>>(w_nk, (__half*)w_tc16, nullptr, N, K, 1, 16,
+                                                                                                     transpose, 0);
+  return launched("pack_weights_tc16<1>");
+}
+
 int mas_pack_gemm_tc(const float* w_nk, float* w_tc, int N, int K, int transpose, void* stream) {
   // w_nk: [N_out][K_in] row-major (a 1x1 convolution weight); transpose=1 packs the [K_in -> N] data-gradient operand
   const int Nn = transpose ? K : N, Kk = transpose ? N : K;

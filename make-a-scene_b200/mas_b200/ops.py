@@ -1107,8 +1107,43 @@ class GeluFn(torch.autograd.Function):
         return dx
 
 
+def linear_f16_on(nout, kin):
+    """Linear layers on the TMA-fed fp16 row GEMM (csrc/gemm_tma.cu): output features % 128 == 0, contraction % 64 == 0,
+    fp16 operand format selected. MAS_LINEAR_F16=0 keeps the register-staged TF32 row GEMM."""
+    return f16_operands() and nout % 128 == 0 and kin % 64 == 0 and os.environ.get("MAS_LINEAR_F16", "1") != "0"
+
+
+def _packed_linear_weight(weight, transpose, dev):
+    """fp16 operand image of an nn.Linear weight [N,K] (transpose: of W^T, the data-gradient operand), cached per parameter
+    version like the convolution packings."""
+    ent = _pack_entry(weight)
+    key = ("lin16", bool(transpose))
+    hit = ent.get(key)
+    if hit is not None and hit.device == dev:
+        return hit
+    n, k = weight.shape
+    wt = torch.empty(n * k, dtype=torch.float16, device=dev)
+    L.call("mas_pack_gemm_tc16", weight.contiguous(), wt, n, k, int(transpose))
+    ent[key] = wt
+    return wt
+
+
+def gemm_rows_f16(x2d, weight, transpose=False, bias=None):
+    """y[M, N] = x2d[M, K] . W^T (+bias) (transpose: x2d[M, N] . W, the data gradient) on mas_gemm_rows_f16: x2d is converted
+    once to fp16 under the power-of-two scale of its max|.| (device scalar; nothing returns to the host)."""
+    M, kc = x2d.shape
+    nout = weight.shape[1] if transpose else weight.shape[0]
+    am = amax(x2d)
+    x16 = torch.empty((M, kc), dtype=torch.float16, device=x2d.device)
+    L.call("mas_to_half", x2d, x16, x2d.numel(), am)
+    y = torch.empty((M, nout), dtype=torch.float32, device=x2d.device)
+    L.call("mas_gemm_rows_f16", x16, M, kc, _packed_linear_weight(weight, transpose, x2d.device), y, nout, nout, bias, None, am, 1.0)
+    return y
+
+
 class LinearFn(torch.autograd.Function):
-    """nn.Linear on the last dim: rows GEMM on the tensor path when out%128==0 and in%32==0, else fp32 SIMT."""
+    """nn.Linear on the last dim: the TMA-fed fp16 row GEMM when out % 128 == 0 and in % 64 == 0 (forward and data gradient),
+    else the register-staged TF32 row GEMM (out % 128 == 0, in % 32 == 0), else fp32 SIMT."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
@@ -1116,8 +1151,11 @@ class LinearFn(torch.autograd.Function):
         x = x.contiguous()
         K, N = x.shape[-1], weight.shape[0]
         R = x.numel() // K
-        y = torch.empty(x.shape[:-1] + (N,), dtype=torch.float32, device=x.device)
-        gemm_w(x, K, weight, y, N, R, bias=bias)
+        if linear_f16_on(N, K):
+            y = gemm_rows_f16(x.view(R, K), weight, False, bias).view(x.shape[:-1] + (N,))
+        else:
+            y = torch.empty(x.shape[:-1] + (N,), dtype=torch.float32, device=x.device)
+            gemm_w(x, K, weight, y, N, R, bias=bias)
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
         return y
@@ -1130,8 +1168,11 @@ class LinearFn(torch.autograd.Function):
         R = x.numel() // K
         dx = None
         if ctx.needs_input_grad[0]:
-            dx = torch.empty_like(x)
-            gemm_w(dy, N, weight, dx, K, R, transpose=True)
+            if linear_f16_on(K, N):
+                dx = gemm_rows_f16(dy.view(R, N), weight, True).view(x.shape)
+            else:
+                dx = torch.empty_like(x)
+                gemm_w(dy, N, weight, dx, K, R, transpose=True)
         dw, db = conv1x1_wgrad_raw(x, dy, R, K, N, ctx.has_bias)
         return dx, dw.view(N, K), db
 

@@ -314,3 +314,38 @@ def test_fused_causal_attention_core_matches_fp32_kernels(B, S, heads, monkeypat
     P = out["fused"][2]
     assert float(P.triu(1).abs().max()) == 0.0
     assert float((P.sum(-1) - 1).abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("R,K,N", [(256, 64, 128), (5120, 1024, 3072), (1000, 4096, 1024), (77, 128, 256)])
+def test_linear_on_tma_fed_f16_row_gemm(R, K, N, monkeypatch):
+    """csrc/gemm_tma.cu (TMA-fed fp16 operands, N = 256 MMAs) behind ops.LinearFn: forward and data gradient against fp64
+    torch; the operands carry 11 significant bits like the TF32 path (tolerance 1e-3), row tails are zero-filled by the copy
+    engine, the weight images are cached per parameter version."""
+    from mas_b200 import _lib as L, ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(R + K + N)
+    x = (torch.randn(R, K, generator=g) * 2 + 0.3)
+    w = torch.randn(N, K, generator=g) * 0.05
+    b = torch.randn(N, generator=g)
+    dy = torch.randn(R, N, generator=g) * 1e-4          # gradient-sized values: the power-of-two operand scale matters
+    xr, wr, br = x.double().requires_grad_(True), w.double().requires_grad_(True), b.double().requires_grad_(True)
+    yr = torch.nn.functional.linear(xr, wr, br)
+    yr.backward(dy.double())
+    monkeypatch.setenv("MAS_LINEAR_F16", "1")
+    xd = x.to(dev).requires_grad_(True)
+    wd = torch.nn.Parameter(w.to(dev))
+    bd = torch.nn.Parameter(b.to(dev))
+    before = L.tc_launch_count()
+    y = ops.LinearFn.apply(xd, wd, bd)
+    y.backward(dy.to(dev))
+    assert L.tc_launch_count() - before >= 2
+    assert rel_err(y, yr.float()) < 1e-3
+    assert rel_err(xd.grad, xr.grad.float()) < 1e-3
+    assert rel_err(wd.grad, wr.grad.float()) < 2e-3 and rel_err(bd.grad, br.grad.float()) < 1e-4
+    ent = ops._pack_entry(wd)
+    assert ("lin16", False) in ent and ("lin16", True) in ent
+    # the register-staged TF32 kernel on the same problem agrees to operand-rounding level
+    monkeypatch.setenv("MAS_LINEAR_F16", "0")
+    x2 = x.to(dev).requires_grad_(True)
+    y2 = ops.LinearFn.apply(x2, wd, bd)
+    assert rel_err(y, y2) < 1e-3
