@@ -168,6 +168,13 @@ int mas_gemm_rows_packed(const float* A, int64_t lda, const float* w_tc, float* 
 int mas_pack_gemm_tc16(const float* w_nk, void* w_tc16, int N, int K, int transpose, void* stream);
 int mas_gemm_rows_f16(const void* x_f16, int64_t M, int K, const void* w_tc16, float* y, int64_t ldy, int N, const float* bias,
                       const float* residual, const float* x_amax, float alpha, void* stream);
+/* Weight gradient of the same layer from the two fp16 copies: dw[N,K] = dy^T . x (reduction over the M rows; dy^T through tensor
+ * memory, x tiles as the copy engine lands them, split-K partials in ws reduced in a fixed order), dbias[N] = column sums of dy
+ * (may be NULL).  x_f16 [M,K] / dy_f16 [M,N] dense, scaled by the operand scales of *x_amax / *dy_amax (NULL: unscaled).
+ * Needs N % 128 == 0 and K % 128 == 0. */
+size_t mas_wgrad_rows_f16_ws_bytes(int64_t M, int N, int K);
+int mas_wgrad_rows_f16(const void* x_f16, const void* dy_f16, int64_t M, int N, int K, float* dw, float* dbias,
+                       const float* x_amax, const float* dy_amax, void* ws, size_t ws_bytes, void* stream);
 /* Diagnostic: one tcgen05.mma D[128x32] = A[128x8].B[32x8]^T with A from shared memory (a_src=0) or tensor memory
  * (a_src=1) and B K-major (b_layout=0) or MN-major (1; 2 = LBO/SBO fields swapped). Used by the tests to pin the
  * descriptor conventions the production kernels rely on. b_layout=99: B descriptor bits / instruction descriptor /

@@ -114,6 +114,8 @@ _SPEC = {
     "mas_sample_topk": (_I, [_P, _L, _I, _I, _F, _I, _P, _P, _P]),
     "mas_pack_gemm_tc16": (_I, [_P, _P, _I, _I, _I, _P]),
     "mas_gemm_rows_f16": (_I, [_P, _L, _I, _P, _P, _L, _I, _P, _P, _P, _F, _P]),
+    "mas_wgrad_rows_f16_ws_bytes": (_Z, [_L, _I, _I]),
+    "mas_wgrad_rows_f16": (_I, [_P, _P, _L, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
     "mas_attn_causal_forward": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
     "mas_ce_forward": (_I, [_P, _L, _P, _P, _P, _P, _L, _I, _P]),
     "mas_ce_backward": (_I, [_P, _L, _P, _P, _P, _P, _P, _L, _L, _I, _P]),

@@ -1108,9 +1108,9 @@ class GeluFn(torch.autograd.Function):
 
 
 def linear_f16_on(nout, kin):
-    """Linear layers on the TMA-fed fp16 row GEMM (csrc/gemm_tma.cu): output features % 128 == 0, contraction % 64 == 0,
-    fp16 operand format selected. MAS_LINEAR_F16=0 keeps the register-staged TF32 row GEMM."""
-    return f16_operands() and nout % 128 == 0 and kin % 64 == 0 and os.environ.get("MAS_LINEAR_F16", "1") != "0"
+    """Linear layers on the TMA-fed fp16 kernels (csrc/gemm_tma.cu: forward, data gradient and weight gradient): both widths
+    multiples of 128, fp16 operand format selected. MAS_LINEAR_F16=0 keeps the register-staged TF32 kernels."""
+    return f16_operands() and nout % 128 == 0 and kin % 128 == 0 and os.environ.get("MAS_LINEAR_F16", "1") != "0"
 
 
 def _packed_linear_weight(weight, transpose, dev):
@@ -1128,22 +1128,38 @@ def _packed_linear_weight(weight, transpose, dev):
     return wt
 
 
-def gemm_rows_f16(x2d, weight, transpose=False, bias=None):
-    """y[M, N] = x2d[M, K] . W^T (+bias) (transpose: x2d[M, N] . W, the data gradient) on mas_gemm_rows_f16: x2d is converted
-    once to fp16 under the power-of-two scale of its max|.| (device scalar; nothing returns to the host)."""
-    M, kc = x2d.shape
-    nout = weight.shape[1] if transpose else weight.shape[0]
+def rows_to_half(x2d):
+    """(fp16 copy of a dense [M,K] matrix under the power-of-two scale of its max|.|, that maximum as a device scalar)."""
     am = amax(x2d)
-    x16 = torch.empty((M, kc), dtype=torch.float16, device=x2d.device)
+    x16 = torch.empty(x2d.shape, dtype=torch.float16, device=x2d.device)
     L.call("mas_to_half", x2d, x16, x2d.numel(), am)
-    y = torch.empty((M, nout), dtype=torch.float32, device=x2d.device)
-    L.call("mas_gemm_rows_f16", x16, M, kc, _packed_linear_weight(weight, transpose, x2d.device), y, nout, nout, bias, None, am, 1.0)
+    return x16, am
+
+
+def gemm_rows_f16(x16, am, weight, transpose=False, bias=None):
+    """y[M, N] = x[M, K] . W^T (+bias) (transpose: x[M, N] . W, the data gradient) on mas_gemm_rows_f16 from the fp16 copy."""
+    M, kc = x16.shape
+    nout = weight.shape[1] if transpose else weight.shape[0]
+    y = torch.empty((M, nout), dtype=torch.float32, device=x16.device)
+    L.call("mas_gemm_rows_f16", x16, M, kc, _packed_linear_weight(weight, transpose, x16.device), y, nout, nout, bias, None, am, 1.0)
     return y
 
 
+def wgrad_rows_f16(x16, am_x, dy16, am_dy, want_bias=True):
+    """dW [N,K] = dy^T . x and the bias gradient from the two fp16 copies (mas_wgrad_rows_f16)."""
+    M, K = x16.shape
+    N = dy16.shape[1]
+    dw = torch.empty((N, K), dtype=torch.float32, device=x16.device)
+    db = torch.empty(N, dtype=torch.float32, device=x16.device) if want_bias else None
+    ws = L.workspace(L.query("mas_wgrad_rows_f16_ws_bytes", M, N, K), x16.device)
+    L.call("mas_wgrad_rows_f16", x16, dy16, M, N, K, dw, db, am_x, am_dy, ws, ws.numel())
+    return dw, db
+
+
 class LinearFn(torch.autograd.Function):
-    """nn.Linear on the last dim: the TMA-fed fp16 row GEMM when out % 128 == 0 and in % 64 == 0 (forward and data gradient),
-    else the register-staged TF32 row GEMM (out % 128 == 0, in % 32 == 0), else fp32 SIMT."""
+    """nn.Linear on the last dim. Both widths % 128 == 0: the TMA-fed fp16 kernels - the input is converted ONCE to fp16 (kept
+    for the weight gradient instead of the fp32 tensor), the output gradient once for both the data and the weight gradient.
+    Else the register-staged TF32 row GEMM (out % 128 == 0, in % 32 == 0), else fp32 SIMT."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
@@ -1151,28 +1167,37 @@ class LinearFn(torch.autograd.Function):
         x = x.contiguous()
         K, N = x.shape[-1], weight.shape[0]
         R = x.numel() // K
-        if linear_f16_on(N, K):
-            y = gemm_rows_f16(x.view(R, K), weight, False, bias).view(x.shape[:-1] + (N,))
-        else:
-            y = torch.empty(x.shape[:-1] + (N,), dtype=torch.float32, device=x.device)
-            gemm_w(x, K, weight, y, N, R, bias=bias)
-        ctx.save_for_backward(x, weight)
+        ctx.f16 = linear_f16_on(N, K)
         ctx.has_bias = bias is not None
+        ctx.xshape = x.shape
+        if ctx.f16:
+            x16, am = rows_to_half(x.view(R, K))
+            y = gemm_rows_f16(x16, am, weight, False, bias).view(x.shape[:-1] + (N,))
+            ctx.save_for_backward(x16, am, weight)
+            return y
+        y = torch.empty(x.shape[:-1] + (N,), dtype=torch.float32, device=x.device)
+        gemm_w(x, K, weight, y, N, R, bias=bias)
+        ctx.save_for_backward(x, weight)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight = ctx.saved_tensors
         dy = dy.contiguous()
+        if ctx.f16:
+            x16, am_x, weight = ctx.saved_tensors
+            N, K = weight.shape
+            R = x16.shape[0]
+            dy16, am_dy = rows_to_half(dy.view(R, N))
+            dx = gemm_rows_f16(dy16, am_dy, weight, True).view(ctx.xshape) if ctx.needs_input_grad[0] else None
+            dw, db = wgrad_rows_f16(x16, am_x, dy16, am_dy, ctx.has_bias)
+            return dx, dw, db
+        x, weight = ctx.saved_tensors
         K, N = x.shape[-1], weight.shape[0]
         R = x.numel() // K
         dx = None
         if ctx.needs_input_grad[0]:
-            if linear_f16_on(K, N):
-                dx = gemm_rows_f16(dy.view(R, N), weight, True).view(x.shape)
-            else:
-                dx = torch.empty_like(x)
-                gemm_w(dy, N, weight, dx, K, R, transpose=True)
+            dx = torch.empty_like(x)
+            gemm_w(dy, N, weight, dx, K, R, transpose=True)
         dw, db = conv1x1_wgrad_raw(x, dy, R, K, N, ctx.has_bias)
         return dx, dw.view(N, K), db
 
