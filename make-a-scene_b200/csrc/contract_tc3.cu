@@ -17,12 +17,14 @@
 //
 // Selected by impl = MAS_IMPL_TC3 of mas_gemm / mas_gemm_batched2: the AttnBlock backward and the token transformer's attention
 // contractions run on it (tests/test_gpu_gemm3.py, tests/test_gpu_transformer.py).
+#include <stdlib.h>
+
 #include "mas_common.cuh"
 
 namespace mas {
 namespace tc3 {
 
-constexpr int BM = 128, KC = 32, STAGES = 2;   // the N tile (128 or 64: attention heads of 64) is a template parameter
+constexpr int BM = 128, KC = 32;   // the N tile (128 or 64: attention heads of 64) and the ring depth are template parameters
 constexpr int NPROD = 256, NTHREADS = 288;   // 8 producer / epilogue warps + the MMA warp
 constexpr int SLOTS = 132;                   // row pitch of an operand plane in 16-byte units (132 % 8 == 4: conflict-free stores)
 constexpr int LBO = SLOTS * 16;              // bytes between k-quads
@@ -122,8 +124,11 @@ struct Quad4 {
   float4 v[4];
 };
 
-template <int BN>
-__global__ void __launch_bounds__(NTHREADS, 1) gemm3_tc(const P3 p) {
+// STAGES = 2: one CTA per SM, loads of chunk k+1 overlap the MMAs of chunk k.  STAGES = 1 (short reductions, K <= 64: the
+// attention heads' 64-wide contractions are two chunks): half the shared memory and a 113-register cap so that two or three
+// CTAs share an SM and overlap each other's load / MMA / epilogue phases instead.
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NTHREADS, STAGES == 1 ? 2 : 1) gemm3_tc(const P3 p) {
   constexpr uint32_t IDESC = make_idesc(BN);
   constexpr int TCOLS = BN < 32 ? 32 : BN;          // tensor-memory columns (power of two >= 32)
   constexpr int B_ITEMS = BN * (KC / 4) / NPROD;    // 16-byte items of the B operand per producer thread (4 or 2)
@@ -289,7 +294,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm3_tc(const P3 p) {
   }
 }
 
-constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE + (2 * STAGES + 1) * 8 + 16;
+template <int STAGES>
+constexpr size_t smem_bytes() { return (size_t)STAGES * STAGE + (2 * STAGES + 1) * 8 + 16; }
 
 }  // namespace tc3
 
@@ -325,17 +331,23 @@ int gemm_tc3_launch2(const float* A, const float* B, float* C, int M, int N, int
   const int zdim = outer * batch;
   static std::atomic<uint64_t> configured{0};
   if (first_on_device(configured)) {
-    cudaError_t e = cudaFuncSetAttribute(tc3::gemm3_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc3::SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc3::gemm3_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc3::SMEM_BYTES);
-    if (e != cudaSuccess) return fail(MAS_ERR_LAUNCH, "cudaFuncSetAttribute(smem=%zu): %s", tc3::SMEM_BYTES, cudaGetErrorString(e));
+    cudaError_t e = cudaFuncSetAttribute(tc3::gemm3_tc<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc3::smem_bytes<2>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc3::gemm3_tc<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc3::smem_bytes<2>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc3::gemm3_tc<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc3::smem_bytes<1>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc3::gemm3_tc<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc3::smem_bytes<1>());
+    if (e != cudaSuccess) return fail(MAS_ERR_LAUNCH, "cudaFuncSetAttribute(smem=%zu): %s", tc3::smem_bytes<2>(), cudaGetErrorString(e));
     mark_device(configured);
   }
+  static const bool shallow_on = [] { const char* e = getenv("MAS_TC3_SHALLOW"); return !(e && e[0] == '0'); }();
+  const bool shallow = shallow_on && K <= 64;     // two chunks at most: co-resident CTAs instead of a 2-stage ring
   if (N % 128 == 0) {
     dim3 grid((unsigned)(N / 128), (unsigned)cdiv(M, tc3::BM), (unsigned)zdim);
-    tc3::gemm3_tc<128><<<grid, tc3::NTHREADS, tc3::SMEM_BYTES, st>>>(p);
+    if (shallow) tc3::gemm3_tc<128, 1><<<grid, tc3::NTHREADS, tc3::smem_bytes<1>(), st>>>(p);
+    else tc3::gemm3_tc<128, 2><<<grid, tc3::NTHREADS, tc3::smem_bytes<2>(), st>>>(p);
   } else {   // attention heads of 64 channels: P.V and the q / k / v gradients of the token transformer
     dim3 grid((unsigned)(N / 64), (unsigned)cdiv(M, tc3::BM), (unsigned)zdim);
-    tc3::gemm3_tc<64><<<grid, tc3::NTHREADS, tc3::SMEM_BYTES, st>>>(p);
+    if (shallow) tc3::gemm3_tc<64, 1><<<grid, tc3::NTHREADS, tc3::smem_bytes<1>(), st>>>(p);
+    else tc3::gemm3_tc<64, 2><<<grid, tc3::NTHREADS, tc3::smem_bytes<2>(), st>>>(p);
   }
   return launched_tc("gemm3_tc");
 }

@@ -204,6 +204,52 @@ __global__ void layernorm_bwd_dx_kernel(const float* __restrict__ dy, const floa
   }
 }
 
+// Block-per-row form for H <= 4096 (the row's dy and x stay in registers: one pass over global memory instead of three
+// dependent warp-strided passes; the warp-per-row kernel above walked H = 1024 in 32 trips per pass).
+__global__ void __launch_bounds__(256) layernorm_bwd_dx_block_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                     const float* __restrict__ gamma, float* __restrict__ dx, int H) {
+  __shared__ float red[2][8];
+  const int64_t row = blockIdx.x;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, Q = H >> 2;
+  const float m = mean[row], rs = rstd[row];
+  const float4* dr = reinterpret_cast<const float4*>(dy + row * H);
+  const float4* xr = reinterpret_cast<const float4*>(x + row * H);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  float4 g[4], xh[4];
+  float a = 0.f, b = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int q = t + 256 * i;
+    if (q < Q) {
+      const float4 d = __ldg(dr + q), xv = __ldg(xr + q), gm = __ldg(g4 + q);
+      g[i] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
+      xh[i] = make_float4((xv.x - m) * rs, (xv.y - m) * rs, (xv.z - m) * rs, (xv.w - m) * rs);
+      a = fmaf(g[i].x, xh[i].x, a); a = fmaf(g[i].y, xh[i].y, a); a = fmaf(g[i].z, xh[i].z, a); a = fmaf(g[i].w, xh[i].w, a);
+      b += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+    } else {
+      g[i] = xh[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if (lane == 0) { red[0][warp] = a; red[1][warp] = b; }
+  __syncthreads();
+  float ta = 0.f, tb = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) { ta += red[0][w]; tb += red[1][w]; }
+  ta /= (float)H;
+  tb /= (float)H;
+  float4* o4 = reinterpret_cast<float4*>(dx + row * H);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int q = t + 256 * i;
+    if (q < Q)
+      o4[q] = make_float4(rs * (g[i].x - tb - xh[i].x * ta), rs * (g[i].y - tb - xh[i].y * ta), rs * (g[i].z - tb - xh[i].z * ta),
+                          rs * (g[i].w - tb - xh[i].w * ta));
+  }
+}
+
 // column sums for dgamma / dbeta: block (32,8) per 32-column tile and row chunk; deterministic two-stage
 constexpr int LN_ROWS = 1024;
 __global__ void layernorm_bwd_param_partial(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
@@ -424,8 +470,14 @@ int mas_layernorm_backward(const float* dy, const float* x, const float* mean, c
                            float* dgamma, float* dbeta, int64_t R, int H, void* ws, size_t ws_bytes, void* stream) {
   MAS_REQUIRE(dy && x && mean && rstd && gamma && dx && R > 0 && H > 0, "layernorm_backward: bad arguments");
   if (ws_bytes < mas_layernorm_ws_bytes(R, H)) return fail(MAS_ERR_WORKSPACE, "layernorm_backward: workspace too small");
-  layernorm_bwd_dx_kernel<<<(unsigned)cdiv(R, 8), 256, 0, S(stream)>>>(dy, x, mean, rstd, gamma, dx, R, H);
-  if (int e = launched("layernorm_bwd_dx")) return e;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (H % 4 == 0 && H <= 4096 && H >= 256 && al16(dy) && al16(x) && al16(gamma) && al16(dx)) {
+    layernorm_bwd_dx_block_kernel<<<(unsigned)R, 256, 0, S(stream)>>>(dy, x, mean, rstd, gamma, dx, H);
+    if (int e = launched("layernorm_bwd_dx_block")) return e;
+  } else {
+    layernorm_bwd_dx_kernel<<<(unsigned)cdiv(R, 8), 256, 0, S(stream)>>>(dy, x, mean, rstd, gamma, dx, R, H);
+    if (int e = launched("layernorm_bwd_dx")) return e;
+  }
   if (dgamma && dbeta) {
     const int chunks = (int)cdiv(R, LN_ROWS);
     layernorm_bwd_param_partial<<<dim3((unsigned)cdiv(H, 32), chunks), dim3(32, 8), 0, S(stream)>>>(dy, x, mean, rstd, R, H, (double*)ws);

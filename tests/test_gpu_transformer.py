@@ -341,7 +341,7 @@ def test_linear_on_tma_fed_f16_row_gemm(R, K, N, monkeypatch):
     assert L.tc_launch_count() - before == 3          # forward, data gradient, weight gradient
     assert rel_err(y, yr.float()) < 1e-3
     assert rel_err(xd.grad, xr.grad.float()) < 1e-3
-    assert rel_err(wd.grad, wr.grad.float()) < 2e-3 and rel_err(bd.grad, br.grad.float()) < 1e-4
+    assert rel_err(wd.grad, wr.grad.float()) < 2e-3 and rel_err(bd.grad, br.grad.float()) < 5e-4   # sums of the fp16-rounded dy
     ent = ops._pack_entry(wd)
     assert ("lin16", False) in ent and ("lin16", True) in ent
     # the register-staged TF32 kernel on the same problem agrees to operand-rounding level
@@ -349,3 +349,31 @@ def test_linear_on_tma_fed_f16_row_gemm(R, K, N, monkeypatch):
     x2 = x.to(dev).requires_grad_(True)
     y2 = ops.LinearFn.apply(x2, wd, bd)
     assert rel_err(y, y2) < 1e-3
+
+
+@pytest.mark.parametrize("R,H,res", [(5, 132, True), (640, 1024, True), (100, 4096, False), (33, 256, False), (7, 8192, False)])
+def test_layernorm_forward_backward_vs_torch(R, H, res):
+    """LayerNormFn (warp-per-row and block-per-row kernels of both directions) against fp64 torch: output, dx, dgamma, dbeta and
+    the residual pass-through."""
+    from mas_b200 import ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(R * 7 + H)
+    x = torch.randn(R, H, generator=g) * 2 + 0.7
+    w, b = torch.randn(H, generator=g), torch.randn(H, generator=g)
+    r = torch.randn(R, H, generator=g) if res else None
+    dy = torch.randn(R, H, generator=g)
+    xr, wr, br = x.double().requires_grad_(True), w.double().requires_grad_(True), b.double().requires_grad_(True)
+    rr = r.double().requires_grad_(True) if res else None
+    yr = torch.nn.functional.layer_norm(xr, (H,), wr, br, 1e-5)
+    if res:
+        yr = yr + rr
+    yr.backward(dy.double())
+    xd, wd, bd = x.to(dev).requires_grad_(True), w.to(dev).requires_grad_(True), b.to(dev).requires_grad_(True)
+    rd = r.to(dev).requires_grad_(True) if res else None
+    y = ops.LayerNormFn.apply(xd, wd, bd, rd, 1e-5)
+    y.backward(dy.to(dev))
+    assert rel_err(y, yr.float()) < 1e-5
+    assert rel_err(xd.grad, xr.grad.float()) < 2e-5
+    assert rel_err(wd.grad, wr.grad.float()) < 1e-5 and rel_err(bd.grad, br.grad.float()) < 1e-5
+    if res:
+        assert torch.equal(rd.grad.cpu(), dy)
