@@ -329,6 +329,49 @@ def vq_metric(dev, pk, sweep=True):
             "all_pairs_ffma_kernel": exact, "sweep": pts}
 
 
+def transformer_metric(dev, batch=8, steps=3, warmup=2):
+    """Tier-2 row: training-step throughput of the token transformer at BASELINE configs[4]'s model (24 layers,
+    1024 wide, 16 heads of 64, 128 text + 256 segmentation + 256 image tokens; random weights, synthetic tokens): forward +
+    cross-entropy over the image tokens + backward (train.py:136-153, no optimizer), CUDA-event timed. Same code as
+    tools/bench_transformer.py. Reported beside the headline, not part of it."""
+    from mas_b200 import _lib
+    from models.transformer import MakeAScene
+    cfg = dict(num_layers=24, hidden_dim=1024, num_attn_heads=16, image_vocab_size=8192, seg_vocab_size=1024, text_vocab_size=49408,
+               image_tokens_per_dim=16, seg_tokens_per_dim=16, text_length=128)
+    torch.manual_seed(0)
+    m = MakeAScene(**cfg).to(dev).train()
+    m.device = dev
+    g = torch.Generator().manual_seed(1234)
+    text = torch.randint(1, 40000, (batch, 128), generator=g).to(dev)
+    seg = torch.randint(0, 1024, (batch, 256), generator=g).to(dev)
+    img = torch.randint(0, 8192, (batch, 256), generator=g).to(dev)
+
+    def step():
+        m.zero_grad(set_to_none=True)
+        loss = m.loss(text, seg, img)
+        loss.backward()
+        return loss
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0, t0 = _lib.launch_count(), _lib.tc_launch_count()
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) * 1e-3 / steps
+    S, H, Ly, V = 640, 1024, 24, 8192
+    flops = 3 * (2 * S * (12 * H * H) * Ly + 2 * 256 * H * V + 2 * 2 * S * S * H * Ly) * batch
+    return {"metric": "token transformer training step (fwd + cross-entropy + bwd), sequence tokens/s", "value": round(batch * S / sec, 1),
+            "unit": "tokens/s", "batch": batch, "seq_len": S, "ms_per_step": round(sec * 1e3, 3), "loss": round(float(loss.detach()), 5),
+            "model_tflops": round(flops / sec / 1e12, 1), "gpu_launches_per_step": (_lib.launch_count() - l0) // steps,
+            "tcgen05_launches_per_step": (_lib.tc_launch_count() - t0) // steps,
+            "kernels": "rows_gemm_t16 / rows_wgrad_t16 (TMA-fed fp16 Linear layers), attn_causal_fwd (fused causal attention core), "
+                       "gemm3_tc (3xTF32 attention gradients), mas_ce_* (fused cross-entropy)"}
+
+
 def _fmt():
     from mas_b200 import ops
     return "fp16 (3x3 convolutions) / tf32 (1x1)" if ops.get_operand_format() == "f16" else "tf32"
@@ -496,6 +539,12 @@ def main():
                     "ms_per_step": sec_e2e / args.steps * 1e3},
             "gpu_launches": int(launches), "clocks": clocks,
             "model_tflops": FLOP_PER_IMG_FWD_BWD * value / 1e12, "roofline": roof, "vq": vq, "attn": attn}
+    if world == 1:   # tier-2 row, beside the headline (never fails the bench line)
+        try:
+            torch.cuda.empty_cache()
+            line["transformer"] = transformer_metric(dev)
+        except Exception as e:  # noqa: BLE001
+            line["transformer"] = {"error": str(e)[:200]}
     if not args.no_cpu_baseline and world == 1:   # reported baseline: rank 0 at N=1 only
         r = cpu_reference_steps(3, 1, batch=2)
         line["cpu_baseline"] = {"value": r["value"], "unit": "images/s", "cores": r["cores"], "kind": r["kind"],
