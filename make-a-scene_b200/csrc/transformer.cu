@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_dx_block_kernel(const float
 }
 
 // column sums for dgamma / dbeta: block (32,8) per 32-column tile and row chunk; deterministic two-stage
-constexpr int LN_ROWS = 1024;
+constexpr int LN_ROWS = 128;    // rows per partial block: 5120 rows x 1024 columns -> 32 x 40 blocks (1024 rows per block left 160 blocks for 148 SMs)
 __global__ void layernorm_bwd_param_partial(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
                                             const float* __restrict__ rstd, int64_t R, int H, double* __restrict__ part) {
   __shared__ double sh[8][32][2];
