@@ -236,6 +236,46 @@ def _emu_more():
             c = np.cumsum(p)
             out[r] = min(int(np.searchsorted(c, uu[r] * c[-1], side="right")), V - 1)
 
+    # ---- fp16 Linear path (csrc/gemm_tma.cu): real fp16 rounding of the operand copies, power-of-two scales from max|.|
+    packs = {}
+
+    def f16(p, n):
+        return np.ctypeslib.as_array((ctypes.c_uint16 * n).from_address(_addr(p))).view(np.float16)
+
+    def scale_of(amax):
+        if amax is None:
+            return 1.0
+        a = float(vec(amax, 1)[0])
+        return 1.0 if not np.isfinite(a) or a <= 0 else 2.0 ** (14 - int(np.floor(np.log2(a))))
+
+    def mas_amax(self, x, n, out):
+        vec(out, 1)[0] = np.abs(vec(x, n)).max()
+
+    def mas_to_half(self, x, y, n, amax):
+        f16(y, n)[...] = (vec(x, n).astype(np.float64) * scale_of(amax)).astype(np.float16)
+
+    def mas_pack_gemm_tc16(self, w, out, N, K, transpose):
+        W = vec(w, N * K).reshape(N, K).astype(np.float16).astype(np.float64)          # operand rounding of the weights
+        packs[_addr(out)] = W.T.copy() if transpose else W                             # rows = output features of the product
+
+    def mas_gemm_rows_f16(self, x16, M, K, wpk, y, ldy, N, bias, residual, x_amax, alpha):
+        X = f16(x16, M * K).reshape(M, K).astype(np.float64) / scale_of(x_amax)
+        Wp = packs[_addr(wpk)]
+        assert Wp.shape == (N, K), (Wp.shape, N, K)
+        o = alpha * (X @ Wp.T)
+        if bias is not None:
+            o = o + vec(bias, N)[None, :]
+        if residual is not None:
+            o = o + _mat(_addr(residual), M, N, ldy, False)
+        _mat(_addr(y), M, N, ldy, False)[...] = o
+
+    def mas_wgrad_rows_f16(self, x16, dy16, M, N, K, dw, db, x_amax, dy_amax, ws, ws_bytes):
+        X = f16(x16, M * K).reshape(M, K).astype(np.float64) / scale_of(x_amax)
+        D = f16(dy16, M * N).reshape(M, N).astype(np.float64) / scale_of(dy_amax)
+        vec(dw, N * K).reshape(N, K)[...] = D.T @ X
+        if db is not None:
+            vec(db, N)[...] = D.sum(0)
+
     for k, v in list(locals().items()):
         if k.startswith("mas_"):
             setattr(Emu, k, v)
@@ -364,3 +404,38 @@ def test_generate_host_logic_against_reference_fixture(emu):
     kth = la.topk(3, dim=-1).values[..., -1]
     assert bool((la.gather(-1, a.unsqueeze(-1)).squeeze(-1) >= kth).all())
     assert "mas_sample_topk" in emu.names
+
+
+def test_linear_fp16_path_host_logic_against_reference_fixture(emu, monkeypatch):
+    """LinearFn's fp16 route (one conversion of the input kept for the weight gradient, one of the output gradient for both
+    gradients, weight images cached per parameter version) above the emulated entries - with real fp16 operand rounding - stays
+    within the production tolerance of the REAL reference's logits and gradients (tests/golden/transformer_wide.pt)."""
+    import os
+    from conftest import GOLDEN, rel_err
+    from mas_b200 import ops
+    from models.transformer import MakeAScene
+    monkeypatch.setattr(ops, "f16_operands", lambda: True)
+    monkeypatch.setenv("MAS_LINEAR_F16", "1")
+    g = torch.load(os.path.join(GOLDEN, "transformer_wide.pt"), weights_only=False)
+    m = MakeAScene(**g["cfg"])
+    m.load_state_dict(g["state_dict"])
+    m.device = torch.device("cpu")
+    loss = m.loss(g["text"], g["seg"], g["img"])
+    assert abs(float(loss.detach()) - float(g["loss"])) < 1e-3 * max(1.0, float(g["loss"]))
+    loss.backward()
+    assert emu.names.count("mas_gemm_rows_f16") == 2 * 4 * g["cfg"]["num_layers"] + 2       # forward + data gradient of every Linear
+    assert emu.names.count("mas_wgrad_rows_f16") == 4 * g["cfg"]["num_layers"] + 1
+    n_lin = 4 * g["cfg"]["num_layers"] + 1
+    assert emu.names.count("mas_to_half") == 2 * n_lin and emu.names.count("mas_pack_gemm_tc16") == 2 * n_lin
+    named = dict(m.named_parameters())
+    for k, gv in g["grads"].items():
+        assert rel_err(named[k].grad, gv) < 5e-3, k
+    # a second step without touching the weights packs nothing; an in-place update repacks
+    before = emu.names.count("mas_pack_gemm_tc16")
+    m.zero_grad()
+    m.loss(g["text"], g["seg"], g["img"]).backward()
+    assert emu.names.count("mas_pack_gemm_tc16") == before
+    with torch.no_grad():
+        m.to_logits[1].weight.add_(0.0)
+    m.loss(g["text"], g["seg"], g["img"]).backward()
+    assert emu.names.count("mas_pack_gemm_tc16") == before + 2
