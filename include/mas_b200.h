@@ -239,11 +239,16 @@ int mas_gemm(const float* A, const float* B, float* C, int M, int N, int K, int 
              int trans_b, float alpha, const float* bias, const float* residual, int impl, void* stream);
 /* Two-level batch: outer x batch matrices, matrix (o, i) at o * outer_stride_? + i * stride_? - the heads of a fused
  * [B, S, 3H] q|k|v activation (transformer.py:77-103) in ONE launch on the 3xTF32 kernel (impl = MAS_IMPL_TC3, outer * batch
- * <= 65535); other impl values run one mas_gemm per outer index.  No bias / residual. */
+ * <= 65535); other impl values run one mas_gemm per outer index.  No bias / residual.
+ * causal: structure hint for the square (queries x keys, key <= query) attention matrices - identically-zero K chunks and
+ * output tiles are skipped by the 3xTF32 kernel (other implementations ignore it; results are the same because the skipped
+ * operand blocks are zero / the skipped outputs are never consumed): 0 none; 1 A[m][k] = 0 for k > m (ctx = P v, dQ = dS k);
+ * 2 A stored [K][M] with A[k][m] = 0 for k < m (dV = P^T dO, dK = dS^T q); 3 outputs with n > m unused, whole tiles above the
+ * diagonal are written as zeros (S = q k^T, dP = dO v^T). */
 int mas_gemm_batched2(const float* A, const float* B, float* C, int M, int N, int K, int outer, int batch, int64_t lda,
                       int64_t ldb, int64_t ldc, int64_t outer_stride_a, int64_t outer_stride_b, int64_t outer_stride_c,
                       int64_t stride_a, int64_t stride_b, int64_t stride_c, int trans_a, int trans_b, float alpha, int impl,
-                      void* stream);
+                      int causal, void* stream);
 /* Column sums of a strided [N,H,W,C] view (bias gradients): out[c] = sum_{n,h,w} x[n,h,w,c]. Deterministic. */
 size_t mas_colsum_ws_bytes(mas_tensor4 t);
 int mas_colsum(const float* x, mas_tensor4 t, float* out, void* ws, size_t ws_bytes, void* stream);
@@ -352,6 +357,10 @@ int mas_layernorm_backward(const float* dy, const float* x, const float* mean, c
 int mas_gelu_forward(const float* x, float* y, int64_t n, void* stream);
 int mas_gelu_backward(const float* dy, const float* x, float* dx, int64_t n, void* stream);
 int mas_softmax_causal_forward(const float* s, float* p, int64_t mats, int rows, int cols, void* stream);
+/* ds = p * (dp - sum_visible(dp * p)) * scale on the visible columns (0..i+cols-rows) of each row, zeros beyond; dp is not read
+ * beyond the visible columns (the causal dP GEMM leaves whole tiles unwritten there); ds may alias dp. */
+int mas_softmax_causal_backward(const float* p, const float* dp, float* ds, int64_t mats, int rows, int cols, float scale,
+                                void* stream);
 int mas_embed3_forward(const float* t0, const int64_t* id0, const float* t1, const int64_t* id1, const float* t2,
                        const int64_t* id2, float* out, int64_t R, int H, int seg, int total, int off, void* stream);
 int mas_embed3_backward(const float* dout, const int64_t* id0, float* d0, const int64_t* id1, float* d1,

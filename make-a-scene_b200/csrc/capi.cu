@@ -26,7 +26,7 @@ int gemm_tc3_launch(const float* A, const float* B, float* C, int M, int N, int 
                     cudaStream_t st);
 int gemm_tc3_launch2(const float* A, const float* B, float* C, int M, int N, int K, int outer, int batch, int64_t lda, int64_t ldb,
                      int64_t ldc, int64_t sa2, int64_t sb2, int64_t sc2, int64_t sa, int64_t sb, int64_t sc, int ta, int tb, float alpha,
-                     const float* bias, const float* res, cudaStream_t st);
+                     const float* bias, const float* res, int causal, cudaStream_t st);
 size_t conv1x1_wgrad_tc_ws(int64_t M, int Cin, int Cout);
 int conv1x1_wgrad_tc_launch(const float* x, int64_t ldx, const float* dy, int64_t ldy, int64_t M, int Cin, int Cout, float* dw,
                             float* dbias, void* ws, size_t ws_bytes, cudaStream_t st);
@@ -132,11 +132,11 @@ int mas_gemm(const float* A, const float* B, float* C, int M, int N, int K, int 
 // one launch on the 3xTF32 kernel; the other implementations run one plain batched call per outer index.
 int mas_gemm_batched2(const float* A, const float* B, float* C, int M, int N, int K, int outer, int batch, int64_t lda, int64_t ldb,
                       int64_t ldc, int64_t outer_stride_a, int64_t outer_stride_b, int64_t outer_stride_c, int64_t stride_a,
-                      int64_t stride_b, int64_t stride_c, int trans_a, int trans_b, float alpha, int impl, void* stream) {
+                      int64_t stride_b, int64_t stride_c, int trans_a, int trans_b, float alpha, int impl, int causal, void* stream) {
   MAS_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && batch > 0 && outer > 0, "gemm_batched2: bad arguments");
-  if (impl == MAS_IMPL_TC3)
+  if (impl == MAS_IMPL_TC3)   // causal (see the header): a hint - the other implementations contract the (zero) blocks too
     return gemm_tc3_launch2(A, B, C, M, N, K, outer, batch, lda, ldb, ldc, outer_stride_a, outer_stride_b, outer_stride_c, stride_a,
-                            stride_b, stride_c, trans_a, trans_b, alpha, nullptr, nullptr, S(stream));
+                            stride_b, stride_c, trans_a, trans_b, alpha, nullptr, nullptr, causal, S(stream));
   for (int o = 0; o < outer; ++o) {
     const int e = mas_gemm(A + (int64_t)o * outer_stride_a, B + (int64_t)o * outer_stride_b, C + (int64_t)o * outer_stride_c, M, N, K,
                            batch, lda, ldb, ldc, stride_a, stride_b, stride_c, trans_a, trans_b, alpha, nullptr, nullptr, impl, stream);

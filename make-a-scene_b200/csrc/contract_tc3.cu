@@ -117,6 +117,11 @@ struct P3 {
   // [B, S, 3H] activation: outer = batch element, inner = head).  inner = batch, s?2 = 0 for the plain batched form.
   int inner;
   int64_t sa2, sb2, sc2;
+  // causal structure of the token transformer's attention matrices (queries x keys, key <= query): whole K chunks / output
+  // tiles that are identically zero are skipped.  1: A[m][k] = 0 for k > m (dQ = dS K, ctx = P V): chunks beyond the row tile;
+  // 2: A stored [K][M] with A[k][m] = 0 for k < m (dV = P^T dO, dK = dS^T Q): chunks before the row tile; 3: only output
+  // entries n <= m are consumed (S = Q K^T, dP = dO V^T): tiles above the diagonal are written as zeros.
+  int causal;
 };
 
 // One operand of one K chunk: 128 rows x 32 k = 1024 quads, four per producer thread; returns them split into hi / lo.
@@ -146,6 +151,11 @@ __global__ void __launch_bounds__(NTHREADS, STAGES == 1 ? 2 : 1) gemm3_tc(const 
   const float* Bb = p.B + (int64_t)zo * p.sb2 + (int64_t)zi * p.sb;
   float* Cb = p.C + (int64_t)zo * p.sc2 + (int64_t)zi * p.sc;
   const int nchunks = p.K / KC;
+  int kc0 = 0, kc1 = nchunks;
+  if (p.causal == 1) kc1 = min(nchunks, (m0 + BM) / KC);
+  else if (p.causal == 2) kc0 = min(nchunks, m0 / KC);
+  else if (p.causal == 3 && n0 >= m0 + BM) kc1 = 0;
+  const bool empty = kc0 >= kc1;          // block-uniform: nothing to contract, the tile is zero
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -215,11 +225,13 @@ __global__ void __launch_bounds__(NTHREADS, STAGES == 1 ? 2 : 1) gemm3_tc(const 
     int stage = 0;
     uint32_t phase = 0;
     Quad4 an, bn;
-    load_op(Ab, p.lda, p.ta, m0, p.M, 0, an, 4);
-    load_op(Bb, p.ldb, p.tb, n0, p.N, 0, bn, B_ITEMS);
-    for (int kc = 0; kc < nchunks; ++kc) {
+    if (!empty) {
+      load_op(Ab, p.lda, p.ta, m0, p.M, kc0, an, 4);
+      load_op(Bb, p.ldb, p.tb, n0, p.N, kc0, bn, B_ITEMS);
+    }
+    for (int kc = kc0; kc < kc1; ++kc) {
       const Quad4 a = an, b = bn;
-      if (kc + 1 < nchunks) {   // next chunk's loads fly while this one is split and stored
+      if (kc + 1 < kc1) {   // next chunk's loads fly while this one is split and stored
         load_op(Ab, p.lda, p.ta, m0, p.M, kc + 1, an, 4);
         load_op(Bb, p.ldb, p.tb, n0, p.N, kc + 1, bn, B_ITEMS);
       }
@@ -243,6 +255,10 @@ __global__ void __launch_bounds__(NTHREADS, STAGES == 1 ? 2 : 1) gemm3_tc(const 
       const int col = chalf * (BN / 2) + cc * 32;
       float v[32];
       tmem_ld32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)col, v);
+      if (empty) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
       __syncwarp();
 #pragma unroll
       for (int j = 0; j < 32; j += 4)
@@ -263,7 +279,7 @@ __global__ void __launch_bounds__(NTHREADS, STAGES == 1 ? 2 : 1) gemm3_tc(const 
     {
       int stage = 0;
       uint32_t phase = 0;
-      for (int kc = 0; kc < nchunks; ++kc) {
+      for (int kc = kc0; kc < kc1; ++kc) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         const uint32_t st = smem_base + (uint32_t)stage * STAGE;
@@ -273,17 +289,17 @@ __global__ void __launch_bounds__(NTHREADS, STAGES == 1 ? 2 : 1) gemm3_tc(const 
 #pragma unroll
           for (int k8 = 0; k8 < KC / 8; ++k8) {
             const uint64_t ko = (uint64_t)((k8 * 2 * LBO) >> 4);
-            mma_tf32_ss(tmem_base, a_hi + ko, b_hi + ko, IDESC, (kc > 0 || k8 > 0) ? 1u : 0u);
+            mma_tf32_ss(tmem_base, a_hi + ko, b_hi + ko, IDESC, (kc > kc0 || k8 > 0) ? 1u : 0u);
             mma_tf32_ss(tmem_base, a_lo + ko, b_hi + ko, IDESC, 1u);
             mma_tf32_ss(tmem_base, a_hi + ko, b_lo + ko, IDESC, 1u);
           }
           mma_commit(empty_bar(stage));
-          if (kc == nchunks - 1) mma_commit(accum_bar);
+          if (kc == kc1 - 1) mma_commit(accum_bar);
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      if (nchunks == 0 && elect_one()) mma_commit(accum_bar);
+      if (empty && elect_one()) mma_commit(accum_bar);
       __syncwarp();
     }
   }
@@ -305,16 +321,18 @@ static inline bool al16q(const void* p) { return (reinterpret_cast<uintptr_t>(p)
 // stored [K][M]; trans_b = 1 means B is stored [N][K] (k contiguous), trans_b = 0 means B is stored [K][N].
 int gemm_tc3_launch2(const float* A, const float* B, float* C, int M, int N, int K, int outer, int batch, int64_t lda, int64_t ldb,
                      int64_t ldc, int64_t sa2, int64_t sb2, int64_t sc2, int64_t sa, int64_t sb, int64_t sc, int ta, int tb, float alpha,
-                     const float* bias, const float* res, cudaStream_t st);
+                     const float* bias, const float* res, int causal, cudaStream_t st);
 int gemm_tc3_launch(const float* A, const float* B, float* C, int M, int N, int K, int batch, int64_t lda, int64_t ldb, int64_t ldc,
                     int64_t sa, int64_t sb, int64_t sc, int ta, int tb, float alpha, const float* bias, const float* res,
                     cudaStream_t st) {
-  return gemm_tc3_launch2(A, B, C, M, N, K, 1, batch, lda, ldb, ldc, 0, 0, 0, sa, sb, sc, ta, tb, alpha, bias, res, st);
+  return gemm_tc3_launch2(A, B, C, M, N, K, 1, batch, lda, ldb, ldc, 0, 0, 0, sa, sb, sc, ta, tb, alpha, bias, res, 0, st);
 }
 // outer x batch matrices: matrix (o, i) lives at o * s?2 + i * s?
 int gemm_tc3_launch2(const float* A, const float* B, float* C, int M, int N, int K, int outer, int batch, int64_t lda, int64_t ldb,
                      int64_t ldc, int64_t sa2, int64_t sb2, int64_t sc2, int64_t sa, int64_t sb, int64_t sc, int ta, int tb, float alpha,
-                     const float* bias, const float* res, cudaStream_t st) {
+                     const float* bias, const float* res, int causal, cudaStream_t st) {
+  if (causal < 0 || causal > 3 || (causal == 2 && !ta) || (causal == 1 && ta))
+    return fail(MAS_ERR_INVALID_ARG, "tc3 gemm: causal mode %d does not fit the operand orientation", causal);
   if (outer < 1 || batch < 1 || (int64_t)outer * batch > 65535) return fail(MAS_ERR_UNSUPPORTED, "tc3 gemm: outer * batch must be in [1, 65535]");
   if (sa2 % 4 || sb2 % 4 || sc2 % 4) return fail(MAS_ERR_UNSUPPORTED, "tc3 gemm: outer strides must be multiples of 4 elements");
   if (bias || res) return fail(MAS_ERR_UNSUPPORTED, "tc3 gemm: bias / residual epilogue not available");
@@ -327,7 +345,7 @@ int gemm_tc3_launch2(const float* A, const float* B, float* C, int M, int N, int
   p.ta = ta ? 1 : 0;        // A stored [K][M]  -> rows (m) contiguous
   p.tb = tb ? 0 : 1;        // B stored [N][K] (tb = 1) is the k-contiguous orientation; [K][N] (tb = 0) is row-contiguous
   p.alpha = alpha;
-  p.inner = batch; p.sa2 = sa2; p.sb2 = sb2; p.sc2 = sc2;
+  p.inner = batch; p.sa2 = sa2; p.sb2 = sb2; p.sc2 = sc2; p.causal = causal;
   const int zdim = outer * batch;
   static std::atomic<uint64_t> configured{0};
   if (first_on_device(configured)) {

@@ -321,6 +321,20 @@ __global__ void softmax_causal_kernel(const float* __restrict__ s, float* __rest
   for (int c = lane; c < cols; c += 32) pr[c] = c <= lim ? expf(sr[c] - mx) * inv : 0.f;
 }
 
+__global__ void softmax_causal_bwd_kernel(const float* __restrict__ p, const float* __restrict__ dp, float* __restrict__ ds,
+                                          int64_t total_rows, int rows, int cols, float scale) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= total_rows) return;
+  const int lane = threadIdx.x & 31;
+  const int i = (int)(row % rows), lim = i + (cols - rows);  // columns 0..lim are visible
+  const float* pr = p + row * cols;
+  const float* dr = dp + row * cols;
+  float dot = 0.f;
+  for (int c = lane; c <= lim; c += 32) dot += pr[c] * dr[c];
+  dot = warp_sum(dot);
+  for (int c = lane; c < cols; c += 32) ds[row * cols + c] = c <= lim ? pr[c] * (dr[c] - dot) * scale : 0.f;
+}
+
 // ---------------------------------------------------------------------------------------------------- embeddings
 // out[(r/seg)*total + off + r%seg][:] = T0[id0[r]] + T1[id1[r % seg or r]] + T2[...]; ids are int64; a table pointer may be null
 __global__ void embed3_fwd_kernel(const float* __restrict__ t0, const int64_t* __restrict__ id0, const float* __restrict__ t1,
@@ -499,6 +513,11 @@ int mas_softmax_causal_forward(const float* s, float* p, int64_t mats, int rows,
   MAS_REQUIRE(mats > 0 && rows > 0 && cols >= rows, "softmax_causal: bad shape");
   softmax_causal_kernel<<<(unsigned)cdiv(mats * rows, 8), 256, 0, S(stream)>>>(s, p, mats * rows, rows, cols);
   return launched("softmax_causal");
+}
+int mas_softmax_causal_backward(const float* p, const float* dp, float* ds, int64_t mats, int rows, int cols, float scale, void* stream) {
+  MAS_REQUIRE(p && dp && ds && mats > 0 && rows > 0 && cols >= rows, "softmax_causal_backward: bad arguments");
+  softmax_causal_bwd_kernel<<<(unsigned)cdiv(mats * rows, 8), 256, 0, S(stream)>>>(p, dp, ds, mats * rows, rows, cols, scale);
+  return launched("softmax_causal_bwd");
 }
 int mas_embed3_forward(const float* t0, const int64_t* id0, const float* t1, const int64_t* id1, const float* t2, const int64_t* id2,
                        float* out, int64_t R, int H, int seg, int total, int off, void* stream) {

@@ -119,7 +119,8 @@ _SPEC = {
     "mas_attn_causal_forward": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
     "mas_ce_forward": (_I, [_P, _L, _P, _P, _P, _P, _L, _I, _P]),
     "mas_ce_backward": (_I, [_P, _L, _P, _P, _P, _P, _P, _L, _L, _I, _P]),
-    "mas_gemm_batched2": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _L, _L, _L, _L, _L, _L, _L, _L, _L, _I, _I, _F, _I, _P]),
+    "mas_gemm_batched2": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _L, _L, _L, _L, _L, _L, _L, _L, _L, _I, _I, _F, _I, _I, _P]),
+    "mas_softmax_causal_backward": (_I, [_P, _P, _P, _L, _I, _I, _F, _P]),
     "mas_bce_ws_bytes": (_Z, [_T]),
     "mas_bce_cl_ws_bytes": (_Z, [_I, _I, _I]),
     "mas_bce_cl_forward": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _Z, _P]),

@@ -46,14 +46,20 @@ class Emu:
         self.names.append(name)
         getattr(self, name)(*a)
 
-    def mas_gemm_batched2(self, A, B, C, M, N, K, outer, batch, lda, ldb, ldc, osa, osb, osc, sa, sb, sc, ta, tb, alpha, impl):
+    def mas_gemm_batched2(self, A, B, C, M, N, K, outer, batch, lda, ldb, ldc, osa, osb, osc, sa, sb, sc, ta, tb, alpha, impl, causal=0):
         a0, b0, c0 = _addr(A), _addr(B), _addr(C)
         for o in range(outer):
             for i in range(batch):
                 Am = _mat(a0 + 4 * (o * osa + i * sa), M, K, lda, bool(ta))          # op(A) [M,K]
                 Bm = _mat(b0 + 4 * (o * osb + i * sb), N, K, ldb, not bool(tb))      # op(B)^T as [N,K]: trans_b = 1 is stored [N][K]
                 Cm = _mat(c0 + 4 * (o * osc + i * sc), M, N, ldc, False)
-                Cm[...] = alpha * (Am.astype(np.float64) @ Bm.astype(np.float64).T)
+                full = alpha * (Am.astype(np.float64) @ Bm.astype(np.float64).T)
+                if causal in (1, 2):       # the kernel skips blocks the hint declares zero: the operand really has to be zero there
+                    Az = Am.astype(np.float64)
+                    assert np.all(np.triu(Az, 1) == 0) if causal == 1 else np.all(np.tril(Az, -1) == 0), "causal hint on a non-triangular operand"
+                if causal == 3:            # tiles above the diagonal may be left as garbage / zeros: poison them to prove nobody reads them
+                    full = np.where(np.tril(np.ones((M, N))) > 0, full, np.nan)
+                Cm[...] = full
 
     def mas_softmax_causal_forward(self, s, p, mats, rows, cols):
         S = _f32(_addr(s), mats * rows * cols).reshape(mats, rows, cols).astype(np.float64)
@@ -62,6 +68,14 @@ class Emu:
         S = np.where(mask, S, -np.inf)
         e = np.exp(S - S.max(-1, keepdims=True))
         out[...] = e / e.sum(-1, keepdims=True)
+
+    def mas_softmax_causal_backward(self, p, dp, ds, mats, rows, cols, scale):
+        P = _f32(_addr(p), mats * rows * cols).reshape(mats, rows, cols).astype(np.float64)
+        dP = _f32(_addr(dp), mats * rows * cols).reshape(mats, rows, cols).astype(np.float64)
+        out = _f32(_addr(ds), mats * rows * cols).reshape(mats, rows, cols)
+        mask = np.tril(np.ones((rows, cols)), cols - rows) > 0
+        dPv = np.where(mask, dP, 0.0)                                   # never reads beyond the visible columns
+        out[...] = np.where(mask, P * (dPv - (dPv * P).sum(-1, keepdims=True)) * scale, 0.0)
 
     def mas_softmax_backward(self, p, dp, ds, rows, cols, scale):
         P = _f32(_addr(p), rows * cols).reshape(rows, cols).astype(np.float64)
