@@ -329,7 +329,38 @@ def vq_metric(dev, pk, sweep=True):
             "all_pairs_ffma_kernel": exact, "sweep": pts}
 
 
-def transformer_metric(dev, batch=8, steps=3, warmup=2):
+def transformer_kernel_rooflines(dev, pk, batch=8):
+    """The three tensor-core kernels of the transformer step, timed live at the model's shapes (CUDA events) against the measured
+    bf16 peak (fp16 MMAs run at the bf16 rate): algorithmic FLOPs only (the hi/lo operand split of the attention core and its
+    second score pass are not counted)."""
+    from mas_b200 import ops
+    M, K, N, S, heads = batch * 640, 1024, 4096, 640, 16
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(M, K, generator=g).to(dev)
+    dy = (torch.randn(M, N, generator=g) * 1e-4).to(dev)
+    w = torch.nn.Parameter((torch.randn(N, K, generator=g) * 0.02).to(dev))
+    b = torch.zeros(N, device=dev)
+    x16, ax = ops.rows_to_half(x)
+    dy16, ad = ops.rows_to_half(dy)
+    qkv = torch.randn(batch, S, 3 * heads * 64, generator=g).to(dev)
+    out = []
+
+    def entry(name, fn, flop, note):
+        sec = time_kernel(fn, iters=10, warm=3)
+        out.append({"kernel": name, "ms": round(sec * 1e3, 4), "tflop_per_s": round(flop / sec / 1e12, 1),
+                    "frac_of_bf16_peak": round(flop / sec / 1e12 / pk["bf16"], 3), "shape": note})
+    entry("rows_gemm_t16 (Linear forward, TMA-fed fp16)", lambda: ops.gemm_rows_f16(x16, ax, w, False, b), 2.0 * M * N * K,
+          "x [%d,%d] . W[%d,%d]^T + b" % (M, K, N, K))
+    entry("rows_gemm_t16 (Linear data gradient)", lambda: ops.gemm_rows_f16(dy16, ad, w, True), 2.0 * M * N * K, "dy [%d,%d] . W" % (M, N))
+    entry("rows_wgrad_t16 + reduction (Linear weight gradient)", lambda: ops.wgrad_rows_f16(x16, ax, dy16, ad), 2.0 * M * N * K,
+          "dy^T [%d,%d] . x [%d,%d]" % (N, M, M, K))
+    blocks = sum(qt + 1 for qt in range(S // 128))
+    entry("attn_causal_fwd + amax (fused causal attention core)", lambda: ops.CausalAttentionFn.apply(qkv, heads),
+          batch * heads * blocks * 2 * 2.0 * 128 * 128 * 64, "batch %d, %d tokens, %d heads of 64, causal key blocks only" % (batch, S, heads))
+    return out
+
+
+def transformer_metric(dev, pk, batch=8, steps=3, warmup=2):
     """Tier-2 row: training-step throughput of the token transformer at BASELINE configs[4]'s model (24 layers,
     1024 wide, 16 heads of 64, 128 text + 256 segmentation + 256 image tokens; random weights, synthetic tokens): forward +
     cross-entropy over the image tokens + backward (train.py:136-153, no optimizer), CUDA-event timed. Same code as
@@ -364,12 +395,17 @@ def transformer_metric(dev, batch=8, steps=3, warmup=2):
     sec = e0.elapsed_time(e1) * 1e-3 / steps
     S, H, Ly, V = 640, 1024, 24, 8192
     flops = 3 * (2 * S * (12 * H * H) * Ly + 2 * 256 * H * V + 2 * 2 * S * S * H * Ly) * batch
+    try:
+        roofs = transformer_kernel_rooflines(dev, pk, batch)
+    except Exception as e:  # noqa: BLE001
+        roofs = {"error": str(e)[:200]}
     return {"metric": "token transformer training step (fwd + cross-entropy + bwd), sequence tokens/s", "value": round(batch * S / sec, 1),
             "unit": "tokens/s", "batch": batch, "seq_len": S, "ms_per_step": round(sec * 1e3, 3), "loss": round(float(loss.detach()), 5),
             "model_tflops": round(flops / sec / 1e12, 1), "gpu_launches_per_step": (_lib.launch_count() - l0) // steps,
             "tcgen05_launches_per_step": (_lib.tc_launch_count() - t0) // steps,
             "kernels": "rows_gemm_t16 / rows_wgrad_t16 (TMA-fed fp16 Linear layers), attn_causal_fwd (fused causal attention core), "
-                       "gemm3_tc (3xTF32 attention gradients), mas_ce_* (fused cross-entropy)"}
+                       "gemm3_tc (3xTF32 attention gradients, causal block skipping), mas_ce_* (fused cross-entropy)",
+            "kernel_rooflines": roofs}
 
 
 def _fmt():
@@ -542,7 +578,7 @@ def main():
     if world == 1:   # tier-2 row, beside the headline (never fails the bench line)
         try:
             torch.cuda.empty_cache()
-            line["transformer"] = transformer_metric(dev)
+            line["transformer"] = transformer_metric(dev, pk)
         except Exception as e:  # noqa: BLE001
             line["transformer"] = {"error": str(e)[:200]}
     if not args.no_cpu_baseline and world == 1:   # reported baseline: rank 0 at N=1 only
