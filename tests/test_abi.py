@@ -3,6 +3,7 @@ host-side module structure mirrors the reference (state_dict keys, init order)."
 import os
 import re
 
+import pytest
 import torch
 
 from conftest import GOLDEN, ROOT
@@ -138,3 +139,23 @@ def test_shadow_and_amax_attachments_follow_the_tensor_version():
     assert getattr(u, "_mas_amax")[0] is am
     u.mul_(2.0)
     assert getattr(u, "_mas_amax")[1] != u._version
+
+
+def test_header_is_plain_c_and_links_against_the_library(tmp_path):
+    """The drop-in boundary is a C ABI: include/mas_b200.h compiles as C99 (no C++ types in the signatures) and a C program
+    links against the shared library and calls an entry that needs no GPU."""
+    import shutil
+    import subprocess
+    from mas_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc on this box")
+    src = tmp_path / "use_abi.c"
+    src.write_text('#include "mas_b200.h"\n#include <stdio.h>\nint main(void) { printf("%d\\n", mas_version()); return mas_last_error() ? 0 : 1; }\n')
+    exe = tmp_path / "use_abi"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-L", libdir, "-lmas_b200",
+                        "-Wl,-rpath," + libdir, "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and int(out.stdout.strip()) == _lib.load().mas_version()
