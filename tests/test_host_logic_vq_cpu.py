@@ -172,8 +172,13 @@ class VqEmu:
             out[..., 1] = s2
 
     def mas_conv3x3_wgrad_tc16(self, x, flags, xs, dy, dys, dw, dbias, mode, gn_table, gn_silu, dy_amax, cout_rows, ws, ws_bytes):
-        assert mode == 0 and gn_table is None, "the emulation covers the stride-1 shadow-fed weight gradient"
-        X = _t(_view4(x, xs, half=bool(flags & 1)).astype(np.float64)).permute(0, 3, 1, 2)
+        assert mode in (0, 2) and gn_table is None, "the emulation covers the stride-1 and the upsampling weight gradient"
+        X = _view4(x, xs, half=bool(flags & 1)).astype(np.float64)
+        if not flags & 1:
+            X = X.astype(np.float16).astype(np.float64)          # fp32 activation converted unscaled by the kernel
+        X = _t(X).permute(0, 3, 1, 2)
+        if mode == 2:
+            X = F.interpolate(X, scale_factor=2.0, mode="nearest")
         if flags & 2:
             D = _view4(dy, dys, half=True).astype(np.float64) / _scale(dy_amax)
         else:                                                    # fp32 dy, rounded to fp16 under the scale of *dy_amax by the kernel
@@ -187,6 +192,57 @@ class VqEmu:
         _f32(dw, cout * cin * 9)[...] = g.numpy().reshape(-1)
         if dbias is not None:
             _f32(dbias, cout)[...] = D.sum((0, 2, 3)).numpy()
+
+    def mas_conv3x3_fprop_tc16(self, x, xs, wpk, bias, residual, y, ys, mode, table, silu, stats_part, x_amax):
+        """Register-staged form: fp32 (strided) input rounded to fp16 under the scale of *x_amax by the kernel; modes S1 (0),
+        UP (2: nearest x2 upsample first), ZS (3: the data gradient of the stride-2 Downsample convolution)."""
+        assert table is None and stats_part is None, "the emulation covers the plain launches of the Up/Downsample layers"
+        kind, W = self.packs[_addr(wpk)]
+        s = _scale(x_amax)
+        X = _t((_view4(x, xs).astype(np.float64) * s).astype(np.float16).astype(np.float64) / s).permute(0, 3, 1, 2)
+        if mode == 2:
+            assert kind == "f"
+            O = F.conv2d(F.interpolate(X, scale_factor=2.0, mode="nearest"), W, padding=1)           # modules.py:55-59
+        elif mode == 3:
+            assert kind == "d"                                  # pad(0,1,0,1) + stride 2 (modules.py:74-78), transposed
+            O = F.conv_transpose2d(X, W, stride=2)[:, :, :2 * xs.h, :2 * xs.w]
+        else:
+            O = F.conv2d(X, W, padding=1) if kind == "f" else F.conv_transpose2d(X, W, padding=1)
+        O = O.permute(0, 2, 3, 1).numpy()
+        assert O.shape == (ys.n, ys.h, ys.w, ys.c), (O.shape, (ys.n, ys.h, ys.w, ys.c))
+        if bias is not None:
+            O = O + _f32(bias, ys.c).astype(np.float64)
+        if residual is not None:
+            O = O + _view4(residual, ys)
+        _view4(y, ys)[...] = O
+
+    def mas_sumpool2x2(self, x, y, N, H, W, C):
+        X = _f32(x, N * 4 * H * W * C).reshape(N, H, 2, W, 2, C).astype(np.float64)
+        _f32(y, N * H * W * C)[...] = X.sum(axis=(2, 4)).reshape(-1)
+
+    def mas_space_to_depth(self, x, y, N, H, W, C):
+        X = _f32(x, N * H * W * C).reshape(N, H // 2, 2, W // 2, 2, C)                      # [n, i, py, j, px, c]
+        _f32(y, N * H * W * C)[...] = X.transpose(0, 1, 3, 2, 4, 5).reshape(-1)           # [n, i, j, (py, px, c)]
+
+    def mas_s2d_pack_weights(self, w, w9, Cout, C):
+        Wm = _f32(w, Cout * C * 9).reshape(Cout, C, 3, 3)
+        out = np.zeros((Cout, 4, C, 3, 3), dtype=np.float32)
+        for py in range(2):
+            for px in range(2):
+                for a in range(2):
+                    for b in range(2):
+                        ty, tx = 2 * a + py, 2 * b + px
+                        if ty <= 2 and tx <= 2:
+                            out[:, py * 2 + px, :, a + 1, b + 1] = Wm[:, :, ty, tx]
+        _f32(w9, Cout * 4 * C * 9)[...] = out.reshape(-1)
+
+    def mas_s2d_unpack_wgrad(self, dw9, dw, Cout, C):
+        D9 = _f32(dw9, Cout * 4 * C * 9).reshape(Cout, 4, C, 3, 3)
+        out = np.zeros((Cout, C, 3, 3), dtype=np.float32)
+        for ty in range(3):
+            for tx in range(3):
+                out[:, :, ty, tx] = D9[:, (ty & 1) * 2 + (tx & 1), :, (ty >> 1) + 1, (tx >> 1) + 1]
+        _f32(dw, Cout * C * 9)[...] = out.reshape(-1)
 
     # ---- 1x1 (shortcut) ----------------------------------------------------------------------------------------------------
     def mas_pack_gemm_tc(self, w, w_tc, N, K, transpose):
@@ -284,7 +340,18 @@ def vq_emu(monkeypatch):
     from mas_b200 import ops
     e = VqEmu()
     monkeypatch.setattr(ops.L, "call", e)
-    monkeypatch.setattr(ops.L, "query", lambda name, *a: 1 << 20)
+    def dense(t):
+        return t.sc == 1 and t.sw == t.c and t.sh == t.w * t.c and t.sn == t.h * t.w * t.c
+
+    def query(name, *a):
+        if name == "mas_conv3x3_tc_eligible":        # include/mas_b200.h: dense NHWC, Cin % 8, Cout % 128, Hout % 16, Wout % 8, S1 / UP / ZS
+            xs, ys, mode = a
+            return int(dense(xs) and dense(ys) and xs.c % 8 == 0 and ys.c % 128 == 0 and ys.h % 16 == 0 and ys.w % 8 == 0 and mode in (0, 2, 3))
+        if name == "mas_conv3x3_wgrad_tc_eligible":  # dense NHWC, Cin % 32, Cout % 128, H, W % 8, S1 / UP
+            xs, dys, mode = a
+            return int(dense(xs) and dense(dys) and xs.c % 32 == 0 and dys.c % 128 == 0 and dys.h % 8 == 0 and dys.w % 8 == 0 and mode in (0, 2))
+        return 1 << 20                                # workspace sizes
+    monkeypatch.setattr(ops.L, "query", query)
     monkeypatch.setattr(ops, "_need_cuda", lambda x: None)
     monkeypatch.setattr(ops, "_tc_on", lambda: True)
     ops._packs.clear()
@@ -356,3 +423,34 @@ def test_block_chains_host_logic_against_reference_fixture(vq_emu, name):
     # one statistics pass for the chain's input only: every later GroupNorm takes its statistics from a producer's epilogue
     assert n.count("mas_gn_stats") == 1, n.count("mas_gn_stats")
     assert n.count("mas_attnblock_forward") == 1 and n.count("mas_attnblock_backward") == 1
+
+
+@pytest.mark.parametrize("name", ["up_128", "up_512", "down_128"])
+def test_up_down_sample_host_logic_against_reference_fixture(vq_emu, name):
+    """Upsample (nearest x2 folded into the convolution; data gradient = transposed convolution + 2x2 sum pool) and Downsample
+    (stride 2 through space-to-depth; data gradient on the zero-stuffed map) above the emulated C-ABI, against the REAL reference."""
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from models import modules as M
+    from oracle.seeded import assert_same_fill, fill_seeded, seeded_input
+    from test_oracle import build_tc_block
+    b = torch.load(os.path.join(GOLDEN, "blocks_tc.pt"), weights_only=False)[name]
+    mod = build_tc_block(name, M)
+    assert_same_fill(fill_seeded(mod, b["seed_w"]), b["param_checks"])
+    # channels-last input, as inside the model (a caller's NCHW tensor would take the general-shape fp32 kernels instead)
+    x = seeded_input(b["shape"], b["seed_x"], 1.5, 0.3).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    y = mod(x)
+    assert _sampled_err(y.contiguous(), b["y"], b["y_norm"]) < 1e-3, name
+    (y * torch.linspace(-1, 1, y.numel()).view(y.shape)).sum().backward()
+    assert _sampled_err(x.grad.contiguous(), b["grad_x"], b["grad_x_norm"]) < 3e-3, name
+    named = dict(mod.named_parameters())
+    for k, gv in b["grads"].items():
+        g = named[k].grad
+        e = _sampled_err(g, gv, b["grad_norms"][k]) if isinstance(gv, tuple) else float((g.double() - gv.double()).norm() / gv.double().norm())
+        assert e < 3e-3, (name, k, e)
+    n = vq_emu.names
+    assert "mas_conv3x3_fprop_tc16" in n and "mas_conv3x3_fprop" not in n          # the tensor-core route
+    if name.startswith("down"):
+        assert n.count("mas_space_to_depth") == 1 and n.count("mas_s2d_pack_weights") == 1 and n.count("mas_s2d_unpack_wgrad") == 1
+    else:
+        assert n.count("mas_sumpool2x2") == 1
