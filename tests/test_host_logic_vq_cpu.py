@@ -331,6 +331,169 @@ class VqEmu:
         if dx_amax is not None:
             _f32(dx_amax, 1)[0] = float(d.abs().max())
 
+    # ---- general-shape fp32 convolution family (the SIMT entries: exact fp32, explicit strides) --------------------------
+    def mas_pack_conv3x3(self, w, wp, Cout, Cin, flip_transpose, rtf32):
+        self.packs[_addr(wp)] = ("d" if flip_transpose else "f", _t(_f32(w, Cout * Cin * 9).reshape(Cout, Cin, 3, 3)))
+
+    @staticmethod
+    def _conv_mode(X, W, kind, mode, out_hw):
+        if kind == "f":
+            if mode == 0:
+                return F.conv2d(X, W, padding=1)
+            if mode == 1:                                     # Downsample: pad (0,1,0,1), stride 2, no padding (modules.py:74-78)
+                return F.conv2d(F.pad(X, (0, 1, 0, 1)), W, stride=2)
+            if mode == 2:                                     # Upsample: nearest x2 first (modules.py:55-59)
+                return F.conv2d(F.interpolate(X, scale_factor=2.0, mode="nearest"), W, padding=1)
+        else:
+            if mode == 0:
+                return F.conv_transpose2d(X, W, padding=1)
+            if mode == 3:                                     # data gradient of the stride-2 convolution
+                return F.conv_transpose2d(X, W, stride=2)[:, :, :out_hw[0], :out_hw[1]]
+        raise AssertionError(("conv mode", kind, mode))
+
+    def mas_conv3x3_fprop(self, x, xs, wp, bias, residual, y, ys, mode, impl):
+        kind, W = self.packs[_addr(wp)]
+        O = self._conv_mode(_t(_view4(x, xs)).permute(0, 3, 1, 2), W, kind, mode, (ys.h, ys.w)).permute(0, 2, 3, 1).numpy()
+        assert O.shape == (ys.n, ys.h, ys.w, ys.c), (O.shape, (ys.n, ys.h, ys.w, ys.c))
+        if bias is not None:
+            O = O + _f32(bias, ys.c).astype(np.float64)
+        if residual is not None:
+            O = O + _view4(residual, ys)
+        _view4(y, ys)[...] = O
+
+    def mas_conv3x3_wgrad(self, x, xs, dy, dys, dw, dbias, mode, impl, gn_table, gn_silu, ws, ws_bytes):
+        assert gn_table is None
+        X = _t(_view4(x, xs)).permute(0, 3, 1, 2)
+        D = _t(_view4(dy, dys)).permute(0, 3, 1, 2)
+        cout, cin = dys.c, xs.c
+        if mode == 1:
+            g = torch.nn.grad.conv2d_weight(F.pad(X, (0, 1, 0, 1)), (cout, cin, 3, 3), D, stride=2)
+        elif mode == 2:
+            g = torch.nn.grad.conv2d_weight(F.interpolate(X, scale_factor=2.0, mode="nearest"), (cout, cin, 3, 3), D, padding=1)
+        else:
+            assert mode == 0
+            g = torch.nn.grad.conv2d_weight(X, (cout, cin, 3, 3), D, padding=1)
+        _f32(dw, cout * cin * 9)[...] = g.numpy().reshape(-1)
+        if dbias is not None:
+            _f32(dbias, cout)[...] = D.sum((0, 2, 3)).numpy()
+
+    # ---- 3-channel edge layers (conv_in / conv_out, modules.py:219,364) ------------------------------------------------------
+    def mas_edge_small_cin_fprop(self, x, xt, w, bias, y, yt, flip_transpose):
+        X = _t(_view4(x, xt)).permute(0, 3, 1, 2)
+        if flip_transpose:                                    # conv_out's data gradient: w is its [3, C, 3, 3] weight
+            O = F.conv_transpose2d(X, _t(_f32(w, 3 * yt.c * 9).reshape(3, yt.c, 3, 3)), padding=1)
+        else:
+            O = F.conv2d(X, _t(_f32(w, yt.c * 3 * 9).reshape(yt.c, 3, 3, 3)), padding=1)
+        O = O.permute(0, 2, 3, 1).numpy()
+        if bias is not None:
+            O = O + _f32(bias, yt.c).astype(np.float64)
+        _view4(y, yt)[...] = O
+
+    def mas_edge_small_cout_fprop(self, x, xt, w, bias, y, yt):
+        O = F.conv2d(_t(_view4(x, xt)).permute(0, 3, 1, 2), _t(_f32(w, 3 * xt.c * 9).reshape(3, xt.c, 3, 3)), padding=1).permute(0, 2, 3, 1).numpy()
+        if bias is not None:
+            O = O + _f32(bias, 3).astype(np.float64)
+        _view4(y, yt)[...] = O
+
+    def _edge_wgrad(self, x, xt, dy, dyt, dw, db):
+        X = _t(_view4(x, xt)).permute(0, 3, 1, 2)
+        D = _t(_view4(dy, dyt)).permute(0, 3, 1, 2)
+        g = torch.nn.grad.conv2d_weight(X, (dyt.c, xt.c, 3, 3), D, padding=1)
+        _f32(dw, dyt.c * xt.c * 9)[...] = g.numpy().reshape(-1)
+        if db is not None:
+            _f32(db, dyt.c)[...] = D.sum((0, 2, 3)).numpy()
+
+    def mas_edge_small_cin_wgrad(self, x, xt, dy, dyt, dw, db, ws, ws_bytes):
+        self._edge_wgrad(x, xt, dy, dyt, dw, db)
+
+    def mas_edge_small_cout_wgrad(self, a, at, dy, dyt, dw, db, ws, ws_bytes):
+        self._edge_wgrad(a, at, dy, dyt, dw, db)
+
+    # ---- fp32 GEMM (1x1 convolutions off the tensor tiles) ------------------------------------------------------------------------
+    def mas_gemm(self, A, B, C, M, N, K, batch, lda, ldb, ldc, sa, sb, sc, ta, tb, alpha, bias, residual, impl):
+        def mat(p, rows, cols, ld, trans):
+            if not trans:
+                return np.lib.stride_tricks.as_strided(_f32(p, (rows - 1) * ld + cols), (rows, cols), (4 * ld, 4))
+            return np.lib.stride_tricks.as_strided(_f32(p, (cols - 1) * ld + rows), (rows, cols), (4, 4 * ld))
+        for i in range(batch):
+            Am = mat(ctypes.c_void_p(_addr(A) + 4 * i * sa), M, K, lda, bool(ta)).astype(np.float64)
+            Bm = mat(ctypes.c_void_p(_addr(B) + 4 * i * sb), N, K, ldb, not bool(tb)).astype(np.float64)
+            o = alpha * (Am @ Bm.T)
+            if bias is not None:
+                o = o + _f32(bias, N)[None, :]
+            if residual is not None:
+                o = o + mat(ctypes.c_void_p(_addr(residual) + 4 * i * sc), M, N, ldc, False)
+            mat(ctypes.c_void_p(_addr(C) + 4 * i * sc), M, N, ldc, False)[...] = o
+
+    # ---- (Sync)BatchNorm of quant_conv, vqvae.py:16 ------------------------------------------------------------------------------
+    @staticmethod
+    def _f64(p, n):
+        return np.ctypeslib.as_array((ctypes.c_double * int(n)).from_address(_addr(p)))
+
+    def mas_bn_stats(self, x, R, C, out):
+        X = _f32(x, R * C).reshape(R, C).astype(np.float64)
+        o = self._f64(out, 2 * C + 1)
+        o[:C], o[C:2 * C], o[2 * C] = X.sum(0), (X * X).sum(0), R
+
+    def mas_bn_finalize(self, stats, count, C, eps, momentum, mean, invstd, running_mean, running_var):
+        st = self._f64(stats, 2 * C + 1)
+        cnt = count if count > 0 else st[2 * C]
+        m = st[:C] / cnt
+        v = st[C:2 * C] / cnt - m * m                                   # biased, what the normalisation uses
+        _f32(mean, C)[...] = m
+        _f32(invstd, C)[...] = 1.0 / np.sqrt(v + eps)
+        if running_mean is not None:
+            rm = _f32(running_mean, C)
+            rm[...] = (1 - momentum) * rm + momentum * m
+        if running_var is not None:
+            rv = _f32(running_var, C)
+            rv[...] = (1 - momentum) * rv + momentum * v * cnt / (cnt - 1)      # unbiased, like nn.(Sync)BatchNorm
+
+    def mas_bn_apply(self, x, mean, invstd, gamma, beta, y, R, C):
+        X = _f32(x, R * C).reshape(R, C).astype(np.float64)
+        _f32(y, R * C)[...] = ((X - _f32(mean, C)) * _f32(invstd, C) * _f32(gamma, C) + _f32(beta, C)).reshape(-1)
+
+    def mas_bn_backward_reduce(self, dy, x, mean, invstd, R, C, out):
+        D = _f32(dy, R * C).reshape(R, C).astype(np.float64)
+        xh = (_f32(x, R * C).reshape(R, C).astype(np.float64) - _f32(mean, C)) * _f32(invstd, C)
+        o = self._f64(out, 2 * C + 1)
+        o[:C], o[C:2 * C], o[2 * C] = D.sum(0), (D * xh).sum(0), R
+
+    def mas_bn_backward_apply(self, dy, x, mean, invstd, gamma, sums_global, sums_local, inv_count, dx, dgamma, dbeta, R, C):
+        D = _f32(dy, R * C).reshape(R, C).astype(np.float64)
+        xh = (_f32(x, R * C).reshape(R, C).astype(np.float64) - _f32(mean, C)) * _f32(invstd, C)
+        sg, sl = self._f64(sums_global, 2 * C + 1), self._f64(sums_local, 2 * C + 1)
+        ic = inv_count if inv_count > 0 else 1.0 / sg[2 * C]
+        _f32(dx, R * C)[...] = (_f32(gamma, C) * _f32(invstd, C) * (D - sg[:C] * ic - xh * sg[C:2 * C] * ic)).reshape(-1)
+        _f32(dgamma, C)[...] = sl[C:2 * C]
+        _f32(dbeta, C)[...] = sl[:C]
+
+    # ---- Codebook, modules.py:501-517 ------------------------------------------------------------------------------------------
+    def mas_vq_forward(self, z, E, R, K, D, beta, idx_out, zq_out, loss_out, ws, ws_bytes):
+        Z = torch.from_numpy(_f32(z, R * D).reshape(R, D).copy())
+        Em = torch.from_numpy(_f32(E, K * D).reshape(K, D).copy())
+        # the reference's fp32 association and first-index tie-break (modules.py:501-505)
+        d = torch.sum(Z ** 2, dim=1, keepdim=True) + torch.sum(Em ** 2, dim=1) - 2 * torch.matmul(Z, Em.t())
+        idx = torch.argmin(d, dim=1)
+        np.ctypeslib.as_array((ctypes.c_int64 * R).from_address(_addr(idx_out)))[...] = idx.numpy()
+        zq = Em[idx].double()
+        _f32(zq_out, R * D)[...] = zq.reshape(-1).numpy()
+        _f32(loss_out, 1)[0] = float((1 + beta) * ((zq - Z.double()) ** 2).mean())
+
+    def mas_vq_backward(self, g_zq, g_loss, z, E, idx, R, K, D, beta, grad_z, grad_E):
+        Z = _f32(z, R * D).reshape(R, D).astype(np.float64)
+        Em = _f32(E, K * D).reshape(K, D).astype(np.float64)
+        ix = np.ctypeslib.as_array((ctypes.c_int64 * R).from_address(_addr(idx)))
+        gl = float(_f32(g_loss, 1)[0]) if g_loss is not None else 0.0
+        if grad_z is not None:
+            gz = gl * (2.0 / (R * D)) * (Z - Em[ix])
+            if g_zq is not None:
+                gz = gz + _f32(g_zq, R * D).reshape(R, D)
+            _f32(grad_z, R * D)[...] = gz.reshape(-1)
+        if grad_E is not None:                                   # zeroed by the caller, accumulated here
+            ge = _f32(grad_E, K * D).reshape(K, D)
+            np.add.at(ge, ix, (gl * (2.0 * beta / (R * D)) * (Em[ix] - Z)).astype(np.float32))
+
     def mas_copy_strided(self, x, xs, y, ys):
         _view4(y, ys)[...] = _view4(x, xs)
 
@@ -454,3 +617,34 @@ def test_up_down_sample_host_logic_against_reference_fixture(vq_emu, name):
         assert n.count("mas_space_to_depth") == 1 and n.count("mas_s2d_pack_weights") == 1 and n.count("mas_s2d_unpack_wgrad") == 1
     else:
         assert n.count("mas_sumpool2x2") == 1
+
+
+def test_whole_model_host_logic_against_reference_fixture(vq_emu):
+    """The whole drop-in VQBASE (Encoder -> quant_conv + BatchNorm -> Codebook -> post_quant_conv -> Decoder, proxy loss,
+    backward) above the emulated C-ABI reproduces the REAL reference on tests/golden/vqbase_tiny.pt: reconstruction, codebook
+    loss, code indices bit for bit, every parameter gradient, the BatchNorm running statistics."""
+    from models import VQBASE
+    g = torch.load(os.path.join(GOLDEN, "vqbase_tiny.pt"), weights_only=False)
+    m = VQBASE(g["ddconfig"], g["n_embed"], g["embed_dim"], 10, 100)
+    m.load_state_dict(g["state_dict"])
+    m.quantize.q_counter = 10 ** 6
+    m.train()
+    x = g["x"]
+    seen = {}
+    hook = m.quantize.register_forward_hook(lambda _m, _i, o: seen.__setitem__("idx", o[2].detach().clone()))
+    dec, diff = m(x)
+    hook.remove()
+    from conftest import rel_err as rel          # quantities that are zero in exact arithmetic (a conv bias in front of a one-channel-per-group GroupNorm) compare on an absolute scale
+    assert dec.shape == g["dec"].shape and dec.is_contiguous() and diff.dim() == 0
+    assert torch.equal(seen["idx"].view(-1), g["idx"].view(-1))
+    assert rel(dec, g["dec"]) < 1e-5 and abs(float(diff.detach()) - float(g["diff"])) < 1e-5 * abs(float(g["diff"]))
+    ((x - dec).abs().mean() + diff).backward()
+    named = dict(m.named_parameters())
+    for k, gv in g["grads"].items():
+        assert named[k].grad is not None, k
+        tol = 1e-4 if float(gv.double().norm()) > 1e-4 * gv.numel() ** 0.5 else 2e-3      # noise-level gradients: the GPU test's bound
+        assert rel(named[k].grad, gv) < tol, (k, rel(named[k].grad, gv))
+    assert rel(m.quant_conv[1].running_mean, g["running_mean"]) < 1e-5 and rel(m.quant_conv[1].running_var, g["running_var"]) < 1e-5
+    assert int(m.quant_conv[1].num_batches_tracked) == 1
+    n = vq_emu.names
+    assert n.count("mas_vq_forward") == 1 and n.count("mas_vq_backward") == 1 and n.count("mas_bn_stats") == 1
