@@ -480,6 +480,13 @@ class VqEmu:
         _f32(zq_out, R * D)[...] = zq.reshape(-1).numpy()
         _f32(loss_out, 1)[0] = float((1 + beta) * ((zq - Z.double()) ** 2).mean())
 
+    def mas_vq_forward_given(self, z, E, idx_in, R, K, D, beta, zq_out, loss_out, ws, ws_bytes):
+        Z = _f32(z, R * D).reshape(R, D).astype(np.float64)
+        Em = _f32(E, K * D).reshape(K, D).astype(np.float64)
+        ix = np.ctypeslib.as_array((ctypes.c_int64 * R).from_address(_addr(idx_in)))
+        _f32(zq_out, R * D)[...] = Em[ix].reshape(-1)
+        _f32(loss_out, 1)[0] = (1 + beta) * ((Em[ix] - Z) ** 2).mean()
+
     def mas_vq_backward(self, g_zq, g_loss, z, E, idx, R, K, D, beta, grad_z, grad_E):
         Z = _f32(z, R * D).reshape(R, D).astype(np.float64)
         Em = _f32(E, K * D).reshape(K, D).astype(np.float64)
@@ -493,6 +500,11 @@ class VqEmu:
         if grad_E is not None:                                   # zeroed by the caller, accumulated here
             ge = _f32(grad_E, K * D).reshape(K, D)
             np.add.at(ge, ix, (gl * (2.0 * beta / (R * D)) * (Em[ix] - Z)).astype(np.float32))
+
+    def mas_nchw_to_nhwc_pad(self, x, y, N, C, CP, H, W):
+        out = np.zeros((N, H, W, CP), dtype=np.float32)
+        out[..., :C] = _f32(x, N * C * H * W).reshape(N, C, H, W).transpose(0, 2, 3, 1)
+        _f32(y, N * H * W * CP)[...] = out.reshape(-1)
 
     def mas_copy_strided(self, x, xs, y, ys):
         _view4(y, ys)[...] = _view4(x, xs)
@@ -648,3 +660,58 @@ def test_whole_model_host_logic_against_reference_fixture(vq_emu):
     assert int(m.quant_conv[1].num_batches_tracked) == 1
     n = vq_emu.names
     assert n.count("mas_vq_forward") == 1 and n.count("mas_vq_backward") == 1 and n.count("mas_bn_stats") == 1
+
+
+def test_img_config_model_host_logic_against_reference_fixture(vq_emu):
+    """The 95M-parameter img_config model (the benchmark's model) at 2 x 3 x 64 x 64 above the emulated C-ABI: every tensor-path
+    ResnetBlock in shadow mode, AttnBlocks, Up / Downsample on the tensor route, the small-extent levels on the general-shape
+    entries, BatchNorm, codebook - against the REAL reference (tests/golden/vqbase_img_64.pt), the way the GPU test checks it:
+    pre-VQ activations, code indices (a mismatch must be a Voronoi-boundary crossing of OUR latent), then decoder output and
+    every gradient with the quantiser pinned to the reference's codes."""
+    from conftest import rel_err
+    from mas_b200 import ops
+    from models import VQBASE
+    g = torch.load(os.path.join(GOLDEN, "vqbase_img_64.pt"), weights_only=False)
+    torch.manual_seed(0)
+    m = VQBASE(g["ddconfig"], 8192, 256, 3000, 12500)                       # seeded init == the reference's init (tests/test_abi.py)
+    with torch.no_grad():
+        m.quantize.embedding.weight.normal_()
+    m.quantize.q_counter = 10 ** 6
+    m.train()
+    x = g["x"]
+    h = {}
+    hk = m.quant_conv.register_forward_hook(lambda _m, _i, o: h.__setitem__("q", o.detach()))
+    hi = m.quantize.register_forward_hook(lambda _m, _i, o: h.__setitem__("idx", o[2].detach()))
+    with torch.no_grad():
+        m(x)
+    hk.remove(); hi.remove()
+    assert rel_err(h["q"], g["quant_in"]) < 3e-3                            # fp16 / TF32-sized operand rounding through 23 layers
+    bad = torch.nonzero(h["idx"].view(-1) != g["idx"].view(-1)).flatten()
+    assert bad.numel() <= 2
+    if bad.numel():                                                         # ours must be the fp64 arg-min of OUR latent
+        zf = h["q"].permute(0, 2, 3, 1).reshape(-1, 256)[bad].double()
+        E = m.quantize.embedding.weight.detach().double()
+        d = (zf * zf).sum(1, keepdim=True) + (E ** 2).sum(1)[None] - 2 * zf @ E.t()
+        mine = d.gather(1, h["idx"].view(-1)[bad][:, None]).squeeze(1)
+        assert bool((mine - d.min(1).values <= 4 * torch.finfo(torch.float32).eps * d.abs().max(1).values).all())
+    # second pass with the decision pinned to the reference's codes: decoder output and every gradient
+    m.quant_conv[1].reset_running_stats()
+    cb = m.quantize
+    idx_ref = g["idx"].view(-1)
+
+    def fwd(z):
+        zq, loss = ops.VQGivenFn.apply(z, cb.embedding.weight, cb.beta, idx_ref)
+        return zq, loss, idx_ref
+    cb.forward = fwd
+    dec, diff = m(x)
+    assert rel_err(dec, g["dec"]) < 5e-3
+    assert abs(float(diff.detach()) - float(g["diff"])) < 5e-3 * abs(float(g["diff"]))
+    ((x - dec).abs().mean() + diff).backward()
+    named = dict(m.named_parameters())
+    for k, gv in g["grads_small"].items():
+        assert rel_err(named[k].grad, gv) < 2e-2, k
+    worst = max(((abs(float(named[k].grad.double().norm()) - v) / max(v, 1e-4 * named[k].numel() ** 0.5)), k) for k, v in g["grad_norms"].items())
+    assert worst[0] < 5e-2, worst
+    n = vq_emu.names
+    # 15 shadow-mode ResnetBlocks at >= 16 x 16: 2 convolutions in each forward pass, 2 more as data gradients in the backward
+    assert n.count("mas_conv3x3_fprop_tc16h") == 90 and n.count("mas_attnblock_forward") == 14 and n.count("mas_vq_forward_given") == 1
