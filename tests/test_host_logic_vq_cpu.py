@@ -186,12 +186,16 @@ class VqEmu:
             D = (_view4(dy, dys).astype(np.float64) * s).astype(np.float16).astype(np.float64) / s
         D = _t(D).permute(0, 3, 1, 2)
         cout, cin = dys.c, xs.c
-        assert cout_rows == cout
+        assert cout_rows == cout or (cout_rows % 128 == 0 and cout_rows > cout)     # padded rows come out zero
         # dw[co, ci, ty, tx] = sum_p dy[p, co] x[p + tap, ci]
         g = torch.nn.grad.conv2d_weight(X, (cout, cin, 3, 3), D, padding=1)
-        _f32(dw, cout * cin * 9)[...] = g.numpy().reshape(-1)
+        out = np.zeros((cout_rows, cin * 9), dtype=np.float32)
+        out[:cout] = g.numpy().reshape(cout, -1)
+        _f32(dw, cout_rows * cin * 9)[...] = out.reshape(-1)
         if dbias is not None:
-            _f32(dbias, cout)[...] = D.sum((0, 2, 3)).numpy()
+            ob = np.zeros(cout_rows, dtype=np.float32)
+            ob[:cout] = D.sum((0, 2, 3)).numpy()
+            _f32(dbias, cout_rows)[...] = ob
 
     def mas_conv3x3_fprop_tc16(self, x, xs, wpk, bias, residual, y, ys, mode, table, silu, stats_part, x_amax):
         """Register-staged form: fp32 (strided) input rounded to fp16 under the scale of *x_amax by the kernel; modes S1 (0),
@@ -209,9 +213,11 @@ class VqEmu:
         else:
             O = F.conv2d(X, W, padding=1) if kind == "f" else F.conv_transpose2d(X, W, padding=1)
         O = O.permute(0, 2, 3, 1).numpy()
-        assert O.shape == (ys.n, ys.h, ys.w, ys.c), (O.shape, (ys.n, ys.h, ys.w, ys.c))
+        rows = O.shape[-1]                                       # weights / bias packed for round_up(Cout, 128) rows,
+        assert O.shape[:3] == (ys.n, ys.h, ys.w) and rows >= ys.c and (rows == ys.c or rows % 128 == 0)   # only ys.c channels are stored
         if bias is not None:
-            O = O + _f32(bias, ys.c).astype(np.float64)
+            O = O + _f32(bias, rows).astype(np.float64)
+        O = O[..., :ys.c]
         if residual is not None:
             O = O + _view4(residual, ys)
         _view4(y, ys)[...] = O
@@ -506,6 +512,29 @@ class VqEmu:
         out[..., :C] = _f32(x, N * C * H * W).reshape(N, C, H, W).transpose(0, 2, 3, 1)
         _f32(y, N * H * W * CP)[...] = out.reshape(-1)
 
+    # ---- weighted BCE-with-logits of the VQ-SEG step, losses/loss_seg.py:15-22 ---------------------------------------------
+    @staticmethod
+    def _bce_views(logits, target, N, C, CP, H, W):
+        X = _f32(logits, N * H * W * CP).reshape(N, H, W, CP)[..., :C].astype(np.float64)            # channels-last, pitch CP
+        T = _f32(target, N * C * H * W).reshape(N, C, H, W).transpose(0, 2, 3, 1).astype(np.float64)    # NCHW target
+        return X, T
+
+    def mas_bce_cl_forward(self, logits, target, pos_weight, N, C, CP, H, W, loss_out, ws, ws_bytes):
+        X, T = self._bce_views(logits, target, N, C, CP, H, W)
+        pw = _f32(pos_weight, C).astype(np.float64)
+        ls = -np.logaddexp(0.0, -X)                               # log sigmoid(x)
+        l1 = -np.logaddexp(0.0, X)                                # log (1 - sigmoid(x))
+        _f32(loss_out, 1)[0] = (-(pw * T * ls + (1 - T) * l1)).mean()
+
+    def mas_bce_cl_backward(self, logits, target, pos_weight, g, N, C, CP, H, W, grad):
+        X, T = self._bce_views(logits, target, N, C, CP, H, W)
+        pw = _f32(pos_weight, C).astype(np.float64)
+        sg = 1.0 / (1.0 + np.exp(-X))
+        gg = float(_f32(g, 1)[0]) if g is not None else 1.0
+        out = np.zeros((N, H, W, CP), dtype=np.float32)           # pad channels written as zeros
+        out[..., :C] = gg * (-(pw * T * (1 - sg)) + (1 - T) * sg) / (N * C * H * W)
+        _f32(grad, N * H * W * CP)[...] = out.reshape(-1)
+
     def mas_copy_strided(self, x, xs, y, ys):
         _view4(y, ys)[...] = _view4(x, xs)
 
@@ -715,3 +744,49 @@ def test_img_config_model_host_logic_against_reference_fixture(vq_emu):
     n = vq_emu.names
     # 15 shadow-mode ResnetBlocks at >= 16 x 16: 2 convolutions in each forward pass, 2 more as data gradients in the backward
     assert n.count("mas_conv3x3_fprop_tc16h") == 90 and n.count("mas_attnblock_forward") == 14 and n.count("mas_vq_forward_given") == 1
+
+
+def test_vqseg_step_host_logic_against_oracle(vq_emu):
+    """The VQ-SEG step (159-channel maps: conv_in zero-padded to 160 input channels, conv_out run for 256 padded rows and returned
+    as a channels-last view of a 160-channel buffer, weighted BCE forward / backward on that padded view, the gradient handed to
+    the convolution's backward without a copy) above the emulated C-ABI against the CPU oracle (losses/loss_seg.py:6-22)."""
+    from conftest import rel_err
+    from mas_b200 import ops
+    from models import VQBASE
+    from oracle import vqgan_oracle as O
+    dd = dict(z_channels=64, in_channels=159, out_channels=159, channels=[128, 128], num_res_blocks=1, resolution=64,
+              attn_resolutions=[], dropout=0.0)
+    torch.manual_seed(0)
+    m = VQBASE(dd, 128, 64, 10, 100)
+    with torch.no_grad():
+        m.quantize.embedding.weight.normal_()
+    m.quantize.q_counter = 10 ** 6
+    m.train()
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    params = {k: v.requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k}
+    sd.update(params)
+    seg = (torch.rand(2, 159, 64, 64, generator=torch.Generator().manual_seed(5)) > 0.9).float()
+    dec_o, diff_o, idx_o = O.vqbase_forward(sd, dd, seg)
+    lo = O.bce_loss_with_quant(diff_o, seg, dec_o)
+    lo.backward()
+    pw = torch.ones(159)
+    pw[153:158] = 20
+    cb = m.quantize
+    idx_ref = idx_o.view(-1)
+
+    def fwd(z):                        # the quantiser's decision pinned to the oracle's, as in the GPU test
+        zq, loss = ops.VQGivenFn.apply(z, cb.embedding.weight, cb.beta, idx_ref)
+        return zq, loss, idx_ref
+    cb.forward = fwd
+    dec, diff = m(seg)
+    assert dec.shape == (2, 159, 64, 64) and ops._cl_pitch(dec) == 160
+    loss = ops.BCELogitsFn.apply(dec, seg, pw) + diff
+    loss.backward()
+    assert rel_err(dec, dec_o) < 2e-3
+    assert abs(float(loss.detach()) - float(lo.detach())) < 2e-3 * abs(float(lo.detach()))
+    named = dict(m.named_parameters())
+    for k, pr in params.items():
+        assert rel_err(named[k].grad, pr.grad) < 1e-2, k
+    n = vq_emu.names
+    assert n.count("mas_bce_cl_forward") == 1 and n.count("mas_bce_cl_backward") == 1 and n.count("mas_nchw_to_nhwc_pad") == 1
+    assert "mas_edge_small_cin_fprop" not in n and "mas_edge_small_cout_fprop" not in n      # both edge layers on the padded tensor route
