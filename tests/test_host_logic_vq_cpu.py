@@ -455,6 +455,9 @@ class VqEmu:
             rv = _f32(running_var, C)
             rv[...] = (1 - momentum) * rv + momentum * v * cnt / (cnt - 1)      # unbiased, like nn.(Sync)BatchNorm
 
+    def mas_bn_invstd(self, running_var, eps, invstd, C):
+        _f32(invstd, C)[...] = 1.0 / np.sqrt(_f32(running_var, C).astype(np.float64) + eps)
+
     def mas_bn_apply(self, x, mean, invstd, gamma, beta, y, R, C):
         X = _f32(x, R * C).reshape(R, C).astype(np.float64)
         _f32(y, R * C)[...] = ((X - _f32(mean, C)) * _f32(invstd, C) * _f32(gamma, C) + _f32(beta, C)).reshape(-1)
@@ -790,3 +793,25 @@ def test_vqseg_step_host_logic_against_oracle(vq_emu):
     n = vq_emu.names
     assert n.count("mas_bce_cl_forward") == 1 and n.count("mas_bce_cl_backward") == 1 and n.count("mas_nchw_to_nhwc_pad") == 1
     assert "mas_edge_small_cin_fprop" not in n and "mas_edge_small_cout_fprop" not in n      # both edge layers on the padded tensor route
+
+
+def test_whole_model_modes_host_logic_against_reference_fixture(vq_emu):
+    """The codebook's warm-up bypass (q_counter < q_init: no quantisation, zero loss, modules.py:482-484) and eval mode (running
+    BatchNorm statistics, no counters / reservoir) above the emulated C-ABI, against the REAL reference (vqbase_tiny_modes.pt)."""
+    from conftest import rel_err
+    from models import VQBASE
+    g = torch.load(os.path.join(GOLDEN, "vqbase_tiny.pt"), weights_only=False)
+    mo = torch.load(os.path.join(GOLDEN, "vqbase_tiny_modes.pt"), weights_only=False)
+    m = VQBASE(g["ddconfig"], g["n_embed"], g["embed_dim"], 10, 100)
+    m.load_state_dict(g["state_dict"])
+    m.train()
+    dec, diff = m(g["x"])                      # q_counter = 1 < q_init: warm-up bypass
+    assert float(diff) == 0.0 and rel_err(dec, mo["dec_bypass"]) < 1e-5
+    assert "mas_vq_forward" not in vq_emu.names
+    m.load_state_dict(g["state_dict"])
+    m.eval()
+    with torch.no_grad():
+        dec, diff = m(g["x"])
+    assert rel_err(dec, mo["dec_eval"]) < 1e-5
+    assert abs(float(diff) - float(mo["diff_eval"])) < 1e-5 * abs(float(mo["diff_eval"]))
+    assert "mas_bn_invstd" in vq_emu.names and vq_emu.names.count("mas_vq_forward") == 1
