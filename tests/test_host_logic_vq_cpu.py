@@ -496,6 +496,23 @@ class VqEmu:
         _f32(zq_out, R * D)[...] = Em[ix].reshape(-1)
         _f32(loss_out, 1)[0] = (1 + beta) * ((Em[ix] - Z) ** 2).mean()
 
+    def mas_vq_gather(self, E, idx, R, K, D, out):
+        ix = np.ctypeslib.as_array((ctypes.c_int64 * R).from_address(_addr(idx)))
+        _f32(out, R * D)[...] = _f32(E, K * D).reshape(K, D)[ix].reshape(-1)
+
+    def mas_kmeans_update(self, x, idx, n, K, D, centres_old, centres_new, shift_out, ws, ws_bytes):
+        X = _f32(x, n * D).reshape(n, D).astype(np.float64)
+        ix = np.ctypeslib.as_array((ctypes.c_int64 * n).from_address(_addr(idx)))
+        old = _f32(centres_old, K * D).reshape(K, D).astype(np.float64)
+        new = old.copy()                                          # an empty cluster keeps its centre
+        cnt = np.bincount(ix, minlength=K)
+        sums = np.zeros((K, D))
+        np.add.at(sums, ix, X)
+        new[cnt > 0] = sums[cnt > 0] / cnt[cnt > 0, None]
+        _f32(centres_new, K * D)[...] = new.reshape(-1)
+        if shift_out is not None:
+            _f32(shift_out, 1)[0] = np.sqrt(((new - old) ** 2).sum())
+
     def mas_vq_backward(self, g_zq, g_loss, z, E, idx, R, K, D, beta, grad_z, grad_E):
         Z = _f32(z, R * D).reshape(R, D).astype(np.float64)
         Em = _f32(E, K * D).reshape(K, D).astype(np.float64)
@@ -815,3 +832,58 @@ def test_whole_model_modes_host_logic_against_reference_fixture(vq_emu):
     assert rel_err(dec, mo["dec_eval"]) < 1e-5
     assert abs(float(diff) - float(mo["diff_eval"])) < 1e-5 * abs(float(mo["diff_eval"]))
     assert "mas_bn_invstd" in vq_emu.names and vq_emu.names.count("mas_vq_forward") == 1
+
+
+def test_codebook_schedule_host_logic_against_the_reference(vq_emu):
+    """Codebook's training-time side paths (modules.py:474-499): step counter, reservoir sampling (10 latents per image, the
+    same two torch.randperm draws per step), warm-up bypass - step by step IDENTICAL to the real reference's Codebook under the
+    same seed up to the first re-initialisation; then our k-means replacement (the reference calls the absent
+    fast_pytorch_kmeans there): triggered on the reference's schedule, lowers the quantisation error, and the following steps
+    quantise against the new centres."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+    from oracle import vendor_ref
+    if not vendor_ref.available():
+        pytest.skip("oracle/_ref not staged (needs /root/reference once)")
+    from models import modules as M
+    R = vendor_ref.load_models().modules
+    K, D, init_steps = 16, 8, 4                                  # collect from step 5, quantise from step 12, re-init every 2 steps
+    torch.manual_seed(3)
+    ours, ref = M.Codebook(K, D, 0.25, init_steps, 60), R.Codebook(K, D, 0.25, init_steps, 60)
+    ref.load_state_dict(ours.state_dict())
+    ours.train(); ref.train()
+    gz = torch.Generator().manual_seed(11)
+    zs = [torch.randn(3, D, 4, 4, generator=gz) for _ in range(16)]
+    for step, z in enumerate(zs[:11], start=1):                  # steps 1 .. q_init - 1: both bypass, both collect from step 5 on
+        torch.manual_seed(100 + step)
+        a = ours(z)
+        torch.manual_seed(100 + step)
+        b = ref(z)
+        assert ours.q_counter == ref.q_counter == step
+        assert a[2] is None and b[2] is None and float(a[1]) == 0.0 and torch.equal(a[0], b[0])
+        if step > init_steps:
+            assert torch.equal(ours.reservoir, ref.reservoir) and ours.reservoir.shape[0] == min(60, 30 * (step - init_steps))
+        else:
+            assert ours.reservoir is None and ref.reservoir is None
+    assert "mas_vq_forward" not in vq_emu.names
+    # step q_init = 12: the first re-initialisation from the reservoir, then quantisation
+    e0 = ours.embedding.weight.detach().clone()
+    res = ours.reservoir.clone()
+    err = lambda E: float(((res[:, None, :] - E[None]) ** 2).sum(-1).min(1).values.mean())
+    zq, loss, idx = ours(zs[11])
+    assert ours.q_counter == 12 and vq_emu.names.count("mas_kmeans_update") >= 1
+    e1 = ours.embedding.weight.detach()
+    assert not torch.equal(e0, e1) and err(e1) < 0.5 * err(e0)                 # U(+-1/K) initial codes vs centres of the latents
+    d = ((zs[11].permute(0, 2, 3, 1).reshape(-1, D)[:, None, :] - e1[None]) ** 2).sum(-1)
+    assert torch.equal(idx.view(-1), d.argmin(1)) and torch.allclose(zq.permute(0, 2, 3, 1).reshape(-1, D), e1[idx.view(-1)])
+    n_re = vq_emu.names.count("mas_kmeans_update")
+    ours(zs[12])                                                  # step 13: (13 - 12) % 2 != 0 -> no re-initialisation
+    assert vq_emu.names.count("mas_kmeans_update") == n_re
+    ours(zs[13])                                                  # step 14: on the schedule again
+    assert vq_emu.names.count("mas_kmeans_update") > n_re
+    # eval mode: no counters, no reservoir updates
+    ours.eval()
+    q, r = ours.q_counter, ours.reservoir.clone()
+    ours(zs[14])
+    assert ours.q_counter == q and torch.equal(ours.reservoir, r)
+    assert torch.equal(ours.get_codebook_entry(idx.view(-1), (3, 4, 4, D)), ours.embedding.weight.detach()[idx.view(-1)].view(3, 4, 4, D).permute(0, 3, 1, 2))
