@@ -1,5 +1,7 @@
 #!/usr/bin/env bash
-# Round-2 closing pass: GPU suite, smoke, headline bench, transformer training / sampling tools, ncu of the new kernels.
+# Round-2 closing pass (the recipe behind profiles/r02b_*, r02_transformer_*, r02_ncu_transformer.md): GPU suite, smoke, headline
+# bench, transformer training / sampling tools, ncu --set full of the new kernels.  tools/gpu_r2g.sh: the later check of the causal
+# block skipping.
 set -u
 cd "$(dirname "$0")/.."
 O=gpurun_out; mkdir -p $O
